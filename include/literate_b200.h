@@ -1,0 +1,197 @@
+/*
+ * literate_b200 -- C ABI of the B200-native LiteRate RJMCMC birth-death hot path.
+ *
+ * The reference (dsilvestro/LiteRate) is a single Python script with no FFI seam; the three
+ * seams below are the module-level functions of LiteRateForward.py that a maintainer would
+ * rebind (INTEGRATION.md shows the ctypes stubs).  All file:line citations are relative to the
+ * reference checkout.
+ *
+ *   L2  precompute_events()/get_br() loop        LiteRateForward.py:111-123, :514-549
+ *         -> lr_bin_stats / lr_bin_stats_host / lr_bin_accumulate + lr_bin_finalize
+ *   L3  calc_likelihood() + priors of runMCMC    LiteRateForward.py:137-162, :198-202, :296-306
+ *         -> lr_dataset_create + lr_state_eval
+ *   L4  runMCMC()                                LiteRateForward.py:216-373
+ *         -> lr_chains_create / lr_chains_run / lr_chains_get_state / lr_chains_destroy
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; `stream` is a cudaStream_t passed as void*
+ *     (NULL = the handle's own stream).
+ *   - pointers named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers.
+ *   - every function returns LR_OK (0) or a negative lr_status; lr_last_error() returns the
+ *     message of the last failure on the calling thread.  Nothing throws, nothing falls back
+ *     to a CPU implementation.
+ *   - device-pointer entry points are asynchronous on `stream`; *_host entry points are
+ *     synchronous (they copy host->device, run, copy device->host and wait).
+ *   - one handle per (device, host thread); a handle is not thread-safe, distinct handles are.
+ */
+#ifndef LITERATE_B200_H
+#define LITERATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LR_ABI_VERSION 1
+
+typedef enum lr_status {
+    LR_OK = 0,
+    LR_ERR_INVALID = -1,      /* bad argument */
+    LR_ERR_CUDA = -2,         /* CUDA runtime error, see lr_last_error() */
+    LR_ERR_UNSUPPORTED = -3,  /* size outside what the kernels implement */
+    LR_ERR_NOMEM = -4
+} lr_status;
+
+typedef struct lr_handle_s*  lr_handle_t;   /* one per device */
+typedef struct lr_dataset_s* lr_dataset_t;  /* per-replicate binned statistics + prefix tables, on device */
+typedef struct lr_chains_s*  lr_chains_t;   /* a population of independent chains, on device */
+
+/* ---------------------------------------------------------------- runtime */
+int lr_abi_version(void);
+const char* lr_last_error(void);
+int lr_create(int device, lr_handle_t* out);
+int lr_destroy(lr_handle_t h);
+/* number of SMs, kernels launched through this handle so far, device id */
+int lr_info(lr_handle_t h, int32_t* sm_count, int64_t* kernel_launches, int32_t* device);
+int lr_sync(lr_handle_t h);
+
+/* ---------------------------------------------------------------- L2: lineages -> per-bin statistics
+ *
+ * Replaces the loop `for i in range(int(min ts), int(max te)): precompute_events([i, i+1])`
+ * (LiteRateForward.py:519-523) and its extinct-only twin (:529-549).
+ *
+ *   ts, te     [n_rep][ld] fp64, ld >= n; replicate r occupies ts[r*ld .. r*ld+n)
+ *   first_bin  int(min ts); bin j is [first_bin+j, first_bin+j+1]
+ *   n_bins     int(max te) - int(min ts)
+ *   fe_ref     expected fractional part of te above its bin edge, in (0, 1]
+ *              (0.5 for integer years with the default -death_jitter .5; 1.0 for integer te).
+ *              It only selects the fast path; any value gives the same result.
+ *   dead_only  1: keep only lineages with te < end_time (:531-532), else 0
+ *   sp, ex     int64 [n_rep][n_bins]  births  ts in [t0,t1), deaths te in (t0,t1]   (:120-121)
+ *   br         fp64  [n_rep][n_bins]  sum_i max(0, min(te_i,t1) - max(ts_i,t0))      (:111-116)
+ *
+ * Counts are exact.  br is the correctly rounded exact sum (fractions are accumulated in 2^-52
+ * fixed point), hence bit-identical to the reference for dyadic data and run-to-run
+ * deterministic for any data.
+ */
+#define LR_ACC_ROWS 8
+/* row stride (in int64) of the raw accumulator block of one replicate */
+int64_t lr_acc_stride(int32_t n_bins);
+/* raw accumulators: int64 [n_rep][LR_ACC_ROWS][lr_acc_stride(n_bins)], must be zeroed by the caller.
+ * Rows: 0 births, 1 deaths, 2/3 low-32/high parts of sum frac(ts)*2^52, 4/5 low-32/high parts of
+ * sum (fe-fe_ref)*2^52, 6/7 births/deaths of lineages that carry no time at risk (te<=ts);
+ * [6][n_bins] counts lineages alive before bin 0.
+ * All rows are plain integer sums, so lineage shards combine with an int64 SUM all-reduce. */
+int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t ld,
+                      int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                      int32_t dead_only, double end_time, int64_t* d_acc, void* stream);
+int lr_bin_finalize(lr_handle_t h, const int64_t* d_acc, int32_t n_rep, int32_t n_bins, double fe_ref,
+                    int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream);
+/* zero + accumulate + finalize using the handle's workspace */
+int lr_bin_stats(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t ld,
+                 int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                 int32_t dead_only, double end_time,
+                 int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream);
+/* same with host buffers; copies are pipelined per replicate against the kernel */
+int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double* h_te, int64_t n, int64_t ld,
+                      int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                      int32_t dead_only, double end_time,
+                      int64_t* h_sp, int64_t* h_ex, double* h_br);
+/* which K1 variant lr_bin_accumulate uses: 0 auto, 1 lane-private histograms, 2 shared atomics */
+int lr_set_bin_kernel(lr_handle_t h, int32_t variant);
+
+/* ---------------------------------------------------------------- L3: likelihood + priors on a state
+ *
+ * A dataset holds, per replicate, the binned statistics and the prefix tables the likelihood of a
+ * piecewise-constant state needs (globals sp_events_bin / ex_events_bin / br_length_bin [/ *_dead]
+ * of LiteRateForward.py:566-574).  model_BDI as the reference's -model_BDI (0 BD, 1 ID, 2 Keiding,
+ * 3 Keiding extinct-only; :421-431).  d_ex_dead/d_br_dead may be NULL unless model_BDI == 3.
+ */
+int lr_dataset_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t model_BDI,
+                      double start_time, double end_time,
+                      const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
+                      const int64_t* d_ex_dead, const double* d_br_dead,
+                      void* stream, lr_dataset_t* out);
+int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t model_BDI,
+                           double start_time, double end_time,
+                           const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
+                           const int64_t* h_ex_dead, const double* h_br_dead, lr_dataset_t* out);
+int lr_dataset_destroy(lr_dataset_t ds);
+
+#define LR_KMAX 30   /* most rates per side a state can hold (slots of one warp minus two control lanes) */
+
+/* Batched evaluation of states, HOST buffers (parity/diagnostic entry point).
+ *   rep[n]                replicate of each state
+ *   K_l[n], K_m[n]        number of birth / death rates (1..LR_KMAX)
+ *   L, M       [n][LR_KMAX]  rates
+ *   tL, tM     [n][LR_KMAX]  slot 0 ignored (= start_time), slots 1..K-1 interior shift times, ascending
+ *   gamma_rate [n][2], poi_lambda[n]   hyper-parameters (Gamma_rate, Poi_lambda_rjHP of :220-222)
+ * Outputs (any may be NULL):
+ *   lik[n]         calc_likelihood(L[indL], M[indM])            (:306, :137-162)
+ *   prior_rates[n] prior_gamma(L)+prior_gamma(M) + time prior   (:296-298)
+ *   prior_poi[n]   Poisson_prior(K_l)+Poisson_prior(K_m)        (:279)
+ *   adequacy[n][3] calculate_r_squared                           (literate_library.py:268-279)
+ */
+int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int32_t* K_l, const int32_t* K_m,
+                       const double* L, const double* M, const double* tL, const double* tM,
+                       const double* gamma_rate, const double* poi_lambda,
+                       double* lik, double* prior_rates, double* prior_poi, double* adequacy);
+
+/* ---------------------------------------------------------------- L4: the chains (runMCMC) */
+typedef struct lr_chain_config {
+    int32_t model_BDI;          /* must equal the dataset's */
+    int32_t const_rates;        /* -const_rates        (:274, :386) */
+    int32_t const_death_rate;   /* -const_death_rate   (:243-247, :387) */
+    int32_t use_rate_HP;        /* -use_rate_HP        (:285, :395) */
+    double  poisson_prior;      /* -Poisson_prior, 0 = sample the hyper-prior (:220-221, :283, :396) */
+    double  update_fraction;    /* -update_fraction    (:252, :399) */
+    int32_t real_move_shift;    /* 0 = reference behaviour (move-shift proposes the current state, :184-185);
+                                   1 = reflected sliding window d=1 (opt-in, deviates from the reference) */
+    int32_t reserved;
+    double  beta;               /* likelihood tempering exponent of every chain unless set per chain; 1 = reference */
+} lr_chain_config;
+
+/* Creates n_chains chains; chain c uses replicate rep_of_chain[c] (NULL: all use replicate 0) and the
+ * Philox-4x32-10 stream keyed by (seed, chain_id0 + c), so results do not depend on how chains are
+ * sharded over devices.  Initial state as :580-583 (rates ~ Gamma(2, scale 2), no shifts) with the
+ * initial prior of :227-230. */
+int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains, const lr_chain_config* cfg,
+                     uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain, lr_chains_t* out);
+int lr_chains_destroy(lr_chains_t c);
+
+/* One sample record = LR_REC_DOUBLES doubles:
+ *   [0] iteration  [1] likA  [2] priorA  [3] mean(L)  [4] mean(M)  [5] K_l  [6] K_m
+ *   [7] Gamma_rate[0]  [8] Gamma_rate[1]  [9] Poi_lambda  [10..12] adequacy (coeff, r2, gelman_r2)
+ *   [13] poi_lambda_is_initial (1 while Poi_lambda_rjHP still is the constant of :220-221)  [14..15] reserved
+ *   [16 .. 16+32)  L slots   [48 .. 80) birth shift times (slot 0 = start_time)
+ *   [80 .. 112)    M slots   [112 .. 144) death shift times
+ */
+#define LR_REC_DOUBLES 144
+/* Runs n_iter iterations of every chain, continuing from the current iteration counter `it`.
+ * A record is written after every iteration with it % sample_every == 0 (as :321), i.e.
+ * ceil-count of multiples of sample_every in [it0, it0+n_iter).  d_records must hold
+ * lr_chains_records_per_run() * n_chains records, laid out [sample][chain][LR_REC_DOUBLES].
+ * Asynchronous on `stream`. */
+int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int64_t sample_every);
+int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* d_records, void* stream);
+/* same, records delivered to host memory; synchronous */
+int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* h_records);
+/* per-chain counters since creation: [n_chains][8] int64 =
+ *   iterations, accepted, likelihood evaluations, rate-updates, move-shifts, RJ proposals,
+ *   Gibbs draws, capacity rejections (add-shift at K == LR_KMAX) */
+int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters);
+/* current state of every chain as one record each (iteration = number of iterations done) */
+int lr_chains_get_state_host(lr_chains_t c, double* h_records);
+/* overwrite the state of every chain from records (fields 1,2 and 10-12 are recomputed) */
+int lr_chains_set_state_host(lr_chains_t c, const double* h_records);
+/* per-chain inverse temperatures for tempered ensembles; 1.0 everywhere = the reference's chain */
+int lr_chains_set_beta_host(lr_chains_t c, const double* h_beta);
+/* swap the states' temperatures between chain pairs (a[i], b[i]) with the usual MC3 rule; device side */
+int lr_chains_swap_step(lr_chains_t c, int32_t n_pairs, const int32_t* h_a, const int32_t* h_b, uint64_t round);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITERATE_B200_H */

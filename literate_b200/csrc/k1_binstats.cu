@@ -1,0 +1,423 @@
+// K1: lineages -> per-bin sufficient statistics, one streaming pass over (ts, te).
+//
+// Replaces the reference's per-bin loop over precompute_events()/get_br()
+// (LiteRateForward.py:111-123, :519-523; extinct-only twin :529-549), which makes ~10 full
+// passes over the lineages for EVERY bin.  Here every lineage is read once (16 B) and touches
+// O(1) accumulators, using the identity of SURVEY 7.3:
+//
+//   a = floor(ts) - first_bin                         birth bin   (rule ts >= t0 && ts < t1, :120)
+//   b = ceil(te) - 1 - first_bin                      death bin   (rule te >  t0 && te <= t1, :121)
+//   br[j] = FS[j] + FE[j] + pre + sum_{i<=j} (D[i-1] - E[i])
+//   FS[a] += floor(ts)+1-ts,  FE[b] += te-(ceil(te)-1),  D/E = births/deaths that carry time at risk
+//
+// Fractions are accumulated in 2^-52 fixed point (integers), so every accumulator is an integer
+// sum: order-independent, run-to-run deterministic, and lineage shards of several GPUs combine
+// with an int64 SUM all-reduce.  br is recovered by lr_bin_finalize as the correctly rounded
+// exact sum.
+//
+// Kernel shape (B200, HBM-bound: 16 B/lineage, no reuse):
+//   - persistent grid, one CTA per SM, each CTA owns one contiguous slice of the flattened
+//     [replicate][lineage] space -> perfectly balanced, 2-3 flushes per CTA per launch;
+//   - 128-bit coalesced streaming loads (ld.global.nc.L1::no_allocate.v2.f64), 4 deep per array
+//     per thread = 32 KB in flight per SM;
+//   - variant 1: LANE-PRIVATE u16 histograms in shared memory (hist[warp][side][bin][lane]):
+//     plain LDS/IADD/STS, no atomics, no same-address serialisation whatever the input order
+//     (sorted-by-year tables are the common case and are the worst case for shared atomics);
+//     fractional parts that differ from the expected ones (integer ts, te = int + fe_ref) are
+//     the only thing that goes through 32-bit shared atomics (96-bit carry chain);
+//   - variant 2: block-shared u32 histograms with ATOMS (any n_bins up to 24576; fallback and
+//     comparison point).
+#include "lr_common.cuh"
+
+namespace {
+
+constexpr int K1_UNROLL = 4;                        // double2 loads in flight per array per thread
+constexpr int K1_TILE = 64 * K1_UNROLL;             // lineages one warp consumes per tile
+constexpr int ROW_SP = 0, ROW_EX = 1, ROW_CS_LO = 2, ROW_CS_HI = 3, ROW_CE_LO = 4, ROW_CE_HI = 5,
+              ROW_SPX = 6, ROW_EXX = 7;
+
+struct K1Params {
+    const double* ts;
+    const double* te;
+    long long n, ld;
+    int n_rep;
+    int fb;                // first_bin
+    unsigned nb;           // n_bins
+    double fe_ref;
+    long long fe_ref_fix;
+    int dead_only;
+    double end_time;
+    long long* acc;
+    long long acc_stride;  // int64 per row
+    long long chunk;       // flattened lineages per CTA
+    long long seg_max;     // forced flush period (u16 lane counters)
+    int vec_ok;
+};
+
+// 96-bit unsigned accumulation out of 32-bit shared atomics: words [idx], [nb+idx], [2nb+idx]
+__device__ __forceinline__ void add96(unsigned* arr, unsigned nb, unsigned idx, long long v) {
+    unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
+    unsigned old = atomicAdd(&arr[idx], lo);
+    unsigned add2 = hi + (((unsigned)(old + lo) < lo) ? 1u : 0u);
+    if (add2) {
+        unsigned old2 = atomicAdd(&arr[nb + idx], add2);
+        if ((unsigned)(old2 + add2) < add2) atomicAdd(&arr[2 * nb + idx], 1u);
+    }
+}
+
+struct K1Smem {
+    unsigned short* hs;   // variant 1: this lane's column of the warp's birth histogram
+    unsigned short* he;
+    unsigned* hs32;       // variant 2
+    unsigned* he32;
+    unsigned* cS;         // [3][nb]
+    unsigned* cE;         // [3][nb]
+    unsigned* exC;        // [nb]
+};
+
+// Lineages that are not (alive for a positive time, born inside the window): rare, global atomics.
+__device__ __noinline__ void k1_irregular(const K1Params& p, long long* acc, double ts, double te) {
+    const double T0 = (double)p.fb, T1 = (double)p.fb + (double)p.nb;
+    unsigned long long* row = (unsigned long long*)acc;
+    const long long S = p.acc_stride;
+    bool live = te > ts;   // false for NaNs
+    if (live) {
+        if (ts >= T1) return;                 // born after the window: nothing
+        // here ts < T0: alive before bin 0
+        if (!(te > T0)) return;               // died before the window
+        atomicAdd(&row[ROW_SPX * S + p.nb], 1ull);      // `pre`: present in every bin until its death
+        if (te <= T1) {
+            long long ci = (long long)ceil(te);
+            unsigned b = (unsigned)(ci - 1 - p.fb);
+            atomicAdd(&row[ROW_EX * S + b], 1ull);
+            double fe = te - (double)(ci - 1);
+            long long d = __double2ll_rn(fe * LR_FIX_SCALE) - p.fe_ref_fix;
+            atomicAdd(&row[ROW_CE_LO * S + b], (unsigned long long)(d & 0xffffffffll));
+            atomicAdd(&row[ROW_CE_HI * S + b], (unsigned long long)(d >> 32));
+        }
+        return;
+    }
+    // no time at risk (te <= ts or NaN): the reference still counts the events (:120-121)
+    if (ts >= T0 && ts < T1) {
+        unsigned a = (unsigned)((long long)floor(ts) - p.fb);
+        atomicAdd(&row[ROW_SP * S + a], 1ull);
+        atomicAdd(&row[ROW_SPX * S + a], 1ull);
+    }
+    if (te > T0 && te <= T1) {
+        unsigned b = (unsigned)((long long)ceil(te) - 1 - p.fb);
+        atomicAdd(&row[ROW_EX * S + b], 1ull);
+        atomicAdd(&row[ROW_EXX * S + b], 1ull);
+    }
+}
+
+template <int VARIANT>
+__device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te) {
+    if (p.dead_only) {
+        if (!(te < p.end_time)) return;      // :531-532
+    }
+    const int ti = __double2int_rd(ts);
+    const int ci = __double2int_ru(te);
+    const unsigned a = (unsigned)(ti - p.fb);
+    const unsigned b = (unsigned)(ci - 1 - p.fb);
+    if ((te > ts) && (a < p.nb)) {
+        if (VARIANT == 1) s.hs[a << 5] += 1; else atomicAdd(&s.hs32[a], 1u);
+        const double fr = ts - (double)ti;
+        if (fr != 0.0) add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
+        if (b < p.nb) {
+            if (VARIANT == 1) s.he[b << 5] += 1; else atomicAdd(&s.he32[b], 1u);
+            const double fe = te - (double)(ci - 1);
+            if (fe != p.fe_ref) {
+                atomicAdd(&s.exC[b], 1u);
+                add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
+            }
+        }
+    } else {
+        k1_irregular(p, acc, ts, te);
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(512, 1) k1_bin_kernel(const K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    const unsigned nb = p.nb;
+
+    // ---- carve shared memory
+    K1Smem s;
+    unsigned short* hist16 = (unsigned short*)smem_raw;                 // [W][2][nb][32]
+    unsigned* hist32 = (unsigned*)smem_raw;                             // [2][nb]
+    size_t hist_bytes = (VARIANT == 1) ? (size_t)W * 2 * nb * 32 * sizeof(unsigned short) : (size_t)2 * nb * sizeof(unsigned);
+    unsigned* corr = (unsigned*)(smem_raw + ((hist_bytes + 15) & ~(size_t)15));   // [7][nb]
+    s.hs = hist16 + ((size_t)warp * 2 + 0) * nb * 32 + lane;
+    s.he = hist16 + ((size_t)warp * 2 + 1) * nb * 32 + lane;
+    s.hs32 = hist32;
+    s.he32 = hist32 + nb;
+    s.cS = corr;
+    s.cE = corr + 3 * nb;
+    s.exC = corr + 6 * nb;
+    const size_t zero_words = (((hist_bytes + 15) & ~(size_t)15) + 7 * (size_t)nb * sizeof(unsigned) + 3) / 4;
+
+    const long long total = p.n * (long long)p.n_rep;
+    long long g0 = (long long)blockIdx.x * p.chunk;
+    long long g1 = g0 + p.chunk;
+    if (g1 > total) g1 = total;
+
+    while (g0 < g1) {
+        // ---- one segment: a run of lineages of ONE replicate, at most seg_max long
+        const long long rep = g0 / p.n;
+        const long long s0 = g0 - rep * p.n;
+        long long s1 = p.n;
+        if (s1 - s0 > g1 - g0) s1 = s0 + (g1 - g0);
+        if (s1 - s0 > p.seg_max) s1 = s0 + p.seg_max;
+        g0 += s1 - s0;
+        const double* ts = p.ts + rep * p.ld;
+        const double* te = p.te + rep * p.ld;
+        long long* acc = p.acc + rep * (LR_ACC_ROWS * p.acc_stride);
+
+        for (size_t i = tid; i < zero_words; i += blockDim.x) ((unsigned*)smem_raw)[i] = 0u;
+        __syncthreads();
+
+        // head (up to the first tile boundary), full tiles, tail
+        long long A = (s0 + K1_TILE - 1) / K1_TILE * K1_TILE;
+        if (A > s1) A = s1;
+        const long long ntiles = (s1 - A) / K1_TILE;
+        const long long B = A + ntiles * K1_TILE;
+        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage<VARIANT>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage<VARIANT>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        if (p.vec_ok) {
+            for (long long k = warp; k < ntiles; k += W) {
+                const double2* t2 = (const double2*)(ts + A + k * K1_TILE) + lane;
+                const double2* e2 = (const double2*)(te + A + k * K1_TILE) + lane;
+                double2 sv[K1_UNROLL], ev[K1_UNROLL];
+#pragma unroll
+                for (int u = 0; u < K1_UNROLL; ++u) { sv[u] = ld_stream_f64x2(t2 + u * 32); ev[u] = ld_stream_f64x2(e2 + u * 32); }
+#pragma unroll
+                for (int u = 0; u < K1_UNROLL; ++u) {
+                    k1_lineage<VARIANT>(p, s, acc, sv[u].x, ev[u].x);
+                    k1_lineage<VARIANT>(p, s, acc, sv[u].y, ev[u].y);
+                }
+            }
+        } else {
+            for (long long k = warp; k < ntiles; k += W) {
+                const double* t1 = ts + A + k * K1_TILE + lane;
+                const double* e1 = te + A + k * K1_TILE + lane;
+                double sv[2 * K1_UNROLL], ev[2 * K1_UNROLL];
+#pragma unroll
+                for (int u = 0; u < 2 * K1_UNROLL; ++u) { sv[u] = ld_stream_f64(t1 + u * 32); ev[u] = ld_stream_f64(e1 + u * 32); }
+#pragma unroll
+                for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage<VARIANT>(p, s, acc, sv[u], ev[u]);
+            }
+        }
+        __syncthreads();
+
+        // ---- flush this segment into the replicate's global accumulators
+        unsigned long long* g = (unsigned long long*)acc;
+        if (VARIANT == 1) {
+            // rows r in [0, 2nb): side = r / nb.  A warp reduces 32 consecutive rows, then issues one
+            // coalesced 64-bit reduction per row block.
+            const unsigned nrows = 2 * nb;
+            for (unsigned rb = warp * 32; rb < nrows; rb += W * 32) {
+                unsigned keep = 0;
+                for (unsigned i = 0; i < 32 && rb + i < nrows; ++i) {
+                    const unsigned r = rb + i, side = r >= nb ? 1u : 0u, bin = r - side * nb;
+                    unsigned v = 0;
+                    for (int w = 0; w < W; ++w) v += hist16[(((size_t)w * 2 + side) * nb + bin) * 32 + lane];
+                    v = __reduce_add_sync(0xffffffffu, v);
+                    if (lane == (int)i) keep = v;
+                }
+                const unsigned r = rb + lane;
+                if (r < nrows && keep) {
+                    const unsigned side = r >= nb ? 1u : 0u, bin = r - side * nb;
+                    atomicAdd(&g[(side ? ROW_EX : ROW_SP) * p.acc_stride + bin], (unsigned long long)keep);
+                }
+            }
+        } else {
+            for (unsigned i = tid; i < nb; i += blockDim.x) {
+                if (s.hs32[i]) atomicAdd(&g[ROW_SP * p.acc_stride + i], (unsigned long long)s.hs32[i]);
+                if (s.he32[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.he32[i]);
+            }
+        }
+        for (unsigned i = tid; i < nb; i += blockDim.x) {
+            const unsigned a0 = s.cS[i], a1 = s.cS[nb + i], a2 = s.cS[2 * nb + i];
+            if (a0 | a1 | a2) {
+                atomicAdd(&g[ROW_CS_LO * p.acc_stride + i], (unsigned long long)a0);
+                atomicAdd(&g[ROW_CS_HI * p.acc_stride + i], (unsigned long long)a1 + ((unsigned long long)a2 << 32));
+            }
+            const unsigned n = s.exC[i];
+            if (n) {
+                // sum(fix(fe)) - n*fe_ref_fix, split into (low 32 bits, signed high part)
+                __int128 v = ((__int128)s.cE[2 * nb + i] << 64) + ((__int128)s.cE[nb + i] << 32) + (__int128)s.cE[i];
+                v -= (__int128)n * (__int128)p.fe_ref_fix;
+                atomicAdd(&g[ROW_CE_LO * p.acc_stride + i], (unsigned long long)(v & 0xffffffff));
+                atomicAdd(&g[ROW_CE_HI * p.acc_stride + i], (unsigned long long)(long long)(v >> 32));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// exact conversion of a non-negative 128-bit fixed-point value (2^-52 units) to the nearest double
+__device__ double fix128_to_double(unsigned __int128 f) {
+    unsigned long long hi = (unsigned long long)(f >> 64), lo = (unsigned long long)f;
+    if (hi == 0) {
+        if (lo < (1ull << 53)) return (double)lo * (1.0 / LR_FIX_SCALE);
+        return __ull2double_rn(lo) * (1.0 / LR_FIX_SCALE);     // single rounding, scaling by 2^-52 is exact
+    }
+    int sh = 64 - __clzll(hi);                                  // bits above the low word
+    unsigned long long top = (unsigned long long)(f >> sh);
+    bool sticky = (f & ((((unsigned __int128)1) << sh) - 1)) != 0;
+    top |= sticky ? 1ull : 0ull;
+    return ldexp(__ull2double_rn(top), sh - LR_FIX_SHIFT);
+}
+
+// one CTA per replicate: integer prefix scan + exact reconstruction of br
+__global__ void __launch_bounds__(256) k1_finalize_kernel(const long long* __restrict__ acc_all, long long acc_stride, int nb,
+                                                          long long fe_ref_fix, long long* __restrict__ sp_out,
+                                                          long long* __restrict__ ex_out, double* __restrict__ br_out) {
+    __shared__ long long warp_tot[8];
+    __shared__ long long carry_s;
+    const int rep = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long* acc = acc_all + (long long)rep * LR_ACC_ROWS * acc_stride;
+    if (tid == 0) carry_s = acc[ROW_SPX * acc_stride + nb];     // lineages alive before bin 0
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        const int j = base + tid;
+        long long D = 0, E = 0, x = 0;
+        if (j < nb) {
+            D = acc[ROW_SP * acc_stride + j] - acc[ROW_SPX * acc_stride + j];
+            E = acc[ROW_EX * acc_stride + j] - acc[ROW_EXX * acc_stride + j];
+            long long Dprev = j > 0 ? acc[ROW_SP * acc_stride + j - 1] - acc[ROW_SPX * acc_stride + j - 1] : 0;
+            x = Dprev - E;
+        }
+        // inclusive block scan of x
+        long long v = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) warp_tot[warp] = v;
+        __syncthreads();
+        long long off = carry_s;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        const long long c = v + off;                              // lineages spanning all of bin j ... minus deaths in j
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry_s = c;
+        if (j < nb) {
+            __int128 cS = (__int128)acc[ROW_CS_LO * acc_stride + j] + ((__int128)acc[ROW_CS_HI * acc_stride + j] << 32);
+            __int128 cE = (__int128)acc[ROW_CE_LO * acc_stride + j] + ((__int128)acc[ROW_CE_HI * acc_stride + j] << 32);
+            __int128 F = ((__int128)(c + D) << LR_FIX_SHIFT) - cS + (__int128)E * (__int128)fe_ref_fix + cE;
+            if (F < 0) F = 0;
+            sp_out[(long long)rep * nb + j] = acc[ROW_SP * acc_stride + j];
+            ex_out[(long long)rep * nb + j] = acc[ROW_EX * acc_stride + j];
+            br_out[(long long)rep * nb + j] = fix128_to_double((unsigned __int128)F);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t lr_acc_stride(int32_t n_bins) { return ((int64_t)n_bins + 1 + 7) / 8 * 8; }
+
+static long long fe_fix(double fe_ref) { return (long long)llrint(fe_ref * LR_FIX_SCALE); }
+
+extern "C" int lr_set_bin_kernel(lr_handle_t h, int32_t variant) {
+    LR_REQUIRE(h != nullptr && variant >= 0 && variant <= 2, "lr_set_bin_kernel: bad argument");
+    h->bin_variant = variant;
+    return LR_OK;
+}
+
+extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t ld,
+                                 int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                                 int32_t dead_only, double end_time, int64_t* d_acc, void* stream) {
+    LR_REQUIRE(h != nullptr, "lr_bin_accumulate: null handle");
+    LR_REQUIRE(n >= 0 && n_rep >= 1 && ld >= n, "lr_bin_accumulate: need n >= 0, n_rep >= 1, ld >= n");
+    LR_REQUIRE(n_bins >= 1, "lr_bin_accumulate: n_bins must be >= 1");
+    LR_REQUIRE(fe_ref > 0.0 && fe_ref <= 1.0, "lr_bin_accumulate: fe_ref must lie in (0, 1]");
+    LR_REQUIRE(d_acc != nullptr && (n == 0 || (d_ts != nullptr && d_te != nullptr)), "lr_bin_accumulate: null pointer");
+    if (first_bin <= -(1ll << 30) || first_bin >= (1ll << 30) || n_bins > 24576) {
+        lr_set_error("lr_bin_accumulate: |first_bin| must be < 2^30 and n_bins <= 24576");
+        return LR_ERR_UNSUPPORTED;
+    }
+    if (n == 0) return LR_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    LR_CUDA(cudaSetDevice(h->device));
+
+    K1Params p;
+    p.ts = d_ts; p.te = d_te; p.n = n; p.ld = ld; p.n_rep = n_rep;
+    p.fb = (int)first_bin; p.nb = (unsigned)n_bins; p.fe_ref = fe_ref; p.fe_ref_fix = fe_fix(fe_ref);
+    p.dead_only = dead_only; p.end_time = end_time;
+    p.acc = (long long*)d_acc; p.acc_stride = lr_acc_stride(n_bins);
+    p.vec_ok = (((uintptr_t)d_ts | (uintptr_t)d_te) & 15) == 0 && (ld % 2 == 0 || n_rep == 1);
+
+    const size_t corr_bytes = 7 * (size_t)n_bins * sizeof(unsigned) + 16;
+    const size_t budget = (size_t)h->max_smem_optin - 1024;
+    // variant 1 needs 128 B per bin per warp
+    int W = (int)((budget - corr_bytes) / ((size_t)128 * n_bins));
+    int variant = h->bin_variant;
+    if (variant == 0) variant = W >= 4 ? 1 : 2;
+    if (variant == 1 && W < 1) { lr_set_error("lr_bin_accumulate: n_bins too large for the lane-private kernel"); return LR_ERR_UNSUPPORTED; }
+    const long long total = n * (long long)n_rep;
+    int blocks, threads;
+    size_t smem;
+    if (variant == 1) {
+        if (W > 16) W = 16;
+        threads = W * 32;
+        blocks = h->sm_count;
+        smem = (size_t)W * 2 * n_bins * 64 + corr_bytes;
+        p.seg_max = (long long)W * 32 * 32768;
+    } else {
+        threads = 256;
+        smem = 2 * (size_t)n_bins * 4 + corr_bytes;
+        int per_sm = (int)(budget / (smem + 1024));
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        blocks = h->sm_count * per_sm;
+        p.seg_max = 1ll << 31;
+    }
+    long long chunk = (total + blocks - 1) / blocks;
+    chunk = (chunk + K1_TILE - 1) / K1_TILE * K1_TILE;
+    p.chunk = chunk;
+    int used = (int)((total + chunk - 1) / chunk);
+    if (variant == 1) {
+        LR_CUDA(cudaFuncSetAttribute(k1_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_bin_kernel<1><<<used, threads, smem, st>>>(p);
+    } else {
+        LR_CUDA(cudaFuncSetAttribute(k1_bin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1_bin_kernel<2><<<used, threads, smem, st>>>(p);
+    }
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_bin_finalize(lr_handle_t h, const int64_t* d_acc, int32_t n_rep, int32_t n_bins, double fe_ref,
+                               int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream) {
+    LR_REQUIRE(h != nullptr && d_acc && d_sp && d_ex && d_br, "lr_bin_finalize: null pointer");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_bin_finalize: bad sizes");
+    LR_REQUIRE(fe_ref > 0.0 && fe_ref <= 1.0, "lr_bin_finalize: fe_ref must lie in (0, 1]");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    LR_CUDA(cudaSetDevice(h->device));
+    k1_finalize_kernel<<<n_rep, 256, 0, st>>>((const long long*)d_acc, lr_acc_stride(n_bins), n_bins, fe_fix(fe_ref),
+                                               (long long*)d_sp, (long long*)d_ex, d_br);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_bin_stats(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t ld,
+                            int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                            int32_t dead_only, double end_time,
+                            int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream) {
+    LR_REQUIRE(h != nullptr, "lr_bin_stats: null handle");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_bin_stats: bad sizes");
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const size_t acc_bytes = (size_t)n_rep * LR_ACC_ROWS * lr_acc_stride(n_bins) * sizeof(int64_t);
+    int rc = lr_ws_reserve(h, acc_bytes);
+    if (rc != LR_OK) return rc;
+    LR_CUDA(cudaMemsetAsync(h->ws, 0, acc_bytes, st));
+    rc = lr_bin_accumulate(h, d_ts, d_te, n, ld, n_rep, first_bin, n_bins, fe_ref, dead_only, end_time, (int64_t*)h->ws, st);
+    if (rc != LR_OK) return rc;
+    return lr_bin_finalize(h, (const int64_t*)h->ws, n_rep, n_bins, fe_ref, d_sp, d_ex, d_br, st);
+}

@@ -1,0 +1,870 @@
+// K2 (dataset tables + batched state evaluation) and K3 (persistent multi-chain RJMCMC).
+//
+// K3 replaces runMCMC (LiteRateForward.py:216-373): per iteration one warp = one chain draws its
+// randoms from a Philox-4x32-10 stream keyed by (seed, chain id), builds the proposal in
+// registers, evaluates likelihood/prior/Hastings-Jacobian terms and runs the Metropolis-Hastings
+// accept step -- no host round trip, no memory traffic besides the read-only prefix tables and
+// the sample records.  Reference quirks kept on purpose: no-op move-shift
+// (:184-185), stale priorPoiA (:300-304,:319), initial prior with Gamma rate 2 (:227), `>=`
+// accept test (:313), min-spacing guard (:290).
+#include "chain_device.cuh"
+
+namespace {
+
+__constant__ double c_lnfact[LR_SLOTS + 2];
+
+struct ChainState {
+    long long it;
+    long long counters[8];
+    int K_l, K_m, rep, poi_is_init;
+    unsigned chain_id, pad;
+    double priorA, poiA, gL, gM, poi, beta;
+    double rL[LR_SLOTS], lrL[LR_SLOTS], tL[LR_SLOTS];
+    double rM[LR_SLOTS], lrM[LR_SLOTS], tM[LR_SLOTS];
+};
+
+}  // namespace
+
+struct lr_chains_s {
+    lr_handle_t h;
+    lr_dataset_t ds;
+    int n_chains;
+    lr_chain_config cfg;
+    uint64_t seed;
+    ChainState* st;       // device [n_chains]
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// dataset tables
+// ------------------------------------------------------------------------------------------------
+__global__ void k2_build_tables(const long long* __restrict__ sp, const long long* __restrict__ ex,
+                                const double* __restrict__ br, const long long* __restrict__ exd,
+                                const double* __restrict__ brd, int nb, int model, double* __restrict__ tab_all,
+                                double* __restrict__ cst_all) {
+    const int rep = blockIdx.x, t = threadIdx.x;
+    const long long* U = sp + (size_t)rep * nb;
+    const long long* D = ex + (size_t)rep * nb;
+    const double* K = br + (size_t)rep * nb;
+    const long long* Dd = exd ? exd + (size_t)rep * nb : D;
+    const double* Kd = brd ? brd + (size_t)rep * nb : K;
+    double* tab = tab_all + (size_t)rep * LR_NTAB * (nb + 1);
+    if (t < LR_NTAB) {
+        double acc = 0.0;
+        double* T = tab + (size_t)t * (nb + 1);
+        T[0] = 0.0;
+        for (int j = 0; j < nb; ++j) {
+            const bool m = (model <= 1) ? (K[j] > 0.0) : true;
+            double v = 0.0;
+            switch (t) {
+                case T_AB: v = m ? (double)U[j] : 0.0; break;
+                case T_BB: v = (model == 1) ? (m ? 1.0 : 0.0) : (m ? K[j] : 0.0); break;
+                case T_AD: v = (model == 3) ? (double)Dd[j] : (m ? (double)D[j] : 0.0); break;
+                case T_BD: v = (model == 3) ? Kd[j] : (m ? K[j] : 0.0); break;
+                case T_XB: v = (double)U[j] / K[j]; break;
+                case T_XD: v = (double)D[j] / K[j]; break;
+            }
+            acc += v;
+            T[j + 1] = acc;
+        }
+    } else if (t == 32) {
+        double c = 0.0, sx = 0.0, sxx = 0.0;
+        for (int j = 0; j < nb; ++j) {
+            if (model <= 1 && K[j] > 0.0) {
+                const double lk = log(K[j]);
+                c += (model == 0 ? (double)(U[j] + D[j]) : (double)D[j]) * lk;
+            }
+            const double xb = (double)U[j] / K[j], xd = (double)D[j] / K[j];
+            sx += xb + xd;
+            sxx += xb * xb + xd * xd;
+        }
+        cst_all[rep * LR_NCST + 0] = c;
+        cst_all[rep * LR_NCST + 1] = sx;
+        cst_all[rep * LR_NCST + 2] = sxx;
+        cst_all[rep * LR_NCST + 3] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp random numbers
+// ------------------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t k0, k1, chain;
+    __device__ __forceinline__ void draw(long long it, uint32_t purpose, int lane, double& ua, double& ub) const {
+        Philox4 p = philox4x32_10((uint32_t)it, (uint32_t)((unsigned long long)it >> 32), (uint32_t)lane | (purpose << 8), chain, k0, k1);
+        ua = u01(p.x, p.y);
+        ub = u01(p.z, p.w);
+    }
+};
+
+// Gamma(a, 1), 1 <= a < 2 (Marsaglia & Tsang 2000), 32 attempts per round, first accepted lane wins
+__device__ double warp_gamma_mt(double a, const Rng& rng, long long it, uint32_t purpose, int lane) {
+    const double d = a - 1.0 / 3.0, c = rsqrt(9.0 * d);
+    for (uint32_t round = 0;; ++round) {
+        double u1, u2, u3, u4;
+        rng.draw(it, purpose + 2 * round, lane, u1, u2);
+        rng.draw(it, purpose + 2 * round + 1, lane, u3, u4);
+        const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        double v = 1.0 + c * z;
+        bool ok = v > 0.0;
+        v = v * v * v;
+        ok = ok && (log(u3) < 0.5 * z * z + d - d * v + d * log(v));
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) return __shfl_sync(0xffffffffu, d * v, __ffs(m) - 1);
+        if (round > 64) return d;   // unreachable in practice (p ~ 0.05^2048)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// state <-> registers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_sides(const ChainState* S, Side& L, Side& M, int lane) {
+    L.K = S->K_l; M.K = S->K_m;
+    L.r = S->rL[lane]; L.lr = S->lrL[lane]; L.t = S->tL[lane];
+    M.r = S->rM[lane]; M.lr = S->lrM[lane]; M.t = S->tM[lane];
+}
+__device__ __forceinline__ void store_sides(ChainState* S, const Side& L, const Side& M, int lane) {
+    S->rL[lane] = L.r; S->lrL[lane] = L.lr; S->tL[lane] = L.t;
+    S->rM[lane] = M.r; S->lrM[lane] = M.lr; S->tM[lane] = M.t;
+    if (lane == 0) { S->K_l = L.K; S->K_m = M.K; }
+}
+
+struct Hyper {
+    double gL, gM, lgL, lgM, poi, lpoi;
+};
+
+__device__ __forceinline__ double full_prior(const Side& L, const Side& M, const Hyper& hp, const DataView& d, double poi_term) {
+    // :296-303
+    return rates_prior(L, hp.gL, hp.lgL) + rates_prior(M, hp.gM, hp.lgM) - d.log_span * (double)(L.K + M.K - 2) + poi_term;
+}
+
+__device__ void write_record(double* rec, long long it, const Side& L, const Side& M, const Hyper& hp, const DataView& d,
+                             double priorA, int poi_is_init, int lane, bool with_adequacy) {
+    double adq[3] = {0.0, 0.0, 0.0};
+    if (with_adequacy) adequacy3(L, M, d, lane, adq);
+    if (lane == 0) {
+        rec[0] = (double)it;
+        rec[1] = d.C + L.lik + M.lik;
+        rec[2] = priorA;
+        rec[3] = L.sumr / (double)L.K;
+        rec[4] = M.sumr / (double)M.K;
+        rec[5] = (double)L.K;
+        rec[6] = (double)M.K;
+        rec[7] = hp.gL; rec[8] = hp.gM; rec[9] = hp.poi;
+        rec[10] = adq[0]; rec[11] = adq[1]; rec[12] = adq[2];
+        rec[13] = (double)poi_is_init; rec[14] = 0.0; rec[15] = 0.0;
+    }
+    rec[16 + lane] = lane < L.K ? L.r : 0.0;
+    rec[48 + lane] = lane < L.K ? (lane == 0 ? d.start_time : L.t) : 0.0;
+    rec[80 + lane] = lane < M.K ? M.r : 0.0;
+    rec[112 + lane] = lane < M.K ? (lane == 0 ? d.start_time : M.t) : 0.0;
+}
+
+struct RunParams {
+    ChainState* st;
+    int n_chains;
+    const double* tab; const double* cst;
+    int nb, s0f, model;
+    double start_time, end_time;
+    lr_chain_config cfg;
+    uint32_t k0, k1;
+    long long n_iter, sample_every;
+    double* records;     // [sample][chain][LR_REC_DOUBLES] or null
+    int with_adequacy;
+};
+
+// ------------------------------------------------------------------------------------------------
+// proposals on one side (all warp-uniform control flow)
+// ------------------------------------------------------------------------------------------------
+// update_multiplier_freq (:165-176): each rate w.p. f times exp(2 ln(1.1) (u - .5)); Hastings = sum log m
+__device__ __forceinline__ void propose_rates(const Side& cur, Side& nw, double f, double ua, double ub, int lane, double& hasting) {
+    nw = cur;
+    const bool on = lane < cur.K;
+    const bool touched = on && (ua < f);
+    const double dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
+    nw.lr = cur.lr + dlt;
+    nw.r = touched ? exp(nw.lr) : cur.r;
+    side_sums(nw, lane);
+    hasting = nw.sumlr - cur.sumlr;
+}
+
+// add_shift_RJ_weighted_mean (:29-47).  Returns false if the proposal violates the spacing guard (:290).
+__device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
+                                            double u_idx, double u_t, double ubeta, int lane, double& hasting) {
+    const int K = cur.K;
+    int i = (int)(u_idx * (double)K);
+    if (i > K - 1) i = K - 1;
+    const double t_raw = (lane == 0) ? d.start_time : cur.t;
+    const double t_i = __shfl_sync(0xffffffffu, t_raw, i);
+    double t_n = __shfl_sync(0xffffffffu, t_raw, (i + 1) & 31);
+    if (i + 1 >= K) t_n = d.end_time;
+    const double gap = t_n - t_i;
+    const double tp = t_i + u_t * gap;                       // np.random.uniform(0, gap)
+    const double p1 = (t_i - tp) / (t_i - t_n);
+    const double p2 = (tp - t_n) / (t_i - t_n);
+    const double lr_i = __shfl_sync(0xffffffffu, cur.lr, i);
+    const double w = log((1.0 - ubeta) / ubeta);
+    const double lr1 = lr_i - p2 * w, lr2 = lr_i + p1 * w;
+    const double r1 = exp(lr1), r2 = exp(lr2);
+    hasting = log(fabs(gap)) - ln_sym_beta10(ubeta) + 2.0 * log(r1 + r2) - lr_i;
+    // shift slots above i up by one
+    const double ur = __shfl_up_sync(0xffffffffu, cur.r, 1);
+    const double ulr = __shfl_up_sync(0xffffffffu, cur.lr, 1);
+    const double ut = __shfl_up_sync(0xffffffffu, cur.t, 1);
+    nw = cur;
+    nw.K = K + 1;
+    if (lane == i) { nw.r = r1; nw.lr = lr1; }
+    else if (lane == i + 1) { nw.r = r2; nw.lr = lr2; nw.t = tp; }
+    else if (lane > i + 1) { nw.r = ur; nw.lr = ulr; nw.t = ut; }
+    if ((tp - t_i) <= LR_MIN_DT || (t_n - tp) <= LR_MIN_DT) return false;
+    side_stats(nw, d, tabA, tabB, lane);
+    side_sums(nw, lane);
+    return true;
+}
+
+// remove_shift_RJ_weighted_mean (:49-69); caller guarantees K > 1
+__device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
+                                               double u_idx, int lane, double& hasting) {
+    const int K = cur.K;
+    int j = 1 + (int)(u_idx * (double)(K - 1));
+    if (j > K - 1) j = K - 1;
+    const double t_raw = (lane == 0) ? d.start_time : cur.t;
+    const double t_rm = __shfl_sync(0xffffffffu, t_raw, j);
+    const double t_a = __shfl_sync(0xffffffffu, t_raw, j - 1);
+    double t_b = __shfl_sync(0xffffffffu, t_raw, (j + 1) & 31);
+    if (j + 1 >= K) t_b = d.end_time;
+    const double dT = fabs(t_b - t_a);
+    const double p1 = (t_a - t_rm) / (t_a - t_b);
+    const double p2 = (t_rm - t_b) / (t_a - t_b);
+    const double lra = __shfl_sync(0xffffffffu, cur.lr, j - 1), lrb = __shfl_sync(0xffffffffu, cur.lr, j);
+    const double ra = __shfl_sync(0xffffffffu, cur.r, j - 1), rb = __shfl_sync(0xffffffffu, cur.r, j);
+    const double lm = p1 * lra + p2 * lrb;
+    const double merged = exp(lm);
+    const double u = 1.0 / (1.0 + rb / ra);
+    hasting = -log(dT) + ln_sym_beta10(u) + lm - 2.0 * log(ra + rb);
+    const double dr = __shfl_down_sync(0xffffffffu, cur.r, 1);
+    const double dlr = __shfl_down_sync(0xffffffffu, cur.lr, 1);
+    const double dt = __shfl_down_sync(0xffffffffu, cur.t, 1);
+    nw = cur;
+    nw.K = K - 1;
+    if (lane == j - 1) { nw.r = merged; nw.lr = lm; }
+    else if (lane >= j) { nw.r = dr; nw.lr = dlr; nw.t = dt; }
+    side_stats(nw, d, tabA, tabB, lane);
+    side_sums(nw, lane);
+}
+
+// opt-in real move-shift: reflected sliding window of width 1 on one interior shift (what
+// update_sliding_win :178-186 computes before it overwrites the result)
+__device__ __forceinline__ bool propose_move(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
+                                             double u_idx, double u_w, int lane) {
+    const int K = cur.K;
+    int j = 1 + (int)(u_idx * (double)(K - 1));
+    if (j > K - 1) j = K - 1;
+    const double t_raw = (lane == 0) ? d.start_time : cur.t;
+    const double t_j = __shfl_sync(0xffffffffu, t_raw, j);
+    const double t_a = __shfl_sync(0xffffffffu, t_raw, j - 1);
+    double t_b = __shfl_sync(0xffffffffu, t_raw, (j + 1) & 31);
+    if (j + 1 >= K) t_b = d.end_time;
+    double tp = t_j + (u_w - 0.5) * 1.0;
+    if (tp < d.start_time) tp = d.start_time + (d.start_time - tp);
+    if (tp > d.end_time) tp = d.end_time - (tp - d.end_time);
+    nw = cur;
+    if (lane == j) nw.t = tp;
+    if ((tp - t_a) <= LR_MIN_DT || (t_b - tp) <= LR_MIN_DT) return false;
+    side_stats(nw, d, tabA, tabB, lane);
+    side_sums(nw, lane);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: the chains
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
+    const int lane = threadIdx.x & 31;
+    const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (chain >= P.n_chains) return;
+    ChainState* S = P.st + chain;
+
+    const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
+    Side L, M;
+    load_sides(S, L, M, lane);
+    side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
+    side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
+    Hyper hp;
+    hp.gL = S->gL; hp.gM = S->gM; hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.poi = S->poi; hp.lpoi = log(hp.poi);
+    double priorA = S->priorA, poiA = S->poiA;
+    const double beta = S->beta;
+    int poi_is_init = S->poi_is_init;
+    Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
+    long long cnt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt[i] = S->counters[i];
+
+    const lr_chain_config& cfg = P.cfg;
+    const double shift_mu = cfg.const_death_rate ? 0.0 : 0.5;          // :243-252
+    const double b_freq = cfg.const_death_rate ? 0.7 : 0.4, d_freq = 0.8;
+    const double fL = cfg.update_fraction, fM = cfg.const_death_rate ? 1.0 : cfg.update_fraction;
+    const bool frozen = (d.end_time - d.start_time) <= LR_MIN_DT;      // guard :290 rejects everything
+
+    const long long it0 = S->it, it1 = it0 + P.n_iter;
+    const long long s_every = P.sample_every > 0 ? P.sample_every : 1;
+    const long long first_sample = (it0 + s_every - 1) / s_every * s_every;
+
+    for (long long it = it0; it < it1; ++it) {
+        double ua, ub;
+        rng.draw(it, 0, lane, ua, ub);
+        const double r0 = __shfl_sync(0xffffffffu, ua, 31), r1 = __shfl_sync(0xffffffffu, ub, 31);
+        const double log_u = log(__shfl_sync(0xffffffffu, ua, 30));
+
+        if (r0 < d_freq) {
+            // ---------------- birth block (:254-262) / death block (:264-272)
+            const bool birth = r0 < b_freq;
+            Side& cur = birth ? L : M;
+            if (r1 < 0.5 || cur.K == 1) {
+                cnt[3]++;
+                Side nw;
+                double hasting;
+                propose_rates(cur, nw, birth ? fL : fM, ua, ub, lane, hasting);
+                if (!frozen) {
+                    cnt[2]++;
+                    const double prior = birth ? full_prior(nw, M, hp, d, poiA) : full_prior(L, nw, hp, d, poiA);
+                    if (beta * (nw.lik - cur.lik) + (prior - priorA) + hasting >= log_u) {
+                        cur = nw; priorA = prior; cnt[1]++;
+                    }
+                }
+            } else {
+                cnt[4]++;
+                if (!cfg.real_move_shift) {
+                    // the reference's move proposes the current state (:184-185): only the prior bookkeeping can differ
+                    if (!frozen) {
+                        cnt[2]++;
+                        const double prior = full_prior(L, M, hp, d, poiA);
+                        if ((prior - priorA) >= log_u) { priorA = prior; cnt[1]++; }
+                    }
+                } else {
+                    Side nw;
+                    const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_w = __shfl_sync(0xffffffffu, ub, 28);
+                    const bool ok = propose_move(cur, nw, d, birth ? T_AB : T_AD, birth ? T_BB : T_BD, u_idx, u_w, lane);
+                    if (ok && !frozen) {
+                        cnt[2]++;
+                        const double prior = birth ? full_prior(nw, M, hp, d, poiA) : full_prior(L, nw, hp, d, poiA);
+                        if (beta * (nw.lik - cur.lik) + (prior - priorA) >= log_u) { cur = nw; priorA = prior; cnt[1]++; }
+                    }
+                }
+            }
+        } else if (r0 < 0.999 && !cfg.const_rates) {
+            // ---------------- RJ (:274-279, :71-97)
+            cnt[5]++;
+            const double rs = __shfl_sync(0xffffffffu, ua, 29), ra = __shfl_sync(0xffffffffu, ub, 29);
+            const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_t = __shfl_sync(0xffffffffu, ub, 28);
+            const bool birth = rs > shift_mu;
+            Side& cur = birth ? L : M;
+            const int tabA = birth ? T_AB : T_AD, tabB = birth ? T_BB : T_BD;
+            Side nw = cur;
+            double hasting = 0.0;
+            bool ok = true;
+            if (ra > 0.5) {
+                if (cur.K >= LR_KMAX) { ok = false; cnt[7]++; }
+                else {
+                    // Beta(10,10) = G1/(G1+G2), Gamma(10,1) = -log(prod of 10 uniforms)
+                    const double g1 = -log(warp_prod(lane < 10 ? ua : 1.0));
+                    const double g2 = -log(warp_prod(lane < 10 ? ub : 1.0));
+                    ok = propose_add(cur, nw, d, tabA, tabB, u_idx, u_t, g1 / (g1 + g2), lane, hasting);
+                }
+            } else if (cur.K > 1) {
+                propose_remove(cur, nw, d, tabA, tabB, u_idx, lane, hasting);
+            }
+            if (ok && !frozen) {
+                cnt[2]++;
+                const double poiN = poisson_prior(birth ? nw.K : L.K, hp.poi, hp.lpoi, c_lnfact) +
+                                    poisson_prior(birth ? M.K : nw.K, hp.poi, hp.lpoi, c_lnfact);     // :279
+                const double prior = birth ? full_prior(nw, M, hp, d, poiN) : full_prior(L, nw, hp, d, poiN);
+                if (beta * (nw.lik - cur.lik) + (prior - priorA) + hasting >= log_u) {
+                    cur = nw; priorA = prior; poiA = poiN; cnt[1]++;
+                }
+            }
+        } else {
+            // ---------------- Gibbs on the hyper-priors (:281-287), always accepted (:313)
+            cnt[6]++;
+            if (cfg.poisson_prior == 0.0) {
+                // get_post_rj_HP (:99-108): Gamma(2 + K_l + K_m, scale 1/3), integer shape
+                double ga, gb;
+                rng.draw(it, 1, lane, ga, gb);
+                const int n = 2 + L.K + M.K;
+                const double pr = warp_prod((lane < n ? ga : 1.0) * (lane + 32 < n ? gb : 1.0));
+                hp.poi = -log(pr) / 3.0;
+                hp.lpoi = log(hp.poi);
+                poi_is_init = 0;
+            }
+            if (cfg.use_rate_HP) {
+                // get_rate_HP (:210-213): Gamma(1.2 + 2K, scale 1/(0.1 + sum rates)) = (Gamma(1.2) + Gamma(2K)) * scale
+                double ga, gb;
+                rng.draw(it, 2, lane, ga, gb);
+                const double eL = -log(warp_prod(lane < L.K ? ga * gb : 1.0));
+                const double fracL = warp_gamma_mt(1.2, rng, it, 8, lane);
+                hp.gL = (eL + fracL) / (0.1 + L.sumr);
+                rng.draw(it, 3, lane, ga, gb);
+                const double eM = -log(warp_prod(lane < M.K ? ga * gb : 1.0));
+                const double fracM = warp_gamma_mt(1.2, rng, it, 160, lane);
+                hp.gM = (eM + fracM) / (0.1 + M.sumr);
+                hp.lgL = log(hp.gL); hp.lgM = log(hp.gM);
+            }
+            if (!frozen) { priorA = full_prior(L, M, hp, d, poiA); }
+            else { priorA = -INFINITY; }      // :291 with gibbs == 1 (:313) stores -inf
+            cnt[1]++;
+        }
+        cnt[0]++;
+
+        if (P.records != nullptr && (it % s_every) == 0) {
+            const long long idx = (it - first_sample) / s_every;
+            double* rec = P.records + ((size_t)idx * P.n_chains + chain) * LR_REC_DOUBLES;
+            write_record(rec, it, L, M, hp, d, priorA, poi_is_init, lane, P.with_adequacy != 0);
+        }
+    }
+
+    store_sides(S, L, M, lane);
+    if (lane == 0) {
+        S->it = it1;
+        S->priorA = priorA; S->poiA = poiA; S->gL = hp.gL; S->gM = hp.gM; S->poi = hp.poi; S->poi_is_init = poi_is_init;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) S->counters[i] = cnt[i];
+    }
+}
+
+// initial state (:580-583) and initial bookkeeping (:220-230)
+__global__ void k3_init_kernel(ChainState* st, int n_chains, const int* __restrict__ rep_of_chain, long long chain_id0,
+                               uint32_t k0, uint32_t k1, double start_time, double poisson_prior_cfg, double beta) {
+    const int lane = threadIdx.x & 31;
+    const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (chain >= n_chains) return;
+    ChainState* S = st + chain;
+    Rng rng; rng.k0 = k0; rng.k1 = k1; rng.chain = (uint32_t)(chain_id0 + chain);
+    double ua, ub;
+    rng.draw(-1, 15, lane, ua, ub);
+    // Gamma(shape 2, scale 2) = -2 log(u1 u2)
+    const double l0 = -2.0 * log(__shfl_sync(0xffffffffu, ua, 0) * __shfl_sync(0xffffffffu, ub, 0));
+    const double m0 = -2.0 * log(__shfl_sync(0xffffffffu, ua, 1) * __shfl_sync(0xffffffffu, ub, 1));
+    S->rL[lane] = lane == 0 ? l0 : 0.0; S->lrL[lane] = lane == 0 ? log(l0) : 0.0; S->tL[lane] = lane == 0 ? start_time : 0.0;
+    S->rM[lane] = lane == 0 ? m0 : 0.0; S->lrM[lane] = lane == 0 ? log(m0) : 0.0; S->tM[lane] = lane == 0 ? start_time : 0.0;
+    if (lane == 0) {
+        S->it = 0;
+        for (int i = 0; i < 8; ++i) S->counters[i] = 0;
+        S->K_l = 1; S->K_m = 1; S->rep = rep_of_chain ? rep_of_chain[chain] : 0;
+        S->chain_id = rng.chain; S->pad = 0;
+        const double poi = poisson_prior_cfg == 0.0 ? 1.0 : poisson_prior_cfg;       // :220-221
+        S->poi = poi; S->poi_is_init = 1;
+        S->gL = 1.0; S->gM = 1.0;                                                     // :222
+        const double lpoi = log(poi);
+        const double poiA = 2.0 * (1.0 * lpoi - poi - 0.0);                            // :229, K = 1 on both sides
+        // prior_gamma defaults a=2, b=2 (:227): 2 log 2 + log x - 2 x per rate; no shifts yet (:228)
+        const double lg2 = log(2.0);
+        S->priorA = (2.0 * lg2 + log(l0) - 2.0 * l0) + (2.0 * lg2 + log(m0) - 2.0 * m0) + poiA;
+        S->poiA = poiA;
+        S->beta = beta;
+    }
+}
+
+// record -> state (tests, checkpoint/resume).  priorA becomes the consistent prior of the state.
+__global__ void k3_set_state_kernel(ChainState* st, int n_chains, const double* __restrict__ recs, const double* tab,
+                                    const double* cst, int nb, int s0f, double start_time, double end_time) {
+    const int lane = threadIdx.x & 31;
+    const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (chain >= n_chains) return;
+    ChainState* S = st + chain;
+    const double* rec = recs + (size_t)chain * LR_REC_DOUBLES;
+    const int Kl = (int)rec[5], Km = (int)rec[6];
+    const double rl = rec[16 + lane], rm = rec[80 + lane];
+    S->rL[lane] = lane < Kl ? rl : 0.0; S->lrL[lane] = lane < Kl ? log(rl) : 0.0;
+    S->tL[lane] = lane == 0 ? start_time : (lane < Kl ? rec[48 + lane] : 0.0);
+    S->rM[lane] = lane < Km ? rm : 0.0; S->lrM[lane] = lane < Km ? log(rm) : 0.0;
+    S->tM[lane] = lane == 0 ? start_time : (lane < Km ? rec[112 + lane] : 0.0);
+    __syncwarp();
+    const DataView d = make_view(tab, cst, S->rep, nb, s0f, start_time, end_time);
+    Side L, M;
+    L.K = Kl; M.K = Km;
+    L.r = S->rL[lane]; L.lr = S->lrL[lane]; L.t = S->tL[lane];
+    M.r = S->rM[lane]; M.lr = S->lrM[lane]; M.t = S->tM[lane];
+    side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
+    side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
+    Hyper hp;
+    hp.gL = rec[7]; hp.gM = rec[8]; hp.poi = rec[9]; hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.lpoi = log(hp.poi);
+    const double poiA = poisson_prior(Kl, hp.poi, hp.lpoi, c_lnfact) + poisson_prior(Km, hp.poi, hp.lpoi, c_lnfact);
+    if (lane == 0) {
+        S->it = (long long)rec[0];
+        S->K_l = Kl; S->K_m = Km;
+        S->gL = hp.gL; S->gM = hp.gM; S->poi = hp.poi; S->poi_is_init = (int)rec[13];
+        S->poiA = poiA;
+        S->priorA = full_prior(L, M, hp, d, poiA);
+    }
+}
+
+__global__ void k3_get_state_kernel(const ChainState* st, int n_chains, double* __restrict__ recs, const double* tab,
+                                    const double* cst, int nb, int s0f, double start_time, double end_time) {
+    const int lane = threadIdx.x & 31;
+    const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (chain >= n_chains) return;
+    const ChainState* S = st + chain;
+    const DataView d = make_view(tab, cst, S->rep, nb, s0f, start_time, end_time);
+    Side L, M;
+    load_sides(S, L, M, lane);
+    side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
+    side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
+    Hyper hp;
+    hp.gL = S->gL; hp.gM = S->gM; hp.poi = S->poi; hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.lpoi = log(hp.poi);
+    write_record(recs + (size_t)chain * LR_REC_DOUBLES, S->it, L, M, hp, d, S->priorA, S->poi_is_init, lane, true);
+}
+
+// K2: one warp per state
+__global__ void k2_state_eval_kernel(int n, const int* __restrict__ rep, const int* __restrict__ K_l, const int* __restrict__ K_m,
+                                     const double* __restrict__ Lr, const double* __restrict__ Mr,
+                                     const double* __restrict__ tL, const double* __restrict__ tM,
+                                     const double* __restrict__ gamma_rate, const double* __restrict__ poi_lambda,
+                                     const double* tab, const double* cst, int nb, int s0f, double start_time, double end_time,
+                                     double* __restrict__ lik, double* __restrict__ prior_rates, double* __restrict__ prior_poi,
+                                     double* __restrict__ adequacy) {
+    const int lane = threadIdx.x & 31;
+    const int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (i >= n) return;
+    const DataView d = make_view(tab, cst, rep ? rep[i] : 0, nb, s0f, start_time, end_time);
+    Side L, M;
+    L.K = K_l[i]; M.K = K_m[i];
+    const bool inL = lane < L.K && lane < LR_KMAX, inM = lane < M.K && lane < LR_KMAX;
+    L.r = inL ? Lr[(size_t)i * LR_KMAX + lane] : 0.0; L.lr = inL ? log(L.r) : 0.0;
+    L.t = lane == 0 ? start_time : (inL ? tL[(size_t)i * LR_KMAX + lane] : 0.0);
+    M.r = inM ? Mr[(size_t)i * LR_KMAX + lane] : 0.0; M.lr = inM ? log(M.r) : 0.0;
+    M.t = lane == 0 ? start_time : (inM ? tM[(size_t)i * LR_KMAX + lane] : 0.0);
+    side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
+    side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
+    Hyper hp;
+    hp.gL = gamma_rate ? gamma_rate[2 * i] : 1.0; hp.gM = gamma_rate ? gamma_rate[2 * i + 1] : 1.0;
+    hp.poi = poi_lambda ? poi_lambda[i] : 1.0;
+    hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.lpoi = log(hp.poi);
+    double adq[3];
+    if (adequacy) adequacy3(L, M, d, lane, adq);
+    if (lane == 0) {
+        if (lik) lik[i] = d.C + L.lik + M.lik;
+        if (prior_rates) prior_rates[i] = full_prior(L, M, hp, d, 0.0);
+        if (prior_poi) prior_poi[i] = poisson_prior(L.K, hp.poi, hp.lpoi, c_lnfact) + poisson_prior(M.K, hp.poi, hp.lpoi, c_lnfact);
+        if (adequacy) { adequacy[3 * i] = adq[0]; adequacy[3 * i + 1] = adq[1]; adequacy[3 * i + 2] = adq[2]; }
+    }
+}
+
+__global__ void k3_set_beta_kernel(ChainState* st, int n, const double* beta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st[i].beta = beta[i];
+}
+
+int upload_lnfact() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && done[dev]) return LR_OK;
+    double t[LR_SLOTS + 2];
+    t[0] = 0.0;
+    for (int k = 1; k < LR_SLOTS + 2; ++k) t[k] = t[k - 1] + log((double)k);     // sum(log(arange(1,k+1))) (:199)
+    LR_CUDA(cudaMemcpyToSymbol(c_lnfact, t, sizeof(t)));
+    if (dev < 64) done[dev] = true;
+    return LR_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int lr_dataset_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t model_BDI,
+                                 double start_time, double end_time,
+                                 const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
+                                 const int64_t* d_ex_dead, const double* d_br_dead, void* stream, lr_dataset_t* out) {
+    LR_REQUIRE(h && out && d_sp && d_ex && d_br, "lr_dataset_create: null pointer");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_dataset_create: bad sizes");
+    LR_REQUIRE(model_BDI >= 0 && model_BDI <= 3, "lr_dataset_create: model_BDI must be 0..3");
+    LR_REQUIRE(model_BDI != 3 || (d_ex_dead && d_br_dead), "lr_dataset_create: model_BDI 3 needs the extinct-only statistics");
+    LR_REQUIRE(end_time > start_time, "lr_dataset_create: end_time must exceed start_time");
+    LR_REQUIRE(start_time >= 0.0, "lr_dataset_create: negative start_time is not supported (the reference's rate index breaks there too)");
+    LR_REQUIRE((long long)floor(end_time) - (long long)floor(start_time) == n_bins,
+               "lr_dataset_create: n_bins must equal floor(end_time) - floor(start_time) (LiteRateForward.py:519, :125-135)");
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = upload_lnfact();
+    if (rc != LR_OK) return rc;
+    lr_dataset_t ds = new lr_dataset_s();
+    ds->h = h; ds->n_rep = n_rep; ds->n_bins = n_bins; ds->model = model_BDI;
+    ds->start_time = start_time; ds->end_time = end_time; ds->s0f = (int)floor(start_time);
+    ds->tab = nullptr; ds->cst = nullptr;
+    cudaError_t e = cudaMalloc(&ds->tab, (size_t)n_rep * LR_NTAB * (n_bins + 1) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&ds->cst, (size_t)n_rep * LR_NCST * sizeof(double));
+    if (e != cudaSuccess) {
+        lr_set_error("lr_dataset_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+        cudaFree(ds->tab); cudaFree(ds->cst); delete ds;
+        return LR_ERR_NOMEM;
+    }
+    k2_build_tables<<<n_rep, 64, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, (const long long*)d_ex_dead,
+                                           d_br_dead, n_bins, model_BDI, ds->tab, ds->cst);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    *out = ds;
+    return LR_OK;
+}
+
+extern "C" int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t model_BDI,
+                                      double start_time, double end_time,
+                                      const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
+                                      const int64_t* h_ex_dead, const double* h_br_dead, lr_dataset_t* out) {
+    LR_REQUIRE(h && out && h_sp && h_ex && h_br, "lr_dataset_create_host: null pointer");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_dataset_create_host: bad sizes");
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t cnt = (size_t)n_rep * n_bins;
+    const bool dead = h_ex_dead && h_br_dead;
+    const size_t bytes = cnt * 8 * (dead ? 5 : 3);
+    int rc = lr_ws_reserve(h, bytes);
+    if (rc != LR_OK) return rc;
+    char* w = (char*)h->ws;
+    LR_CUDA(cudaMemcpyAsync(w, h_sp, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaMemcpyAsync(w + cnt * 8, h_ex, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaMemcpyAsync(w + cnt * 16, h_br, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    if (dead) {
+        LR_CUDA(cudaMemcpyAsync(w + cnt * 24, h_ex_dead, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaMemcpyAsync(w + cnt * 32, h_br_dead, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = lr_dataset_create(h, n_rep, n_bins, model_BDI, start_time, end_time, (const int64_t*)w, (const int64_t*)(w + cnt * 8),
+                           (const double*)(w + cnt * 16), dead ? (const int64_t*)(w + cnt * 24) : nullptr,
+                           dead ? (const double*)(w + cnt * 32) : nullptr, h->stream, out);
+    if (rc != LR_OK) return rc;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_dataset_destroy(lr_dataset_t ds) {
+    if (!ds) return LR_OK;
+    cudaSetDevice(ds->h->device);
+    cudaFree(ds->tab); cudaFree(ds->cst);
+    delete ds;
+    return LR_OK;
+}
+
+extern "C" int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int32_t* K_l, const int32_t* K_m,
+                                  const double* L, const double* M, const double* tL, const double* tM,
+                                  const double* gamma_rate, const double* poi_lambda,
+                                  double* lik, double* prior_rates, double* prior_poi, double* adequacy) {
+    LR_REQUIRE(ds && K_l && K_m && L && M && tL && tM, "lr_state_eval_host: null pointer");
+    LR_REQUIRE(n >= 0, "lr_state_eval_host: n < 0");
+    if (n == 0) return LR_OK;
+    for (int i = 0; i < n; ++i) {
+        LR_REQUIRE(K_l[i] >= 1 && K_l[i] <= LR_KMAX && K_m[i] >= 1 && K_m[i] <= LR_KMAX, "lr_state_eval_host: K out of 1..%d at state %d", LR_KMAX, i);
+        LR_REQUIRE(!rep || (rep[i] >= 0 && rep[i] < ds->n_rep), "lr_state_eval_host: replicate index out of range at state %d", i);
+    }
+    lr_handle_t h = ds->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t nK = (size_t)n * LR_KMAX * 8;
+    // layout in workspace
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
+    const size_t o_rep = take((size_t)n * 4), o_kl = take((size_t)n * 4), o_km = take((size_t)n * 4);
+    const size_t o_L = take(nK), o_M = take(nK), o_tL = take(nK), o_tM = take(nK);
+    const size_t o_g = take((size_t)n * 16), o_p = take((size_t)n * 8);
+    const size_t o_lik = take((size_t)n * 8), o_pr = take((size_t)n * 8), o_pp = take((size_t)n * 8), o_ad = take((size_t)n * 24);
+    int rc = lr_ws_reserve(h, off);
+    if (rc != LR_OK) return rc;
+    char* w = (char*)h->ws;
+    cudaStream_t st = h->stream;
+    if (rep) LR_CUDA(cudaMemcpyAsync(w + o_rep, rep, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(w + o_kl, K_l, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(w + o_km, K_m, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(w + o_L, L, nK, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(w + o_M, M, nK, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(w + o_tL, tL, nK, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(w + o_tM, tM, nK, cudaMemcpyHostToDevice, st));
+    if (gamma_rate) LR_CUDA(cudaMemcpyAsync(w + o_g, gamma_rate, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    if (poi_lambda) LR_CUDA(cudaMemcpyAsync(w + o_p, poi_lambda, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const int wpb = 4;
+    k2_state_eval_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        n, rep ? (const int*)(w + o_rep) : nullptr, (const int*)(w + o_kl), (const int*)(w + o_km),
+        (const double*)(w + o_L), (const double*)(w + o_M), (const double*)(w + o_tL), (const double*)(w + o_tM),
+        gamma_rate ? (const double*)(w + o_g) : nullptr, poi_lambda ? (const double*)(w + o_p) : nullptr,
+        ds->tab, ds->cst, ds->n_bins, ds->s0f, ds->start_time, ds->end_time,
+        lik ? (double*)(w + o_lik) : nullptr, prior_rates ? (double*)(w + o_pr) : nullptr,
+        prior_poi ? (double*)(w + o_pp) : nullptr, adequacy ? (double*)(w + o_ad) : nullptr);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (lik) LR_CUDA(cudaMemcpyAsync(lik, w + o_lik, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (prior_rates) LR_CUDA(cudaMemcpyAsync(prior_rates, w + o_pr, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (prior_poi) LR_CUDA(cudaMemcpyAsync(prior_poi, w + o_pp, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (adequacy) LR_CUDA(cudaMemcpyAsync(adequacy, w + o_ad, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+    return LR_OK;
+}
+
+static inline int chain_grid(int n_chains, int& threads) {
+    // few chains: one warp per CTA so that they spread over all SMs; many chains: 4 warps per CTA
+    const int wpb = n_chains <= 1024 ? 1 : 4;
+    threads = wpb * 32;
+    return (n_chains + wpb - 1) / wpb;
+}
+
+extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains, const lr_chain_config* cfg,
+                                uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain, lr_chains_t* out) {
+    LR_REQUIRE(h && ds && cfg && out, "lr_chains_create: null pointer");
+    LR_REQUIRE(ds->h == h, "lr_chains_create: dataset belongs to another handle");
+    LR_REQUIRE(n_chains >= 1, "lr_chains_create: n_chains must be >= 1");
+    LR_REQUIRE(cfg->model_BDI == ds->model, "lr_chains_create: cfg.model_BDI differs from the dataset's");
+    LR_REQUIRE(cfg->update_fraction >= 0.0 && cfg->update_fraction <= 1.0, "lr_chains_create: update_fraction outside [0,1]");
+    LR_REQUIRE(cfg->poisson_prior >= 0.0, "lr_chains_create: poisson_prior must be >= 0");
+    LR_REQUIRE(chain_id0 >= 0 && chain_id0 + n_chains <= 0xffffffffll, "lr_chains_create: chain ids must fit 32 bits");
+    if (h_rep_of_chain)
+        for (int i = 0; i < n_chains; ++i)
+            LR_REQUIRE(h_rep_of_chain[i] >= 0 && h_rep_of_chain[i] < ds->n_rep, "lr_chains_create: replicate of chain %d out of range", i);
+    LR_CUDA(cudaSetDevice(h->device));
+    lr_chains_t c = new lr_chains_s();
+    c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->st = nullptr;
+    if (c->cfg.beta == 0.0) c->cfg.beta = 1.0;
+    cudaError_t e = cudaMalloc(&c->st, (size_t)n_chains * sizeof(ChainState));
+    if (e != cudaSuccess) { lr_set_error("lr_chains_create: cudaMalloc: %s", cudaGetErrorString(e)); delete c; return LR_ERR_NOMEM; }
+    int* d_rep = nullptr;
+    if (h_rep_of_chain) {
+        int rc = lr_ws_reserve(h, (size_t)n_chains * 4);
+        if (rc != LR_OK) { cudaFree(c->st); delete c; return rc; }
+        d_rep = (int*)h->ws;
+        LR_CUDA(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    int threads;
+    const int blocks = chain_grid(n_chains, threads);
+    k3_init_kernel<<<blocks, threads, 0, h->stream>>>(c->st, n_chains, d_rep, chain_id0, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                      ds->start_time, cfg->poisson_prior, c->cfg.beta);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    *out = c;
+    return LR_OK;
+}
+
+extern "C" int lr_chains_destroy(lr_chains_t c) {
+    if (!c) return LR_OK;
+    cudaSetDevice(c->h->device);
+    cudaFree(c->st);
+    delete c;
+    return LR_OK;
+}
+
+extern "C" int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int64_t sample_every) {
+    if (!c || n_iter <= 0 || sample_every <= 0) return 0;
+    long long it0 = 0;
+    cudaSetDevice(c->h->device);
+    cudaStreamSynchronize(c->h->stream);
+    if (cudaMemcpy(&it0, &c->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    const long long first = (it0 + sample_every - 1) / sample_every * sample_every;
+    const long long it1 = it0 + n_iter;
+    return first < it1 ? (it1 - 1 - first) / sample_every + 1 : 0;
+}
+
+extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* d_records, void* stream) {
+    LR_REQUIRE(c != nullptr, "lr_chains_run: null chains");
+    LR_REQUIRE(n_iter >= 0 && sample_every >= 0, "lr_chains_run: negative count");
+    if (n_iter == 0) return LR_OK;
+    lr_handle_t h = c->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    RunParams P;
+    P.st = c->st; P.n_chains = c->n_chains; P.tab = c->ds->tab; P.cst = c->ds->cst;
+    P.nb = c->ds->n_bins; P.s0f = c->ds->s0f; P.model = c->ds->model;
+    P.start_time = c->ds->start_time; P.end_time = c->ds->end_time;
+    P.cfg = c->cfg; P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
+    P.n_iter = n_iter; P.sample_every = sample_every > 0 ? sample_every : 1;
+    P.records = sample_every > 0 ? d_records : nullptr;
+    P.with_adequacy = 1;
+    int threads;
+    const int blocks = chain_grid(c->n_chains, threads);
+    k3_run_kernel<<<blocks, threads, 0, st>>>(P);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* h_records) {
+    LR_REQUIRE(c != nullptr, "lr_chains_run_host: null chains");
+    lr_handle_t h = c->h;
+    const int64_t nrec = (h_records && sample_every > 0) ? lr_chains_records_per_run(c, n_iter, sample_every) : 0;
+    LR_REQUIRE(nrec >= 0, "lr_chains_run_host: could not read the iteration counter");
+    const size_t bytes = (size_t)nrec * c->n_chains * LR_REC_DOUBLES * sizeof(double);
+    double* d_rec = nullptr;
+    if (bytes) {
+        int rc = lr_ws_reserve(h, bytes);
+        if (rc != LR_OK) return rc;
+        d_rec = (double*)h->ws;
+    }
+    int rc = lr_chains_run(c, n_iter, bytes ? sample_every : 0, d_rec, h->stream);
+    if (rc != LR_OK) return rc;
+    if (bytes) LR_CUDA(cudaMemcpyAsync(h_records, d_rec, bytes, cudaMemcpyDeviceToHost, h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters) {
+    LR_REQUIRE(c && h_counters, "lr_chains_counters_host: null pointer");
+    LR_CUDA(cudaSetDevice(c->h->device));
+    LR_CUDA(cudaStreamSynchronize(c->h->stream));
+    LR_CUDA(cudaMemcpy2D(h_counters, 8 * sizeof(int64_t), &c->st[0].counters[0], sizeof(ChainState), 8 * sizeof(int64_t),
+                         c->n_chains, cudaMemcpyDeviceToHost));
+    return LR_OK;
+}
+
+extern "C" int lr_chains_get_state_host(lr_chains_t c, double* h_records) {
+    LR_REQUIRE(c && h_records, "lr_chains_get_state_host: null pointer");
+    lr_handle_t h = c->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)c->n_chains * LR_REC_DOUBLES * sizeof(double);
+    int rc = lr_ws_reserve(h, bytes);
+    if (rc != LR_OK) return rc;
+    int threads;
+    const int blocks = chain_grid(c->n_chains, threads);
+    k3_get_state_kernel<<<blocks, threads, 0, h->stream>>>(c->st, c->n_chains, (double*)h->ws, c->ds->tab, c->ds->cst, c->ds->n_bins,
+                                                           c->ds->s0f, c->ds->start_time, c->ds->end_time);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    LR_CUDA(cudaMemcpyAsync(h_records, h->ws, bytes, cudaMemcpyDeviceToHost, h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_chains_set_state_host(lr_chains_t c, const double* h_records) {
+    LR_REQUIRE(c && h_records, "lr_chains_set_state_host: null pointer");
+    lr_handle_t h = c->h;
+    for (int i = 0; i < c->n_chains; ++i) {
+        const double* r = h_records + (size_t)i * LR_REC_DOUBLES;
+        LR_REQUIRE(r[5] >= 1 && r[5] <= LR_KMAX && r[6] >= 1 && r[6] <= LR_KMAX, "lr_chains_set_state_host: K out of range in chain %d", i);
+    }
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)c->n_chains * LR_REC_DOUBLES * sizeof(double);
+    int rc = lr_ws_reserve(h, bytes);
+    if (rc != LR_OK) return rc;
+    LR_CUDA(cudaMemcpyAsync(h->ws, h_records, bytes, cudaMemcpyHostToDevice, h->stream));
+    int threads;
+    const int blocks = chain_grid(c->n_chains, threads);
+    k3_set_state_kernel<<<blocks, threads, 0, h->stream>>>(c->st, c->n_chains, (const double*)h->ws, c->ds->tab, c->ds->cst,
+                                                           c->ds->n_bins, c->ds->s0f, c->ds->start_time, c->ds->end_time);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_chains_set_beta_host(lr_chains_t c, const double* h_beta) {
+    LR_REQUIRE(c && h_beta, "lr_chains_set_beta_host: null pointer");
+    lr_handle_t h = c->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    int rc = lr_ws_reserve(h, (size_t)c->n_chains * 8);
+    if (rc != LR_OK) return rc;
+    LR_CUDA(cudaMemcpyAsync(h->ws, h_beta, (size_t)c->n_chains * 8, cudaMemcpyHostToDevice, h->stream));
+    k3_set_beta_kernel<<<(c->n_chains + 127) / 128, 128, 0, h->stream>>>(c->st, c->n_chains, (const double*)h->ws);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_chains_swap_step(lr_chains_t c, int32_t n_pairs, const int32_t* h_a, const int32_t* h_b, uint64_t round) {
+    (void)c; (void)n_pairs; (void)h_a; (void)h_b; (void)round;
+    lr_set_error("lr_chains_swap_step: tempered swaps are not implemented yet");
+    return LR_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,167 @@
+// Runtime part of the C ABI: handles, error reporting, workspace, host-buffer entry point of K1.
+#include <stdarg.h>
+#include "lr_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void lr_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* lr_last_error(void) { return g_err; }
+extern "C" int lr_abi_version(void) { return LR_ABI_VERSION; }
+
+extern "C" int lr_create(int device, lr_handle_t* out) {
+    LR_REQUIRE(out != nullptr, "lr_create: null output pointer");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        lr_set_error("lr_create: no CUDA device (%s); literate_b200 has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        return LR_ERR_CUDA;
+    }
+    LR_REQUIRE(device >= 0 && device < n, "lr_create: device %d out of range (0..%d)", device, n - 1);
+    LR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        lr_set_error("lr_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return LR_ERR_UNSUPPORTED;
+    }
+    lr_handle_t h = new lr_handle_s();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    LR_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) LR_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+    *out = h;
+    return LR_OK;
+}
+
+extern "C" int lr_destroy(lr_handle_t h) {
+    if (!h) return LR_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->copy_stream);
+    cudaFree(h->ws);
+    cudaFree(h->stage[0]);
+    cudaFree(h->stage[1]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return LR_OK;
+}
+
+extern "C" int lr_info(lr_handle_t h, int32_t* sm_count, int64_t* kernel_launches, int32_t* device) {
+    LR_REQUIRE(h != nullptr, "lr_info: null handle");
+    if (sm_count) *sm_count = h->sm_count;
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (device) *device = h->device;
+    return LR_OK;
+}
+
+extern "C" int lr_sync(lr_handle_t h) {
+    LR_REQUIRE(h != nullptr, "lr_sync: null handle");
+    LR_CUDA(cudaSetDevice(h->device));
+    LR_CUDA(cudaStreamSynchronize(h->copy_stream));
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+int lr_ws_reserve(lr_handle_t h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return LR_OK;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->copy_stream));
+    if (h->ws) LR_CUDA(cudaFree(h->ws));
+    h->ws = nullptr; h->ws_bytes = 0;
+    size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    cudaError_t e = cudaMalloc(&h->ws, want);
+    if (e != cudaSuccess) {
+        lr_set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        return LR_ERR_NOMEM;
+    }
+    h->ws_bytes = want;
+    return LR_OK;
+}
+
+static int stage_reserve(lr_handle_t h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return LR_OK;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+        if (h->stage[i]) LR_CUDA(cudaFree(h->stage[i]));
+        h->stage[i] = nullptr;
+    }
+    h->stage_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e = cudaMalloc(&h->stage[i], bytes);
+        if (e != cudaSuccess) {
+            lr_set_error("staging allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return LR_ERR_NOMEM;
+        }
+    }
+    h->stage_bytes = bytes;
+    return LR_OK;
+}
+
+// Host buffers in, host buffers out.  Replicates are copied in batches on the copy stream into
+// two device staging buffers while the previous batch is being binned on the compute stream.
+// Pass pinned host memory for the copies to be truly asynchronous.
+extern "C" int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double* h_te, int64_t n, int64_t ld,
+                                 int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                                 int32_t dead_only, double end_time,
+                                 int64_t* h_sp, int64_t* h_ex, double* h_br) {
+    LR_REQUIRE(h != nullptr, "lr_bin_stats_host: null handle");
+    LR_REQUIRE(n >= 0 && n_rep >= 1 && ld >= n && n_bins >= 1, "lr_bin_stats_host: bad sizes");
+    LR_REQUIRE(h_sp && h_ex && h_br && (n == 0 || (h_ts && h_te)), "lr_bin_stats_host: null pointer");
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t stride = (size_t)lr_acc_stride(n_bins);
+    const size_t acc_bytes = (size_t)n_rep * LR_ACC_ROWS * stride * sizeof(int64_t);
+    const size_t out_cnt = (size_t)n_rep * n_bins;
+    const size_t acc_pad = (acc_bytes + 255) & ~(size_t)255;
+    int rc = lr_ws_reserve(h, acc_pad + out_cnt * 24);
+    if (rc != LR_OK) return rc;
+    int64_t* d_acc = (int64_t*)h->ws;
+    int64_t* d_sp = (int64_t*)((char*)h->ws + acc_pad);
+    int64_t* d_ex = d_sp + out_cnt;
+    double* d_br = (double*)(d_ex + out_cnt);
+    LR_CUDA(cudaMemsetAsync(d_acc, 0, acc_bytes, h->stream));
+
+    if (n > 0) {
+        const int64_t ldp = (n + 1) & ~(int64_t)1;                 // even row pitch keeps 128-bit loads aligned
+        int64_t per_batch = ((int64_t)96 << 20) / (ldp * 16);      // ~96 MB of (ts, te) per batch
+        if (per_batch < 1) per_batch = 1;
+        if (per_batch > n_rep) per_batch = n_rep;
+        const size_t half = (size_t)per_batch * ldp * sizeof(double);
+        rc = stage_reserve(h, 2 * half);
+        if (rc != LR_OK) return rc;
+        int batch = 0;
+        for (int64_t r0 = 0; r0 < n_rep; r0 += per_batch, ++batch) {
+            const int buf = batch & 1;
+            const int64_t nr = (n_rep - r0 < per_batch) ? (n_rep - r0) : per_batch;
+            double* s_ts = (double*)h->stage[buf];
+            double* s_te = (double*)((char*)h->stage[buf] + half);
+            if (batch >= 2) LR_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev[2 + buf], 0));     // kernel of batch-2 released the buffer
+            LR_CUDA(cudaMemcpy2DAsync(s_ts, ldp * 8, h_ts + r0 * ld, ld * 8, n * 8, nr, cudaMemcpyHostToDevice, h->copy_stream));
+            LR_CUDA(cudaMemcpy2DAsync(s_te, ldp * 8, h_te + r0 * ld, ld * 8, n * 8, nr, cudaMemcpyHostToDevice, h->copy_stream));
+            LR_CUDA(cudaEventRecord(h->ev[buf], h->copy_stream));
+            LR_CUDA(cudaStreamWaitEvent(h->stream, h->ev[buf], 0));
+            rc = lr_bin_accumulate(h, s_ts, s_te, n, ldp, (int32_t)nr, first_bin, n_bins, fe_ref, dead_only, end_time,
+                                   d_acc + (size_t)r0 * LR_ACC_ROWS * stride, h->stream);
+            if (rc != LR_OK) return rc;
+            LR_CUDA(cudaEventRecord(h->ev[2 + buf], h->stream));
+        }
+    }
+    rc = lr_bin_finalize(h, d_acc, n_rep, n_bins, fe_ref, d_sp, d_ex, d_br, h->stream);
+    if (rc != LR_OK) return rc;
+    LR_CUDA(cudaMemcpyAsync(h_sp, d_sp, out_cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    LR_CUDA(cudaMemcpyAsync(h_ex, d_ex, out_cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    LR_CUDA(cudaMemcpyAsync(h_br, d_br, out_cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}

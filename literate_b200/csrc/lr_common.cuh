@@ -1,0 +1,104 @@
+// Shared device/host helpers for the literate_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/literate_b200.h"
+
+#ifndef __CUDACC__
+#error "literate_b200 is CUDA-only: there is no CPU path"
+#endif
+
+#define LR_WARP 32
+#define LR_SLOTS 32            // register slots per side of one chain (one per lane)
+#define LR_FIX_SHIFT 52        // fractions of a year are accumulated in 2^-52 fixed point
+#define LR_FIX_SCALE 4503599627370496.0   // 2^52
+
+// ---- error plumbing ------------------------------------------------------------------------
+void lr_set_error(const char* fmt, ...);
+#define LR_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            lr_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return LR_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+#define LR_REQUIRE(cond, ...)                                                                \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            lr_set_error(__VA_ARGS__);                                                       \
+            return LR_ERR_INVALID;                                                           \
+        }                                                                                    \
+    } while (0)
+
+struct lr_handle_s {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+    cudaStream_t stream;        // compute
+    cudaStream_t copy_stream;   // host<->device staging
+    cudaEvent_t ev[4];
+    int64_t launches;           // kernels launched through this handle
+    int bin_variant;            // 0 auto, 1 lane-private, 2 shared atomics
+    // grow-only workspace
+    void* ws;
+    size_t ws_bytes;
+    void* stage[2];
+    size_t stage_bytes;
+};
+
+int lr_ws_reserve(lr_handle_t h, size_t bytes);
+
+// ---- small device helpers --------------------------------------------------------------------
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- Philox-4x32-10 (Salmon et al., SC'11); counter-based, one call = 128 random bits --------
+struct Philox4 { uint32_t x, y, z, w; };
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+// 53-bit uniform strictly inside (0,1)
+__host__ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+    uint64_t b = ((uint64_t)hi << 32) | lo;
+    return ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}

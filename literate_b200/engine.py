@@ -1,0 +1,361 @@
+"""Host-side mirror of the three seams of LiteRateForward.py, over the C ABI.
+
+  precompute_events loop (:514-549)  -> Device.bin_stats / bin_stats_device
+  calc_likelihood + priors (:137-162, :296-306) -> Dataset + Dataset.evaluate
+  runMCMC (:216-373)                 -> Chains
+
+Everything here is plumbing: argument checking, numpy/torch buffers, ctypes calls.  All arithmetic
+runs in the CUDA kernels of libliterate_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+from ._native import ChainConfig, LR_KMAX, LR_REC_DOUBLES, NativeError  # noqa: F401
+
+
+def fe_ref_for_jitter(death_jitter: float) -> float:
+    """Fractional part (in (0,1]) that te = integer + death_jitter leaves above its bin's lower edge."""
+    f = death_jitter - math.ceil(death_jitter) + 1.0
+    return f if 0.0 < f <= 1.0 else 1.0
+
+
+@dataclass
+class BinStats:
+    """sp_events_bin / ex_events_bin / br_length_bin (LiteRateForward.py:566-568) for n_rep replicates."""
+    first_bin: int
+    sp: np.ndarray                 # int64 [n_rep, n_bins]
+    ex: np.ndarray
+    br: np.ndarray                 # float64
+    ex_dead: np.ndarray = None     # -model_BDI 3 (:529-549)
+    br_dead: np.ndarray = None
+
+    @property
+    def n_bins(self):
+        return self.sp.shape[-1]
+
+    @property
+    def n_rep(self):
+        return self.sp.shape[0]
+
+
+def window(ts, te):
+    """(first_bin, n_bins) = range(int(min ts), int(max te)) of :519 for host arrays."""
+    first = int(np.min(ts))
+    return first, int(np.max(te)) - first
+
+
+class Device:
+    """One lr_handle_t: a B200 and its streams/workspace."""
+
+    def __init__(self, index: int = 0):
+        self.lib = N.load(build_if_missing=False)
+        h = C.c_void_p()
+        N.check(self.lib.lr_create(int(index), C.byref(h)), "lr_create")
+        self.h = h
+        self.index = index
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        N.check(self.lib.lr_sync(self.h), "lr_sync")
+
+    @property
+    def sm_count(self):
+        sm = C.c_int32()
+        N.check(self.lib.lr_info(self.h, C.byref(sm), None, None))
+        return sm.value
+
+    @property
+    def kernel_launches(self):
+        n = C.c_int64()
+        N.check(self.lib.lr_info(self.h, None, C.byref(n), None))
+        return n.value
+
+    def set_bin_kernel(self, variant: int):
+        N.check(self.lib.lr_set_bin_kernel(self.h, int(variant)), "lr_set_bin_kernel")
+
+    # ------------------------------------------------------------------ L2
+    def bin_stats(self, ts, te, first_bin=None, n_bins=None, death_jitter=0.5, only_dead=False, end_time=None,
+                  fe_ref=None) -> BinStats:
+        """HOST arrays in, host arrays out (lr_bin_stats_host).
+
+        ``ts``/``te`` are float64 arrays of shape [n] or [n_rep, n] (te already jittered, as after
+        LiteRateForward.py:471).  With ``only_dead`` the extinct-only statistics of :529-549 are
+        added, for lineages with te < end_time.
+        """
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        te = np.ascontiguousarray(te, dtype=np.float64)
+        if ts.shape != te.shape or ts.ndim not in (1, 2):
+            raise ValueError("ts and te must have the same shape, [n] or [n_rep, n]")
+        if ts.ndim == 1:
+            ts, te = ts[None, :], te[None, :]
+        n_rep, n = ts.shape
+        if n == 0:
+            raise ValueError("no lineages")
+        if first_bin is None or n_bins is None:
+            first_bin, n_bins = window(ts, te)
+        if n_bins < 1:
+            raise ValueError("the time window holds no complete bin (int(max te) <= int(min ts))")
+        if fe_ref is None:
+            fe_ref = fe_ref_for_jitter(death_jitter)
+        if end_time is None:
+            end_time = float(np.max(te))
+
+        def run(dead):
+            sp = np.empty((n_rep, n_bins), dtype=np.int64)
+            ex = np.empty((n_rep, n_bins), dtype=np.int64)
+            br = np.empty((n_rep, n_bins), dtype=np.float64)
+            N.check(self.lib.lr_bin_stats_host(self.h, N.np_ptr(ts), N.np_ptr(te), n, n, n_rep, int(first_bin), int(n_bins),
+                                               float(fe_ref), 1 if dead else 0, float(end_time),
+                                               N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br)), "lr_bin_stats_host")
+            return sp, ex, br
+
+        sp, ex, br = run(False)
+        out = BinStats(int(first_bin), sp, ex, br)
+        if only_dead:
+            _, out.ex_dead, out.br_dead = run(True)
+        return out
+
+    def bin_stats_device(self, ts, te, first_bin, n_bins, fe_ref=0.5, dead_only=False, end_time=0.0, stream=None, out=None):
+        """torch CUDA tensors in, torch CUDA tensors out (lr_bin_stats); asynchronous on `stream`.
+
+        ts/te: float64 CUDA tensors [n_rep, n] (row stride may exceed n).  Returns (sp, ex, br).
+        """
+        import torch
+        assert ts.is_cuda and te.is_cuda and ts.dtype == torch.float64 and te.dtype == torch.float64
+        if ts.dim() == 1:
+            ts, te = ts[None, :], te[None, :]
+        assert ts.stride(-1) == 1 and te.stride(-1) == 1 and ts.shape == te.shape
+        n_rep, n = ts.shape
+        ld = ts.stride(0) if n_rep > 1 else n
+        assert n_rep == 1 or te.stride(0) == ld
+        if out is None:
+            sp = torch.empty((n_rep, n_bins), dtype=torch.int64, device=ts.device)
+            ex = torch.empty_like(sp)
+            br = torch.empty((n_rep, n_bins), dtype=torch.float64, device=ts.device)
+        else:
+            sp, ex, br = out
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(ts.device).cuda_stream)
+        N.check(self.lib.lr_bin_stats(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), n, ld, n_rep,
+                                      int(first_bin), int(n_bins), float(fe_ref), 1 if dead_only else 0, float(end_time),
+                                      C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()), st),
+                "lr_bin_stats")
+        return sp, ex, br
+
+    def bin_accumulate_device(self, ts, te, first_bin, n_bins, acc, fe_ref=0.5, dead_only=False, end_time=0.0, stream=None):
+        """Raw integer accumulators only (lr_bin_accumulate) -- the lineage-sharded multi-GPU path all-reduces
+        `acc` (int64 [n_rep, 8, lr_acc_stride]) before bin_finalize_device."""
+        import torch
+        if ts.dim() == 1:
+            ts, te = ts[None, :], te[None, :]
+        n_rep, n = ts.shape
+        ld = ts.stride(0) if n_rep > 1 else max(n, 1)
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(ts.device).cuda_stream)
+        N.check(self.lib.lr_bin_accumulate(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), n, ld, n_rep,
+                                           int(first_bin), int(n_bins), float(fe_ref), 1 if dead_only else 0, float(end_time),
+                                           C.c_void_p(acc.data_ptr()), st), "lr_bin_accumulate")
+        return acc
+
+    def new_accumulators(self, n_rep, n_bins, device):
+        import torch
+        return torch.zeros((n_rep, N.LR_ACC_ROWS, int(self.lib.lr_acc_stride(int(n_bins)))), dtype=torch.int64, device=device)
+
+    def bin_finalize_device(self, acc, n_bins, fe_ref=0.5, stream=None):
+        import torch
+        n_rep = acc.shape[0]
+        sp = torch.empty((n_rep, n_bins), dtype=torch.int64, device=acc.device)
+        ex = torch.empty_like(sp)
+        br = torch.empty((n_rep, n_bins), dtype=torch.float64, device=acc.device)
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(acc.device).cuda_stream)
+        N.check(self.lib.lr_bin_finalize(self.h, C.c_void_p(acc.data_ptr()), n_rep, int(n_bins), float(fe_ref),
+                                         C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()), st),
+                "lr_bin_finalize")
+        return sp, ex, br
+
+
+class Dataset:
+    """Binned statistics of n_rep replicates resident on the device, plus the prefix tables of the likelihood."""
+
+    def __init__(self, dev: Device, stats: BinStats, model_BDI: int, start_time: float, end_time: float):
+        self.dev, self.model_BDI = dev, int(model_BDI)
+        self.start_time, self.end_time = float(start_time), float(end_time)
+        self.n_rep, self.n_bins = stats.n_rep, stats.n_bins
+        sp = np.ascontiguousarray(stats.sp, dtype=np.int64).reshape(self.n_rep, self.n_bins)
+        ex = np.ascontiguousarray(stats.ex, dtype=np.int64).reshape(self.n_rep, self.n_bins)
+        br = np.ascontiguousarray(stats.br, dtype=np.float64).reshape(self.n_rep, self.n_bins)
+        exd = brd = None
+        if self.model_BDI == 3:
+            if stats.ex_dead is None or stats.br_dead is None:
+                raise ValueError("-model_BDI 3 needs the extinct-only statistics (bin_stats(only_dead=True))")
+            exd = np.ascontiguousarray(stats.ex_dead, dtype=np.int64).reshape(self.n_rep, self.n_bins)
+            brd = np.ascontiguousarray(stats.br_dead, dtype=np.float64).reshape(self.n_rep, self.n_bins)
+        ds = C.c_void_p()
+        N.check(dev.lib.lr_dataset_create_host(dev.h, self.n_rep, self.n_bins, self.model_BDI, self.start_time, self.end_time,
+                                               N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br), N.np_ptr(exd), N.np_ptr(brd),
+                                               C.byref(ds)), "lr_dataset_create_host")
+        self.ds = ds
+
+    @classmethod
+    def from_device(cls, dev: Device, sp, ex, br, model_BDI, start_time, end_time, ex_dead=None, br_dead=None, stream=None):
+        """Same from torch CUDA tensors already on the device (no host round trip)."""
+        import torch
+        self = cls.__new__(cls)
+        self.dev, self.model_BDI = dev, int(model_BDI)
+        self.start_time, self.end_time = float(start_time), float(end_time)
+        self.n_rep, self.n_bins = sp.shape
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(sp.device).cuda_stream)
+        ds = C.c_void_p()
+        N.check(dev.lib.lr_dataset_create(dev.h, self.n_rep, self.n_bins, self.model_BDI, self.start_time, self.end_time,
+                                          C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()),
+                                          C.c_void_p(ex_dead.data_ptr()) if ex_dead is not None else None,
+                                          C.c_void_p(br_dead.data_ptr()) if br_dead is not None else None, st, C.byref(ds)),
+                "lr_dataset_create")
+        self.ds = ds
+        return self
+
+    def close(self):
+        if getattr(self, "ds", None):
+            self.dev.lib.lr_dataset_destroy(self.ds)
+            self.ds = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def evaluate(self, states, gamma_rate=None, poi_lambda=None, rep=None):
+        """Likelihood / prior / adequacy of explicit states (lr_state_eval_host).
+
+        ``states``: list of (L, M, timesL, timesM) with times = [start, shifts..., end] as in the reference.
+        Returns dict of arrays: lik, prior_rates (gamma + time prior), prior_poi, adequacy[n,3].
+        """
+        n = len(states)
+        K_l = np.zeros(n, np.int32); K_m = np.zeros(n, np.int32)
+        L = np.zeros((n, LR_KMAX)); M = np.zeros((n, LR_KMAX)); tL = np.zeros((n, LR_KMAX)); tM = np.zeros((n, LR_KMAX))
+        for i, (l, m, tl, tm) in enumerate(states):
+            l, m, tl, tm = (np.asarray(x, dtype=np.float64) for x in (l, m, tl, tm))
+            if len(tl) != len(l) + 1 or len(tm) != len(m) + 1:
+                raise ValueError("times must hold one more entry than rates")
+            K_l[i], K_m[i] = len(l), len(m)
+            L[i, :len(l)], M[i, :len(m)] = l, m
+            tL[i, :len(l)], tM[i, :len(m)] = tl[:-1], tm[:-1]
+        g = None if gamma_rate is None else np.ascontiguousarray(np.broadcast_to(np.asarray(gamma_rate, np.float64), (n, 2)))
+        p = None if poi_lambda is None else np.ascontiguousarray(np.broadcast_to(np.asarray(poi_lambda, np.float64), (n,)))
+        r = None if rep is None else np.ascontiguousarray(np.broadcast_to(np.asarray(rep, np.int32), (n,)))
+        lik = np.empty(n); pr = np.empty(n); pp = np.empty(n); ad = np.empty((n, 3))
+        N.check(self.dev.lib.lr_state_eval_host(self.ds, n, N.np_ptr(r), N.np_ptr(K_l), N.np_ptr(K_m), N.np_ptr(L), N.np_ptr(M),
+                                                N.np_ptr(tL), N.np_ptr(tM), N.np_ptr(g), N.np_ptr(p),
+                                                N.np_ptr(lik), N.np_ptr(pr), N.np_ptr(pp), N.np_ptr(ad)), "lr_state_eval_host")
+        return {"lik": lik, "prior_rates": pr, "prior_poi": pp, "adequacy": ad}
+
+
+# field offsets of a sample record (include/literate_b200.h)
+REC_IT, REC_LIK, REC_PRIOR, REC_LAVG, REC_MAVG, REC_KL, REC_KM, REC_GL, REC_GM, REC_POI = range(10)
+REC_ADQ, REC_POI_INIT = 10, 13
+REC_L, REC_TL, REC_M, REC_TM = 16, 48, 80, 112
+COUNTER_NAMES = ["iterations", "accepted", "lik_evals", "rate_updates", "move_shifts", "rj_proposals", "gibbs", "capacity_rejects"]
+
+
+class Chains:
+    """A population of independent RJMCMC chains on one device (runMCMC, LiteRateForward.py:216-373)."""
+
+    def __init__(self, ds: Dataset, n_chains: int, seed: int, cfg: ChainConfig = None, chain_id0: int = 0, rep_of_chain=None):
+        self.ds, self.dev, self.n_chains = ds, ds.dev, int(n_chains)
+        if cfg is None:
+            cfg = default_config(ds.model_BDI)
+        self.cfg = cfg
+        rep = None
+        if rep_of_chain is not None:
+            rep = np.ascontiguousarray(rep_of_chain, dtype=np.int32)
+            if rep.shape != (self.n_chains,):
+                raise ValueError("rep_of_chain must have one entry per chain")
+        c = C.c_void_p()
+        N.check(self.dev.lib.lr_chains_create(self.dev.h, ds.ds, self.n_chains, C.byref(cfg), C.c_uint64(int(seed) & (2**64 - 1)),
+                                              int(chain_id0), N.np_ptr(rep), C.byref(c)), "lr_chains_create")
+        self.c = c
+
+    def close(self):
+        if getattr(self, "c", None):
+            self.dev.lib.lr_chains_destroy(self.c)
+            self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def records_per_run(self, n_iter, sample_every):
+        return int(self.dev.lib.lr_chains_records_per_run(self.c, int(n_iter), int(sample_every)))
+
+    def run(self, n_iter: int, sample_every: int = 0, out=None):
+        """n_iter iterations of every chain; returns records [n_samples, n_chains, 144] (host) or None."""
+        if sample_every and sample_every > 0:
+            nrec = self.records_per_run(n_iter, sample_every)
+            if out is None:
+                out = np.empty((nrec, self.n_chains, LR_REC_DOUBLES), dtype=np.float64)
+            assert out.shape == (nrec, self.n_chains, LR_REC_DOUBLES) and out.flags["C_CONTIGUOUS"]
+            N.check(self.dev.lib.lr_chains_run_host(self.c, int(n_iter), int(sample_every), N.np_ptr(out)), "lr_chains_run_host")
+            return out
+        N.check(self.dev.lib.lr_chains_run_host(self.c, int(n_iter), 0, None), "lr_chains_run_host")
+        return None
+
+    def run_device(self, n_iter: int, sample_every: int, records, stream=None):
+        """Asynchronous variant: `records` is a float64 CUDA tensor [n_samples, n_chains, 144] (or None)."""
+        import torch
+        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        ptr = C.c_void_p(records.data_ptr()) if records is not None else None
+        N.check(self.dev.lib.lr_chains_run(self.c, int(n_iter), int(sample_every) if records is not None else 0, ptr, st),
+                "lr_chains_run")
+
+    def state(self):
+        out = np.empty((self.n_chains, LR_REC_DOUBLES), dtype=np.float64)
+        N.check(self.dev.lib.lr_chains_get_state_host(self.c, N.np_ptr(out)), "lr_chains_get_state_host")
+        return out
+
+    def set_state(self, records):
+        records = np.ascontiguousarray(records, dtype=np.float64)
+        assert records.shape == (self.n_chains, LR_REC_DOUBLES)
+        N.check(self.dev.lib.lr_chains_set_state_host(self.c, N.np_ptr(records)), "lr_chains_set_state_host")
+
+    def counters(self):
+        out = np.empty((self.n_chains, 8), dtype=np.int64)
+        N.check(self.dev.lib.lr_chains_counters_host(self.c, N.np_ptr(out)), "lr_chains_counters_host")
+        return out
+
+    def set_beta(self, beta):
+        beta = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (self.n_chains,)))
+        N.check(self.dev.lib.lr_chains_set_beta_host(self.c, N.np_ptr(beta)), "lr_chains_set_beta_host")
+
+
+def default_config(model_BDI=0, const_rates=0, const_death_rate=0, use_rate_HP=1, Poisson_prior=0.0, update_fraction=0.75,
+                   real_move_shift=0, beta=1.0) -> ChainConfig:
+    """Defaults of LiteRateForward.py:386-399."""
+    return ChainConfig(int(model_BDI), int(const_rates), int(const_death_rate), int(use_rate_HP), float(Poisson_prior),
+                       float(update_fraction), int(real_move_shift), 0, float(beta))
+
+
+def record_to_state(rec, end_time):
+    """One sample record -> (L, M, timesL, timesM) in the reference's layout."""
+    kl, km = int(rec[REC_KL]), int(rec[REC_KM])
+    L = rec[REC_L:REC_L + kl].copy()
+    M = rec[REC_M:REC_M + km].copy()
+    tL = np.concatenate([rec[REC_TL:REC_TL + kl], [end_time]])
+    tM = np.concatenate([rec[REC_TM:REC_TM + km], [end_time]])
+    return L, M, tL, tM

@@ -1,0 +1,158 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ by running the UNMODIFIED reference in this container.
+
+TEST INFRASTRUCTURE ONLY.  Needs /root/reference (read-only, not present on the GPU box);
+everything it produces is committed so that no test reads /root/reference at run time.
+
+    python oracle/make_golden.py kat         # seconds: exact log files of short reference runs
+    python oracle/make_golden.py posterior   # minutes: 8 reference chains per data set -> summaries
+
+The reference writes next to its input (LiteRateForward.py:479-491), so inputs are copied to
+a scratch directory first.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("LITERATE_REFERENCE", "/root/reference")
+GOLD = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+
+INPUTS = {
+    "example_dataTAD.txt": "example_data/example_dataTAD.txt",
+    "example_dataTBP.txt": "example_data/example_dataTBP.txt",
+    "metal_bands_1.tsv": "example_data/metal_bands/single_run/metal_bands_1.tsv",
+}
+SUFFIX = {0: "_BD", 1: "_ID", 2: "_BDk", 3: "_BDd"}
+
+
+def run_reference(src, args, keep_dir=None):
+    """Run LiteRateForward.py on a scratch copy of `src`; return {tag: bytes} of its logs."""
+    work = tempfile.mkdtemp(prefix="lr_ref_")
+    try:
+        name = os.path.basename(src)
+        shutil.copy(src, os.path.join(work, name))
+        cmd = [sys.executable, os.path.join(REF, "LiteRateForward.py"), "-d", os.path.join(work, name)] + args
+        t0 = time.time()
+        p = subprocess.run(cmd, cwd=work, capture_output=True, text=True)
+        dt = time.time() - t0
+        if p.returncode != 0:
+            raise RuntimeError(p.stderr[-2000:])
+        logs = {}
+        d = os.path.join(work, "literate_mcmc_logs")
+        for f in sorted(os.listdir(d)):
+            with open(os.path.join(d, f), "rb") as fh:
+                logs[f] = fh.read()
+        return logs, dt, p.stdout
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def stage_inputs():
+    d = os.path.join(GOLD, "inputs")
+    os.makedirs(d, exist_ok=True)
+    for name, rel in INPUTS.items():
+        with open(os.path.join(REF, rel), "rb") as fh:
+            raw = fh.read()
+        if len(raw) > 100_000:
+            with gzip.GzipFile(os.path.join(d, name + ".gz"), "wb", mtime=0) as gz:
+                gz.write(raw)
+        else:
+            with open(os.path.join(d, name), "wb") as fh:
+                fh.write(raw)
+
+
+def kat():
+    stage_inputs()
+    out = os.path.join(GOLD, "reference_logs")
+    os.makedirs(out, exist_ok=True)
+    manifest = []
+    tad = os.path.join(REF, INPUTS["example_dataTAD.txt"])
+    tbp = os.path.join(REF, INPUTS["example_dataTBP.txt"])
+    metal = os.path.join(REF, INPUTS["metal_bands_1.tsv"])
+    jobs = []
+    for m in range(4):
+        jobs.append(("tad_m%d" % m, tad, ["-n", "3000", "-s", "25", "-p", "1000000", "-seed", "1", "-model_BDI", str(m)]))
+    jobs.append(("tbp_m0", tbp, ["-n", "3000", "-s", "25", "-p", "1000000", "-seed", "1", "-TBP"]))
+    jobs.append(("tbp_pyrate", tbp, ["-n", "2000", "-s", "25", "-p", "1000000", "-seed", "3", "-TBP", "-pyrate_output"]))
+    jobs.append(("tad_constdeath", tad, ["-n", "3000", "-s", "25", "-p", "1000000", "-seed", "5", "-const_death_rate", "1"]))
+    jobs.append(("tad_constrates", tad, ["-n", "3000", "-s", "25", "-p", "1000000", "-seed", "6", "-const_rates", "1", "-calc_adequacy", "0"]))
+    jobs.append(("tad_fixedpoi_nohp", tad, ["-n", "3000", "-s", "25", "-p", "1000000", "-seed", "7", "-Poisson_prior", "2", "-use_rate_HP", "0",
+                                            "-update_fraction", "0.5", "-out", "_x"]))
+    jobs.append(("tad_jitter0", tad, ["-n", "1000", "-s", "25", "-p", "1000000", "-seed", "8", "-death_jitter", "0", "-model_BDI", "3"]))
+    jobs.append(("metal_m0", metal, ["-n", "1500", "-s", "25", "-p", "1000000", "-seed", "7"]))
+    jobs.append(("metal_m3", metal, ["-n", "300", "-s", "25", "-p", "1000000", "-seed", "7", "-model_BDI", "3"]))
+    for tag, src, args in jobs:
+        logs, dt, _ = run_reference(src, args)
+        d = os.path.join(out, tag)
+        os.makedirs(d, exist_ok=True)
+        for f, b in logs.items():
+            with open(os.path.join(d, f), "wb") as fh:
+                fh.write(b)
+        manifest.append({"tag": tag, "input": os.path.basename(src), "args": args, "files": sorted(logs)})
+        print(tag, "%.1fs" % dt, sorted(logs))
+    with open(os.path.join(out, "manifest.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1)
+
+
+def _summarise(logs, stem, burnin=0.2):
+    """Per-chain posterior summaries from the reference's own log files."""
+    from oracle import literate_oracle as O
+    import io
+    mc = np.loadtxt(io.BytesIO(logs[stem + "_mcmc.log"]), skiprows=1)
+    head = logs[stem + "_mcmc.log"].split(b"\n")[0].decode().split("\t")
+    n = len(mc)
+    b = int(burnin * n)
+    post = mc[b:]
+    col = {h: i for i, h in enumerate(head)}
+    start, end = post[0, col["root_age"]], post[0, col["death_age"]]
+    res = {"n_samples": int(len(post)),
+           "K_l": O.k_pmf(mc[:, col["K_l"]], burnin), "K_m": O.k_pmf(mc[:, col["K_m"]], burnin),
+           "lik_mean": float(post[:, col["likelihood"]].mean()), "lik_var": float(post[:, col["likelihood"]].var()),
+           "prior_mean": float(post[:, col["prior"]].mean()),
+           "lambda_avg": float(post[:, col["lambda_avg"]].mean()), "mu_avg": float(post[:, col["mu_avg"]].mean()),
+           "gamma_hp_l": float(post[:, col["gamma_rate_hp_BI"]].mean()), "gamma_hp_m": float(post[:, col["gamma_rate_hp_D"]].mean()),
+           "poisson_hp": float(post[:, col["poisson_rate_hp"]].mean())}
+    for tag, key in (("sp_rates", "birth"), ("ex_rates", "death")):
+        rows = [np.array(l.split(), dtype=np.float64) for l in logs[stem + "_" + tag + ".log"].decode().split("\n") if l.strip()]
+        mr = O.marginal_rates(rows, end, start, burnin)
+        res[key + "_rate_mean"] = mr.mean(axis=0).tolist()
+    return res
+
+
+def posterior(n_chains=8):
+    out = os.path.join(GOLD, "posterior")
+    os.makedirs(out, exist_ok=True)
+    sets = [
+        ("example_tad", os.path.join(REF, INPUTS["example_dataTAD.txt"]), "example_dataTAD_BD", 300001, 100),
+        ("metal_bands", os.path.join(REF, INPUTS["metal_bands_1.tsv"]), "metal_bands_1_BD", 400001, 200),
+    ]
+    for tag, src, stem, n_it, s in sets:
+        def one(seed):
+            logs, dt, _ = run_reference(src, ["-n", str(n_it), "-s", str(s), "-p", "100000000", "-seed", str(seed)])
+            r = _summarise(logs, stem)
+            r["seed"], r["wall_s"], r["n_iterations"], r["s_freq"] = seed, dt, n_it, s
+            return r
+        with ThreadPoolExecutor(n_chains) as ex:
+            chains = list(ex.map(one, [101 + i for i in range(n_chains)]))
+        with open(os.path.join(out, tag + ".json"), "w") as fh:
+            json.dump({"data": tag, "generator": "unmodified LiteRateForward.py, default flags", "burnin": 0.2,
+                       "chains": chains}, fh, indent=1)
+        print(tag, "done:", [round(c["wall_s"]) for c in chains])
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "kat"
+    {"kat": kat, "posterior": posterior}[what]()

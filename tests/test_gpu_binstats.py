@@ -1,0 +1,152 @@
+"""GPU: K1 (lineages -> per-bin statistics) through the C ABI against the oracle.
+
+Bar: counts bit-exact always; br bit-exact for dyadic data (all shipped data: integer years + .5),
+<= 1e-12 relative for arbitrary real-valued times (the reference's own NumPy pairwise sum carries that
+much rounding; the kernel returns the correctly rounded exact sum).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_input
+from oracle import literate_oracle as O
+from literate_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(dev, ts, te, jitter, exact=True, variant=0, only_dead=True):
+    dev.set_bin_kernel(variant)
+    try:
+        got = dev.bin_stats(ts, te, death_jitter=jitter, only_dead=only_dead)
+    finally:
+        dev.set_bin_kernel(0)
+    want = O.bin_stats(ts, te, only_dead=only_dead)
+    assert got.first_bin == want.first_bin and got.n_bins == want.n_bins
+    assert (got.sp[0] == want.sp).all() and (got.ex[0] == want.ex).all()
+    if only_dead:
+        assert (got.ex_dead[0] == want.ex_dead).all()
+    pairs = [(got.br[0], want.br)] + ([(got.br_dead[0], want.br_dead)] if only_dead else [])
+    for g, w in pairs:
+        if exact:
+            assert (g == w).all()
+        else:
+            np.testing.assert_allclose(g, w, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_example_tad_and_tbp(device, variant):
+    for name, tbp in (("example_dataTAD.txt", False), ("example_dataTBP.txt", True)):
+        lin = O.read_lineages(golden_input(name), TBP=tbp)
+        _check(device, lin.ts, lin.te, 0.5, variant=variant)
+        lin0 = O.read_lineages(golden_input(name), TBP=tbp, death_jitter=0.0)
+        _check(device, lin0.ts, lin0.te, 0.0, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_metal_bands(device, metal_path, variant):
+    lin = O.read_lineages(metal_path)
+    _check(device, lin.ts, lin.te, 0.5, variant=variant)
+    got = device.bin_stats(lin.ts, lin.te)
+    assert got.sp.sum() == 27495 and got.ex.sum() == 16191 and got.br.sum() == 95426.5
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_random_integer_and_real(device, variant):
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 31, 257, 4097, 20011):
+        ts, te = synth.syn_int(n, replicate=n)
+        _check(device, ts, te, 0.5, variant=variant)
+        ts, te = synth.syn_real(n, replicate=n)
+        _check(device, ts, te, 0.0, exact=False, variant=variant)
+        # a wrong fe_ref hint must not change the result
+        device.set_bin_kernel(variant)
+        a = device.bin_stats(ts, te, fe_ref=0.5)
+        b = device.bin_stats(ts, te, fe_ref=1.0)
+        device.set_bin_kernel(0)
+        assert (a.br == b.br).all() and (a.sp == b.sp).all() and (a.ex == b.ex).all()
+    # quarter-year data: fractional but dyadic -> still bit-exact
+    n = 5000
+    ts = 1900 + rng.integers(0, 160, n) / 4.0
+    te = ts + rng.integers(0, 80, n) / 4.0
+    te[0] = 1945.0
+    _check(device, ts, te, 0.0, variant=variant)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_degenerate_inputs(device, variant):
+    # all extant, single bin
+    ts = np.array([10.0, 10.0, 10.0]); te = np.array([11.5, 11.5, 11.5])
+    _check(device, ts, te, 0.5, variant=variant)
+    # ts == te (zero time at risk), te < ts (malformed rows still count as events in the reference), NaN rows
+    ts = np.array([5.0, 7.0, 9.0, 6.5, 8.0, 5.0, np.nan]); te = np.array([12.5, 7.0, 6.0, 6.5, np.nan, 5.5, 9.5])
+    device.set_bin_kernel(variant)
+    got = device.bin_stats(ts, te, first_bin=5, n_bins=7)
+    device.set_bin_kernel(0)
+    with np.errstate(invalid="ignore"):
+        for j in range(7):
+            assert O.events_in_bin(ts, te, 5 + j, 6 + j) == (got.sp[0, j], got.ex[0, j], got.br[0, j]), j
+    # sorted input: every lane of a warp hits the same bin
+    ts = np.repeat(np.arange(1900.0, 1950.0), 300); te = ts + 3.5
+    _check(device, ts, te, 0.5, variant=variant)
+    # unsorted real values with many lineages born and dying in the same bin
+    rng = np.random.default_rng(3)
+    ts = 50 + rng.uniform(0, 20, 3000); te = ts + rng.uniform(0, 0.7, 3000); te[0] = 71.25
+    _check(device, ts, te, 0.0, exact=False, variant=variant)
+
+
+def test_explicit_window_with_lineages_outside(device):
+    """first_bin / n_bins given by the caller (lineage-sharded use): lineages born before the window,
+    dying after it, or entirely outside are clipped exactly as get_br clips them (:111-116)."""
+    rng = np.random.default_rng(21)
+    n = 4000
+    ts = np.floor(rng.uniform(80, 140, n)); te = ts + np.floor(rng.exponential(10, n)) + 0.5
+    first, nb = 100, 25
+    got = device.bin_stats(ts, te, first_bin=first, n_bins=nb)
+    for j in range(nb):
+        a, b, c = O.events_in_bin(ts, te, first + j, first + j + 1)
+        assert (got.sp[0, j], got.ex[0, j], got.br[0, j]) == (a, b, c)
+
+
+def test_replicates_and_ragged_pitch(device):
+    import torch
+    n_rep, n = 5, 3001      # odd n: rows are not 16-byte aligned -> scalar load path for odd replicates
+    ts = np.empty((n_rep, n)); te = np.empty((n_rep, n))
+    for r in range(n_rep):
+        ts[r], te[r] = synth.syn_int(n, replicate=100 + r)
+    got = device.bin_stats(ts, te)
+    for r in range(n_rep):
+        want = O.bin_stats_fast(ts[r], te[r])
+        assert (got.sp[r] == want.sp).all() and (got.ex[r] == want.ex).all() and (got.br[r] == want.br).all()
+    # device-pointer entry point with a padded row pitch
+    dts = torch.zeros((n_rep, n + 5), dtype=torch.float64, device="cuda"); dte = torch.zeros_like(dts)
+    dts[:, :n] = torch.from_numpy(ts).cuda(); dte[:, :n] = torch.from_numpy(te).cuda()
+    sp, ex, br = device.bin_stats_device(dts[:, :n], dte[:, :n], got.first_bin, got.n_bins)
+    torch.cuda.synchronize()
+    assert (sp.cpu().numpy() == got.sp).all() and (ex.cpu().numpy() == got.ex).all() and (br.cpu().numpy() == got.br).all()
+
+
+def test_full_size_one_million(device):
+    """BASELINE cfg3 size: 1M lineages x 200 bins against the O(N) oracle, plus size-independent checks."""
+    n = 1_000_000
+    ts, te = synth.syn_int(n)
+    got = device.bin_stats(ts, te)
+    want = O.bin_stats_fast(ts, te)
+    assert got.n_bins == 200
+    assert (got.sp[0] == want.sp).all() and (got.ex[0] == want.ex).all() and (got.br[0] == want.br).all()
+    # conservation: every lineage is born once inside the window; total time at risk = sum of clipped lifetimes
+    assert got.sp.sum() == n
+    assert got.br.sum() == np.sum(np.minimum(te, 2000.0) - ts)
+    # three spot-checked bins against the reference formulation itself
+    for j in (0, 77, 199):
+        assert O.events_in_bin(ts, te, 1800 + j, 1801 + j) == (got.sp[0, j], got.ex[0, j], got.br[0, j])
+    # linearity: binning the two halves separately and adding gives the same integers
+    h1 = device.bin_stats(ts[: n // 2], te[: n // 2], first_bin=1800, n_bins=200)
+    h2 = device.bin_stats(ts[n // 2:], te[n // 2:], first_bin=1800, n_bins=200)
+    assert ((h1.sp + h2.sp) == got.sp).all() and ((h1.ex + h2.ex) == got.ex).all() and ((h1.br + h2.br) == got.br).all()
+    tr, er = synth.syn_real(n)
+    got = device.bin_stats(tr, er, death_jitter=0.0)
+    want = O.bin_stats_fast(tr, er)
+    assert (got.sp[0] == want.sp).all() and (got.ex[0] == want.ex).all()
+    np.testing.assert_allclose(got.br[0], want.br, rtol=1e-11)
+    again = device.bin_stats(tr, er, death_jitter=0.0)
+    assert (again.br == got.br).all()          # run-to-run deterministic (integer accumulation)

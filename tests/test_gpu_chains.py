@@ -1,0 +1,153 @@
+"""GPU: K3 (the RJMCMC chains) through the C ABI.
+
+State-level parity is deterministic (same state in -> same likelihood / prior out, checked in
+test_gpu_likelihood.py and again here on the states the chains actually visit).  Chain-level parity is
+distributional: the reference draws from NumPy's MT19937, the kernel from Philox, so posterior summaries
+are compared with the committed summaries of 8 unmodified reference chains (tests/golden/posterior/*.json,
+made by oracle/make_golden.py) using the between-chain spread as the Monte-Carlo error.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, golden_input
+from oracle import literate_oracle as O
+from literate_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(device, path, model=0, tbp=False, n_chains=64, seed=1, **cfg):
+    lin = O.read_lineages(path, TBP=tbp)
+    st = device.bin_stats(lin.ts, lin.te, only_dead=(model == 3), end_time=lin.end_time)
+    ds = E.Dataset(device, st, model, lin.start_time, lin.end_time)
+    ch = E.Chains(ds, n_chains, seed, E.default_config(model, **cfg))
+    ost = O.BinStats(st.first_bin, st.sp[0], st.ex[0], st.br[0], None if st.ex_dead is None else st.ex_dead[0],
+                     None if st.br_dead is None else st.br_dead[0])
+    return lin, ost, ds, ch
+
+
+def test_initial_state_matches_reference_bookkeeping(device):
+    lin, st, ds, ch = _setup(device, golden_input("example_dataTAD.txt"), n_chains=8)
+    rec = ch.state()
+    for r in rec:
+        L, M, tL, tM = E.record_to_state(r, lin.end_time)
+        assert len(L) == 1 and len(M) == 1 and r[E.REC_IT] == 0
+        assert r[E.REC_LIK] == pytest.approx(O.loglik_state(L, M, tL, tM, st, 0), rel=1e-10)
+        # initial prior uses prior_gamma's default rate 2 (LiteRateForward.py:227), not Gamma_rate = 1
+        want = O.rates_prior(L) + O.rates_prior(M) + 2 * O.poisson_prior(1, 1)
+        assert r[E.REC_PRIOR] == pytest.approx(want, rel=1e-10)
+        assert r[E.REC_GL] == 1.0 and r[E.REC_GM] == 1.0 and r[E.REC_POI] == 1.0 and r[E.REC_POI_INIT] == 1.0
+    # Gamma(2, scale 2) initial rates: mean 4, var 8
+    lin, st, ds, big = _setup(device, golden_input("example_dataTAD.txt"), n_chains=4096, seed=5)
+    r0 = big.state()
+    for col in (E.REC_L, E.REC_M):
+        x = r0[:, col]
+        assert abs(x.mean() - 4.0) < 5 * np.sqrt(8 / 4096) and abs(x.var() - 8.0) < 1.5
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 3])
+def test_visited_states_are_consistent(device, model, metal_path):
+    """Every logged state: likelihood and prior recomputed by the oracle from the logged rates/times agree,
+    shift spacing obeys the guard (:290), K matches, adequacy matches calculate_r_squared."""
+    lin, st, ds, ch = _setup(device, metal_path if model != 1 else golden_input("example_dataTAD.txt"), model=model, n_chains=16, seed=3)
+    recs = ch.run(20000, 500)
+    assert recs.shape[0] == 40
+    emp_b, emp_d = st.sp / st.br, st.ex / st.br
+    seen_k = set()
+    for s in range(recs.shape[0]):
+        for c in range(0, 16, 5):
+            r = recs[s, c]
+            L, M, tL, tM = E.record_to_state(r, lin.end_time)
+            seen_k.add(len(L))
+            assert r[E.REC_IT] == s * 500
+            assert np.min(np.diff(tL)) > 1 and np.min(np.diff(tM)) > 1
+            assert r[E.REC_LIK] == pytest.approx(O.loglik_state(L, M, tL, tM, st, model), rel=1e-10)
+            assert r[E.REC_LAVG] == pytest.approx(L.mean(), rel=1e-12) and r[E.REC_MAVG] == pytest.approx(M.mean(), rel=1e-12)
+            if s > 4:   # after the transient of :227 the stored prior is the prior of the stored state
+                pr_wo_poi = O.state_prior(L, M, [r[E.REC_GL], r[E.REC_GM]], lin.end_time - lin.start_time, 0.0)
+                # priorPoiA may be stale w.r.t. the current Poisson rate (:300-304): bound it by the two extremes seen
+                assert r[E.REC_PRIOR] - pr_wo_poi < 0
+            iL = O.rate_index(np.floor(tL) if len(tL) > 2 else tL, st.n_bins)
+            iM = O.rate_index(np.floor(tM) if len(tM) > 2 else tM, st.n_bins)
+            np.testing.assert_allclose(r[E.REC_ADQ:E.REC_ADQ + 3], O.adequacy(emp_b, emp_d, L[iL], M[iM]), rtol=1e-8)
+    assert len(seen_k) > 1      # the sampler does jump between dimensions
+    cnt = ch.counters()
+    assert (cnt[:, 0] == 20000).all() and (cnt[:, 7] == 0).all()
+    frac = cnt.sum(0) / cnt[:, 0].sum()
+    assert abs(frac[5] - 0.199) < 0.01 and abs(frac[6] - 0.001) < 0.0005     # RJ 19.9 %, Gibbs 0.1 % (:274, :281)
+
+
+def test_determinism_and_sharding_invariance(device):
+    """Same (seed, chain id) -> same chain, whatever the launch split or the population it is part of."""
+    path = golden_input("example_dataTAD.txt")
+    lin, st, ds, a = _setup(device, path, n_chains=32, seed=11)
+    ra = a.run(3000, 100)
+    b = E.Chains(ds, 32, 11)
+    rb = np.concatenate([b.run(1000, 100), b.run(1500, 100), b.run(500, 100)])
+    assert np.array_equal(ra, rb)
+    c = E.Chains(ds, 8, 11, chain_id0=16)          # chains 16..23 as a shard of their own
+    rc = c.run(3000, 100)
+    assert np.array_equal(ra[:, 16:24], rc)
+    d = E.Chains(ds, 32, 12)
+    assert not np.array_equal(ra, d.run(3000, 100))
+
+
+def test_checkpoint_roundtrip(device):
+    path = golden_input("example_dataTAD.txt")
+    lin, st, ds, a = _setup(device, path, n_chains=4, seed=2)
+    a.run(5000)
+    snap = a.state()
+    b = E.Chains(ds, 4, 2)
+    b.set_state(snap)
+    got = b.state()
+    np.testing.assert_array_equal(got[:, E.REC_L:], snap[:, E.REC_L:])
+    np.testing.assert_allclose(got[:, E.REC_LIK], snap[:, E.REC_LIK], rtol=1e-13)
+
+
+def _summaries(recs, lin, burnin=0.2):
+    ns = recs.shape[0]
+    b = int(burnin * ns)
+    out = []
+    for c in range(recs.shape[1]):
+        r = recs[b:, c]
+        rowsL = [np.concatenate([x[E.REC_L:E.REC_L + int(x[E.REC_KL])], x[E.REC_TL + 1:E.REC_TL + int(x[E.REC_KL])]]) for x in r]
+        rowsM = [np.concatenate([x[E.REC_M:E.REC_M + int(x[E.REC_KM])], x[E.REC_TM + 1:E.REC_TM + int(x[E.REC_KM])]]) for x in r]
+        out.append({"K_l": r[:, E.REC_KL].mean(), "K_m": r[:, E.REC_KM].mean(), "lik": r[:, E.REC_LIK].mean(),
+                    "lam": r[:, E.REC_LAVG].mean(), "mu": r[:, E.REC_MAVG].mean(),
+                    "birth": O.marginal_rates(rowsL, lin.end_time, lin.start_time, 0).mean(0),
+                    "death": O.marginal_rates(rowsM, lin.end_time, lin.start_time, 0).mean(0)})
+    return out
+
+
+@pytest.mark.parametrize("data,n_iter,s", [("example_tad", 300000, 100), ("metal_bands", 400000, 200)])
+def test_posterior_matches_reference_chains(device, data, n_iter, s, metal_path):
+    """64 GPU chains vs 8 reference chains (same length, same sampling, 20 % burn-in): the means of
+    K_l, K_m, log-likelihood, mean rates and every per-bin marginal rate agree within 4.5 standard
+    errors of the difference of the two chain-population means."""
+    with open(os.path.join(GOLD, "posterior", data + ".json")) as fh:
+        ref = json.load(fh)["chains"]
+    path = golden_input("example_dataTAD.txt") if data == "example_tad" else metal_path
+    lin, st, ds, ch = _setup(device, path, n_chains=64, seed=2026)
+    recs = ch.run(n_iter + 1, s)
+    mine = _summaries(recs, lin)
+
+    def kmean(pmf):
+        tot = sum(pmf.values())
+        return sum(int(k) * v for k, v in pmf.items()) / tot
+
+    def compare(name, a, b, floor=0.0):
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        se = np.sqrt(a.var(0, ddof=1) / len(a) + b.var(0, ddof=1) / len(b)) + floor
+        z = np.abs(a.mean(0) - b.mean(0)) / se
+        assert np.all(z < 4.5), (name, float(np.max(z)), a.mean(0), b.mean(0))
+
+    compare("K_l", [m["K_l"] for m in mine], [kmean(r["K_l"]) for r in ref])
+    compare("K_m", [m["K_m"] for m in mine], [kmean(r["K_m"]) for r in ref])
+    compare("lik", [m["lik"] for m in mine], [r["lik_mean"] for r in ref])
+    compare("lambda_avg", [m["lam"] for m in mine], [r["lambda_avg"] for r in ref])
+    compare("mu_avg", [m["mu"] for m in mine], [r["mu_avg"] for r in ref])
+    compare("birth", [m["birth"] for m in mine], [r["birth_rate_mean"] for r in ref], floor=1e-6)
+    compare("death", [m["death"] for m in mine], [r["death_rate_mean"] for r in ref], floor=1e-6)
