@@ -19,6 +19,15 @@ from . import _native as N
 from ._native import ChainConfig, LR_KMAX, LR_REC_DOUBLES, NativeError  # noqa: F401
 
 
+def _stream_ptr(stream, device=None):
+    """cudaStream_t for the C ABI.  NULL means "the handle's own stream" there, so torch's legacy default
+    stream (handle 0) is passed as cudaStreamLegacy (0x1)."""
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream(device).cuda_stream
+    return C.c_void_p(int(stream) if int(stream) != 0 else 1)
+
+
 def fe_ref_for_jitter(death_jitter: float) -> float:
     """Fractional part (in (0,1]) that te = integer + death_jitter leaves above its bin's lower edge."""
     f = death_jitter - math.ceil(death_jitter) + 1.0
@@ -150,7 +159,7 @@ class Device:
             br = torch.empty((n_rep, n_bins), dtype=torch.float64, device=ts.device)
         else:
             sp, ex, br = out
-        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(ts.device).cuda_stream)
+        st = _stream_ptr(stream, ts.device)
         N.check(self.lib.lr_bin_stats(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), n, ld, n_rep,
                                       int(first_bin), int(n_bins), float(fe_ref), 1 if dead_only else 0, float(end_time),
                                       C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()), st),
@@ -165,7 +174,7 @@ class Device:
             ts, te = ts[None, :], te[None, :]
         n_rep, n = ts.shape
         ld = ts.stride(0) if n_rep > 1 else max(n, 1)
-        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(ts.device).cuda_stream)
+        st = _stream_ptr(stream, ts.device)
         N.check(self.lib.lr_bin_accumulate(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), n, ld, n_rep,
                                            int(first_bin), int(n_bins), float(fe_ref), 1 if dead_only else 0, float(end_time),
                                            C.c_void_p(acc.data_ptr()), st), "lr_bin_accumulate")
@@ -181,7 +190,7 @@ class Device:
         sp = torch.empty((n_rep, n_bins), dtype=torch.int64, device=acc.device)
         ex = torch.empty_like(sp)
         br = torch.empty((n_rep, n_bins), dtype=torch.float64, device=acc.device)
-        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(acc.device).cuda_stream)
+        st = _stream_ptr(stream, acc.device)
         N.check(self.lib.lr_bin_finalize(self.h, C.c_void_p(acc.data_ptr()), n_rep, int(n_bins), float(fe_ref),
                                          C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()), st),
                 "lr_bin_finalize")
@@ -218,7 +227,7 @@ class Dataset:
         self.dev, self.model_BDI = dev, int(model_BDI)
         self.start_time, self.end_time = float(start_time), float(end_time)
         self.n_rep, self.n_bins = sp.shape
-        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(sp.device).cuda_stream)
+        st = _stream_ptr(stream, sp.device)
         ds = C.c_void_p()
         N.check(dev.lib.lr_dataset_create(dev.h, self.n_rep, self.n_bins, self.model_BDI, self.start_time, self.end_time,
                                           C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()),
@@ -319,7 +328,7 @@ class Chains:
     def run_device(self, n_iter: int, sample_every: int, records, stream=None):
         """Asynchronous variant: `records` is a float64 CUDA tensor [n_samples, n_chains, 144] (or None)."""
         import torch
-        st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        st = _stream_ptr(stream)
         ptr = C.c_void_p(records.data_ptr()) if records is not None else None
         N.check(self.dev.lib.lr_chains_run(self.c, int(n_iter), int(sample_every) if records is not None else 0, ptr, st),
                 "lr_chains_run")

@@ -1,0 +1,285 @@
+"""Drop-in command line for the RJMCMC birth-death path of LiteRateForward.py.
+
+Same 21 flags, same input parsing (TAD / -TBP, 3 or 4 columns, trailing tabs, CRLF), same output
+directory, file names, headers and row layout (LiteRateForward.py:376-512, :321-359, :558-564).
+All numerical work (binning, likelihood, proposals, accept step) happens in the CUDA kernels of
+libliterate_b200.so; this module parses, launches and writes text.
+
+New flags (absent from the reference): -chains, -device, -launch_iters, -real_move_shift, -quiet.
+With -chains 1 (default) file names are exactly the reference's; with more chains each chain k
+writes <stem><model><out>_chain<k>_{mcmc,sp_rates,ex_rates}.log, which plotRJforward.v3.py's
+`*mcmc.log` glob and its .replace('mcmc.log', ...) still resolve, and they share one div.log each.
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import os
+import sys
+import time
+from warnings import warn
+
+import numpy as np
+
+from . import engine as E
+
+BANNER = "\n\n             LiteRate - 20200206  (literate_b200: B200-native RJMCMC path)\n"
+MODEL_SUFFIX = {0: "_BD", 1: "_ID", 2: "_BDk", 3: "_BDd"}          # :422-427
+MCMC_COLS = ["it", "posterior", "likelihood", "prior", "lambda_avg", "mu_avg", "K_l", "K_m", "root_age", "death_age",
+             "gamma_rate_hp_BI", "gamma_rate_hp_D", "poisson_rate_hp"]   # :496-502
+ADEQUACY_COLS = ["corr_coeff", "rsquared", "gelman_r2"]
+
+
+def build_parser():
+    """The reference's parser (:376-401), flag for flag, plus the new multi-chain flags."""
+    p = argparse.ArgumentParser(prog="LiteRateForward.py")
+    p.add_argument('-v', action='version', version='%(prog)s')
+    p.add_argument('-d', type=str, help='data file', default="", metavar="")
+    p.add_argument('-n', type=int, help='n. MCMC iterations', default=10000000, metavar=10000000)
+    p.add_argument('-p', type=int, help='print frequency', default=1000, metavar=1000)
+    p.add_argument('-s', type=int, help='sampling frequency', default=1000, metavar=1000)
+    p.add_argument('-seed', type=int, help='seed (set to -1 to make it random)', default=-1, metavar=-1)
+    p.add_argument('-const_rates', type=int, help="set to: 1 for constant B/I and D rates", default=0, metavar=0)
+    p.add_argument('-const_death_rate', type=int, help="set to: 1 for constant D rates", default=0, metavar=0)
+    p.add_argument('-model_BDI', type=int, help='0: birth-death; 1: immigration-death; 2 birth-death (Keiding likelihood); '
+                   '3 Keiding likelihood, only no extant', default=0, metavar=0)
+    p.add_argument('-TBP', help='Default is AD. Include for TBP.', default=False, action='store_true')
+    p.add_argument('-pyrate_output', help='Make output PyRate-compatible', default=False, action='store_true')
+    p.add_argument('-first_year', type=int, help='different start of the dataset (TAD only)', default=-1, metavar=-1)
+    p.add_argument('-last_year', type=int, help='different end of the dataset (TAD only)', default=-1, metavar=-1)
+    p.add_argument('-death_jitter', type=float, help='amount to jitter death times', default=.5, metavar=.5)
+    p.add_argument('-use_rate_HP', type=int, help='0: no hyper-prior on rates, 1: hyper-prior on rates', default=1, metavar=1)
+    p.add_argument('-Poisson_prior', type=float, help='0: use hyper-prior on n. shifts, >0: fixed prior on n. shifts', default=0, metavar=0)
+    p.add_argument('-rm_first_bin', type=float, help='if set to 1 it removes the first time bin', default=0, metavar=0)
+    p.add_argument('-calc_adequacy', type=int, help='if set to 1 calculates and log to file adequacy', default=1, metavar=1)
+    p.add_argument('-update_fraction', type=float, help='', default=0.75, metavar=0.75)
+    p.add_argument('-out', type=str, help='output name suffix', default="", metavar="")
+    p.add_argument('-rev_se', type=int, help='reversed order of ts and te in input file', default=0, metavar=0)
+    # ---- not in the reference
+    p.add_argument('-chains', type=int, help='number of independent chains run concurrently on the GPU', default=1, metavar=1)
+    p.add_argument('-device', type=int, help='CUDA device index', default=0, metavar=0)
+    p.add_argument('-launch_iters', type=int, help='iterations per kernel launch (0: choose)', default=0, metavar=0)
+    p.add_argument('-real_move_shift', type=int, help='1: move-shift really moves the shift (the reference proposes the '
+                   'current state, LiteRateForward.py:184-185)', default=0, metavar=0)
+    p.add_argument('-quiet', type=int, help='1: no per-iteration progress on stdout', default=0, metavar=0)
+    return p
+
+
+def parse_lineages(path, TBP=False, rev_se=0, first_year=-1, last_year=-1, death_jitter=0.5):
+    """TSV -> (ts, te, start_time, end_time, true_root_age), LiteRateForward.py:439-476.
+
+    -first_year raises IndexError in the reference whenever it filters anything (:460-461); the intended
+    order of literate_library.parse_ts_te (literate_library.py:216-222) is implemented instead.
+    """
+    tbl = np.genfromtxt(path, skip_header=1)
+    if tbl.ndim == 1:
+        tbl = tbl[None, :]
+    if tbl.shape[1] == 4:
+        warn('Four column (with clade) LiteRate input is deprecated. Use three columns.', FutureWarning)
+        ts_y, te_y = tbl[:, 2], tbl[:, 3]
+    elif rev_se:
+        ts_y, te_y = tbl[:, 2], tbl[:, 1]
+    else:
+        ts_y, te_y = tbl[:, 1], tbl[:, 2]
+    if TBP:
+        root = np.max(ts_y)
+        ts, te = root - ts_y, root - te_y
+    else:
+        root = 0
+        if first_year != -1:
+            keep = ts_y >= first_year
+            ts_y, te_y = ts_y[keep], te_y[keep]
+        if last_year != -1:
+            keep = ts_y <= last_year
+            ts, te = ts_y[keep], te_y[keep] + 0.0
+            te[te > last_year] = last_year
+        else:
+            ts, te = ts_y, te_y
+    te = te + death_jitter
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    te = np.ascontiguousarray(te, dtype=np.float64)
+    return ts, te, np.min(ts), np.max(te), root
+
+
+def _fmt(x):
+    """str() of what the reference puts in a row: Python ints stay ints, floats use the shortest repr
+    (str(np.float64) == repr(float) for every finite value)."""
+    if isinstance(x, (int, np.integer)):
+        return str(int(x))
+    return repr(float(x))
+
+
+def write_div_log(path, sp, ex, br):
+    """div.log (:558-564): header ends in '\\n', the csv.writer rows in '\\r\\n'."""
+    with open(path, "w", newline="") as fh:
+        fh.write('sp_events\tex_events\tbr_length\n')
+        w = csv.writer(fh, delimiter='\t')
+        for a, b, c in zip(sp.tolist(), ex.tolist(), br.tolist()):
+            w.writerow((a, b, repr(float(c))))
+
+
+class ChainLogWriter:
+    """The three per-chain log files of :493-512 and their rows (:321-359)."""
+
+    def __init__(self, stem, calc_adequacy, pyrate_output, start_time, end_time, true_root_age, poisson_prior):
+        self.calc_adequacy, self.pyrate = calc_adequacy, pyrate_output
+        self.start_time, self.end_time, self.root = start_time, end_time, true_root_age
+        self.poisson_prior = poisson_prior
+        self.mcmc = open(stem + "_mcmc.log", "w")
+        self.sp = open(stem + "_sp_rates.log", "w")
+        self.ex = open(stem + "_ex_rates.log", "w")
+        self.mcmc.write('\t'.join(MCMC_COLS + (ADEQUACY_COLS if calc_adequacy else [])) + '\n')
+
+    def write(self, rec):
+        kl, km = int(rec[E.REC_KL]), int(rec[E.REC_KM])
+        L, M = rec[E.REC_L:E.REC_L + kl], rec[E.REC_M:E.REC_M + km]
+        sL, sM = rec[E.REC_TL + 1:E.REC_TL + kl], rec[E.REC_TM + 1:E.REC_TM + km]
+        lik, prior = rec[E.REC_LIK], rec[E.REC_PRIOR]
+        if self.pyrate:       # :325-326: root_age, root_age - max(timesLA) (= root - end_time)
+            ages = [_fmt(self.root), _fmt(np.float64(self.root - self.end_time))]
+            sL, sM = self.root - sL, self.root - sM
+        else:
+            ages = [_fmt(np.float64(self.start_time)), _fmt(np.float64(self.end_time))]
+        if rec[E.REC_POI_INIT]:   # Poi_lambda_rjHP is still the Python constant of :220-221
+            poi = "1" if self.poisson_prior == 0 else repr(float(self.poisson_prior))
+        else:
+            poi = repr(float(rec[E.REC_POI]))
+        row = [str(int(rec[E.REC_IT])), repr(float(lik + prior)), repr(float(lik)), repr(float(prior)),
+               repr(float(rec[E.REC_LAVG])), repr(float(rec[E.REC_MAVG])), str(kl), str(km)] + ages + \
+              [repr(float(rec[E.REC_GL])), repr(float(rec[E.REC_GM])), poi]
+        if self.calc_adequacy:
+            row += [repr(float(v)) for v in rec[E.REC_ADQ:E.REC_ADQ + 3]]
+        self.mcmc.write('\t'.join(row) + '\n')
+        self.sp.write('\t'.join([repr(float(v)) for v in L] + [repr(float(v)) for v in sL]) + '\n')
+        self.ex.write('\t'.join([repr(float(v)) for v in M] + [repr(float(v)) for v in sM]) + '\n')
+
+    def flush(self):
+        self.mcmc.flush(); self.sp.flush(); self.ex.flush()
+
+    def close(self):
+        self.mcmc.close(); self.sp.close(); self.ex.close()
+
+
+def _print_state(rec, end_time, calc_adequacy):
+    """The progress block of :362-370 (chain 0)."""
+    L, M, tL, tM = E.record_to_state(rec, end_time)
+    with np.printoptions(suppress=True, precision=3):
+        print(int(rec[E.REC_IT]), rec[E.REC_LIK], rec[E.REC_PRIOR])
+        print("\tsp.times:", tL)
+        print("\tex.times:", tM)
+        print("\tsp.rates:", L)
+        print("\tex.rates:", M)
+        if calc_adequacy:
+            print("\tR^2:", rec[E.REC_ADQ + 1])
+
+
+def run(args, device=None):
+    """Everything LiteRateForward.py does after argument parsing; returns the list of mcmc.log paths."""
+    print(BANNER)
+    if args.seed == -1:                                   # :405-407
+        rseed = int(np.random.randint(0, 9999))
+    else:
+        rseed = args.seed
+    if args.model_BDI not in MODEL_SUFFIX:
+        raise SystemExit("-model_BDI must be 0, 1, 2 or 3")
+    if args.chains < 1:
+        raise SystemExit("-chains must be >= 1")
+    out_name = MODEL_SUFFIX[args.model_BDI] + args.out
+    only_dead = args.model_BDI == 3
+
+    ts, te, start_time, end_time, true_root_age = parse_lineages(args.d, args.TBP, args.rev_se, args.first_year,
+                                                                 args.last_year, args.death_jitter)
+    out_dir = os.path.dirname(args.d)                     # :479-491
+    if out_dir == "":
+        out_dir = os.getcwd()
+    file_name = os.path.splitext(os.path.basename(args.d))[0]
+    out_dir = "%s/literate_mcmc_logs" % (out_dir)
+    try:
+        os.mkdir(out_dir)
+    except OSError as e:
+        print(e)
+
+    dev = device if device is not None else E.Device(args.device)
+    t0 = time.time()
+    stats = dev.bin_stats(ts, te, death_jitter=args.death_jitter, only_dead=only_dead, end_time=float(end_time))
+    t_bin = time.time() - t0
+    sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
+    print(ex.tolist())                                     # :526-527
+    print(br.sum(), range(stats.first_bin, stats.first_bin + stats.n_bins))
+    if only_dead:
+        print(len(stats.ex_dead[0]), len(sp))
+    if args.rm_first_bin:
+        # The reference drops element 0 of the three vectors (:552-556) but keeps an n_bins+1 long rate index and
+        # dies with IndexError at the first likelihood; here the window itself starts one bin later.
+        stats = E.BinStats(stats.first_bin + 1, stats.sp[:, 1:], stats.ex[:, 1:], stats.br[:, 1:],
+                           None if stats.ex_dead is None else stats.ex_dead[:, 1:],
+                           None if stats.br_dead is None else stats.br_dead[:, 1:])
+        sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
+        start_time = np.float64(np.floor(start_time) + 1)
+
+    stem = "%s/%s%s" % (out_dir, file_name, out_name)
+    write_div_log(stem + "_div.log", sp, ex, br)
+    if args.calc_adequacy:                                 # print_empirical_rates, literate_library.py:260-266
+        with np.errstate(divide="ignore", invalid="ignore"), np.printoptions(suppress=True, precision=3):
+            print("EMPIRICAL BIRTH RATES:"); print(sp / br)
+            print("EMPIRICAL DEATH RATES:"); print(ex / br)
+
+    ds = E.Dataset(dev, stats, args.model_BDI, float(start_time), float(end_time))
+    cfg = E.default_config(args.model_BDI, args.const_rates, args.const_death_rate, args.use_rate_HP, args.Poisson_prior,
+                           args.update_fraction, args.real_move_shift)
+    chains = E.Chains(ds, args.chains, rseed, cfg)
+
+    writers, paths = [], []
+    for k in range(args.chains):
+        st = stem if args.chains == 1 else "%s_chain%d" % (stem, k)
+        writers.append(ChainLogWriter(st, args.calc_adequacy, args.pyrate_output, start_time, end_time, true_root_age,
+                                      args.Poisson_prior))
+        paths.append(st + "_mcmc.log")
+        if args.chains > 1 and k > 0:                      # one div.log per chain name so every *mcmc.log has its sibling
+            write_div_log(st + "_div.log", sp, ex, br)
+    if args.chains > 1:
+        write_div_log("%s_chain0_div.log" % stem, sp, ex, br)
+
+    s_freq, p_freq = max(1, args.s), max(1, args.p)
+    every = int(np.gcd(s_freq, p_freq))
+    per_launch = args.launch_iters
+    if per_launch <= 0:
+        # keep one launch's records under ~256 MB
+        max_rec = max(1, (256 << 20) // (args.chains * E.LR_REC_DOUBLES * 8))
+        per_launch = max(every, min(max_rec * every, 2_000_000))
+    per_launch = max(every, per_launch // every * every)
+    done = 0
+    t_run = time.time()
+    while done < args.n:
+        n_it = min(per_launch, args.n - done)
+        recs = chains.run(n_it, every)
+        for r in range(recs.shape[0]):
+            it = int(recs[r, 0, E.REC_IT])
+            if it % s_freq == 0:
+                for k in range(args.chains):
+                    writers[k].write(recs[r, k])
+            if it % p_freq == 0 and not args.quiet:
+                _print_state(recs[r, 0], float(end_time), args.calc_adequacy)
+        for w in writers:
+            w.flush()
+        done += n_it
+    t_run = time.time() - t_run
+    for w in writers:
+        w.close()
+    cnt = chains.counters().sum(0)
+    if not args.quiet:
+        print("literate_b200: %d chains x %d iterations in %.3f s (%.3g it/s, %.3g likelihood evaluations/s); binning %.4f s"
+              % (args.chains, args.n, t_run, args.chains * args.n / max(t_run, 1e-9), cnt[2] / max(t_run, 1e-9), t_bin))
+    chains.close(); ds.close()
+    return paths
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.d == "":
+        raise SystemExit("no input file: use -d <table of lineages>")
+    run(args)
+
+
+if __name__ == "__main__":
+    main()
