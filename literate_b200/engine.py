@@ -368,3 +368,35 @@ def record_to_state(rec, end_time):
     tL = np.concatenate([rec[REC_TL:REC_TL + kl], [end_time]])
     tM = np.concatenate([rec[REC_TM:REC_TM + km], [end_time]])
     return L, M, tL, tM
+
+
+def run_rjmcmc(dev: Device, ts, te, n_chains, n_iter, sample_every, seed=1, cfg: ChainConfig = None, model_BDI=0,
+               first_bin=None, n_bins=None, death_jitter=0.5, start_time=None, end_time=None, rep_of_chain=None,
+               chain_id0=0, out=None):
+    """Host tables in, sample records out: the whole hot path in one call (what forward.py does per input file).
+
+    ts/te: float64 host arrays [n] or [n_rep, n] (te already jittered).  Binning (K1), tables (K2) and the chains (K3)
+    run on the device; the copies of the lineages to the device are pipelined against K1.  Returns
+    (records [n_samples, n_chains, 144], BinStats).
+    """
+    ts = np.asarray(ts); te = np.asarray(te)
+    if first_bin is None or n_bins is None:
+        first_bin, n_bins = window(ts, te)
+    if start_time is None:
+        start_time = float(np.min(ts))
+    if end_time is None:
+        end_time = float(np.max(te))
+    if cfg is None:
+        cfg = default_config(model_BDI)
+    stats = dev.bin_stats(ts, te, first_bin=first_bin, n_bins=n_bins, death_jitter=death_jitter,
+                          only_dead=(cfg.model_BDI == 3), end_time=end_time)
+    ds = Dataset(dev, stats, cfg.model_BDI, start_time, end_time)
+    try:
+        ch = Chains(ds, n_chains, seed, cfg, chain_id0=chain_id0, rep_of_chain=rep_of_chain)
+        try:
+            rec = ch.run(n_iter, sample_every, out=out)
+        finally:
+            ch.close()
+    finally:
+        ds.close()
+    return rec, stats

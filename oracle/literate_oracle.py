@@ -108,6 +108,21 @@ def events_in_bin(ts, te, t0, t1):
     return n_sp, n_ex, time_at_risk(ts, te, t0, t1)
 
 
+def events_in_bin_asref(ts, te, t0, t1):
+    """Same three numbers as :func:`events_in_bin`, computed with the SAME NumPy operations the
+    reference issues (:111-123): index sets through ``nonzero`` + ``np.intersect1d`` (two sorts) for
+    the counts, two array copies + two masked stores for the clip.  ~20x slower than
+    :func:`events_in_bin`; used where the reference's *cost* is what is measured (bench.py's CPU
+    baseline), and checked against :func:`events_in_bin` in the CPU tests."""
+    born = np.intersect1d((ts >= t0).nonzero()[0], (ts < t1).nonzero()[0])
+    died = np.intersect1d((te > t0).nonzero()[0], (te <= t1).nonzero()[0])
+    lo, hi = ts + 0., te + 0.
+    lo[lo < t0] = t0
+    hi[hi > t1] = t1
+    span = hi - lo
+    return len(born), len(died), np.sum(span[span > 0])
+
+
 def bin_range(ts, te):
     """range(int(min ts), int(max te)) of :519."""
     return range(int(np.min(ts)), int(np.max(te)))
@@ -613,3 +628,80 @@ def marginal_rates(rows, start_age, end_age, burnin=0.2):
         h = np.histogram(shifts, bins=edges)[0]
         out.append(rates[np.cumsum(h)])
     return np.array(out)
+
+
+# --------------------------------------------------------------------------------------
+# integer accumulators of the one-pass binning (include/literate_b200.h: lr_bin_accumulate /
+# lr_bin_finalize) restated with Python integers -- the checker of the lineage-sharded path, where
+# shards are combined by an integer SUM before the per-bin values are reconstructed.  The identity is
+# SURVEY 7.3; bin_stats() above (the reference's per-bin formulation) stays the ground truth.
+# --------------------------------------------------------------------------------------
+ACC_ROWS = 8
+FIX = 1 << 52
+
+
+def acc_stride(n_bins):
+    return (n_bins + 1 + 7) // 8 * 8
+
+
+def raw_accumulators(ts, te, first_bin, n_bins, fe_ref=0.5, dead_only=False, end_time=None):
+    """int64 [8, acc_stride]: rows births, deaths, sum frac(ts) (low 32 bits / rest, 2^-52 units),
+    sum (fe - fe_ref) (same split), births/deaths of lineages without time at risk; [6][n_bins] = lineages
+    alive before bin 0."""
+    S = acc_stride(n_bins)
+    acc = [[0] * S for _ in range(ACC_ROWS)]
+    ref_fix = int(round(fe_ref * FIX))
+    T0, T1 = first_bin, first_bin + n_bins
+    cs = [0] * n_bins
+    ce = [0] * n_bins
+    for s, e in zip(np.asarray(ts, float).tolist(), np.asarray(te, float).tolist()):
+        if dead_only and not (e < end_time):
+            continue
+        if e > s:
+            if s >= T1:
+                continue
+            if s >= T0:
+                a = math.floor(s) - first_bin
+                acc[0][a] += 1
+                cs[a] += int(round((s - math.floor(s)) * FIX))
+            else:
+                if not (e > T0):
+                    continue
+                acc[6][n_bins] += 1
+            if e <= T1:
+                b = math.ceil(e) - 1 - first_bin
+                acc[1][b] += 1
+                ce[b] += int(round((e - (math.ceil(e) - 1)) * FIX)) - ref_fix
+        else:                                   # no time at risk (te <= ts, or NaN): events still count (:120-121)
+            if s >= T0 and s < T1:
+                a = math.floor(s) - first_bin
+                acc[0][a] += 1
+                acc[6][a] += 1
+            if e > T0 and e <= T1:
+                b = math.ceil(e) - 1 - first_bin
+                acc[1][b] += 1
+                acc[7][b] += 1
+    for j in range(n_bins):
+        acc[2][j], acc[3][j] = cs[j] & 0xffffffff, cs[j] >> 32
+        acc[4][j], acc[5][j] = ce[j] & 0xffffffff, ce[j] >> 32
+    return np.array(acc, dtype=np.int64)
+
+
+def finalize_accumulators(acc, n_bins, fe_ref=0.5):
+    """(sp, ex, br) from (possibly summed) raw accumulators; br is the correctly rounded exact sum."""
+    a = [[int(v) for v in row] for row in np.asarray(acc).tolist()]
+    ref_fix = int(round(fe_ref * FIX))
+    sp = np.array(a[0][:n_bins], dtype=np.int64)
+    ex = np.array(a[1][:n_bins], dtype=np.int64)
+    br = np.zeros(n_bins)
+    c = a[6][n_bins]
+    d_prev = 0
+    for j in range(n_bins):
+        D, E = a[0][j] - a[6][j], a[1][j] - a[7][j]
+        c += d_prev - E
+        cS = a[2][j] + (a[3][j] << 32)
+        cE = a[4][j] + (a[5][j] << 32)
+        F = ((c + D) << 52) - cS + E * ref_fix + cE
+        br[j] = max(F, 0) / FIX            # int / int: correctly rounded
+        d_prev = D
+    return sp, ex, br
