@@ -99,8 +99,6 @@ int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double* h_te, int
                       int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
                       int32_t dead_only, double end_time,
                       int64_t* h_sp, int64_t* h_ex, double* h_br);
-/* which K1 variant lr_bin_accumulate uses: 0 auto, 1 lane-private histograms, 2 shared atomics */
-int lr_set_bin_kernel(lr_handle_t h, int32_t variant);
 
 /* ---------------------------------------------------------------- L3: likelihood + priors on a state
  *
@@ -149,7 +147,8 @@ typedef struct lr_chain_config {
     double  update_fraction;    /* -update_fraction    (:252, :399) */
     int32_t real_move_shift;    /* 0 = reference behaviour (move-shift proposes the current state, :184-185);
                                    1 = reflected sliding window d=1 (opt-in, deviates from the reference) */
-    int32_t reserved;
+    int32_t loop_variant;       /* build of the chain loop: 0 choose by population size, 1 latency-optimised (few chains),
+                                   2 compact (thousands of chains resident); results are identical */
     double  beta;               /* likelihood tempering exponent of every chain unless set per chain; 1 = reference */
 } lr_chain_config;
 
@@ -164,7 +163,8 @@ int lr_chains_destroy(lr_chains_t c);
 /* One sample record = LR_REC_DOUBLES doubles:
  *   [0] iteration  [1] likA  [2] priorA  [3] mean(L)  [4] mean(M)  [5] K_l  [6] K_m
  *   [7] Gamma_rate[0]  [8] Gamma_rate[1]  [9] Poi_lambda  [10..12] adequacy (coeff, r2, gelman_r2)
- *   [13] poi_lambda_is_initial (1 while Poi_lambda_rjHP still is the constant of :220-221)  [14..15] reserved
+ *   [13] poi_lambda_is_initial (1 while Poi_lambda_rjHP still is the constant of :220-221)
+ *   [14] beta (inverse temperature of the chain when the record was written; 1 = the reference's chain)  [15] reserved
  *   [16 .. 16+32)  L slots   [48 .. 80) birth shift times (slot 0 = start_time)
  *   [80 .. 112)    M slots   [112 .. 144) death shift times
  */
@@ -178,18 +178,33 @@ int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int64_t sample_
 int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* d_records, void* stream);
 /* same, records delivered to host memory; synchronous */
 int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* h_records);
-/* per-chain counters since creation: [n_chains][8] int64 =
+/* per-chain counters since creation: [n_chains][LR_NCOUNTERS] int64 =
  *   iterations, accepted, likelihood evaluations, rate-updates, move-shifts, RJ proposals,
- *   Gibbs draws, capacity rejections (add-shift at K == LR_KMAX) */
+ *   Gibbs draws, capacity rejections (add-shift at K == LR_KMAX), temperature swaps proposed, swaps accepted */
+#define LR_NCOUNTERS 10
 int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters);
 /* current state of every chain as one record each (iteration = number of iterations done) */
 int lr_chains_get_state_host(lr_chains_t c, double* h_records);
 /* overwrite the state of every chain from records (fields 1,2 and 10-12 are recomputed) */
 int lr_chains_set_state_host(lr_chains_t c, const double* h_records);
-/* per-chain inverse temperatures for tempered ensembles; 1.0 everywhere = the reference's chain */
+
+/* ---------------------------------------------------------------- tempered ensembles (Metropolis-coupled MCMC)
+ * New; the reference has no tempering.  A chain with beta = 1 is the reference's chain; a heated chain raises the
+ * likelihood to the power beta < 1.  Chains are grouped into ladders of `ladder` consecutive GLOBAL chain ids; a swap
+ * round exchanges TEMPERATURES (not states) between temperature neighbours of a ladder with the usual MC3 rule.
+ */
+/* per-chain inverse temperatures */
 int lr_chains_set_beta_host(lr_chains_t c, const double* h_beta);
-/* swap the states' temperatures between chain pairs (a[i], b[i]) with the usual MC3 rule; device side */
-int lr_chains_swap_step(lr_chains_t c, int32_t n_pairs, const int32_t* h_a, const int32_t* h_b, uint64_t round);
+/* d_info[n_chains][2] = (likelihood, beta) of every chain: the 16 bytes per chain a swap round exchanges; async on `stream` */
+int lr_chains_swap_info(lr_chains_t c, double* d_info, void* stream);
+/* apply swap round `round` to this shard (global chain ids [first, first + n_chains)) given the gathered table
+ * d_info_all[n_all][2] of the whole ensemble (an all-gather of every rank's lr_chains_swap_info when ladders span
+ * devices; the shard's own table when they do not).  Even rounds pair temperature ranks (0,1)(2,3).., odd rounds (1,2)(3,4)..;
+ * the decision of a pair is a Philox draw keyed by (seed, ladder, round, pair), identical on every rank.  Async on `stream`. */
+int lr_chains_swap_apply(lr_chains_t c, const double* d_info_all, int64_t n_all, int64_t first, int32_t ladder,
+                         uint64_t round, void* stream);
+/* single-device convenience: swap_info + swap_apply on the handle's stream for ladders that live on this device */
+int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round);
 
 #ifdef __cplusplus
 }

@@ -15,16 +15,17 @@ LR_ABI_VERSION = 1
 LR_ACC_ROWS = 8
 LR_KMAX = 30
 LR_REC_DOUBLES = 144
+LR_NCOUNTERS = 10
 LR_OK = 0
 
 # every symbol include/literate_b200.h declares (checked by the CPU tests)
 EXPORTS = [
     "lr_abi_version", "lr_last_error", "lr_create", "lr_destroy", "lr_info", "lr_sync",
-    "lr_acc_stride", "lr_bin_accumulate", "lr_bin_finalize", "lr_bin_stats", "lr_bin_stats_host", "lr_set_bin_kernel",
+    "lr_acc_stride", "lr_bin_accumulate", "lr_bin_finalize", "lr_bin_stats", "lr_bin_stats_host",
     "lr_dataset_create", "lr_dataset_create_host", "lr_dataset_destroy", "lr_state_eval_host",
     "lr_chains_create", "lr_chains_destroy", "lr_chains_records_per_run", "lr_chains_run", "lr_chains_run_host",
     "lr_chains_counters_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
-    "lr_chains_swap_step",
+    "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step",
 ]
 
 
@@ -32,7 +33,7 @@ class ChainConfig(C.Structure):
     """lr_chain_config"""
     _fields_ = [("model_BDI", C.c_int32), ("const_rates", C.c_int32), ("const_death_rate", C.c_int32),
                 ("use_rate_HP", C.c_int32), ("poisson_prior", C.c_double), ("update_fraction", C.c_double),
-                ("real_move_shift", C.c_int32), ("reserved", C.c_int32), ("beta", C.c_double)]
+                ("real_move_shift", C.c_int32), ("loop_variant", C.c_int32), ("beta", C.c_double)]
 
 
 class NativeError(RuntimeError):
@@ -74,7 +75,6 @@ def load(build_if_missing=False):
     sig("lr_bin_finalize", C.c_int, vp, vp, i32, i32, f64, vp, vp, vp, vp)
     sig("lr_bin_stats", C.c_int, vp, vp, vp, i64, i64, i32, i64, i32, f64, i32, f64, vp, vp, vp, vp)
     sig("lr_bin_stats_host", C.c_int, vp, vp, vp, i64, i64, i32, i64, i32, f64, i32, f64, vp, vp, vp)
-    sig("lr_set_bin_kernel", C.c_int, vp, i32)
     sig("lr_dataset_create", C.c_int, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp, P(vp))
     sig("lr_dataset_create_host", C.c_int, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, P(vp))
     sig("lr_dataset_destroy", C.c_int, vp)
@@ -88,7 +88,9 @@ def load(build_if_missing=False):
     sig("lr_chains_get_state_host", C.c_int, vp, vp)
     sig("lr_chains_set_state_host", C.c_int, vp, vp)
     sig("lr_chains_set_beta_host", C.c_int, vp, vp)
-    sig("lr_chains_swap_step", C.c_int, vp, i32, vp, vp, u64)
+    sig("lr_chains_swap_info", C.c_int, vp, vp, vp)
+    sig("lr_chains_swap_apply", C.c_int, vp, vp, i64, i64, i32, u64, vp)
+    sig("lr_chains_swap_step", C.c_int, vp, i32, u64)
     if lib.lr_abi_version() != LR_ABI_VERSION:
         raise NativeError("libliterate_b200.so ABI version mismatch; rebuild with `python -m literate_b200.build --force`")
     _lib = lib

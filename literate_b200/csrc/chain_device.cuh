@@ -114,9 +114,6 @@ __device__ __forceinline__ double rates_prior(const Side& s, double g, double lo
 __device__ __forceinline__ double poisson_prior(int k, double lam, double log_lam, const double* lnfact) {
     return (double)k * log_lam - lam - lnfact[k];
 }
-__device__ __forceinline__ double ln_sym_beta10(double u) {
-    return (LR_SHAPE_BETA - 1.0) * (log(u) + log1p(-u)) - LR_BETA_NORM;
-}
 
 // calculate_r_squared (literate_library.py:268-279) in closed form from segment sums
 __device__ __forceinline__ void adequacy3(const Side& L, const Side& M, const DataView& d, int lane, double out[3]) {

@@ -16,17 +16,19 @@
 // exact sum.
 //
 // Kernel shape (B200, HBM-bound: 16 B/lineage, no reuse):
-//   - persistent grid, one CTA per SM, each CTA owns one contiguous slice of the flattened
-//     [replicate][lineage] space -> perfectly balanced, 2-3 flushes per CTA per launch;
-//   - 128-bit coalesced streaming loads (ld.global.nc.L1::no_allocate.v2.f64), 4 deep per array
-//     per thread = 32 KB in flight per SM;
-//   - variant 1: LANE-PRIVATE u16 histograms in shared memory (hist[warp][side][bin][lane]):
-//     plain LDS/IADD/STS, no atomics, no same-address serialisation whatever the input order
-//     (sorted-by-year tables are the common case and are the worst case for shared atomics);
-//     fractional parts that differ from the expected ones (integer ts, te = int + fe_ref) are
-//     the only thing that goes through 32-bit shared atomics (96-bit carry chain);
-//   - variant 2: block-shared u32 histograms with ATOMS (any n_bins up to 24576; fallback and
-//     comparison point).
+//   - grid = 4 CTAs of 256 threads per SM (64 registers/thread), each CTA owns one contiguous slice of the
+//     flattened [replicate][lineage] space -> perfectly balanced, 2-3 flushes per CTA per launch;
+//   - 128-bit coalesced streaming loads (ld.global.nc.L1::no_allocate.v2.f64), 4 deep per array per thread
+//     = 128 KB in flight per SM;
+//   - block-shared u32 histograms updated with shared-memory atomics (ATOMS.POPC.INC: lanes that hit the same bin
+//     are merged by the hardware, so year-sorted tables cost the same as shuffled ones); fractional parts that
+//     differ from the expected ones (integer ts, te = int + fe_ref) go through a 96-bit carry chain of 32-bit
+//     shared atomics;
+//   - measured on B200 (1M lineages x 64..256 replicates x 200 bins): 6.2-6.8 TB/s on integer-year tables
+//     (dram__bytes_read = the algorithmic 16 B/lineage), 4.1 TB/s on real-valued times (stalls on the returning
+//     atomics of the carry chain).  Two designs were measured and dropped: lane-private u16 histograms without
+//     atomics (2.1 TB/s: 8 warps/SM cannot hide the serialised read-modify-write chains) and a joint
+//     (birth bin, lifetime) table with one atomic per lineage (5.8 TB/s: more index arithmetic than it saves).
 #include "lr_common.cuh"
 
 namespace {
@@ -50,7 +52,7 @@ struct K1Params {
     long long* acc;
     long long acc_stride;  // int64 per row
     long long chunk;       // flattened lineages per CTA
-    long long seg_max;     // forced flush period (u16 lane counters)
+    long long seg_max;     // forced flush period
     int vec_ok;
 };
 
@@ -66,10 +68,8 @@ __device__ __forceinline__ void add96(unsigned* arr, unsigned nb, unsigned idx, 
 }
 
 struct K1Smem {
-    unsigned short* hs;   // variant 1: this lane's column of the warp's birth histogram
-    unsigned short* he;
-    unsigned* hs32;       // variant 2
-    unsigned* he32;
+    unsigned* hs32;       // [nb] births
+    unsigned* he32;       // [nb] deaths
     unsigned* cS;         // [3][nb]
     unsigned* cE;         // [3][nb]
     unsigned* exC;        // [nb]
@@ -110,7 +110,6 @@ __device__ __noinline__ void k1_irregular(const K1Params& p, long long* acc, dou
     }
 }
 
-template <int VARIANT>
 __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te) {
     if (p.dead_only) {
         if (!(te < p.end_time)) return;      // :531-532
@@ -120,11 +119,11 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
     const unsigned a = (unsigned)(ti - p.fb);
     const unsigned b = (unsigned)(ci - 1 - p.fb);
     if ((te > ts) && (a < p.nb)) {
-        if (VARIANT == 1) s.hs[a << 5] += 1; else atomicAdd(&s.hs32[a], 1u);
+        atomicAdd(&s.hs32[a], 1u);
         const double fr = ts - (double)ti;
         if (fr != 0.0) add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
         if (b < p.nb) {
-            if (VARIANT == 1) s.he[b << 5] += 1; else atomicAdd(&s.he32[b], 1u);
+            atomicAdd(&s.he32[b], 1u);
             const double fe = te - (double)(ci - 1);
             if (fe != p.fe_ref) {
                 atomicAdd(&s.exC[b], 1u);
@@ -136,26 +135,21 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
     }
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(512, 1) k1_bin_kernel(const K1Params p) {
+__global__ void __launch_bounds__(256, 4) k1_bin_kernel(const K1Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const unsigned nb = p.nb;
 
-    // ---- carve shared memory
+    // ---- carve shared memory: [2][nb] histograms, [7][nb] fraction accumulators
     K1Smem s;
-    unsigned short* hist16 = (unsigned short*)smem_raw;                 // [W][2][nb][32]
-    unsigned* hist32 = (unsigned*)smem_raw;                             // [2][nb]
-    size_t hist_bytes = (VARIANT == 1) ? (size_t)W * 2 * nb * 32 * sizeof(unsigned short) : (size_t)2 * nb * sizeof(unsigned);
-    unsigned* corr = (unsigned*)(smem_raw + ((hist_bytes + 15) & ~(size_t)15));   // [7][nb]
-    s.hs = hist16 + ((size_t)warp * 2 + 0) * nb * 32 + lane;
-    s.he = hist16 + ((size_t)warp * 2 + 1) * nb * 32 + lane;
+    unsigned* hist32 = (unsigned*)smem_raw;
     s.hs32 = hist32;
     s.he32 = hist32 + nb;
+    unsigned* corr = hist32 + 2 * nb;
     s.cS = corr;
     s.cE = corr + 3 * nb;
     s.exC = corr + 6 * nb;
-    const size_t zero_words = (((hist_bytes + 15) & ~(size_t)15) + 7 * (size_t)nb * sizeof(unsigned) + 3) / 4;
+    const size_t zero_words = 9 * (size_t)nb;
 
     const long long total = p.n * (long long)p.n_rep;
     long long g0 = (long long)blockIdx.x * p.chunk;
@@ -182,8 +176,8 @@ __global__ void __launch_bounds__(512, 1) k1_bin_kernel(const K1Params p) {
         if (A > s1) A = s1;
         const long long ntiles = (s1 - A) / K1_TILE;
         const long long B = A + ntiles * K1_TILE;
-        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage<VARIANT>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
-        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage<VARIANT>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
         if (p.vec_ok) {
             for (long long k = warp; k < ntiles; k += W) {
                 const double2* t2 = (const double2*)(ts + A + k * K1_TILE) + lane;
@@ -193,8 +187,8 @@ __global__ void __launch_bounds__(512, 1) k1_bin_kernel(const K1Params p) {
                 for (int u = 0; u < K1_UNROLL; ++u) { sv[u] = ld_stream_f64x2(t2 + u * 32); ev[u] = ld_stream_f64x2(e2 + u * 32); }
 #pragma unroll
                 for (int u = 0; u < K1_UNROLL; ++u) {
-                    k1_lineage<VARIANT>(p, s, acc, sv[u].x, ev[u].x);
-                    k1_lineage<VARIANT>(p, s, acc, sv[u].y, ev[u].y);
+                    k1_lineage(p, s, acc, sv[u].x, ev[u].x);
+                    k1_lineage(p, s, acc, sv[u].y, ev[u].y);
                 }
             }
         } else {
@@ -205,37 +199,16 @@ __global__ void __launch_bounds__(512, 1) k1_bin_kernel(const K1Params p) {
 #pragma unroll
                 for (int u = 0; u < 2 * K1_UNROLL; ++u) { sv[u] = ld_stream_f64(t1 + u * 32); ev[u] = ld_stream_f64(e1 + u * 32); }
 #pragma unroll
-                for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage<VARIANT>(p, s, acc, sv[u], ev[u]);
+                for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage(p, s, acc, sv[u], ev[u]);
             }
         }
         __syncthreads();
 
         // ---- flush this segment into the replicate's global accumulators
         unsigned long long* g = (unsigned long long*)acc;
-        if (VARIANT == 1) {
-            // rows r in [0, 2nb): side = r / nb.  A warp reduces 32 consecutive rows, then issues one
-            // coalesced 64-bit reduction per row block.
-            const unsigned nrows = 2 * nb;
-            for (unsigned rb = warp * 32; rb < nrows; rb += W * 32) {
-                unsigned keep = 0;
-                for (unsigned i = 0; i < 32 && rb + i < nrows; ++i) {
-                    const unsigned r = rb + i, side = r >= nb ? 1u : 0u, bin = r - side * nb;
-                    unsigned v = 0;
-                    for (int w = 0; w < W; ++w) v += hist16[(((size_t)w * 2 + side) * nb + bin) * 32 + lane];
-                    v = __reduce_add_sync(0xffffffffu, v);
-                    if (lane == (int)i) keep = v;
-                }
-                const unsigned r = rb + lane;
-                if (r < nrows && keep) {
-                    const unsigned side = r >= nb ? 1u : 0u, bin = r - side * nb;
-                    atomicAdd(&g[(side ? ROW_EX : ROW_SP) * p.acc_stride + bin], (unsigned long long)keep);
-                }
-            }
-        } else {
-            for (unsigned i = tid; i < nb; i += blockDim.x) {
-                if (s.hs32[i]) atomicAdd(&g[ROW_SP * p.acc_stride + i], (unsigned long long)s.hs32[i]);
-                if (s.he32[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.he32[i]);
-            }
+        for (unsigned i = tid; i < nb; i += blockDim.x) {
+            if (s.hs32[i]) atomicAdd(&g[ROW_SP * p.acc_stride + i], (unsigned long long)s.hs32[i]);
+            if (s.he32[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.he32[i]);
         }
         for (unsigned i = tid; i < nb; i += blockDim.x) {
             const unsigned a0 = s.cS[i], a1 = s.cS[nb + i], a2 = s.cS[2 * nb + i];
@@ -322,12 +295,6 @@ extern "C" int64_t lr_acc_stride(int32_t n_bins) { return ((int64_t)n_bins + 1 +
 
 static long long fe_fix(double fe_ref) { return (long long)llrint(fe_ref * LR_FIX_SCALE); }
 
-extern "C" int lr_set_bin_kernel(lr_handle_t h, int32_t variant) {
-    LR_REQUIRE(h != nullptr && variant >= 0 && variant <= 2, "lr_set_bin_kernel: bad argument");
-    h->bin_variant = variant;
-    return LR_OK;
-}
-
 extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t ld,
                                  int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
                                  int32_t dead_only, double end_time, int64_t* d_acc, void* stream) {
@@ -351,42 +318,20 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     p.acc = (long long*)d_acc; p.acc_stride = lr_acc_stride(n_bins);
     p.vec_ok = (((uintptr_t)d_ts | (uintptr_t)d_te) & 15) == 0 && (ld % 2 == 0 || n_rep == 1);
 
-    const size_t corr_bytes = 7 * (size_t)n_bins * sizeof(unsigned) + 16;
+    const size_t smem = 9 * (size_t)n_bins * sizeof(unsigned);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
-    // variant 1 needs 128 B per bin per warp
-    int W = (int)((budget - corr_bytes) / ((size_t)128 * n_bins));
-    int variant = h->bin_variant;
-    if (variant == 0) variant = W >= 4 ? 1 : 2;
-    if (variant == 1 && W < 1) { lr_set_error("lr_bin_accumulate: n_bins too large for the lane-private kernel"); return LR_ERR_UNSUPPORTED; }
+    int per_sm = (int)(budget / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const int threads = 256, blocks = h->sm_count * per_sm;
+    p.seg_max = 1ll << 31;             // u32 counters: at most 2^31 lineages between flushes
     const long long total = n * (long long)n_rep;
-    int blocks, threads;
-    size_t smem;
-    if (variant == 1) {
-        if (W > 16) W = 16;
-        threads = W * 32;
-        blocks = h->sm_count;
-        smem = (size_t)W * 2 * n_bins * 64 + corr_bytes;
-        p.seg_max = (long long)W * 32 * 32768;
-    } else {
-        threads = 256;
-        smem = 2 * (size_t)n_bins * 4 + corr_bytes;
-        int per_sm = (int)(budget / (smem + 1024));
-        if (per_sm > 4) per_sm = 4;
-        if (per_sm < 1) per_sm = 1;
-        blocks = h->sm_count * per_sm;
-        p.seg_max = 1ll << 31;
-    }
     long long chunk = (total + blocks - 1) / blocks;
     chunk = (chunk + K1_TILE - 1) / K1_TILE * K1_TILE;
     p.chunk = chunk;
-    int used = (int)((total + chunk - 1) / chunk);
-    if (variant == 1) {
-        LR_CUDA(cudaFuncSetAttribute(k1_bin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_bin_kernel<1><<<used, threads, smem, st>>>(p);
-    } else {
-        LR_CUDA(cudaFuncSetAttribute(k1_bin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1_bin_kernel<2><<<used, threads, smem, st>>>(p);
-    }
+    const int used = (int)((total + chunk - 1) / chunk);
+    LR_CUDA(cudaFuncSetAttribute(k1_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_bin_kernel<<<used, threads, smem, st>>>(p);
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;

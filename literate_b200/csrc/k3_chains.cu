@@ -12,10 +12,11 @@
 namespace {
 
 __constant__ double c_lnfact[LR_SLOTS + 2];
+constexpr int LR_COMPACT_ABOVE = 640;   // chains; see profiles/ (k3 variants)
 
 struct ChainState {
     long long it;
-    long long counters[8];
+    long long counters[LR_NCOUNTERS];   // 0..7 maintained by k3_run_kernel, 8..9 by the tempered-swap kernel
     int K_l, K_m, rep, poi_is_init;
     unsigned chain_id, pad;
     double priorA, poiA, gL, gM, poi, beta;
@@ -139,8 +140,8 @@ __device__ __forceinline__ double full_prior(const Side& L, const Side& M, const
     return rates_prior(L, hp.gL, hp.lgL) + rates_prior(M, hp.gM, hp.lgM) - d.log_span * (double)(L.K + M.K - 2) + poi_term;
 }
 
-__device__ void write_record(double* rec, long long it, const Side& L, const Side& M, const Hyper& hp, const DataView& d,
-                             double priorA, int poi_is_init, int lane, bool with_adequacy) {
+__device__ __noinline__ void write_record(double* rec, long long it, const Side& L, const Side& M, const Hyper& hp, const DataView& d,
+                             double priorA, int poi_is_init, double beta, int lane, bool with_adequacy) {
     double adq[3] = {0.0, 0.0, 0.0};
     if (with_adequacy) adequacy3(L, M, d, lane, adq);
     if (lane == 0) {
@@ -153,7 +154,7 @@ __device__ void write_record(double* rec, long long it, const Side& L, const Sid
         rec[6] = (double)M.K;
         rec[7] = hp.gL; rec[8] = hp.gM; rec[9] = hp.poi;
         rec[10] = adq[0]; rec[11] = adq[1]; rec[12] = adq[2];
-        rec[13] = (double)poi_is_init; rec[14] = 0.0; rec[15] = 0.0;
+        rec[13] = (double)poi_is_init; rec[14] = beta; rec[15] = 0.0;
     }
     rec[16 + lane] = lane < L.K ? L.r : 0.0;
     rec[48 + lane] = lane < L.K ? (lane == 0 ? d.start_time : L.t) : 0.0;
@@ -175,23 +176,42 @@ struct RunParams {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Two instantiations of the loop from one source (template parameter C = "compact"):
+//   C = false  few chains (<= ~1 warp per scheduler): latency of the dependent chain decides.  Logarithms and
+//              exponentials are inlined so that independent ones interleave, and the loop body is instantiated once
+//              per side so that no register of a Side is selected at run time.
+//   C = true   thousands of chains resident: instruction fetch decides (ncu: 54 % of stall samples were no_inst with a
+//              45 KB hot footprint against a 32 KB instruction cache).  One out-of-line copy of log/exp, one copy of the
+//              loop body with the side selected at run time.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ double ool_log(double x) { return log(x); }
+__device__ __noinline__ double ool_exp(double x) { return exp(x); }
+template <bool C> __device__ __forceinline__ double xlog(double x) { if constexpr (C) return ool_log(x); else return log(x); }
+template <bool C> __device__ __forceinline__ double xexp(double x) { if constexpr (C) return ool_exp(x); else return exp(x); }
+
+// ------------------------------------------------------------------------------------------------
 // proposals on one side (all warp-uniform control flow)
 // ------------------------------------------------------------------------------------------------
 // update_multiplier_freq (:165-176): each rate w.p. f times exp(2 ln(1.1) (u - .5)); Hastings = sum log m
+template <bool C>
 __device__ __forceinline__ void propose_rates(const Side& cur, Side& nw, double f, double ua, double ub, int lane, double& hasting) {
     nw = cur;
     const bool on = lane < cur.K;
     const bool touched = on && (ua < f);
     const double dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
     nw.lr = cur.lr + dlt;
-    nw.r = touched ? exp(nw.lr) : cur.r;
+    const double e = xexp<C>(nw.lr);
+    nw.r = touched ? e : cur.r;
     side_sums(nw, lane);
     hasting = nw.sumlr - cur.sumlr;
 }
 
 // add_shift_RJ_weighted_mean (:29-47).  Returns false if the proposal violates the spacing guard (:290).
+// The Beta(10,10) variate is u = g1/(g1+g2) with g1, g2 ~ Gamma(10,1) (-log of the product of 10 uniforms each); every
+// logarithm of u the reference takes (log((1-u)/u) :41-42, beta.logpdf :22-23) is assembled from log g1, log g2, log(g1+g2).
+template <bool C>
 __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
-                                            double u_idx, double u_t, double ubeta, int lane, double& hasting) {
+                                            double u_idx, double u_t, double ua, double ub, int lane, double& hasting) {
     const int K = cur.K;
     int i = (int)(u_idx * (double)K);
     if (i > K - 1) i = K - 1;
@@ -201,13 +221,18 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
     if (i + 1 >= K) t_n = d.end_time;
     const double gap = t_n - t_i;
     const double tp = t_i + u_t * gap;                       // np.random.uniform(0, gap)
+    if ((tp - t_i) <= LR_MIN_DT || (t_n - tp) <= LR_MIN_DT) return false;
     const double p1 = (t_i - tp) / (t_i - t_n);
     const double p2 = (tp - t_n) / (t_i - t_n);
     const double lr_i = __shfl_sync(0xffffffffu, cur.lr, i);
-    const double w = log((1.0 - ubeta) / ubeta);
+    const double g1 = -xlog<C>(warp_prod(lane < 10 ? ua : 1.0));
+    const double g2 = -xlog<C>(warp_prod(lane < 10 ? ub : 1.0));
+    const double lg1 = xlog<C>(g1), lg2 = xlog<C>(g2), lgs = xlog<C>(g1 + g2);
+    const double w = lg2 - lg1;                              // log((1-u)/u)
     const double lr1 = lr_i - p2 * w, lr2 = lr_i + p1 * w;
-    const double r1 = exp(lr1), r2 = exp(lr2);
-    hasting = log(fabs(gap)) - ln_sym_beta10(ubeta) + 2.0 * log(r1 + r2) - lr_i;
+    const double r1 = xexp<C>(lr1), r2 = xexp<C>(lr2);
+    const double ln_beta = (LR_SHAPE_BETA - 1.0) * (lg1 + lg2 - 2.0 * lgs) - LR_BETA_NORM;
+    hasting = xlog<C>(fabs(gap)) - ln_beta + 2.0 * xlog<C>(r1 + r2) - lr_i;
     // shift slots above i up by one
     const double ur = __shfl_up_sync(0xffffffffu, cur.r, 1);
     const double ulr = __shfl_up_sync(0xffffffffu, cur.lr, 1);
@@ -217,13 +242,14 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
     if (lane == i) { nw.r = r1; nw.lr = lr1; }
     else if (lane == i + 1) { nw.r = r2; nw.lr = lr2; nw.t = tp; }
     else if (lane > i + 1) { nw.r = ur; nw.lr = ulr; nw.t = ut; }
-    if ((tp - t_i) <= LR_MIN_DT || (t_n - tp) <= LR_MIN_DT) return false;
     side_stats(nw, d, tabA, tabB, lane);
     side_sums(nw, lane);
     return true;
 }
 
-// remove_shift_RJ_weighted_mean (:49-69); caller guarantees K > 1
+// remove_shift_RJ_weighted_mean (:49-69); caller guarantees K > 1.  u = ra/(ra+rb): log u and log(1-u) come from the
+// stored log-rates and the one logarithm of (ra+rb) the Jacobian needs anyway.
+template <bool C>
 __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
                                                double u_idx, int lane, double& hasting) {
     const int K = cur.K;
@@ -240,9 +266,10 @@ __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const 
     const double lra = __shfl_sync(0xffffffffu, cur.lr, j - 1), lrb = __shfl_sync(0xffffffffu, cur.lr, j);
     const double ra = __shfl_sync(0xffffffffu, cur.r, j - 1), rb = __shfl_sync(0xffffffffu, cur.r, j);
     const double lm = p1 * lra + p2 * lrb;
-    const double merged = exp(lm);
-    const double u = 1.0 / (1.0 + rb / ra);
-    hasting = -log(dT) + ln_sym_beta10(u) + lm - 2.0 * log(ra + rb);
+    const double merged = xexp<C>(lm);
+    const double ls = xlog<C>(ra + rb);
+    const double ln_beta = (LR_SHAPE_BETA - 1.0) * (lra + lrb - 2.0 * ls) - LR_BETA_NORM;
+    hasting = -xlog<C>(dT) + ln_beta + lm - 2.0 * ls;
     const double dr = __shfl_down_sync(0xffffffffu, cur.r, 1);
     const double dlr = __shfl_down_sync(0xffffffffu, cur.lr, 1);
     const double dt = __shfl_down_sync(0xffffffffu, cur.t, 1);
@@ -277,9 +304,141 @@ __device__ __forceinline__ bool propose_move(const Side& cur, Side& nw, const Da
     return true;
 }
 
+// Metropolis-Hastings test `x >= log(u)` (:313).  The double-precision logarithm is only evaluated when a
+// single-precision bracket of log(u) (error bound: __logf <= 2^-21.4 absolute on [.5,2], 3 ulp elsewhere, plus the
+// rounding of u to float) cannot decide; the decision is the one the exact comparison gives.
+__device__ __forceinline__ bool mh_accept(double x, double u) {
+    if (x >= 0.0) return true;                     // log(u) < 0 for every u in (0,1)
+    const float lf = __logf((float)u);
+    const float err = 2e-6f * (1.0f + fabsf(lf));
+    if (x >= (double)(lf + err)) return true;
+    if (x < (double)(lf - err)) return false;      // also taken for x = -inf; NaN falls through and is rejected below
+    return x >= ool_log(u);
+}
+
+// everything of a chain that is not one of the two sides
+struct ChainRegs {
+    Hyper hp;
+    double priorA, poiA, beta;
+    int poi_is_init;
+    long long cnt[8];
+};
+// hyper-parameters and table ids as seen from the side a proposal works on
+struct SideView {
+    double g_cur, lg_cur, g_oth, lg_oth;
+    int tabA, tabB;
+};
+__device__ __forceinline__ SideView side_view(const Hyper& hp, bool birth) {
+    SideView v;
+    v.g_cur = birth ? hp.gL : hp.gM; v.lg_cur = birth ? hp.lgL : hp.lgM;
+    v.g_oth = birth ? hp.gM : hp.gL; v.lg_oth = birth ? hp.lgM : hp.lgL;
+    v.tabA = birth ? T_AB : T_AD; v.tabB = birth ? T_BB : T_BD;
+    return v;
+}
+
+// birth block (:254-262) / death block (:264-272) on side `cur`; `oth` is the other side
+template <bool C>
+__device__ __forceinline__ void block_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+                                           const lr_chain_config& cfg, double f, double r1, double ua, double ub, double u_acc,
+                                           bool frozen, int lane) {
+    const double p_oth = rates_prior(oth, v.g_oth, v.lg_oth) - d.log_span * (double)(cur.K + oth.K - 2) + c.poiA;   // :296-303
+    if (r1 < 0.5 || cur.K == 1) {
+        c.cnt[3]++;
+        Side nw;
+        double hasting;
+        propose_rates<C>(cur, nw, f, ua, ub, lane, hasting);
+        if (!frozen) {
+            c.cnt[2]++;
+            const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
+            if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, u_acc)) {
+                cur.r = nw.r; cur.lr = nw.lr; cur.sumlr = nw.sumlr; cur.sumr = nw.sumr; cur.lik = nw.lik;
+                c.priorA = prior; c.cnt[1]++;
+            }
+        }
+    } else {
+        c.cnt[4]++;
+        if (!cfg.real_move_shift) {
+            // the reference's move proposes the current state (:184-185): only the prior bookkeeping can differ
+            if (!frozen) {
+                c.cnt[2]++;
+                const double prior = rates_prior(cur, v.g_cur, v.lg_cur) + p_oth;
+                if (mh_accept(prior - c.priorA, u_acc)) { c.priorA = prior; c.cnt[1]++; }
+            }
+        } else {
+            Side nw;
+            const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_w = __shfl_sync(0xffffffffu, ub, 28);
+            const bool ok = propose_move(cur, nw, d, v.tabA, v.tabB, u_idx, u_w, lane);
+            if (ok && !frozen) {
+                c.cnt[2]++;
+                const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
+                if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA), u_acc)) { cur = nw; c.priorA = prior; c.cnt[1]++; }
+            }
+        }
+    }
+}
+
+// RJMCMC (:71-97, :274-279) on side `cur`
+template <bool C>
+__device__ __forceinline__ void rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d, double ra,
+                                        double ua, double ub, double u_acc, bool frozen, int lane) {
+    const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_t = __shfl_sync(0xffffffffu, ub, 28);
+    Side nw = cur;
+    double hasting = 0.0;
+    bool ok = true;
+    if (ra > 0.5) {
+        if (cur.K >= LR_KMAX) { ok = false; c.cnt[7]++; }
+        else ok = propose_add<C>(cur, nw, d, v.tabA, v.tabB, u_idx, u_t, ua, ub, lane, hasting);
+    } else if (cur.K > 1) {
+        propose_remove<C>(cur, nw, d, v.tabA, v.tabB, u_idx, lane, hasting);
+    }
+    if (ok && !frozen) {
+        c.cnt[2]++;
+        const double poiN = poisson_prior(nw.K, c.hp.poi, c.hp.lpoi, c_lnfact) + poisson_prior(oth.K, c.hp.poi, c.hp.lpoi, c_lnfact);   // :279
+        const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + rates_prior(oth, v.g_oth, v.lg_oth)
+                             - d.log_span * (double)(nw.K + oth.K - 2) + poiN;
+        if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, u_acc)) {
+            cur = nw; c.priorA = prior; c.poiA = poiN; c.cnt[1]++;
+        }
+    }
+}
+
+// Gibbs on the hyper-priors (:281-287), always accepted (:313); one iteration in a thousand, kept out of line
+__device__ __noinline__ void gibbs_step(const Side& L, const Side& M, ChainRegs& c, const DataView& d, const lr_chain_config& cfg,
+                                        const Rng& rng, long long it, bool frozen, int lane) {
+    c.cnt[6]++;
+    Hyper& hp = c.hp;
+    if (cfg.poisson_prior == 0.0) {
+        // get_post_rj_HP (:99-108): Gamma(2 + K_l + K_m, scale 1/3), integer shape
+        double ga, gb;
+        rng.draw(it, 1, lane, ga, gb);
+        const int n = 2 + L.K + M.K;
+        const double pr = warp_prod((lane < n ? ga : 1.0) * (lane + 32 < n ? gb : 1.0));
+        hp.poi = -ool_log(pr) / 3.0;
+        hp.lpoi = ool_log(hp.poi);
+        c.poi_is_init = 0;
+    }
+    if (cfg.use_rate_HP) {
+        // get_rate_HP (:210-213): Gamma(1.2 + 2K, scale 1/(0.1 + sum rates)) = (Gamma(1.2) + Gamma(2K)) * scale
+        double ga, gb;
+        rng.draw(it, 2, lane, ga, gb);
+        const double eL = -ool_log(warp_prod(lane < L.K ? ga * gb : 1.0));
+        const double fracL = warp_gamma_mt(1.2, rng, it, 8, lane);
+        hp.gL = (eL + fracL) / (0.1 + L.sumr);
+        rng.draw(it, 3, lane, ga, gb);
+        const double eM = -ool_log(warp_prod(lane < M.K ? ga * gb : 1.0));
+        const double fracM = warp_gamma_mt(1.2, rng, it, 160, lane);
+        hp.gM = (eM + fracM) / (0.1 + M.sumr);
+        hp.lgL = ool_log(hp.gL); hp.lgM = ool_log(hp.gM);
+    }
+    if (!frozen) { c.priorA = full_prior(L, M, hp, d, c.poiA); }
+    else { c.priorA = -INFINITY; }      // :291 with gibbs == 1 (:313) stores -inf
+    c.cnt[1]++;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: the chains
 // ------------------------------------------------------------------------------------------------
+template <bool C>
 __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
     const int lane = threadIdx.x & 31;
     const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -291,15 +450,12 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
     load_sides(S, L, M, lane);
     side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
     side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
-    Hyper hp;
-    hp.gL = S->gL; hp.gM = S->gM; hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.poi = S->poi; hp.lpoi = log(hp.poi);
-    double priorA = S->priorA, poiA = S->poiA;
-    const double beta = S->beta;
-    int poi_is_init = S->poi_is_init;
+    ChainRegs c;
+    c.hp.gL = S->gL; c.hp.gM = S->gM; c.hp.lgL = log(c.hp.gL); c.hp.lgM = log(c.hp.gM); c.hp.poi = S->poi; c.hp.lpoi = log(c.hp.poi);
+    c.priorA = S->priorA; c.poiA = S->poiA; c.beta = S->beta; c.poi_is_init = S->poi_is_init;
     Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
-    long long cnt[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cnt[i] = S->counters[i];
+    for (int i = 0; i < 8; ++i) c.cnt[i] = S->counters[i];
 
     const lr_chain_config& cfg = P.cfg;
     const double shift_mu = cfg.const_death_rate ? 0.0 : 0.5;          // :243-252
@@ -309,126 +465,51 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
 
     const long long it0 = S->it, it1 = it0 + P.n_iter;
     const long long s_every = P.sample_every > 0 ? P.sample_every : 1;
-    const long long first_sample = (it0 + s_every - 1) / s_every * s_every;
+    long long next_sample = P.records != nullptr ? (it0 + s_every - 1) / s_every * s_every : it1;   // no 64-bit division in the loop
+    double* rec = P.records + (size_t)chain * LR_REC_DOUBLES;
 
     for (long long it = it0; it < it1; ++it) {
         double ua, ub;
         rng.draw(it, 0, lane, ua, ub);
         const double r0 = __shfl_sync(0xffffffffu, ua, 31), r1 = __shfl_sync(0xffffffffu, ub, 31);
-        const double log_u = log(__shfl_sync(0xffffffffu, ua, 30));
+        const double u_acc = __shfl_sync(0xffffffffu, ua, 30);
 
         if (r0 < d_freq) {
-            // ---------------- birth block (:254-262) / death block (:264-272)
             const bool birth = r0 < b_freq;
-            Side& cur = birth ? L : M;
-            if (r1 < 0.5 || cur.K == 1) {
-                cnt[3]++;
-                Side nw;
-                double hasting;
-                propose_rates(cur, nw, birth ? fL : fM, ua, ub, lane, hasting);
-                if (!frozen) {
-                    cnt[2]++;
-                    const double prior = birth ? full_prior(nw, M, hp, d, poiA) : full_prior(L, nw, hp, d, poiA);
-                    if (beta * (nw.lik - cur.lik) + (prior - priorA) + hasting >= log_u) {
-                        cur = nw; priorA = prior; cnt[1]++;
-                    }
-                }
+            if constexpr (C) {
+                block_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, cfg, birth ? fL : fM, r1, ua, ub, u_acc, frozen, lane);
             } else {
-                cnt[4]++;
-                if (!cfg.real_move_shift) {
-                    // the reference's move proposes the current state (:184-185): only the prior bookkeeping can differ
-                    if (!frozen) {
-                        cnt[2]++;
-                        const double prior = full_prior(L, M, hp, d, poiA);
-                        if ((prior - priorA) >= log_u) { priorA = prior; cnt[1]++; }
-                    }
-                } else {
-                    Side nw;
-                    const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_w = __shfl_sync(0xffffffffu, ub, 28);
-                    const bool ok = propose_move(cur, nw, d, birth ? T_AB : T_AD, birth ? T_BB : T_BD, u_idx, u_w, lane);
-                    if (ok && !frozen) {
-                        cnt[2]++;
-                        const double prior = birth ? full_prior(nw, M, hp, d, poiA) : full_prior(L, nw, hp, d, poiA);
-                        if (beta * (nw.lik - cur.lik) + (prior - priorA) >= log_u) { cur = nw; priorA = prior; cnt[1]++; }
-                    }
-                }
+                if (birth) block_step<C>(L, M, side_view(c.hp, true), c, d, cfg, fL, r1, ua, ub, u_acc, frozen, lane);
+                else block_step<C>(M, L, side_view(c.hp, false), c, d, cfg, fM, r1, ua, ub, u_acc, frozen, lane);
             }
         } else if (r0 < 0.999 && !cfg.const_rates) {
-            // ---------------- RJ (:274-279, :71-97)
-            cnt[5]++;
+            c.cnt[5]++;
             const double rs = __shfl_sync(0xffffffffu, ua, 29), ra = __shfl_sync(0xffffffffu, ub, 29);
-            const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_t = __shfl_sync(0xffffffffu, ub, 28);
             const bool birth = rs > shift_mu;
-            Side& cur = birth ? L : M;
-            const int tabA = birth ? T_AB : T_AD, tabB = birth ? T_BB : T_BD;
-            Side nw = cur;
-            double hasting = 0.0;
-            bool ok = true;
-            if (ra > 0.5) {
-                if (cur.K >= LR_KMAX) { ok = false; cnt[7]++; }
-                else {
-                    // Beta(10,10) = G1/(G1+G2), Gamma(10,1) = -log(prod of 10 uniforms)
-                    const double g1 = -log(warp_prod(lane < 10 ? ua : 1.0));
-                    const double g2 = -log(warp_prod(lane < 10 ? ub : 1.0));
-                    ok = propose_add(cur, nw, d, tabA, tabB, u_idx, u_t, g1 / (g1 + g2), lane, hasting);
-                }
-            } else if (cur.K > 1) {
-                propose_remove(cur, nw, d, tabA, tabB, u_idx, lane, hasting);
-            }
-            if (ok && !frozen) {
-                cnt[2]++;
-                const double poiN = poisson_prior(birth ? nw.K : L.K, hp.poi, hp.lpoi, c_lnfact) +
-                                    poisson_prior(birth ? M.K : nw.K, hp.poi, hp.lpoi, c_lnfact);     // :279
-                const double prior = birth ? full_prior(nw, M, hp, d, poiN) : full_prior(L, nw, hp, d, poiN);
-                if (beta * (nw.lik - cur.lik) + (prior - priorA) + hasting >= log_u) {
-                    cur = nw; priorA = prior; poiA = poiN; cnt[1]++;
-                }
+            if constexpr (C) {
+                rj_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, ra, ua, ub, u_acc, frozen, lane);
+            } else {
+                if (birth) rj_step<C>(L, M, side_view(c.hp, true), c, d, ra, ua, ub, u_acc, frozen, lane);
+                else rj_step<C>(M, L, side_view(c.hp, false), c, d, ra, ua, ub, u_acc, frozen, lane);
             }
         } else {
-            // ---------------- Gibbs on the hyper-priors (:281-287), always accepted (:313)
-            cnt[6]++;
-            if (cfg.poisson_prior == 0.0) {
-                // get_post_rj_HP (:99-108): Gamma(2 + K_l + K_m, scale 1/3), integer shape
-                double ga, gb;
-                rng.draw(it, 1, lane, ga, gb);
-                const int n = 2 + L.K + M.K;
-                const double pr = warp_prod((lane < n ? ga : 1.0) * (lane + 32 < n ? gb : 1.0));
-                hp.poi = -log(pr) / 3.0;
-                hp.lpoi = log(hp.poi);
-                poi_is_init = 0;
-            }
-            if (cfg.use_rate_HP) {
-                // get_rate_HP (:210-213): Gamma(1.2 + 2K, scale 1/(0.1 + sum rates)) = (Gamma(1.2) + Gamma(2K)) * scale
-                double ga, gb;
-                rng.draw(it, 2, lane, ga, gb);
-                const double eL = -log(warp_prod(lane < L.K ? ga * gb : 1.0));
-                const double fracL = warp_gamma_mt(1.2, rng, it, 8, lane);
-                hp.gL = (eL + fracL) / (0.1 + L.sumr);
-                rng.draw(it, 3, lane, ga, gb);
-                const double eM = -log(warp_prod(lane < M.K ? ga * gb : 1.0));
-                const double fracM = warp_gamma_mt(1.2, rng, it, 160, lane);
-                hp.gM = (eM + fracM) / (0.1 + M.sumr);
-                hp.lgL = log(hp.gL); hp.lgM = log(hp.gM);
-            }
-            if (!frozen) { priorA = full_prior(L, M, hp, d, poiA); }
-            else { priorA = -INFINITY; }      // :291 with gibbs == 1 (:313) stores -inf
-            cnt[1]++;
+            gibbs_step(L, M, c, d, cfg, rng, it, frozen, lane);
         }
-        cnt[0]++;
+        c.cnt[0]++;
 
-        if (P.records != nullptr && (it % s_every) == 0) {
-            const long long idx = (it - first_sample) / s_every;
-            double* rec = P.records + ((size_t)idx * P.n_chains + chain) * LR_REC_DOUBLES;
-            write_record(rec, it, L, M, hp, d, priorA, poi_is_init, lane, P.with_adequacy != 0);
+        if (it == next_sample) {                // it % sample_every == 0 (:321)
+            write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
+            rec += (size_t)P.n_chains * LR_REC_DOUBLES;
+            next_sample += s_every;
         }
     }
 
     store_sides(S, L, M, lane);
     if (lane == 0) {
         S->it = it1;
-        S->priorA = priorA; S->poiA = poiA; S->gL = hp.gL; S->gM = hp.gM; S->poi = hp.poi; S->poi_is_init = poi_is_init;
+        S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) S->counters[i] = cnt[i];
+        for (int i = 0; i < 8; ++i) S->counters[i] = c.cnt[i];
     }
 }
 
@@ -449,7 +530,7 @@ __global__ void k3_init_kernel(ChainState* st, int n_chains, const int* __restri
     S->rM[lane] = lane == 0 ? m0 : 0.0; S->lrM[lane] = lane == 0 ? log(m0) : 0.0; S->tM[lane] = lane == 0 ? start_time : 0.0;
     if (lane == 0) {
         S->it = 0;
-        for (int i = 0; i < 8; ++i) S->counters[i] = 0;
+        for (int i = 0; i < LR_NCOUNTERS; ++i) S->counters[i] = 0;
         S->K_l = 1; S->K_m = 1; S->rep = rep_of_chain ? rep_of_chain[chain] : 0;
         S->chain_id = rng.chain; S->pad = 0;
         const double poi = poisson_prior_cfg == 0.0 ? 1.0 : poisson_prior_cfg;       // :220-221
@@ -512,7 +593,7 @@ __global__ void k3_get_state_kernel(const ChainState* st, int n_chains, double* 
     side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
     Hyper hp;
     hp.gL = S->gL; hp.gM = S->gM; hp.poi = S->poi; hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.lpoi = log(hp.poi);
-    write_record(recs + (size_t)chain * LR_REC_DOUBLES, S->it, L, M, hp, d, S->priorA, S->poi_is_init, lane, true);
+    write_record(recs + (size_t)chain * LR_REC_DOUBLES, S->it, L, M, hp, d, S->priorA, S->poi_is_init, S->beta, lane, true);
 }
 
 // K2: one warp per state
@@ -553,6 +634,79 @@ __global__ void k2_state_eval_kernel(int n, const int* __restrict__ rep, const i
 __global__ void k3_set_beta_kernel(ChainState* st, int n, const double* beta) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st[i].beta = beta[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// tempered ensembles (Metropolis-coupled MCMC).  New: the reference has no tempering (SURVEY A-15); a chain with
+// beta = 1 is the reference's chain, heated chains raise the likelihood to the power beta < 1.
+// ------------------------------------------------------------------------------------------------
+// (likelihood, beta) of every chain: the 16 bytes per chain a swap round exchanges
+__global__ void k3_swap_info_kernel(const ChainState* st, int n_chains, double* __restrict__ info, const double* tab, const double* cst,
+                                    int nb, int s0f, double start_time, double end_time) {
+    const int lane = threadIdx.x & 31;
+    const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (chain >= n_chains) return;
+    const ChainState* S = st + chain;
+    const DataView d = make_view(tab, cst, S->rep, nb, s0f, start_time, end_time);
+    Side L, M;
+    load_sides(S, L, M, lane);
+    side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
+    side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
+    if (lane == 0) { info[2 * chain] = d.C + L.lik + M.lik; info[2 * chain + 1] = S->beta; }
+}
+
+// One swap round.  Chains are grouped into ladders of `ladder` consecutive GLOBAL chain ids; within a ladder the
+// members are ordered by temperature and neighbours (2p + parity, 2p + 1 + parity) exchange their TEMPERATURES with
+// probability min(1, exp((beta_i - beta_j)(lik_j - lik_i))).  Every rank holding a member of a ladder recomputes the
+// whole ladder's decisions from the gathered (lik, beta) table and a Philox draw keyed by (seed, ladder, round, pair),
+// so the outcome is identical everywhere and no state crosses the interconnect.
+__global__ void k3_swap_apply_kernel(ChainState* st, int n_local, const double* __restrict__ info_all, long long n_all, long long first,
+                                     int ladder, unsigned long long round, uint32_t k0, uint32_t k1) {
+    const int lane = threadIdx.x & 31;
+    const int local = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (local >= n_local) return;
+    const long long g = first + local;
+    const long long lad = g / ladder;
+    const int me = (int)(g - lad * ladder);
+    const long long m = lad * ladder + lane;
+    const bool on = lane < ladder && m < n_all;
+    const double lik = on ? info_all[2 * m] : 0.0;
+    const double beta = on ? info_all[2 * m + 1] : -1.0;
+    // rank by temperature: 0 = coldest (largest beta); ties broken by position
+    int rank = 0;
+    for (int k = 0; k < ladder; ++k) {
+        const double bk = __shfl_sync(0xffffffffu, beta, k);
+        if (bk > beta || (bk == beta && k < lane)) rank++;
+    }
+    const int parity = (int)(round & 1ull);
+    const int q = rank - parity;
+    int partner_rank = -1;
+    if (on && q >= 0) {
+        partner_rank = (q ^ 1) + parity;
+        if (partner_rank >= ladder) partner_rank = -1;
+    }
+    int partner = -1;
+    for (int k = 0; k < ladder; ++k) {
+        const int rk = __shfl_sync(0xffffffffu, rank, k);
+        const bool onk = __shfl_sync(0xffffffffu, (int)on, k) != 0;
+        if (onk && rk == partner_rank) partner = k;
+    }
+    const double lik_p = __shfl_sync(0xffffffffu, lik, partner < 0 ? 0 : partner);
+    const double beta_p = __shfl_sync(0xffffffffu, beta, partner < 0 ? 0 : partner);
+    bool accept = false;
+    if (partner >= 0) {
+        const int pair = (rank < partner_rank ? rank : partner_rank);
+        const Philox4 r = philox4x32_10((uint32_t)round, (uint32_t)(round >> 32), (uint32_t)pair | (0x5157u << 16), (uint32_t)lad, k0, k1 ^ 0x7e3a9u);
+        const double u = u01(r.x, r.y);
+        accept = log(u) <= (beta - beta_p) * (lik_p - lik);
+    }
+    if (lane == me) {
+        ChainState* S = st + local;
+        if (partner >= 0) {
+            S->counters[8] += 1;
+            if (accept) { S->counters[9] += 1; S->beta = beta_p; }
+        }
+    }
 }
 
 int upload_lnfact() {
@@ -711,6 +865,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
     LR_REQUIRE(cfg->model_BDI == ds->model, "lr_chains_create: cfg.model_BDI differs from the dataset's");
     LR_REQUIRE(cfg->update_fraction >= 0.0 && cfg->update_fraction <= 1.0, "lr_chains_create: update_fraction outside [0,1]");
     LR_REQUIRE(cfg->poisson_prior >= 0.0, "lr_chains_create: poisson_prior must be >= 0");
+    LR_REQUIRE(cfg->loop_variant >= 0 && cfg->loop_variant <= 2, "lr_chains_create: loop_variant must be 0, 1 or 2");
     LR_REQUIRE(chain_id0 >= 0 && chain_id0 + n_chains <= 0xffffffffll, "lr_chains_create: chain ids must fit 32 bits");
     if (h_rep_of_chain)
         for (int i = 0; i < n_chains; ++i)
@@ -775,7 +930,11 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     P.with_adequacy = 1;
     int threads;
     const int blocks = chain_grid(c->n_chains, threads);
-    k3_run_kernel<<<blocks, threads, 0, st>>>(P);
+    // loop_variant: 0 = choose by population size (measured cross-over on B200), 1 = latency build, 2 = compact build
+    int variant = c->cfg.loop_variant;
+    if (variant == 0) variant = c->n_chains <= LR_COMPACT_ABOVE ? 1 : 2;
+    if (variant == 1) k3_run_kernel<false><<<blocks, threads, 0, st>>>(P);
+    else k3_run_kernel<true><<<blocks, threads, 0, st>>>(P);
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;
@@ -804,7 +963,7 @@ extern "C" int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters) {
     LR_REQUIRE(c && h_counters, "lr_chains_counters_host: null pointer");
     LR_CUDA(cudaSetDevice(c->h->device));
     LR_CUDA(cudaStreamSynchronize(c->h->stream));
-    LR_CUDA(cudaMemcpy2D(h_counters, 8 * sizeof(int64_t), &c->st[0].counters[0], sizeof(ChainState), 8 * sizeof(int64_t),
+    LR_CUDA(cudaMemcpy2D(h_counters, LR_NCOUNTERS * sizeof(int64_t), &c->st[0].counters[0], sizeof(ChainState), LR_NCOUNTERS * sizeof(int64_t),
                          c->n_chains, cudaMemcpyDeviceToHost));
     return LR_OK;
 }
@@ -863,8 +1022,43 @@ extern "C" int lr_chains_set_beta_host(lr_chains_t c, const double* h_beta) {
     return LR_OK;
 }
 
-extern "C" int lr_chains_swap_step(lr_chains_t c, int32_t n_pairs, const int32_t* h_a, const int32_t* h_b, uint64_t round) {
-    (void)c; (void)n_pairs; (void)h_a; (void)h_b; (void)round;
-    lr_set_error("lr_chains_swap_step: tempered swaps are not implemented yet");
-    return LR_ERR_UNSUPPORTED;
+extern "C" int lr_chains_swap_info(lr_chains_t c, double* d_info, void* stream) {
+    LR_REQUIRE(c && d_info, "lr_chains_swap_info: null pointer");
+    lr_handle_t h = c->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int threads;
+    const int blocks = chain_grid(c->n_chains, threads);
+    k3_swap_info_kernel<<<blocks, threads, 0, st>>>(c->st, c->n_chains, d_info, c->ds->tab, c->ds->cst, c->ds->n_bins, c->ds->s0f,
+                                                    c->ds->start_time, c->ds->end_time);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_chains_swap_apply(lr_chains_t c, const double* d_info_all, int64_t n_all, int64_t first, int32_t ladder,
+                                    uint64_t round, void* stream) {
+    LR_REQUIRE(c && d_info_all, "lr_chains_swap_apply: null pointer");
+    LR_REQUIRE(ladder >= 2 && ladder <= 32, "lr_chains_swap_apply: ladder size must be 2..32");
+    LR_REQUIRE(first >= 0 && first + c->n_chains <= n_all, "lr_chains_swap_apply: this shard [first, first + n_chains) lies outside the gathered table");
+    lr_handle_t h = c->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int threads;
+    const int blocks = chain_grid(c->n_chains, threads);
+    k3_swap_apply_kernel<<<blocks, threads, 0, st>>>(c->st, c->n_chains, d_info_all, n_all, first, ladder, round,
+                                                     (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round) {
+    LR_REQUIRE(c != nullptr, "lr_chains_swap_step: null chains");
+    lr_handle_t h = c->h;
+    int rc = lr_ws_reserve(h, (size_t)c->n_chains * 16);
+    if (rc != LR_OK) return rc;
+    rc = lr_chains_swap_info(c, (double*)h->ws, h->stream);
+    if (rc != LR_OK) return rc;
+    return lr_chains_swap_apply(c, (const double*)h->ws, c->n_chains, 0, ladder, round, h->stream);
 }

@@ -41,7 +41,6 @@ struct lr_handle_s {
     cudaStream_t copy_stream;   // host<->device staging
     cudaEvent_t ev[4];
     int64_t launches;           // kernels launched through this handle
-    int bin_variant;            // 0 auto, 1 lane-private, 2 shared atomics
     // grow-only workspace
     void* ws;
     size_t ws_bytes;

@@ -95,9 +95,6 @@ class Device:
         N.check(self.lib.lr_info(self.h, None, C.byref(n), None))
         return n.value
 
-    def set_bin_kernel(self, variant: int):
-        N.check(self.lib.lr_set_bin_kernel(self.h, int(variant)), "lr_set_bin_kernel")
-
     # ------------------------------------------------------------------ L2
     def bin_stats(self, ts, te, first_bin=None, n_bins=None, death_jitter=0.5, only_dead=False, end_time=None,
                   fe_ref=None) -> BinStats:
@@ -276,9 +273,10 @@ class Dataset:
 
 # field offsets of a sample record (include/literate_b200.h)
 REC_IT, REC_LIK, REC_PRIOR, REC_LAVG, REC_MAVG, REC_KL, REC_KM, REC_GL, REC_GM, REC_POI = range(10)
-REC_ADQ, REC_POI_INIT = 10, 13
+REC_ADQ, REC_POI_INIT, REC_BETA = 10, 13, 14
 REC_L, REC_TL, REC_M, REC_TM = 16, 48, 80, 112
-COUNTER_NAMES = ["iterations", "accepted", "lik_evals", "rate_updates", "move_shifts", "rj_proposals", "gibbs", "capacity_rejects"]
+COUNTER_NAMES = ["iterations", "accepted", "lik_evals", "rate_updates", "move_shifts", "rj_proposals", "gibbs", "capacity_rejects",
+                 "swaps_proposed", "swaps_accepted"]
 
 
 class Chains:
@@ -344,20 +342,68 @@ class Chains:
         N.check(self.dev.lib.lr_chains_set_state_host(self.c, N.np_ptr(records)), "lr_chains_set_state_host")
 
     def counters(self):
-        out = np.empty((self.n_chains, 8), dtype=np.int64)
+        out = np.empty((self.n_chains, N.LR_NCOUNTERS), dtype=np.int64)
         N.check(self.dev.lib.lr_chains_counters_host(self.c, N.np_ptr(out)), "lr_chains_counters_host")
         return out
 
+    # ---- tempered ensembles (new; the reference has no MC3)
     def set_beta(self, beta):
         beta = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (self.n_chains,)))
         N.check(self.dev.lib.lr_chains_set_beta_host(self.c, N.np_ptr(beta)), "lr_chains_set_beta_host")
 
+    def swap_step(self, ladder: int, round_: int):
+        """One swap round for ladders of `ladder` consecutive chains that all live on this device."""
+        N.check(self.dev.lib.lr_chains_swap_step(self.c, int(ladder), C.c_uint64(int(round_))), "lr_chains_swap_step")
+
+    def run_tempered(self, n_iter: int, sample_every: int, ladder: int, swap_every: int, round0: int = 0, swap=None):
+        """n_iter iterations with a swap round every `swap_every` iterations (ladders on this device unless `swap`
+        -- a callable round -> None, e.g. parallel.tempered_swap bound to this shard -- is given).
+        Returns (records of ALL chains [n_samples, n_chains, 144], number of swap rounds done); filter on
+        records[..., REC_BETA] == 1 for the cold chains (cold_records())."""
+        out, done, rnd = [], 0, int(round0)
+        while done < n_iter:
+            n = min(int(swap_every), n_iter - done)
+            r = self.run(n, sample_every)
+            if r is not None and len(r):
+                out.append(r)
+            done += n
+            if done < n_iter or n == swap_every:
+                if swap is None:
+                    self.swap_step(ladder, rnd)
+                else:
+                    swap(rnd)
+                rnd += 1
+        recs = np.concatenate(out) if out else np.empty((0, self.n_chains, LR_REC_DOUBLES))
+        return recs, rnd - int(round0)
+
+    def swap_info_device(self, info, stream=None):
+        """(likelihood, beta) of every chain into the float64 CUDA tensor info[n_chains, 2]."""
+        N.check(self.dev.lib.lr_chains_swap_info(self.c, C.c_void_p(info.data_ptr()), _stream_ptr(stream, info.device)), "lr_chains_swap_info")
+        return info
+
+    def swap_apply_device(self, info_all, first: int, ladder: int, round_: int, stream=None):
+        """Apply a swap round given the gathered table info_all[n_all, 2] of the whole ensemble (see parallel.tempered_swap)."""
+        N.check(self.dev.lib.lr_chains_swap_apply(self.c, C.c_void_p(info_all.data_ptr()), int(info_all.shape[0]), int(first), int(ladder),
+                                                  C.c_uint64(int(round_)), _stream_ptr(stream, info_all.device)), "lr_chains_swap_apply")
+
 
 def default_config(model_BDI=0, const_rates=0, const_death_rate=0, use_rate_HP=1, Poisson_prior=0.0, update_fraction=0.75,
-                   real_move_shift=0, beta=1.0) -> ChainConfig:
+                   real_move_shift=0, beta=1.0, loop_variant=0) -> ChainConfig:
     """Defaults of LiteRateForward.py:386-399."""
     return ChainConfig(int(model_BDI), int(const_rates), int(const_death_rate), int(use_rate_HP), float(Poisson_prior),
-                       float(update_fraction), int(real_move_shift), 0, float(beta))
+                       float(update_fraction), int(real_move_shift), int(loop_variant), float(beta))
+
+
+def cold_records(records, ladder: int):
+    """[n_samples, n_chains, 144] of a tempered run -> [n_samples, n_chains // ladder, 144]: per ladder and sample, the
+    record of the member that held beta = 1 when the sample was written."""
+    ns, nc, w = records.shape
+    r = records.reshape(ns, nc // ladder, ladder, w)
+    idx = np.argmax(r[..., REC_BETA], axis=2)
+    out = np.take_along_axis(r, idx[:, :, None, None], axis=2)[:, :, 0, :]
+    if not np.all(out[..., REC_BETA] == 1.0):
+        raise ValueError("a ladder has no chain at beta = 1")
+    return out
 
 
 def record_to_state(rec, end_time):

@@ -109,6 +109,17 @@ def gather_swap_info(info_local, group=None):
     return out
 
 
+def tempered_swap(chains, first: int, ladder: int, round_: int, group=None):
+    """One swap round of an ensemble whose ladders may span ranks: local (lik, beta) table -> all-gather (16 B per
+    chain over NCCL) -> every rank applies the round to its own shard.  Every rank must hold the same number of chains."""
+    import torch
+    info = torch.empty((chains.n_chains, 2), dtype=torch.float64, device=torch.device("cuda", chains.dev.index))
+    chains.swap_info_device(info)
+    allinfo = gather_swap_info(info, group)
+    chains.swap_apply_device(allinfo, first, ladder, round_)
+    return allinfo
+
+
 def temperature_ladder(n_temps: int, delta: float = 0.1):
     """Incremental-heating ladder beta_k = 1 / (1 + delta * k) (MrBayes/PyRate convention), beta_0 = 1 = the reference's chain."""
     return 1.0 / (1.0 + delta * np.arange(n_temps, dtype=np.float64))

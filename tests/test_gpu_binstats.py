@@ -14,12 +14,8 @@ from literate_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _check(dev, ts, te, jitter, exact=True, variant=0, only_dead=True):
-    dev.set_bin_kernel(variant)
-    try:
-        got = dev.bin_stats(ts, te, death_jitter=jitter, only_dead=only_dead)
-    finally:
-        dev.set_bin_kernel(0)
+def _check(dev, ts, te, jitter, exact=True, only_dead=True):
+    got = dev.bin_stats(ts, te, death_jitter=jitter, only_dead=only_dead)
     want = O.bin_stats(ts, te, only_dead=only_dead)
     assert got.first_bin == want.first_bin and got.n_bins == want.n_bins
     assert (got.sp[0] == want.sp).all() and (got.ex[0] == want.ex).all()
@@ -33,65 +29,57 @@ def _check(dev, ts, te, jitter, exact=True, variant=0, only_dead=True):
             np.testing.assert_allclose(g, w, rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-def test_example_tad_and_tbp(device, variant):
+def test_example_tad_and_tbp(device):
     for name, tbp in (("example_dataTAD.txt", False), ("example_dataTBP.txt", True)):
         lin = O.read_lineages(golden_input(name), TBP=tbp)
-        _check(device, lin.ts, lin.te, 0.5, variant=variant)
+        _check(device, lin.ts, lin.te, 0.5)
         lin0 = O.read_lineages(golden_input(name), TBP=tbp, death_jitter=0.0)
-        _check(device, lin0.ts, lin0.te, 0.0, variant=variant)
+        _check(device, lin0.ts, lin0.te, 0.0)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-def test_metal_bands(device, metal_path, variant):
+def test_metal_bands(device, metal_path):
     lin = O.read_lineages(metal_path)
-    _check(device, lin.ts, lin.te, 0.5, variant=variant)
+    _check(device, lin.ts, lin.te, 0.5)
     got = device.bin_stats(lin.ts, lin.te)
     assert got.sp.sum() == 27495 and got.ex.sum() == 16191 and got.br.sum() == 95426.5
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-def test_random_integer_and_real(device, variant):
+def test_random_integer_and_real(device):
     rng = np.random.default_rng(11)
     for n in (1, 2, 31, 257, 4097, 20011):
         ts, te = synth.syn_int(n, replicate=n)
-        _check(device, ts, te, 0.5, variant=variant)
+        _check(device, ts, te, 0.5)
         ts, te = synth.syn_real(n, replicate=n)
-        _check(device, ts, te, 0.0, exact=False, variant=variant)
+        _check(device, ts, te, 0.0, exact=False)
         # a wrong fe_ref hint must not change the result
-        device.set_bin_kernel(variant)
         a = device.bin_stats(ts, te, fe_ref=0.5)
         b = device.bin_stats(ts, te, fe_ref=1.0)
-        device.set_bin_kernel(0)
         assert (a.br == b.br).all() and (a.sp == b.sp).all() and (a.ex == b.ex).all()
     # quarter-year data: fractional but dyadic -> still bit-exact
     n = 5000
     ts = 1900 + rng.integers(0, 160, n) / 4.0
     te = ts + rng.integers(0, 80, n) / 4.0
     te[0] = 1945.0
-    _check(device, ts, te, 0.0, variant=variant)
+    _check(device, ts, te, 0.0)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
-def test_degenerate_inputs(device, variant):
+def test_degenerate_inputs(device):
     # all extant, single bin
     ts = np.array([10.0, 10.0, 10.0]); te = np.array([11.5, 11.5, 11.5])
-    _check(device, ts, te, 0.5, variant=variant)
+    _check(device, ts, te, 0.5)
     # ts == te (zero time at risk), te < ts (malformed rows still count as events in the reference), NaN rows
     ts = np.array([5.0, 7.0, 9.0, 6.5, 8.0, 5.0, np.nan]); te = np.array([12.5, 7.0, 6.0, 6.5, np.nan, 5.5, 9.5])
-    device.set_bin_kernel(variant)
     got = device.bin_stats(ts, te, first_bin=5, n_bins=7)
-    device.set_bin_kernel(0)
     with np.errstate(invalid="ignore"):
         for j in range(7):
             assert O.events_in_bin(ts, te, 5 + j, 6 + j) == (got.sp[0, j], got.ex[0, j], got.br[0, j]), j
     # sorted input: every lane of a warp hits the same bin
     ts = np.repeat(np.arange(1900.0, 1950.0), 300); te = ts + 3.5
-    _check(device, ts, te, 0.5, variant=variant)
+    _check(device, ts, te, 0.5)
     # unsorted real values with many lineages born and dying in the same bin
     rng = np.random.default_rng(3)
     ts = 50 + rng.uniform(0, 20, 3000); te = ts + rng.uniform(0, 0.7, 3000); te[0] = 71.25
-    _check(device, ts, te, 0.0, exact=False, variant=variant)
+    _check(device, ts, te, 0.0, exact=False)
 
 
 def test_explicit_window_with_lineages_outside(device):

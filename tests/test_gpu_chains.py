@@ -95,6 +95,16 @@ def test_determinism_and_sharding_invariance(device):
     assert not np.array_equal(ra, d.run(3000, 100))
 
 
+def test_loop_builds_give_identical_chains(device, metal_path):
+    """The latency-optimised and the compact build of the chain loop (lr_chain_config.loop_variant) are the same
+    arithmetic: identical records, bit for bit."""
+    lin, st, ds, a = _setup(device, metal_path, n_chains=24, seed=5, loop_variant=1)
+    b = E.Chains(ds, 24, 5, E.default_config(0, loop_variant=2))
+    ra, rb = a.run(30000, 250), b.run(30000, 250)
+    assert np.array_equal(ra, rb)
+    assert np.array_equal(a.counters(), b.counters())
+
+
 def test_checkpoint_roundtrip(device):
     path = golden_input("example_dataTAD.txt")
     lin, st, ds, a = _setup(device, path, n_chains=4, seed=2)
