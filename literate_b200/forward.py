@@ -5,10 +5,15 @@ directory, file names, headers and row layout (LiteRateForward.py:376-512, :321-
 All numerical work (binning, likelihood, proposals, accept step) happens in the CUDA kernels of
 libliterate_b200.so; this module parses, launches and writes text.
 
-New flags (absent from the reference): -chains, -device, -launch_iters, -real_move_shift, -quiet.
+New flags (absent from the reference): -chains, -device, -launch_iters, -real_move_shift, -temper,
+-swap_every, -temper_delta, -quiet.
 With -chains 1 (default) file names are exactly the reference's; with more chains each chain k
-writes <stem><model><out>_chain<k>_{mcmc,sp_rates,ex_rates}.log, which plotRJforward.v3.py's
-`*mcmc.log` glob and its .replace('mcmc.log', ...) still resolve, and they share one div.log each.
+writes <stem><model><out>_chain<k>_{mcmc,sp_rates,ex_rates,div}.log, which plotRJforward.v3.py's
+`*mcmc.log` glob and its .replace('mcmc.log', ...) still resolve.
+With -temper T > 1 every logged chain is the cold member (beta = 1, the reference's chain) of a ladder of T
+Metropolis-coupled chains; only cold samples reach the logs (SURVEY A-15).
+Under torchrun (one process per GPU) the chains are block-partitioned over the ranks; chain k keeps its name and
+its Philox stream whatever the number of GPUs.
 """
 from __future__ import annotations
 
@@ -22,6 +27,7 @@ from warnings import warn
 import numpy as np
 
 from . import engine as E
+from . import parallel as P
 
 BANNER = "\n\n             LiteRate - 20200206  (literate_b200: B200-native RJMCMC path)\n"
 MODEL_SUFFIX = {0: "_BD", 1: "_ID", 2: "_BDk", 3: "_BDd"}          # :422-427
@@ -61,6 +67,9 @@ def build_parser():
     p.add_argument('-launch_iters', type=int, help='iterations per kernel launch (0: choose)', default=0, metavar=0)
     p.add_argument('-real_move_shift', type=int, help='1: move-shift really moves the shift (the reference proposes the '
                    'current state, LiteRateForward.py:184-185)', default=0, metavar=0)
+    p.add_argument('-temper', type=int, help='temperatures per logged chain (1: no tempering, as the reference)', default=1, metavar=1)
+    p.add_argument('-swap_every', type=int, help='iterations between temperature-swap rounds', default=1000, metavar=1000)
+    p.add_argument('-temper_delta', type=float, help='ladder beta_k = 1/(1 + delta k)', default=0.1, metavar=0.1)
     p.add_argument('-quiet', type=int, help='1: no per-iteration progress on stdout', default=0, metavar=0)
     return p
 
@@ -175,15 +184,26 @@ def _print_state(rec, end_time, calc_adequacy):
 
 def run(args, device=None):
     """Everything LiteRateForward.py does after argument parsing; returns the list of mcmc.log paths."""
-    print(BANNER)
+    rank, local_rank, world = P.env_world()
+    lead = rank == 0
+    if not lead:
+        args.quiet = 1
+    if lead:
+        print(BANNER)
     if args.seed == -1:                                   # :405-407
         rseed = int(np.random.randint(0, 9999))
+        if world > 1:
+            raise SystemExit("give -seed explicitly when running on several GPUs (every rank must use the same one)")
     else:
         rseed = args.seed
     if args.model_BDI not in MODEL_SUFFIX:
         raise SystemExit("-model_BDI must be 0, 1, 2 or 3")
     if args.chains < 1:
         raise SystemExit("-chains must be >= 1")
+    if not (1 <= args.temper <= 32):
+        raise SystemExit("-temper must be 1..32")
+    if args.chains < world:
+        raise SystemExit("-chains must be at least the number of GPUs")
     out_name = MODEL_SUFFIX[args.model_BDI] + args.out
     only_dead = args.model_BDI == 3
 
@@ -197,17 +217,19 @@ def run(args, device=None):
     try:
         os.mkdir(out_dir)
     except OSError as e:
-        print(e)
+        if lead:
+            print(e)
 
-    dev = device if device is not None else E.Device(args.device)
+    dev = device if device is not None else E.Device(local_rank if world > 1 else args.device)
     t0 = time.time()
     stats = dev.bin_stats(ts, te, death_jitter=args.death_jitter, only_dead=only_dead, end_time=float(end_time))
     t_bin = time.time() - t0
     sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
-    print(ex.tolist())                                     # :526-527
-    print(br.sum(), range(stats.first_bin, stats.first_bin + stats.n_bins))
-    if only_dead:
-        print(len(stats.ex_dead[0]), len(sp))
+    if lead:
+        print(ex.tolist())                                     # :526-527
+        print(br.sum(), range(stats.first_bin, stats.first_bin + stats.n_bins))
+        if only_dead:
+            print(len(stats.ex_dead[0]), len(sp))
     if args.rm_first_bin:
         # The reference drops element 0 of the three vectors (:552-556) but keeps an n_bins+1 long rate index and
         # dies with IndexError at the first likelihood; here the window itself starts one bin later.
@@ -218,8 +240,7 @@ def run(args, device=None):
         start_time = np.float64(np.floor(start_time) + 1)
 
     stem = "%s/%s%s" % (out_dir, file_name, out_name)
-    write_div_log(stem + "_div.log", sp, ex, br)
-    if args.calc_adequacy:                                 # print_empirical_rates, literate_library.py:260-266
+    if args.calc_adequacy and lead:                        # print_empirical_rates, literate_library.py:260-266
         with np.errstate(divide="ignore", invalid="ignore"), np.printoptions(suppress=True, precision=3):
             print("EMPIRICAL BIRTH RATES:"); print(sp / br)
             print("EMPIRICAL DEATH RATES:"); print(ex / br)
@@ -227,36 +248,43 @@ def run(args, device=None):
     ds = E.Dataset(dev, stats, args.model_BDI, float(start_time), float(end_time))
     cfg = E.default_config(args.model_BDI, args.const_rates, args.const_death_rate, args.use_rate_HP, args.Poisson_prior,
                            args.update_fraction, args.real_move_shift)
-    chains = E.Chains(ds, args.chains, rseed, cfg)
+    # this rank's block of the logged chains; every logged chain is a ladder of T device chains with consecutive ids
+    T = args.temper
+    c0, n_local = P.shard_range(args.chains, world, rank)
+    chains = E.Chains(ds, n_local * T, rseed, cfg, chain_id0=c0 * T)
+    if T > 1:
+        chains.set_beta(np.tile(P.temperature_ladder(T, args.temper_delta), n_local))
 
     writers, paths = [], []
-    for k in range(args.chains):
+    for k in range(c0, c0 + n_local):
         st = stem if args.chains == 1 else "%s_chain%d" % (stem, k)
         writers.append(ChainLogWriter(st, args.calc_adequacy, args.pyrate_output, start_time, end_time, true_root_age,
                                       args.Poisson_prior))
         paths.append(st + "_mcmc.log")
-        if args.chains > 1 and k > 0:                      # one div.log per chain name so every *mcmc.log has its sibling
-            write_div_log(st + "_div.log", sp, ex, br)
-    if args.chains > 1:
-        write_div_log("%s_chain0_div.log" % stem, sp, ex, br)
+        write_div_log(st + "_div.log", sp, ex, br)         # every *mcmc.log has its sibling div.log
 
     s_freq, p_freq = max(1, args.s), max(1, args.p)
     every = int(np.gcd(s_freq, p_freq))
     per_launch = args.launch_iters
     if per_launch <= 0:
         # keep one launch's records under ~256 MB
-        max_rec = max(1, (256 << 20) // (args.chains * E.LR_REC_DOUBLES * 8))
+        max_rec = max(1, (256 << 20) // (n_local * T * E.LR_REC_DOUBLES * 8))
         per_launch = max(every, min(max_rec * every, 2_000_000))
     per_launch = max(every, per_launch // every * every)
-    done = 0
+    done, rounds = 0, 0
     t_run = time.time()
     while done < args.n:
         n_it = min(per_launch, args.n - done)
-        recs = chains.run(n_it, every)
+        if T > 1:
+            recs, r = chains.run_tempered(n_it, every, T, max(1, args.swap_every), round0=rounds)
+            rounds += r
+            recs = E.cold_records(recs, T)
+        else:
+            recs = chains.run(n_it, every)
         for r in range(recs.shape[0]):
             it = int(recs[r, 0, E.REC_IT])
             if it % s_freq == 0:
-                for k in range(args.chains):
+                for k in range(n_local):
                     writers[k].write(recs[r, k])
             if it % p_freq == 0 and not args.quiet:
                 _print_state(recs[r, 0], float(end_time), args.calc_adequacy)
@@ -269,7 +297,9 @@ def run(args, device=None):
     cnt = chains.counters().sum(0)
     if not args.quiet:
         print("literate_b200: %d chains x %d iterations in %.3f s (%.3g it/s, %.3g likelihood evaluations/s); binning %.4f s"
-              % (args.chains, args.n, t_run, args.chains * args.n / max(t_run, 1e-9), cnt[2] / max(t_run, 1e-9), t_bin))
+              % (n_local * T, args.n, t_run, n_local * T * args.n / max(t_run, 1e-9), cnt[2] / max(t_run, 1e-9), t_bin))
+        if T > 1:
+            print("literate_b200: %d swap rounds, %.3f of the proposed temperature swaps accepted" % (rounds, cnt[9] / max(cnt[8], 1)))
     chains.close(); ds.close()
     return paths
 
