@@ -329,4 +329,9 @@ def run_cuda(a):
 
 if __name__ == "__main__":
     args = _args()
+    # stdout carries exactly one JSON line: native libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w")
     sys.exit(run_reference(args) if args.impl == "reference" else run_cuda(args))
