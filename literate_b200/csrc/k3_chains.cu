@@ -12,13 +12,12 @@
 namespace {
 
 __constant__ double c_lnfact[LR_SLOTS + 2];
-constexpr int LR_COMPACT_ABOVE = 640;   // chains; see profiles/ (k3 variants)
 
 struct ChainState {
     long long it;
     long long counters[LR_NCOUNTERS];   // 0..7 maintained by k3_run_kernel, 8..9 by the tempered-swap kernel
     int K_l, K_m, rep, poi_is_init;
-    unsigned chain_id, pad;
+    unsigned chain_id, consistent;
     double priorA, poiA, gL, gM, poi, beta;
     double rL[LR_SLOTS], lrL[LR_SLOTS], tL[LR_SLOTS];
     double rM[LR_SLOTS], lrM[LR_SLOTS], tM[LR_SLOTS];
@@ -100,7 +99,7 @@ struct Rng {
 };
 
 // Gamma(a, 1), 1 <= a < 2 (Marsaglia & Tsang 2000), 32 attempts per round, first accepted lane wins
-__device__ double warp_gamma_mt(double a, const Rng& rng, long long it, uint32_t purpose, int lane) {
+__device__ __noinline__ double warp_gamma_mt(double a, const Rng rng, long long it, uint32_t purpose, int lane) {
     const double d = a - 1.0 / 3.0, c = rsqrt(9.0 * d);
     for (uint32_t round = 0;; ++round) {
         double u1, u2, u3, u4;
@@ -140,7 +139,9 @@ __device__ __forceinline__ double full_prior(const Side& L, const Side& M, const
     return rates_prior(L, hp.gL, hp.lgL) + rates_prior(M, hp.gM, hp.lgM) - d.log_span * (double)(L.K + M.K - 2) + poi_term;
 }
 
-__device__ __noinline__ void write_record(double* rec, long long it, const Side& L, const Side& M, const Hyper& hp, const DataView& d,
+// (cold functions take their arguments BY VALUE: a reference into a __noinline__ callee would make the caller keep the
+// chain's state in local memory for the whole loop)
+__device__ __noinline__ void write_record(double* rec, long long it, const Side L, const Side M, const Hyper hp, const DataView d,
                              double priorA, int poi_is_init, double beta, int lane, bool with_adequacy) {
     double adq[3] = {0.0, 0.0, 0.0};
     if (with_adequacy) adequacy3(L, M, d, lane, adq);
@@ -176,63 +177,173 @@ struct RunParams {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Two instantiations of the loop from one source (template parameter C = "compact"):
-//   C = false  few chains (<= ~1 warp per scheduler): latency of the dependent chain decides.  Logarithms and
-//              exponentials are inlined so that independent ones interleave, and the loop body is instantiated once
-//              per side so that no register of a Side is selected at run time.
-//   C = true   thousands of chains resident: instruction fetch decides (ncu: 54 % of stall samples were no_inst with a
-//              45 KB hot footprint against a 32 KB instruction cache).  One out-of-line copy of log/exp, one copy of the
-//              loop body with the side selected at run time.
+// The loop, in two builds of one source.
+//
+// Everything an iteration takes from the random stream is independent of the chain's state: the branch uniforms, the
+// per-rate multipliers exp(2 ln 1.1 (u - .5)) of the rate update, the Beta(10,10) variate of the add-shift move with
+// its logarithms, a single-precision bracket of log(u) for the accept test.  make_draws() computes all of it from the
+// counter-based Philox stream of (seed, chain, iteration).
+//
+//   SPECIALISED (few chains; ncu: one warp per scheduler, 54 % of stall samples on fixed-latency dependencies):
+//       one CTA of 4 warps per chain.  Warps 1-3 are PRODUCERS: each runs make_draws() for every third iteration and
+//       publishes it into a shared-memory ring (release/acquire flags).  Warp 0 is the CHAIN warp: it only does the
+//       state-dependent part (segment statistics, sums, prior, accept, commit), so Philox, the exponentials of the
+//       multipliers and the five logarithms of the add-shift move leave its dependency chain.
+//   COMPACT (thousands of chains resident; ncu: 54 % no_inst with a 45 KB hot footprint): one warp per chain calls
+//       make_draws() inline, one out-of-line copy of log/exp, side selected at run time, 92 registers.
+// Both run the same arithmetic on the same random numbers: identical chains, bit for bit (tested).
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ double ool_log(double x) { return log(x); }
 __device__ __noinline__ double ool_exp(double x) { return exp(x); }
 template <bool C> __device__ __forceinline__ double xlog(double x) { if constexpr (C) return ool_log(x); else return log(x); }
 template <bool C> __device__ __forceinline__ double xexp(double x) { if constexpr (C) return ool_exp(x); else return exp(x); }
 
+struct Draws {
+    double u_acc;                  // the accept uniform (:313)
+    double thr_hi, thr_lo;         // single-precision bracket of log(u_acc): x >= thr_hi accepts, x < thr_lo rejects
+    int kind;                      // proposal type decided by the branch uniforms alone (:234, :74): DK_* << 1 | birth side
+    double u_idx, u_t;             // RJMCMC / move: segment or shift index, position inside the segment
+    double w, ln_beta;             // add-shift: log((1-u)/u) and beta.logpdf(u; 10, 10) of the Beta variate u (:22-23, :41-42)
+    double m, dlt;                 // this lane's rate multiplier and its logarithm (1, 0 when the rate is not touched) (:165-176)
+};
+
+// proposal kinds (Draws::kind >> 1)
+#define DK_BLOCK_RATE 0     // birth/death block, rate multiplier (:258, :268)
+#define DK_BLOCK_MOVE 1     // birth/death block, move-shift unless the side has a single rate (:261, :271)
+#define DK_RJ_ADD 2
+#define DK_RJ_REMOVE 3
+#define DK_GIBBS 4
+
+struct LoopConsts {
+    double shift_mu, b_freq, d_freq, fL, fM;
+    int const_rates, real_move_shift;
+};
+__device__ __forceinline__ LoopConsts loop_consts(const lr_chain_config& cfg) {
+    LoopConsts k;
+    k.shift_mu = cfg.const_death_rate ? 0.0 : 0.5;          // :243-252
+    k.b_freq = cfg.const_death_rate ? 0.7 : 0.4; k.d_freq = 0.8;
+    k.fL = cfg.update_fraction; k.fM = cfg.const_death_rate ? 1.0 : cfg.update_fraction;
+    k.const_rates = cfg.const_rates; k.real_move_shift = cfg.real_move_shift;
+    return k;
+}
+
+template <bool C>
+__device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int lane, const LoopConsts& k) {
+    Draws q;
+    double ua, ub;
+    rng.draw(it, 0, lane, ua, ub);
+    const double r0 = __shfl_sync(0xffffffffu, ua, 31), r1 = __shfl_sync(0xffffffffu, ub, 31);   // np.random.random(2) of :234
+    q.u_acc = __shfl_sync(0xffffffffu, ua, 30);
+    // bracket of log(u) for the accept test (error bound: __logf <= 2^-21.4 absolute on [.5,2], 3 ulp elsewhere, plus the
+    // rounding of u to float)
+    const float lf = __logf((float)q.u_acc);
+    const float err = 2e-6f * (1.0f + fabsf(lf));
+    q.thr_hi = (double)(lf + err); q.thr_lo = (double)(lf - err);
+    q.u_idx = 0.0; q.u_t = 0.0; q.w = 0.0; q.ln_beta = 0.0; q.m = 1.0; q.dlt = 0.0;
+    if (r0 < k.d_freq) {
+        // update_multiplier_freq (:165-176): each rate w.p. f times exp(2 ln(1.1) (u - .5))
+        const bool birth = r0 < k.b_freq;
+        const double f = birth ? k.fL : k.fM;
+        const bool touched = ua < f;
+        q.dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
+        q.m = xexp<C>(q.dlt);                               // exp(0) = 1 exactly
+        q.kind = ((r1 < 0.5 ? DK_BLOCK_RATE : DK_BLOCK_MOVE) << 1) | (birth ? 1 : 0);
+        if (k.real_move_shift) { q.u_idx = __shfl_sync(0xffffffffu, ua, 28); q.u_t = __shfl_sync(0xffffffffu, ub, 28); }
+    } else if (r0 < 0.999 && !k.const_rates) {
+        const double rs = __shfl_sync(0xffffffffu, ua, 29), ra = __shfl_sync(0xffffffffu, ub, 29);   // np.random.random(2) of :74
+        q.u_idx = __shfl_sync(0xffffffffu, ua, 28); q.u_t = __shfl_sync(0xffffffffu, ub, 28);
+        const bool birth = rs > k.shift_mu;
+        if (ra > 0.5) {
+            // Beta(10,10) = G1/(G1+G2), Gamma(10,1) = -log(prod of 10 uniforms); every logarithm of u the reference takes
+            // is assembled from log g1, log g2, log(g1+g2)
+            const double g1 = -xlog<C>(warp_prod(lane < 10 ? ua : 1.0));
+            const double g2 = -xlog<C>(warp_prod(lane < 10 ? ub : 1.0));
+            const double lg1 = xlog<C>(g1), lg2 = xlog<C>(g2), lgs = xlog<C>(g1 + g2);
+            q.w = lg2 - lg1;
+            q.ln_beta = (LR_SHAPE_BETA - 1.0) * (lg1 + lg2 - 2.0 * lgs) - LR_BETA_NORM;
+            q.kind = (DK_RJ_ADD << 1) | (birth ? 1 : 0);
+        } else {
+            q.kind = (DK_RJ_REMOVE << 1) | (birth ? 1 : 0);
+        }
+    } else {
+        q.kind = DK_GIBBS << 1;
+    }
+    return q;
+}
+
+// ---- shared-memory ring between the producer warps and the chain warp (SPECIALISED build).
+// The unit of hand-off is a BATCH of RING_BATCH consecutive iterations: batch b is produced by warp 1 + b % 3 into slot
+// b % RING_DEPTH and published with one release store; the chain warp acquires once per batch and releases the slot
+// when it has taken the batch's last iteration.
+constexpr int RING_PRODUCERS = 3;
+constexpr int RING_BATCH = 8;
+constexpr int RING_DEPTH = 6;          // batches in flight: two per producer
+struct RingIter {
+    double m[32], dlt[32];
+    double sc[16];                     // u_acc u_idx u_t w ln_beta thr_hi thr_lo kind
+};
+struct Ring {
+    RingIter it[RING_DEPTH][RING_BATCH];
+    unsigned long long full[RING_DEPTH];   // b + 1 once batch b is published
+    unsigned long long done[RING_DEPTH];   // b + 1 once batch b has been consumed
+};
+__device__ __forceinline__ unsigned long long ld_acquire_cta(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.cta.shared.u64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ring_store(RingIter& S, const Draws& q, int lane) {
+    S.m[lane] = q.m; S.dlt[lane] = q.dlt;
+    double v = q.u_acc;
+    v = lane == 1 ? q.u_idx : v; v = lane == 2 ? q.u_t : v; v = lane == 3 ? q.w : v; v = lane == 4 ? q.ln_beta : v;
+    v = lane == 5 ? q.thr_hi : v; v = lane == 6 ? q.thr_lo : v; v = lane == 7 ? __longlong_as_double((long long)q.kind) : v;
+    if (lane < 8) S.sc[lane] = v;
+}
+__device__ __forceinline__ Draws ring_load(const RingIter& S, int lane) {
+    Draws q;
+    q.m = S.m[lane]; q.dlt = S.dlt[lane];
+    q.u_acc = S.sc[0]; q.u_idx = S.sc[1]; q.u_t = S.sc[2]; q.w = S.sc[3]; q.ln_beta = S.sc[4];
+    q.thr_hi = S.sc[5]; q.thr_lo = S.sc[6]; q.kind = (int)__double_as_longlong(S.sc[7]);
+    return q;
+}
+
 // ------------------------------------------------------------------------------------------------
 // proposals on one side (all warp-uniform control flow)
 // ------------------------------------------------------------------------------------------------
-// update_multiplier_freq (:165-176): each rate w.p. f times exp(2 ln(1.1) (u - .5)); Hastings = sum log m
-template <bool C>
-__device__ __forceinline__ void propose_rates(const Side& cur, Side& nw, double f, double ua, double ub, int lane, double& hasting) {
+// update_multiplier_freq (:165-176): q * m as the reference does; Hastings = sum log m.  The log-rate follows by
+// addition and is re-derived from the rate every LR_RESYNC iterations so that the two never drift apart.
+__device__ __forceinline__ void propose_rates(const Side& cur, Side& nw, const Draws& q, int lane, double& hasting) {
     nw = cur;
     const bool on = lane < cur.K;
-    const bool touched = on && (ua < f);
-    const double dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
-    nw.lr = cur.lr + dlt;
-    const double e = xexp<C>(nw.lr);
-    nw.r = touched ? e : cur.r;
+    nw.lr = cur.lr + (on ? q.dlt : 0.0);
+    nw.r = cur.r * (on ? q.m : 1.0);
     side_sums(nw, lane);
     hasting = nw.sumlr - cur.sumlr;
 }
 
 // add_shift_RJ_weighted_mean (:29-47).  Returns false if the proposal violates the spacing guard (:290).
-// The Beta(10,10) variate is u = g1/(g1+g2) with g1, g2 ~ Gamma(10,1) (-log of the product of 10 uniforms each); every
-// logarithm of u the reference takes (log((1-u)/u) :41-42, beta.logpdf :22-23) is assembled from log g1, log g2, log(g1+g2).
 template <bool C>
 __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
-                                            double u_idx, double u_t, double ua, double ub, int lane, double& hasting) {
+                                            const Draws& q, int lane, double& hasting) {
     const int K = cur.K;
-    int i = (int)(u_idx * (double)K);
+    int i = (int)(q.u_idx * (double)K);
     if (i > K - 1) i = K - 1;
     const double t_raw = (lane == 0) ? d.start_time : cur.t;
     const double t_i = __shfl_sync(0xffffffffu, t_raw, i);
     double t_n = __shfl_sync(0xffffffffu, t_raw, (i + 1) & 31);
     if (i + 1 >= K) t_n = d.end_time;
     const double gap = t_n - t_i;
-    const double tp = t_i + u_t * gap;                       // np.random.uniform(0, gap)
+    const double tp = t_i + q.u_t * gap;                     // np.random.uniform(0, gap)
     if ((tp - t_i) <= LR_MIN_DT || (t_n - tp) <= LR_MIN_DT) return false;
     const double p1 = (t_i - tp) / (t_i - t_n);
     const double p2 = (tp - t_n) / (t_i - t_n);
     const double lr_i = __shfl_sync(0xffffffffu, cur.lr, i);
-    const double g1 = -xlog<C>(warp_prod(lane < 10 ? ua : 1.0));
-    const double g2 = -xlog<C>(warp_prod(lane < 10 ? ub : 1.0));
-    const double lg1 = xlog<C>(g1), lg2 = xlog<C>(g2), lgs = xlog<C>(g1 + g2);
-    const double w = lg2 - lg1;                              // log((1-u)/u)
-    const double lr1 = lr_i - p2 * w, lr2 = lr_i + p1 * w;
+    const double lr1 = lr_i - p2 * q.w, lr2 = lr_i + p1 * q.w;
     const double r1 = xexp<C>(lr1), r2 = xexp<C>(lr2);
-    const double ln_beta = (LR_SHAPE_BETA - 1.0) * (lg1 + lg2 - 2.0 * lgs) - LR_BETA_NORM;
-    hasting = xlog<C>(fabs(gap)) - ln_beta + 2.0 * xlog<C>(r1 + r2) - lr_i;
+    hasting = xlog<C>(fabs(gap)) - q.ln_beta + 2.0 * xlog<C>(r1 + r2) - lr_i;
     // shift slots above i up by one
     const double ur = __shfl_up_sync(0xffffffffu, cur.r, 1);
     const double ulr = __shfl_up_sync(0xffffffffu, cur.lr, 1);
@@ -251,9 +362,9 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
 // stored log-rates and the one logarithm of (ra+rb) the Jacobian needs anyway.
 template <bool C>
 __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
-                                               double u_idx, int lane, double& hasting) {
+                                               const Draws& q, int lane, double& hasting) {
     const int K = cur.K;
-    int j = 1 + (int)(u_idx * (double)(K - 1));
+    int j = 1 + (int)(q.u_idx * (double)(K - 1));
     if (j > K - 1) j = K - 1;
     const double t_raw = (lane == 0) ? d.start_time : cur.t;
     const double t_rm = __shfl_sync(0xffffffffu, t_raw, j);
@@ -284,16 +395,16 @@ __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const 
 // opt-in real move-shift: reflected sliding window of width 1 on one interior shift (what
 // update_sliding_win :178-186 computes before it overwrites the result)
 __device__ __forceinline__ bool propose_move(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
-                                             double u_idx, double u_w, int lane) {
+                                             const Draws& q, int lane) {
     const int K = cur.K;
-    int j = 1 + (int)(u_idx * (double)(K - 1));
+    int j = 1 + (int)(q.u_idx * (double)(K - 1));
     if (j > K - 1) j = K - 1;
     const double t_raw = (lane == 0) ? d.start_time : cur.t;
     const double t_j = __shfl_sync(0xffffffffu, t_raw, j);
     const double t_a = __shfl_sync(0xffffffffu, t_raw, j - 1);
     double t_b = __shfl_sync(0xffffffffu, t_raw, (j + 1) & 31);
     if (j + 1 >= K) t_b = d.end_time;
-    double tp = t_j + (u_w - 0.5) * 1.0;
+    double tp = t_j + (q.u_t - 0.5) * 1.0;
     if (tp < d.start_time) tp = d.start_time + (d.start_time - tp);
     if (tp > d.end_time) tp = d.end_time - (tp - d.end_time);
     nw = cur;
@@ -304,16 +415,12 @@ __device__ __forceinline__ bool propose_move(const Side& cur, Side& nw, const Da
     return true;
 }
 
-// Metropolis-Hastings test `x >= log(u)` (:313).  The double-precision logarithm is only evaluated when a
-// single-precision bracket of log(u) (error bound: __logf <= 2^-21.4 absolute on [.5,2], 3 ulp elsewhere, plus the
-// rounding of u to float) cannot decide; the decision is the one the exact comparison gives.
-__device__ __forceinline__ bool mh_accept(double x, double u) {
-    if (x >= 0.0) return true;                     // log(u) < 0 for every u in (0,1)
-    const float lf = __logf((float)u);
-    const float err = 2e-6f * (1.0f + fabsf(lf));
-    if (x >= (double)(lf + err)) return true;
-    if (x < (double)(lf - err)) return false;      // also taken for x = -inf; NaN falls through and is rejected below
-    return x >= ool_log(u);
+// Metropolis-Hastings test `x >= log(u)` (:313).  The double-precision logarithm is only evaluated when the
+// single-precision bracket [thr_lo, thr_hi] of log(u) cannot decide; the decision is the one the exact comparison gives.
+__device__ __forceinline__ bool mh_accept(double x, const Draws& q) {
+    if (x >= q.thr_hi) return true;
+    if (x < q.thr_lo) return false;                // also taken for x = -inf
+    return x >= ool_log(q.u_acc);                  // NaN lands here and is rejected
 }
 
 // everything of a chain that is not one of the two sides
@@ -321,6 +428,8 @@ struct ChainRegs {
     Hyper hp;
     double priorA, poiA, beta;
     int poi_is_init;
+    int consistent;                // priorA is the prior of the current state under the current hyper-parameters and poiA
+                                   // (false only between the initial state of :227 and the first accepted proposal)
     long long cnt[8];
 };
 // hyper-parameters and table ids as seen from the side a proposal works on
@@ -339,39 +448,43 @@ __device__ __forceinline__ SideView side_view(const Hyper& hp, bool birth) {
 // birth block (:254-262) / death block (:264-272) on side `cur`; `oth` is the other side
 template <bool C>
 __device__ __forceinline__ void block_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
-                                           const lr_chain_config& cfg, double f, double r1, double ua, double ub, double u_acc,
-                                           bool frozen, int lane) {
+                                           const lr_chain_config& cfg, const Draws& q, bool frozen, int lane) {
+    const bool rate = (q.kind >> 1) == DK_BLOCK_RATE || cur.K == 1;
+    if (!rate && !cfg.real_move_shift && c.consistent && !frozen) {
+        // The reference's move proposes the current state (:184-185): prior - priorA = 0, always accepted, nothing changes.
+        c.cnt[4]++; c.cnt[2]++; c.cnt[1]++;
+        return;
+    }
     const double p_oth = rates_prior(oth, v.g_oth, v.lg_oth) - d.log_span * (double)(cur.K + oth.K - 2) + c.poiA;   // :296-303
-    if (r1 < 0.5 || cur.K == 1) {
+    if (rate) {
         c.cnt[3]++;
         Side nw;
         double hasting;
-        propose_rates<C>(cur, nw, f, ua, ub, lane, hasting);
+        propose_rates(cur, nw, q, lane, hasting);
         if (!frozen) {
             c.cnt[2]++;
             const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
-            if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, u_acc)) {
+            if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, q)) {
                 cur.r = nw.r; cur.lr = nw.lr; cur.sumlr = nw.sumlr; cur.sumr = nw.sumr; cur.lik = nw.lik;
-                c.priorA = prior; c.cnt[1]++;
+                c.priorA = prior; c.consistent = 1; c.cnt[1]++;
             }
         }
     } else {
         c.cnt[4]++;
         if (!cfg.real_move_shift) {
-            // the reference's move proposes the current state (:184-185): only the prior bookkeeping can differ
+            // same no-op move while priorA still is the initial prior of :227: only the prior bookkeeping can differ
             if (!frozen) {
                 c.cnt[2]++;
                 const double prior = rates_prior(cur, v.g_cur, v.lg_cur) + p_oth;
-                if (mh_accept(prior - c.priorA, u_acc)) { c.priorA = prior; c.cnt[1]++; }
+                if (mh_accept(prior - c.priorA, q)) { c.priorA = prior; c.consistent = 1; c.cnt[1]++; }
             }
         } else {
             Side nw;
-            const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_w = __shfl_sync(0xffffffffu, ub, 28);
-            const bool ok = propose_move(cur, nw, d, v.tabA, v.tabB, u_idx, u_w, lane);
+            const bool ok = propose_move(cur, nw, d, v.tabA, v.tabB, q, lane);
             if (ok && !frozen) {
                 c.cnt[2]++;
                 const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
-                if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA), u_acc)) { cur = nw; c.priorA = prior; c.cnt[1]++; }
+                if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA), q)) { cur = nw; c.priorA = prior; c.consistent = 1; c.cnt[1]++; }
             }
         }
     }
@@ -379,72 +492,132 @@ __device__ __forceinline__ void block_step(Side& cur, const Side& oth, const Sid
 
 // RJMCMC (:71-97, :274-279) on side `cur`
 template <bool C>
-__device__ __forceinline__ void rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d, double ra,
-                                        double ua, double ub, double u_acc, bool frozen, int lane) {
-    const double u_idx = __shfl_sync(0xffffffffu, ua, 28), u_t = __shfl_sync(0xffffffffu, ub, 28);
+__device__ __forceinline__ void rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+                                        const Draws& q, bool frozen, int lane) {
     Side nw = cur;
     double hasting = 0.0;
     bool ok = true;
-    if (ra > 0.5) {
+    if ((q.kind >> 1) == DK_RJ_ADD) {
         if (cur.K >= LR_KMAX) { ok = false; c.cnt[7]++; }
-        else ok = propose_add<C>(cur, nw, d, v.tabA, v.tabB, u_idx, u_t, ua, ub, lane, hasting);
+        else ok = propose_add<C>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
     } else if (cur.K > 1) {
-        propose_remove<C>(cur, nw, d, v.tabA, v.tabB, u_idx, lane, hasting);
+        propose_remove<C>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
     }
     if (ok && !frozen) {
         c.cnt[2]++;
         const double poiN = poisson_prior(nw.K, c.hp.poi, c.hp.lpoi, c_lnfact) + poisson_prior(oth.K, c.hp.poi, c.hp.lpoi, c_lnfact);   // :279
         const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + rates_prior(oth, v.g_oth, v.lg_oth)
                              - d.log_span * (double)(nw.K + oth.K - 2) + poiN;
-        if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, u_acc)) {
-            cur = nw; c.priorA = prior; c.poiA = poiN; c.cnt[1]++;
+        if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, q)) {
+            cur = nw; c.priorA = prior; c.poiA = poiN; c.consistent = 1; c.cnt[1]++;
         }
     }
 }
 
-// Gibbs on the hyper-priors (:281-287), always accepted (:313); one iteration in a thousand, kept out of line
-__device__ __noinline__ void gibbs_step(const Side& L, const Side& M, ChainRegs& c, const DataView& d, const lr_chain_config& cfg,
-                                        const Rng& rng, long long it, bool frozen, int lane) {
-    c.cnt[6]++;
-    Hyper& hp = c.hp;
-    if (cfg.poisson_prior == 0.0) {
+// Gibbs on the hyper-priors (:281-287), always accepted (:313); one iteration in a thousand, kept out of line.
+// Arguments and result by value (see write_record).
+struct GibbsOut { Hyper hp; double priorA; int poi_is_init; };
+__device__ __noinline__ GibbsOut gibbs_step(const Side L, const Side M, Hyper hp, double poiA, int poi_is_init, const DataView d,
+                                            int sample_poisson, int use_rate_HP, const Rng rng, long long it, bool frozen, int lane) {
+    if (sample_poisson) {
         // get_post_rj_HP (:99-108): Gamma(2 + K_l + K_m, scale 1/3), integer shape
         double ga, gb;
         rng.draw(it, 1, lane, ga, gb);
         const int n = 2 + L.K + M.K;
         const double pr = warp_prod((lane < n ? ga : 1.0) * (lane + 32 < n ? gb : 1.0));
-        hp.poi = -ool_log(pr) / 3.0;
-        hp.lpoi = ool_log(hp.poi);
-        c.poi_is_init = 0;
+        hp.poi = -log(pr) / 3.0;
+        hp.lpoi = log(hp.poi);
+        poi_is_init = 0;
     }
-    if (cfg.use_rate_HP) {
+    if (use_rate_HP) {
         // get_rate_HP (:210-213): Gamma(1.2 + 2K, scale 1/(0.1 + sum rates)) = (Gamma(1.2) + Gamma(2K)) * scale
         double ga, gb;
         rng.draw(it, 2, lane, ga, gb);
-        const double eL = -ool_log(warp_prod(lane < L.K ? ga * gb : 1.0));
+        const double eL = -log(warp_prod(lane < L.K ? ga * gb : 1.0));
         const double fracL = warp_gamma_mt(1.2, rng, it, 8, lane);
         hp.gL = (eL + fracL) / (0.1 + L.sumr);
         rng.draw(it, 3, lane, ga, gb);
-        const double eM = -ool_log(warp_prod(lane < M.K ? ga * gb : 1.0));
+        const double eM = -log(warp_prod(lane < M.K ? ga * gb : 1.0));
         const double fracM = warp_gamma_mt(1.2, rng, it, 160, lane);
         hp.gM = (eM + fracM) / (0.1 + M.sumr);
-        hp.lgL = ool_log(hp.gL); hp.lgM = ool_log(hp.gM);
+        hp.lgL = log(hp.gL); hp.lgM = log(hp.gM);
     }
-    if (!frozen) { c.priorA = full_prior(L, M, hp, d, c.poiA); }
-    else { c.priorA = -INFINITY; }      // :291 with gibbs == 1 (:313) stores -inf
-    c.cnt[1]++;
+    GibbsOut o;
+    o.hp = hp; o.poi_is_init = poi_is_init;
+    o.priorA = frozen ? -INFINITY : full_prior(L, M, hp, d, poiA);      // :291 with gibbs == 1 (:313) stores -inf
+    return o;
+}
+
+// log-rates follow the rates by addition inside the loop; every LR_RESYNC iterations they are re-derived from the rates
+// (at fixed iteration numbers, so that a chain does not depend on how a run is split into launches or sampled)
+// The COMPACT build calls the cold functions through these by-reference wrappers ON PURPOSE: the escaping addresses make
+// the compiler keep the two Sides and the ChainRegs in local memory (L1-resident, 368 B per thread) instead of registers,
+// 96 instead of 192 registers per thread.  With thousands of chains resident the extra warps hide more latency than the
+// local loads cost (B200, 16384 chains: 2.01 G it/s against 1.48-1.77 G it/s for register-resident builds at 168/128
+// registers); the SPECIALISED build wants the opposite and calls the by-value functions directly.
+__device__ __noinline__ void gibbs_step_ref(const Side& L, const Side& M, ChainRegs& c, const DataView& d, int sample_poisson,
+                                            int use_rate_HP, const Rng& rng, long long it, bool frozen, int lane) {
+    const GibbsOut g = gibbs_step(L, M, c.hp, c.poiA, c.poi_is_init, d, sample_poisson, use_rate_HP, rng, it, frozen, lane);
+    c.hp = g.hp; c.priorA = g.priorA; c.poi_is_init = g.poi_is_init;
+}
+__device__ __noinline__ void write_record_ref(double* rec, long long it, const Side& L, const Side& M, const ChainRegs& c, const DataView& d,
+                                              int lane, bool with_adequacy) {
+    write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, with_adequacy);
+}
+
+#define LR_RESYNC 1024
+__device__ __forceinline__ void resync_log_rates(Side& L, Side& M, int lane) {
+    const double a = ool_log(L.r), b = ool_log(M.r);      // inactive lanes hold 0: -inf, discarded
+    L.lr = lane < L.K ? a : 0.0;
+    M.lr = lane < M.K ? b : 0.0;
+    side_sums(L, lane); side_sums(M, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: the chains
+// K3: the chains.  SPEC = warp-specialised build (blockDim = 128: chain warp + 3 producer warps, one chain per CTA);
+// otherwise compact build (one warp per chain, any blockDim that is a multiple of 32).
 // ------------------------------------------------------------------------------------------------
-template <bool C>
+template <bool SPEC>
 __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
+    constexpr bool C = !SPEC;
     const int lane = threadIdx.x & 31;
-    const int chain = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int warp = threadIdx.x >> 5;
+    const int chain = SPEC ? (int)blockIdx.x : (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (chain >= P.n_chains) return;
     ChainState* S = P.st + chain;
+    const lr_chain_config& cfg = P.cfg;
+    const LoopConsts K = loop_consts(cfg);
+    Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
+    const long long it0 = S->it, it1 = it0 + P.n_iter;
 
+    Ring* ring_p = nullptr;
+    if constexpr (SPEC) {
+        __shared__ Ring ring;
+        ring_p = &ring;
+        if (threadIdx.x < RING_DEPTH) { ring.full[threadIdx.x] = 0ull; ring.done[threadIdx.x] = 0ull; }
+        __syncthreads();                    // it0 was read above: the chain warp rewrites S->it only at the very end
+        if (warp > 0) {
+            // ---------------- producer warps: batches b = warp-1, warp-1+3, ... of RING_BATCH iterations each
+            const long long n_batches = (P.n_iter + RING_BATCH - 1) / RING_BATCH;
+            int s = warp - 1;                       // slot of batch b is b % RING_DEPTH, tracked without a division
+            for (long long b = warp - 1; b < n_batches; b += RING_PRODUCERS) {
+                // wait until the previous occupant of the slot (batch b - RING_DEPTH) has been consumed; back off while
+                // waiting so that the polling does not compete with the chain warp for the shared-memory pipe
+                while ((long long)ld_acquire_cta(&ring.done[s]) < b - RING_DEPTH + 1) __nanosleep(200);
+                const long long j0 = b * RING_BATCH;
+#pragma unroll 1
+                for (int i = 0; i < RING_BATCH; ++i) {
+                    if (j0 + i < P.n_iter) ring_store(ring.it[s][i], make_draws<false>(rng, it0 + j0 + i, lane, K), lane);
+                }
+                __syncwarp();
+                if (lane == 0) st_release_cta(&ring.full[s], (unsigned long long)(b + 1));
+                s += RING_PRODUCERS; if (s >= RING_DEPTH) s -= RING_DEPTH;
+            }
+            return;
+        }
+    }
+
+    // ---------------- the chain warp
     const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
     Side L, M;
     load_sides(S, L, M, lane);
@@ -452,53 +625,66 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
     side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
     ChainRegs c;
     c.hp.gL = S->gL; c.hp.gM = S->gM; c.hp.lgL = log(c.hp.gL); c.hp.lgM = log(c.hp.gM); c.hp.poi = S->poi; c.hp.lpoi = log(c.hp.poi);
-    c.priorA = S->priorA; c.poiA = S->poiA; c.beta = S->beta; c.poi_is_init = S->poi_is_init;
-    Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
+    c.priorA = S->priorA; c.poiA = S->poiA; c.beta = S->beta; c.poi_is_init = S->poi_is_init; c.consistent = (int)S->consistent;
 #pragma unroll
     for (int i = 0; i < 8; ++i) c.cnt[i] = S->counters[i];
-
-    const lr_chain_config& cfg = P.cfg;
-    const double shift_mu = cfg.const_death_rate ? 0.0 : 0.5;          // :243-252
-    const double b_freq = cfg.const_death_rate ? 0.7 : 0.4, d_freq = 0.8;
-    const double fL = cfg.update_fraction, fM = cfg.const_death_rate ? 1.0 : cfg.update_fraction;
     const bool frozen = (d.end_time - d.start_time) <= LR_MIN_DT;      // guard :290 rejects everything
 
-    const long long it0 = S->it, it1 = it0 + P.n_iter;
     const long long s_every = P.sample_every > 0 ? P.sample_every : 1;
     long long next_sample = P.records != nullptr ? (it0 + s_every - 1) / s_every * s_every : it1;   // no 64-bit division in the loop
+    long long next_resync = (it0 + LR_RESYNC - 1) / LR_RESYNC * LR_RESYNC;
     double* rec = P.records + (size_t)chain * LR_REC_DOUBLES;
+    int slot = 0, in_batch = 0;
+    long long batch = 0;
 
     for (long long it = it0; it < it1; ++it) {
-        double ua, ub;
-        rng.draw(it, 0, lane, ua, ub);
-        const double r0 = __shfl_sync(0xffffffffu, ua, 31), r1 = __shfl_sync(0xffffffffu, ub, 31);
-        const double u_acc = __shfl_sync(0xffffffffu, ua, 30);
-
-        if (r0 < d_freq) {
-            const bool birth = r0 < b_freq;
-            if constexpr (C) {
-                block_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, cfg, birth ? fL : fM, r1, ua, ub, u_acc, frozen, lane);
-            } else {
-                if (birth) block_step<C>(L, M, side_view(c.hp, true), c, d, cfg, fL, r1, ua, ub, u_acc, frozen, lane);
-                else block_step<C>(M, L, side_view(c.hp, false), c, d, cfg, fM, r1, ua, ub, u_acc, frozen, lane);
+        Draws q;
+        if constexpr (SPEC) {
+            Ring& R = *ring_p;
+            if (in_batch == 0) { while (ld_acquire_cta(&R.full[slot]) != (unsigned long long)(batch + 1)) { } }
+            q = ring_load(R.it[slot][in_batch], lane);
+            if (++in_batch == RING_BATCH || it + 1 == it1) {
+                __syncwarp();
+                if (lane == 0) st_release_cta(&R.done[slot], (unsigned long long)(batch + 1));
+                in_batch = 0; ++batch; if (++slot == RING_DEPTH) slot = 0;
             }
-        } else if (r0 < 0.999 && !cfg.const_rates) {
-            c.cnt[5]++;
-            const double rs = __shfl_sync(0xffffffffu, ua, 29), ra = __shfl_sync(0xffffffffu, ub, 29);
-            const bool birth = rs > shift_mu;
+        }
+        else q = make_draws<true>(rng, it, lane, K);
+
+        const int kind = q.kind >> 1;
+        const bool birth = (q.kind & 1) != 0;
+        if (kind <= DK_BLOCK_MOVE) {
             if constexpr (C) {
-                rj_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, ra, ua, ub, u_acc, frozen, lane);
+                block_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, cfg, q, frozen, lane);
             } else {
-                if (birth) rj_step<C>(L, M, side_view(c.hp, true), c, d, ra, ua, ub, u_acc, frozen, lane);
-                else rj_step<C>(M, L, side_view(c.hp, false), c, d, ra, ua, ub, u_acc, frozen, lane);
+                if (birth) block_step<C>(L, M, side_view(c.hp, true), c, d, cfg, q, frozen, lane);
+                else block_step<C>(M, L, side_view(c.hp, false), c, d, cfg, q, frozen, lane);
+            }
+        } else if (kind != DK_GIBBS) {
+            c.cnt[5]++;
+            if constexpr (C) {
+                rj_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, q, frozen, lane);
+            } else {
+                if (birth) rj_step<C>(L, M, side_view(c.hp, true), c, d, q, frozen, lane);
+                else rj_step<C>(M, L, side_view(c.hp, false), c, d, q, frozen, lane);
             }
         } else {
-            gibbs_step(L, M, c, d, cfg, rng, it, frozen, lane);
+            c.cnt[6]++;
+            if constexpr (C) {
+                gibbs_step_ref(L, M, c, d, cfg.poisson_prior == 0.0 ? 1 : 0, cfg.use_rate_HP, rng, it, frozen, lane);
+            } else {
+                const GibbsOut g = gibbs_step(L, M, c.hp, c.poiA, c.poi_is_init, d, cfg.poisson_prior == 0.0 ? 1 : 0, cfg.use_rate_HP, rng, it, frozen, lane);
+                c.hp = g.hp; c.priorA = g.priorA; c.poi_is_init = g.poi_is_init;
+            }
+            c.consistent = 1;
+            c.cnt[1]++;
         }
         c.cnt[0]++;
 
+        if (it == next_resync) { resync_log_rates(L, M, lane); next_resync += LR_RESYNC; }
         if (it == next_sample) {                // it % sample_every == 0 (:321)
-            write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
+            if constexpr (C) write_record_ref(rec, it, L, M, c, d, lane, P.with_adequacy != 0);
+            else write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
             rec += (size_t)P.n_chains * LR_REC_DOUBLES;
             next_sample += s_every;
         }
@@ -507,7 +693,7 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
     store_sides(S, L, M, lane);
     if (lane == 0) {
         S->it = it1;
-        S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init;
+        S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init; S->consistent = (unsigned)c.consistent;
 #pragma unroll
         for (int i = 0; i < 8; ++i) S->counters[i] = c.cnt[i];
     }
@@ -532,7 +718,7 @@ __global__ void k3_init_kernel(ChainState* st, int n_chains, const int* __restri
         S->it = 0;
         for (int i = 0; i < LR_NCOUNTERS; ++i) S->counters[i] = 0;
         S->K_l = 1; S->K_m = 1; S->rep = rep_of_chain ? rep_of_chain[chain] : 0;
-        S->chain_id = rng.chain; S->pad = 0;
+        S->chain_id = rng.chain; S->consistent = 0;     // the initial prior uses Gamma rate 2 (:227), the loop rate 1
         const double poi = poisson_prior_cfg == 0.0 ? 1.0 : poisson_prior_cfg;       // :220-221
         S->poi = poi; S->poi_is_init = 1;
         S->gL = 1.0; S->gM = 1.0;                                                     // :222
@@ -577,6 +763,7 @@ __global__ void k3_set_state_kernel(ChainState* st, int n_chains, const double* 
         S->gL = hp.gL; S->gM = hp.gM; S->poi = hp.poi; S->poi_is_init = (int)rec[13];
         S->poiA = poiA;
         S->priorA = full_prior(L, M, hp, d, poiA);
+        S->consistent = 1;
     }
 }
 
@@ -930,11 +1117,14 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     P.with_adequacy = 1;
     int threads;
     const int blocks = chain_grid(c->n_chains, threads);
-    // loop_variant: 0 = choose by population size (measured cross-over on B200), 1 = latency build, 2 = compact build
+    // loop_variant: 0 = choose by population size (measured cross-over on B200), 1 = warp-specialised build
+    // (one CTA of 4 warps per chain), 2 = compact build (one warp per chain)
+    // The specialised build holds 2 CTAs (= 2 chains) per SM; beyond one wave of it the compact build wins (B200, 148 SMs:
+    // 296 chains 545 M it/s specialised; 384 chains 372 M specialised vs 392 M compact; 512: 485 M vs 597 M).
     int variant = c->cfg.loop_variant;
-    if (variant == 0) variant = c->n_chains <= LR_COMPACT_ABOVE ? 1 : 2;
-    if (variant == 1) k3_run_kernel<false><<<blocks, threads, 0, st>>>(P);
-    else k3_run_kernel<true><<<blocks, threads, 0, st>>>(P);
+    if (variant == 0) variant = c->n_chains <= 2 * h->sm_count ? 1 : 2;
+    if (variant == 1) k3_run_kernel<true><<<c->n_chains, 128, 0, st>>>(P);
+    else k3_run_kernel<false><<<blocks, threads, 0, st>>>(P);
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;

@@ -96,8 +96,9 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
     return o;
 }
-// 53-bit uniform strictly inside (0,1)
-__host__ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
-    uint64_t b = ((uint64_t)hi << 32) | lo;
-    return ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+// uniform strictly inside (0,1) from 52 random bits: the bits become the mantissa of a double in [1,2) (no integer to
+// floating-point conversion), shifted down by 1 and up by half a step: values (k + 1/2) 2^-52, k = 0 .. 2^52-1
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+    const double x = __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+    return (x - 1.0) + 1.1102230246251565e-16;
 }
