@@ -31,6 +31,7 @@ struct lr_chains_s {
     int n_chains;
     lr_chain_config cfg;
     uint64_t seed;
+    int64_t chain_id0;    // global id of chain 0 of this shard
     ChainState* st;       // device [n_chains]
 };
 
@@ -847,8 +848,8 @@ __global__ void k3_swap_info_kernel(const ChainState* st, int n_chains, double* 
 // probability min(1, exp((beta_i - beta_j)(lik_j - lik_i))).  Every rank holding a member of a ladder recomputes the
 // whole ladder's decisions from the gathered (lik, beta) table and a Philox draw keyed by (seed, ladder, round, pair),
 // so the outcome is identical everywhere and no state crosses the interconnect.
-__global__ void k3_swap_apply_kernel(ChainState* st, int n_local, const double* __restrict__ info_all, long long n_all, long long first,
-                                     int ladder, unsigned long long round, uint32_t k0, uint32_t k1) {
+__global__ void k3_swap_apply_kernel(ChainState* st, int n_local, const double* __restrict__ info_all, long long table_first,
+                                     long long n_all, long long first, int ladder, unsigned long long round, uint32_t k0, uint32_t k1) {
     const int lane = threadIdx.x & 31;
     const int local = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (local >= n_local) return;
@@ -856,9 +857,9 @@ __global__ void k3_swap_apply_kernel(ChainState* st, int n_local, const double* 
     const long long lad = g / ladder;
     const int me = (int)(g - lad * ladder);
     const long long m = lad * ladder + lane;
-    const bool on = lane < ladder && m < n_all;
-    const double lik = on ? info_all[2 * m] : 0.0;
-    const double beta = on ? info_all[2 * m + 1] : -1.0;
+    const bool on = lane < ladder && m >= table_first && m < table_first + n_all;     // table row of global chain m: m - table_first
+    const double lik = on ? info_all[2 * (m - table_first)] : 0.0;
+    const double beta = on ? info_all[2 * (m - table_first) + 1] : -1.0;
     // rank by temperature: 0 = coldest (largest beta); ties broken by position
     int rank = 0;
     for (int k = 0; k < ladder; ++k) {
@@ -1059,7 +1060,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
             LR_REQUIRE(h_rep_of_chain[i] >= 0 && h_rep_of_chain[i] < ds->n_rep, "lr_chains_create: replicate of chain %d out of range", i);
     LR_CUDA(cudaSetDevice(h->device));
     lr_chains_t c = new lr_chains_s();
-    c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->st = nullptr;
+    c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->chain_id0 = chain_id0; c->st = nullptr;
     if (c->cfg.beta == 0.0) c->cfg.beta = 1.0;
     cudaError_t e = cudaMalloc(&c->st, (size_t)n_chains * sizeof(ChainState));
     if (e != cudaSuccess) { lr_set_error("lr_chains_create: cudaMalloc: %s", cudaGetErrorString(e)); delete c; return LR_ERR_NOMEM; }
@@ -1226,29 +1227,39 @@ extern "C" int lr_chains_swap_info(lr_chains_t c, double* d_info, void* stream) 
     return LR_OK;
 }
 
-extern "C" int lr_chains_swap_apply(lr_chains_t c, const double* d_info_all, int64_t n_all, int64_t first, int32_t ladder,
-                                    uint64_t round, void* stream) {
-    LR_REQUIRE(c && d_info_all, "lr_chains_swap_apply: null pointer");
-    LR_REQUIRE(ladder >= 2 && ladder <= 32, "lr_chains_swap_apply: ladder size must be 2..32");
-    LR_REQUIRE(first >= 0 && first + c->n_chains <= n_all, "lr_chains_swap_apply: this shard [first, first + n_chains) lies outside the gathered table");
+static int swap_apply(lr_chains_t c, const double* d_info_all, int64_t table_first, int64_t n_all, int64_t first, int32_t ladder,
+                      uint64_t round, void* stream, const char* who) {
+    LR_REQUIRE(c && d_info_all, "%s: null pointer", who);
+    LR_REQUIRE(ladder >= 2 && ladder <= 32, "%s: ladder size must be 2..32", who);
+    LR_REQUIRE(first >= table_first && first + c->n_chains <= table_first + n_all,
+               "%s: this shard [first, first + n_chains) lies outside the gathered table", who);
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int threads;
     const int blocks = chain_grid(c->n_chains, threads);
-    k3_swap_apply_kernel<<<blocks, threads, 0, st>>>(c->st, c->n_chains, d_info_all, n_all, first, ladder, round,
+    k3_swap_apply_kernel<<<blocks, threads, 0, st>>>(c->st, c->n_chains, d_info_all, table_first, n_all, first, ladder, round,
                                                      (uint32_t)c->seed, (uint32_t)(c->seed >> 32));
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;
 }
 
+extern "C" int lr_chains_swap_apply(lr_chains_t c, const double* d_info_all, int64_t n_all, int64_t first, int32_t ladder,
+                                    uint64_t round, void* stream) {
+    return swap_apply(c, d_info_all, 0, n_all, first, ladder, round, stream, "lr_chains_swap_apply");
+}
+
 extern "C" int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round) {
     LR_REQUIRE(c != nullptr, "lr_chains_swap_step: null chains");
+    LR_REQUIRE(ladder >= 2 && c->chain_id0 % ladder == 0 && c->n_chains % ladder == 0,
+               "lr_chains_swap_step: the shard must hold whole ladders (chain_id0 and n_chains multiples of the ladder size); "
+               "use lr_chains_swap_info + an all-gather + lr_chains_swap_apply for ladders that span devices");
     lr_handle_t h = c->h;
     int rc = lr_ws_reserve(h, (size_t)c->n_chains * 16);
     if (rc != LR_OK) return rc;
     rc = lr_chains_swap_info(c, (double*)h->ws, h->stream);
     if (rc != LR_OK) return rc;
-    return lr_chains_swap_apply(c, (const double*)h->ws, c->n_chains, 0, ladder, round, h->stream);
+    // ladders and their Philox keys are numbered by GLOBAL chain id, so the outcome does not depend on the sharding
+    return swap_apply(c, (const double*)h->ws, c->chain_id0, c->n_chains, c->chain_id0, ladder, round, h->stream, "lr_chains_swap_step");
 }

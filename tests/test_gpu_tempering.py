@@ -76,6 +76,15 @@ def test_swap_outcome_is_independent_of_sharding(device):
             whole.run(300); a.run(300); b.run(300)
         sw, sa, sb = whole.state(), a.state(), b.state()
         assert np.array_equal(sw, np.concatenate([sa, sb]))
+        if T == 4:
+            # shards that hold whole ladders may use the local swap_step: ladders are keyed by GLOBAL chain id
+            for rnd in range(4, 8):
+                whole.swap_step(T, rnd); a.swap_step(T, rnd); b.swap_step(T, rnd)
+                assert np.array_equal(np.concatenate([a.state(), b.state()]), whole.state())
+                whole.run(200); a.run(200); b.run(200)
+        else:
+            with pytest.raises(E.NativeError):
+                a.swap_step(T, 99)          # a ladder of 16 does not fit a shard of 8
 
 
 def test_cold_chains_sample_the_untempered_posterior(device):
