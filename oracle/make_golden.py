@@ -6,6 +6,7 @@ everything it produces is committed so that no test reads /root/reference at run
 
     python oracle/make_golden.py kat         # seconds: exact log files of short reference runs
     python oracle/make_golden.py posterior   # minutes: 8 reference chains per data set -> summaries
+    python oracle/make_golden.py plots       # ~30 s: the reference's plotRJforward.v3.py on two of the kat runs -> .r files
 
 The reference writes next to its input (LiteRateForward.py:479-491), so inputs are copied to
 a scratch directory first.
@@ -132,6 +133,27 @@ def _summarise(logs, stem, burnin=0.2):
     return res
 
 
+def plots():
+    """tests/golden/plots/<tag>_RTT_plots.r: what the UNMODIFIED plotRJforward.v3.py writes for the log files of two kat runs
+    (posterior-summary fixtures: K pmf, marginal rates + HPD, shift frequencies, net rate; the bf2/bf6 lines come from an
+    unseeded prior simulation and differ from run to run)."""
+    out = os.path.join(GOLD, "plots")
+    os.makedirs(out, exist_ok=True)
+    for tag in ("tad_m0", "metal_m0"):
+        work = tempfile.mkdtemp(prefix="lr_plot_")
+        try:
+            src = os.path.join(GOLD, "reference_logs", tag)
+            for f in os.listdir(src):
+                shutil.copy(os.path.join(src, f), work)
+            p = subprocess.run([sys.executable, os.path.join(REF, "plotRJforward.v3.py"), work], cwd=work, capture_output=True, text=True)
+            r = [f for f in os.listdir(work) if f.endswith("_RTT_plots.r")]
+            if not r:
+                raise RuntimeError(p.stderr[-2000:])
+            shutil.copy(os.path.join(work, r[0]), os.path.join(out, tag + "_RTT_plots.r"))
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+
+
 def posterior(n_chains=8):
     out = os.path.join(GOLD, "posterior")
     os.makedirs(out, exist_ok=True)
@@ -155,4 +177,4 @@ def posterior(n_chains=8):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "kat"
-    {"kat": kat, "posterior": posterior}[what]()
+    {"kat": kat, "posterior": posterior, "plots": plots}[what]()
