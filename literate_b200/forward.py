@@ -12,6 +12,8 @@ writes <stem><model><out>_chain<k>_{mcmc,sp_rates,ex_rates,div}.log, which plotR
 `*mcmc.log` glob and its .replace('mcmc.log', ...) still resolve.
 With -temper T > 1 every logged chain is the cold member (beta = 1, the reference's chain) of a ladder of T
 Metropolis-coupled chains; only cold samples reach the logs (SURVEY A-15).
+-d may name a directory of tables (stochastic imputations of one data set): each table is a replicate binned in the same
+kernel launch, chain k runs on table k % n_tables and writes <table stem><model><out>[_chain<j>]_*.log.
 Under torchrun (one process per GPU) the chains are block-partitioned over the ranks; chain k keeps its name and
 its Philox stream whatever the number of GPUs.
 """
@@ -19,6 +21,7 @@ from __future__ import annotations
 
 import argparse
 import csv
+import glob
 import os
 import sys
 import time
@@ -207,12 +210,33 @@ def run(args, device=None):
     out_name = MODEL_SUFFIX[args.model_BDI] + args.out
     only_dead = args.model_BDI == 3
 
-    ts, te, start_time, end_time, true_root_age = parse_lineages(args.d, args.TBP, args.rev_se, args.first_year,
-                                                                 args.last_year, args.death_jitter)
-    out_dir = os.path.dirname(args.d)                     # :479-491
-    if out_dir == "":
-        out_dir = os.getcwd()
-    file_name = os.path.splitext(os.path.basename(args.d))[0]
+    # -d may name a DIRECTORY of tables (stochastic imputations of one data set, the reference's "100 chains on 100
+    # imputations" workflow, 3_interpreting_literate_results_final.ipynb:208): every table is one replicate, binned in the
+    # same K1 launch over a common time window; chain k runs on replicate k % n_tables.
+    if os.path.isdir(args.d):
+        tables = sorted(f for f in glob.glob(os.path.join(args.d, "*")) if os.path.isfile(f) and f.lower().endswith((".tsv", ".txt")))
+        if not tables:
+            raise SystemExit("no .tsv/.txt table in " + args.d)
+        out_dir = args.d.rstrip("/")
+    else:
+        tables = [args.d]
+        out_dir = os.path.dirname(args.d)                 # :479-491
+        if out_dir == "":
+            out_dir = os.getcwd()
+    parsed = [parse_lineages(f, args.TBP, args.rev_se, args.first_year, args.last_year, args.death_jitter) for f in tables]
+    n_tab = len(parsed)
+    if args.chains == 1 and n_tab > 1:
+        args.chains = n_tab                               # default: one chain per table
+    if args.chains % n_tab:
+        raise SystemExit("-chains must be a multiple of the number of tables (%d)" % n_tab)
+    start_time, end_time = min(p[2] for p in parsed), max(p[3] for p in parsed)
+    true_root_age = parsed[0][4]
+    n_max = max(len(p[0]) for p in parsed)
+    ts = np.full((n_tab, n_max), np.nan); te = np.full((n_tab, n_max), np.nan)      # NaN rows carry no event and no time at risk
+    for i, p in enumerate(parsed):
+        ts[i, :len(p[0])], te[i, :len(p[1])] = p[0], p[1]
+    file_names = [os.path.splitext(os.path.basename(f))[0] for f in tables]
+    file_name = file_names[0]
     out_dir = "%s/literate_mcmc_logs" % (out_dir)
     try:
         os.mkdir(out_dir)
@@ -222,7 +246,8 @@ def run(args, device=None):
 
     dev = device if device is not None else E.Device(local_rank if world > 1 else args.device)
     t0 = time.time()
-    stats = dev.bin_stats(ts, te, death_jitter=args.death_jitter, only_dead=only_dead, end_time=float(end_time))
+    stats = dev.bin_stats(ts, te, first_bin=int(start_time), n_bins=int(end_time) - int(start_time), death_jitter=args.death_jitter,
+                          only_dead=only_dead, end_time=float(end_time))
     t_bin = time.time() - t0
     sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
     if lead:
@@ -239,7 +264,6 @@ def run(args, device=None):
         sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
         start_time = np.float64(np.floor(start_time) + 1)
 
-    stem = "%s/%s%s" % (out_dir, file_name, out_name)
     if args.calc_adequacy and lead:                        # print_empirical_rates, literate_library.py:260-266
         with np.errstate(divide="ignore", invalid="ignore"), np.printoptions(suppress=True, precision=3):
             print("EMPIRICAL BIRTH RATES:"); print(sp / br)
@@ -251,17 +275,21 @@ def run(args, device=None):
     # this rank's block of the logged chains; every logged chain is a ladder of T device chains with consecutive ids
     T = args.temper
     c0, n_local = P.shard_range(args.chains, world, rank)
-    chains = E.Chains(ds, n_local * T, rseed, cfg, chain_id0=c0 * T)
+    rep_of_chain = np.repeat(np.arange(c0, c0 + n_local) % n_tab, T).astype(np.int32)      # logged chain k -> table k % n_tab
+    chains = E.Chains(ds, n_local * T, rseed, cfg, chain_id0=c0 * T, rep_of_chain=rep_of_chain)
     if T > 1:
         chains.set_beta(np.tile(P.temperature_ladder(T, args.temper_delta), n_local))
 
     writers, paths = [], []
     for k in range(c0, c0 + n_local):
-        st = stem if args.chains == 1 else "%s_chain%d" % (stem, k)
+        r = k % n_tab
+        st = "%s/%s%s" % (out_dir, file_names[r], out_name)
+        if args.chains > n_tab:
+            st += "_chain%d" % (k // n_tab)
         writers.append(ChainLogWriter(st, args.calc_adequacy, args.pyrate_output, start_time, end_time, true_root_age,
                                       args.Poisson_prior))
         paths.append(st + "_mcmc.log")
-        write_div_log(st + "_div.log", sp, ex, br)         # every *mcmc.log has its sibling div.log
+        write_div_log(st + "_div.log", stats.sp[r], stats.ex[r], stats.br[r])     # every *mcmc.log has its sibling div.log
 
     s_freq, p_freq = max(1, args.s), max(1, args.p)
     every = int(np.gcd(s_freq, p_freq))

@@ -91,6 +91,35 @@ def test_logs_feed_the_posterior_summariser(tmp_path):
     assert 0 < s.bf2 < s.bf6 < 1 and s.birth.k_counts.sum() == len(rows)
 
 
+def test_directory_of_imputations(tmp_path):
+    """-d <directory>: every table is a replicate; ragged tables are padded, each gets its own div.log and chains."""
+    base = O.read_lineages(golden_input("example_dataTAD.txt"), death_jitter=0.0)
+    rng = np.random.default_rng(8)
+    d_in = tmp_path / "imps"
+    d_in.mkdir()
+    tabs = []
+    for i in range(3):
+        keep = rng.random(len(base.ts)) < (1.0 if i == 0 else 0.9)          # replicates of different length
+        keep[[np.argmin(base.ts), np.argmax(base.te)]] = True                # same window for all
+        ts, te = base.ts[keep], np.maximum(base.ts[keep], base.te[keep] - rng.integers(0, 2, keep.sum()) * (i > 0))
+        te[np.argmax(base.te[keep])] = base.te.max()
+        tabs.append((ts, te))
+        with open(d_in / ("imp_%d.tsv" % i), "w") as fh:
+            fh.write("id\tts\tte\n")
+            for j, (a, b) in enumerate(zip(ts, te)):
+                fh.write("%d\t%d\t%d\n" % (j, a, b))
+    F.main(["-d", str(d_in), "-n", "2001", "-s", "100", "-seed", "4", "-chains", "6", "-quiet", "1"])
+    d = os.path.join(str(d_in), "literate_mcmc_logs")
+    for i, (ts, te) in enumerate(tabs):
+        st = O.bin_stats(ts, te + 0.5)
+        for j in range(2):
+            stem = os.path.join(d, "imp_%d_BD_chain%d" % (i, j))
+            div = np.loadtxt(stem + "_div.log", skiprows=1)
+            assert np.array_equal(div[:, 0], st.sp) and np.array_equal(div[:, 1], st.ex) and np.array_equal(div[:, 2], st.br)
+            lin = O.Lineages(ts, te + 0.5, base.ts.min(), base.te.max() + 0.5, 0)
+            _check_logs(stem, lin, st, 0, 21)
+
+
 def test_same_seed_same_files(tmp_path):
     a, b = tmp_path / "a", tmp_path / "b"
     a.mkdir(); b.mkdir()
