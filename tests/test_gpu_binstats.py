@@ -95,6 +95,21 @@ def test_explicit_window_with_lineages_outside(device):
         assert (got.sp[0, j], got.ex[0, j], got.br[0, j]) == (a, b, c)
 
 
+def test_many_bins_and_single_bin(device):
+    """Window sizes at both ends: one bin, and 6000 one-year bins (216 KB of shared histograms, one CTA per SM)."""
+    ts = np.array([3.0, 3.0, 3.25]); te = np.array([3.5, 4.5, 3.75])
+    _check(device, ts, te, 0.5, only_dead=False)
+    rng = np.random.default_rng(31)
+    n = 50_000
+    ts = np.floor(rng.uniform(0, 6000, n)); te = np.minimum(ts + np.floor(rng.exponential(40, n)), 6000) + 0.5
+    ts[0], te[0] = 0.0, 6000.5
+    got = device.bin_stats(ts, te)
+    want = O.bin_stats_fast(ts, te)
+    assert got.n_bins == 6000 and (got.sp[0] == want.sp).all() and (got.ex[0] == want.ex).all() and (got.br[0] == want.br).all()
+    for j in (0, 1234, 5999):
+        assert O.events_in_bin(ts, te, j, j + 1) == (got.sp[0, j], got.ex[0, j], got.br[0, j])
+
+
 def test_replicates_and_ragged_pitch(device):
     import torch
     n_rep, n = 5, 3001      # odd n: rows are not 16-byte aligned -> scalar load path for odd replicates

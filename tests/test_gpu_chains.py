@@ -105,6 +105,47 @@ def test_loop_builds_give_identical_chains(device, metal_path):
     assert np.array_equal(a.counters(), b.counters())
 
 
+def test_loop_builds_identical_for_ragged_launch_lengths(device):
+    """The producer/consumer ring of the specialised build hands iterations over in batches of 8: launches of 1, 7, 8, 9, ...
+    iterations (partial first/last batches, sampling on and off) must still be the compact build's chain, bit for bit."""
+    lin, st, ds, a = _setup(device, golden_input("example_dataTAD.txt"), n_chains=9, seed=21, loop_variant=1)
+    b = E.Chains(ds, 9, 21, E.default_config(0, loop_variant=2))
+    for k, n in enumerate([1, 7, 8, 9, 23, 64, 65, 1000, 3, 1025, 4096, 5]):
+        s = [0, 1, 5][k % 3]
+        ra, rb = a.run(n, s), b.run(n, s)
+        if s:
+            assert np.array_equal(ra, rb), (k, n, s)
+        assert np.array_equal(a.state(), b.state()), (k, n)
+    assert np.array_equal(a.counters(), b.counters())
+
+
+def test_many_rates_per_side_and_capacity(device, metal_path):
+    """States with up to LR_KMAX = 30 rates per side: likelihood parity holds there, add-shift proposals at capacity are
+    rejected and counted, and the chain keeps running."""
+    lin, st, ds, ch = _setup(device, metal_path, n_chains=6, seed=8)
+    rng = np.random.default_rng(12)
+    rec = ch.state()
+    K = 30
+    for r in rec:
+        for off_r, off_t, kcol in ((E.REC_L, E.REC_TL, E.REC_KL), (E.REC_M, E.REC_TM, E.REC_KM)):
+            r[kcol] = K
+            r[off_r:off_r + K] = rng.gamma(2.0, 0.2, K)
+            r[off_t + 1:off_t + K] = lin.start_time + 1.05 * np.arange(1, K) + rng.uniform(0, 0.04, K - 1)   # spacing > 1
+    ch.set_state(rec)
+    got = ch.state()
+    for r in got:
+        L, M, tL, tM = E.record_to_state(r, lin.end_time)
+        assert len(L) == K and len(M) == K
+        assert r[E.REC_LIK] == pytest.approx(O.loglik_state(L, M, tL, tM, st, 0), rel=1e-10)
+    recs = ch.run(4000, 100)
+    cnt = ch.counters()
+    assert cnt[:, 7].sum() > 0                     # add-shift at capacity: rejected and counted
+    assert (recs[:, :, E.REC_KL] <= K).all() and (recs[:, :, E.REC_KM] <= K).all() and np.isfinite(recs[:, :, E.REC_LIK]).all()
+    r = recs[-1, 0]
+    L, M, tL, tM = E.record_to_state(r, lin.end_time)
+    assert r[E.REC_LIK] == pytest.approx(O.loglik_state(L, M, tL, tM, st, 0), rel=1e-10)
+
+
 def test_checkpoint_roundtrip(device):
     path = golden_input("example_dataTAD.txt")
     lin, st, ds, a = _setup(device, path, n_chains=4, seed=2)
