@@ -634,6 +634,7 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
     const long long s_every = P.sample_every > 0 ? P.sample_every : 1;
     long long next_sample = P.records != nullptr ? (it0 + s_every - 1) / s_every * s_every : it1;   // no 64-bit division in the loop
     long long next_resync = (it0 + LR_RESYNC - 1) / LR_RESYNC * LR_RESYNC;
+    long long next_event = next_resync < next_sample ? next_resync : next_sample;
     double* rec = P.records + (size_t)chain * LR_REC_DOUBLES;
     int slot = 0, in_batch = 0;
     long long batch = 0;
@@ -682,12 +683,15 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
         }
         c.cnt[0]++;
 
-        if (it == next_resync) { resync_log_rates(L, M, lane); next_resync += LR_RESYNC; }
-        if (it == next_sample) {                // it % sample_every == 0 (:321)
-            if constexpr (C) write_record_ref(rec, it, L, M, c, d, lane, P.with_adequacy != 0);
-            else write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
-            rec += (size_t)P.n_chains * LR_REC_DOUBLES;
-            next_sample += s_every;
+        if (it == next_event) {                     // one comparison per iteration for the two rare events
+            if (it == next_resync) { resync_log_rates(L, M, lane); next_resync += LR_RESYNC; }
+            if (it == next_sample) {                // it % sample_every == 0 (:321)
+                if constexpr (C) write_record_ref(rec, it, L, M, c, d, lane, P.with_adequacy != 0);
+                else write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
+                rec += (size_t)P.n_chains * LR_REC_DOUBLES;
+                next_sample += s_every;
+            }
+            next_event = next_resync < next_sample ? next_resync : next_sample;
         }
     }
 
@@ -935,11 +939,14 @@ extern "C" int lr_dataset_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, i
     ds->h = h; ds->n_rep = n_rep; ds->n_bins = n_bins; ds->model = model_BDI;
     ds->start_time = start_time; ds->end_time = end_time; ds->s0f = (int)floor(start_time);
     ds->tab = nullptr; ds->cst = nullptr;
-    cudaError_t e = cudaMalloc(&ds->tab, (size_t)n_rep * LR_NTAB * (n_bins + 1) * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&ds->cst, (size_t)n_rep * LR_NCST * sizeof(double));
+    // stream-ordered allocation: creating/destroying datasets and chains never synchronises the device, so a pipeline can
+    // set up batch k+1 while the chains of batch k are still running (cudaFree would wait for them)
+    cudaError_t e = cudaMallocAsync((void**)&ds->tab, (size_t)n_rep * LR_NTAB * (n_bins + 1) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&ds->cst, (size_t)n_rep * LR_NCST * sizeof(double), st);
     if (e != cudaSuccess) {
-        lr_set_error("lr_dataset_create: cudaMalloc failed: %s", cudaGetErrorString(e));
-        cudaFree(ds->tab); cudaFree(ds->cst); delete ds;
+        lr_set_error("lr_dataset_create: cudaMallocAsync failed: %s", cudaGetErrorString(e));
+        if (ds->tab) cudaFreeAsync(ds->tab, st);
+        delete ds;
         return LR_ERR_NOMEM;
     }
     k2_build_tables<<<n_rep, 64, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, (const long long*)d_ex_dead,
@@ -981,7 +988,7 @@ extern "C" int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bi
 extern "C" int lr_dataset_destroy(lr_dataset_t ds) {
     if (!ds) return LR_OK;
     cudaSetDevice(ds->h->device);
-    cudaFree(ds->tab); cudaFree(ds->cst);
+    cudaFreeAsync(ds->tab, ds->h->stream); cudaFreeAsync(ds->cst, ds->h->stream);
     delete ds;
     return LR_OK;
 }
@@ -1062,12 +1069,12 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
     lr_chains_t c = new lr_chains_s();
     c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->chain_id0 = chain_id0; c->st = nullptr;
     if (c->cfg.beta == 0.0) c->cfg.beta = 1.0;
-    cudaError_t e = cudaMalloc(&c->st, (size_t)n_chains * sizeof(ChainState));
-    if (e != cudaSuccess) { lr_set_error("lr_chains_create: cudaMalloc: %s", cudaGetErrorString(e)); delete c; return LR_ERR_NOMEM; }
+    cudaError_t e = cudaMallocAsync((void**)&c->st, (size_t)n_chains * sizeof(ChainState), h->stream);
+    if (e != cudaSuccess) { lr_set_error("lr_chains_create: cudaMallocAsync: %s", cudaGetErrorString(e)); delete c; return LR_ERR_NOMEM; }
     int* d_rep = nullptr;
     if (h_rep_of_chain) {
         int rc = lr_ws_reserve(h, (size_t)n_chains * 4);
-        if (rc != LR_OK) { cudaFree(c->st); delete c; return rc; }
+        if (rc != LR_OK) { cudaFreeAsync(c->st, h->stream); delete c; return rc; }
         d_rep = (int*)h->ws;
         LR_CUDA(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * 4, cudaMemcpyHostToDevice, h->stream));
     }
@@ -1085,7 +1092,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
 extern "C" int lr_chains_destroy(lr_chains_t c) {
     if (!c) return LR_OK;
     cudaSetDevice(c->h->device);
-    cudaFree(c->st);
+    cudaFreeAsync(c->st, c->h->stream);
     delete c;
     return LR_OK;
 }

@@ -35,6 +35,14 @@ extern "C" int lr_create(int device, lr_handle_t* out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    // Datasets and chains are allocated stream-ordered (cudaMallocAsync).  Keep freed blocks in the device's pool instead of
+    // returning them to the driver at every synchronisation (measured: 75-290 ms of unmapping per device-wide sync).
+    {
+        cudaMemPool_t pool;
+        LR_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        LR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     LR_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) LR_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));

@@ -324,9 +324,10 @@ class Chains:
         return None
 
     def run_device(self, n_iter: int, sample_every: int, records, stream=None):
-        """Asynchronous variant: `records` is a float64 CUDA tensor [n_samples, n_chains, 144] (or None)."""
+        """Asynchronous variant: `records` is a float64 CUDA tensor [n_samples, n_chains, 144] (or None).
+        stream: a cudaStream_t, None = torch's current stream, "handle" = the Device's own compute stream."""
         import torch
-        st = _stream_ptr(stream)
+        st = C.c_void_p(None) if isinstance(stream, str) and stream == "handle" else _stream_ptr(stream)
         ptr = C.c_void_p(records.data_ptr()) if records is not None else None
         N.check(self.dev.lib.lr_chains_run(self.c, int(n_iter), int(sample_every) if records is not None else 0, ptr, st),
                 "lr_chains_run")
@@ -446,3 +447,70 @@ def run_rjmcmc(dev: Device, ts, te, n_chains, n_iter, sample_every, seed=1, cfg:
     finally:
         ds.close()
     return rec, stats
+
+
+class Pipeline:
+    """The hot path over a stream of batches, double-buffered: while the chains of batch k run (K3: no memory traffic),
+    the tables of batch k+1 are copied to the device and binned (PCIe + K1: hardly any SM time).  Two handles on the same
+    GPU keep the two halves on independent streams; allocation is stream-ordered, so nothing synchronises the device.
+
+        pipe = Pipeline(0)
+        for ts, te in batches:
+            done = pipe.push(ts, te, n_chains, n_iter, sample_every, ...)   # -> (records, BinStats) of the PREVIOUS batch, or None
+        last = pipe.flush()
+    """
+
+    def __init__(self, device_index: int = 0):
+        self.dev_bin = Device(device_index)
+        self.dev_run = Device(device_index)
+        self.index = device_index
+        self._inflight = None
+
+    def _collect(self, out):
+        import torch
+        t, self._inflight = self._inflight, None
+        if t is None:
+            return None
+        self.dev_run.sync()                          # the chains of the previous batch (normally long finished)
+        host = None
+        if t["rec"] is not None:
+            if out is not None:                      # numpy array or (pinned) torch tensor
+                (out if isinstance(out, torch.Tensor) else torch.from_numpy(out)).copy_(t["rec"])
+                host = out
+            else:
+                host = t["rec"].cpu().numpy()
+        t["ch"].close(); t["ds"].close()
+        return host, t["stats"]
+
+    def push(self, ts, te, n_chains, n_iter, sample_every, seed=1, cfg: ChainConfig = None, model_BDI=0, first_bin=None,
+             n_bins=None, death_jitter=0.5, start_time=None, end_time=None, rep_of_chain=None, chain_id0=0, out=None):
+        """Bin this batch (overlapping the chains of the previous one), hand back the previous batch's result (copied into
+        `out` if given), then launch this batch's chains asynchronously."""
+        import torch
+        ts = np.asarray(ts); te = np.asarray(te)
+        if first_bin is None or n_bins is None:
+            first_bin, n_bins = window(ts, te)
+        if start_time is None:
+            start_time = float(np.min(ts))
+        if end_time is None:
+            end_time = float(np.max(te))
+        if cfg is None:
+            cfg = default_config(model_BDI)
+        stats = self.dev_bin.bin_stats(ts, te, first_bin=first_bin, n_bins=n_bins, death_jitter=death_jitter,
+                                       only_dead=(cfg.model_BDI == 3), end_time=end_time)          # H2D + K1, synchronous
+        prev = self._collect(out)
+        ds = Dataset(self.dev_run, stats, cfg.model_BDI, start_time, end_time)
+        ch = Chains(ds, n_chains, seed, cfg, chain_id0=chain_id0, rep_of_chain=rep_of_chain)
+        n_rec = ch.records_per_run(n_iter, sample_every) if sample_every else 0
+        rec = torch.empty((n_rec, n_chains, LR_REC_DOUBLES), dtype=torch.float64, device=torch.device("cuda", self.index)) if n_rec else None
+        ch.run_device(n_iter, sample_every, rec, stream="handle")                                   # asynchronous
+        self._inflight = {"ds": ds, "ch": ch, "rec": rec, "stats": stats}
+        return prev
+
+    def flush(self, out=None):
+        """Result of the last pushed batch."""
+        return self._collect(out)
+
+    def close(self):
+        self._collect(None)
+        self.dev_bin.close(); self.dev_run.close()
