@@ -6,6 +6,7 @@ everything it produces is committed so that no test reads /root/reference at run
 
     python oracle/make_golden.py kat         # seconds: exact log files of short reference runs
     python oracle/make_golden.py posterior   # minutes: 8 reference chains per data set -> summaries
+    python oracle/make_golden.py posterior_flags   # ~10 min: 8 reference chains per non-default flag set (example TAD)
     python oracle/make_golden.py plots       # ~30 s: the reference's plotRJforward.v3.py on two of the kat runs -> .r files
 
 The reference writes next to its input (LiteRateForward.py:479-491), so inputs are copied to
@@ -154,6 +155,35 @@ def plots():
             shutil.rmtree(work, ignore_errors=True)
 
 
+FLAG_SETS = [   # tag, extra arguments, model suffix
+    ("tad_constdeath", ["-const_death_rate", "1"], "_BD"),
+    ("tad_constrates", ["-const_rates", "1"], "_BD"),
+    ("tad_fixedpoi_nohp", ["-Poisson_prior", "2", "-use_rate_HP", "0"], "_BD"),
+    ("tad_keiding", ["-model_BDI", "2"], "_BDk"),
+    ("tad_immigration", ["-model_BDI", "1"], "_ID"),
+    ("tad_keiding_dead", ["-model_BDI", "3"], "_BDd"),
+]
+
+
+def posterior_flags(n_chains=8, n_it=200001, s=100):
+    """Posterior summaries of 8 unmodified reference chains for every non-default sampler configuration (example TAD)."""
+    out = os.path.join(GOLD, "posterior")
+    os.makedirs(out, exist_ok=True)
+    src = os.path.join(REF, INPUTS["example_dataTAD.txt"])
+    for tag, extra, suffix in FLAG_SETS:
+        def one(seed):
+            logs, dt, _ = run_reference(src, ["-n", str(n_it), "-s", str(s), "-p", "100000000", "-seed", str(seed)] + extra)
+            r = _summarise(logs, "example_dataTAD" + suffix)
+            r["seed"], r["wall_s"], r["n_iterations"], r["s_freq"] = seed, dt, n_it, s
+            return r
+        with ThreadPoolExecutor(n_chains) as ex:
+            chains = list(ex.map(one, [301 + i for i in range(n_chains)]))
+        with open(os.path.join(out, tag + ".json"), "w") as fh:
+            json.dump({"data": "example_tad", "generator": "unmodified LiteRateForward.py " + " ".join(extra), "args": extra, "burnin": 0.2,
+                       "chains": chains}, fh, indent=1)
+        print(tag, "done:", [round(c["wall_s"]) for c in chains], flush=True)
+
+
 def posterior(n_chains=8):
     out = os.path.join(GOLD, "posterior")
     os.makedirs(out, exist_ok=True)
@@ -177,4 +207,4 @@ def posterior(n_chains=8):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "kat"
-    {"kat": kat, "posterior": posterior, "plots": plots}[what]()
+    {"kat": kat, "posterior": posterior, "posterior_flags": posterior_flags, "plots": plots}[what]()

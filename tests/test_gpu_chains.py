@@ -173,18 +173,7 @@ def _summaries(recs, lin, burnin=0.2):
     return out
 
 
-@pytest.mark.parametrize("data,n_iter,s", [("example_tad", 300000, 100), ("metal_bands", 400000, 200)])
-def test_posterior_matches_reference_chains(device, data, n_iter, s, metal_path):
-    """64 GPU chains vs 8 reference chains (same length, same sampling, 20 % burn-in): the means of
-    K_l, K_m, log-likelihood, mean rates and every per-bin marginal rate agree within 4.5 standard
-    errors of the difference of the two chain-population means."""
-    with open(os.path.join(GOLD, "posterior", data + ".json")) as fh:
-        ref = json.load(fh)["chains"]
-    path = golden_input("example_dataTAD.txt") if data == "example_tad" else metal_path
-    lin, st, ds, ch = _setup(device, path, n_chains=64, seed=2026)
-    recs = ch.run(n_iter + 1, s)
-    mine = _summaries(recs, lin)
-
+def _compare_with_reference(mine, ref, what=("K_l", "K_m", "lik", "lambda_avg", "mu_avg", "birth", "death")):
     def kmean(pmf):
         tot = sum(pmf.values())
         return sum(int(k) * v for k, v in pmf.items()) / tot
@@ -195,10 +184,59 @@ def test_posterior_matches_reference_chains(device, data, n_iter, s, metal_path)
         z = np.abs(a.mean(0) - b.mean(0)) / se
         assert np.all(z < 4.5), (name, float(np.max(z)), a.mean(0), b.mean(0))
 
-    compare("K_l", [m["K_l"] for m in mine], [kmean(r["K_l"]) for r in ref])
-    compare("K_m", [m["K_m"] for m in mine], [kmean(r["K_m"]) for r in ref])
+    if "K_l" in what:
+        compare("K_l", [m["K_l"] for m in mine], [kmean(r["K_l"]) for r in ref], floor=1e-9)
+    if "K_m" in what:
+        compare("K_m", [m["K_m"] for m in mine], [kmean(r["K_m"]) for r in ref], floor=1e-9)
     compare("lik", [m["lik"] for m in mine], [r["lik_mean"] for r in ref])
     compare("lambda_avg", [m["lam"] for m in mine], [r["lambda_avg"] for r in ref])
     compare("mu_avg", [m["mu"] for m in mine], [r["mu_avg"] for r in ref])
     compare("birth", [m["birth"] for m in mine], [r["birth_rate_mean"] for r in ref], floor=1e-6)
     compare("death", [m["death"] for m in mine], [r["death_rate_mean"] for r in ref], floor=1e-6)
+
+
+@pytest.mark.parametrize("data,n_iter,s", [("example_tad", 300000, 100), ("metal_bands", 400000, 200)])
+def test_posterior_matches_reference_chains(device, data, n_iter, s, metal_path):
+    """64 GPU chains vs 8 reference chains (same length, same sampling, 20 % burn-in): the means of
+    K_l, K_m, log-likelihood, mean rates and every per-bin marginal rate agree within 4.5 standard
+    errors of the difference of the two chain-population means."""
+    with open(os.path.join(GOLD, "posterior", data + ".json")) as fh:
+        ref = json.load(fh)["chains"]
+    path = golden_input("example_dataTAD.txt") if data == "example_tad" else metal_path
+    lin, st, ds, ch = _setup(device, path, n_chains=64, seed=2026)
+    recs = ch.run(n_iter + 1, s)
+    _compare_with_reference(_summaries(recs, lin), ref)
+
+
+FLAG_SETS = {   # tests/golden/posterior/<tag>.json, made by `oracle/make_golden.py posterior_flags` from the unmodified reference
+    "tad_constdeath": dict(model=0, const_death_rate=1),           # -const_death_rate 1 (:243-247)
+    "tad_constrates": dict(model=0, const_rates=1),                # -const_rates 1 (:274, :281)
+    "tad_fixedpoi_nohp": dict(model=0, Poisson_prior=2.0, use_rate_HP=0),    # -Poisson_prior 2 -use_rate_HP 0 (:220-221, :283-286)
+    "tad_keiding": dict(model=2),                                  # -model_BDI 2 (:137-148)
+    "tad_immigration": dict(model=1),                              # -model_BDI 1 (:151-153)
+    "tad_keiding_dead": dict(model=3),                             # -model_BDI 3 (:529-549)
+}
+
+
+@pytest.mark.parametrize("tag", sorted(FLAG_SETS))
+def test_posterior_matches_reference_for_every_sampler_configuration(device, tag):
+    """The same comparison for each non-default flag set: constant death rate / constant rates (RJ disabled on one or both
+    sides), fixed Poisson prior without rate hyper-prior (no Gibbs moves), and the three other likelihoods."""
+    p = os.path.join(GOLD, "posterior", tag + ".json")
+    if not os.path.exists(p):
+        pytest.skip("fixture not generated")
+    with open(p) as fh:
+        ref = json.load(fh)["chains"]
+    cfg = dict(FLAG_SETS[tag])
+    model = cfg.pop("model")
+    lin, st, ds, ch = _setup(device, golden_input("example_dataTAD.txt"), model=model, n_chains=64, seed=77, **cfg)
+    recs = ch.run(ref[0]["n_iterations"], ref[0]["s_freq"])
+    mine = _summaries(recs, lin)
+    if tag == "tad_constrates":
+        assert all(m["K_l"] == 1 and m["K_m"] == 1 for m in mine)
+    if tag == "tad_constdeath":
+        assert all(m["K_m"] == 1 for m in mine)
+    _compare_with_reference(mine, ref)
+    cnt = ch.counters().sum(0)
+    if tag == "tad_constrates":
+        assert cnt[5] == 0 and abs(cnt[6] / cnt[0] - 0.2) < 0.005          # every r0 >= .8 goes to the Gibbs branch (:281)
