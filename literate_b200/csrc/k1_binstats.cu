@@ -16,24 +16,25 @@
 // exact sum.
 //
 // Kernel shape (B200, HBM-bound: 16 B/lineage, no reuse):
-//   - grid = 4 CTAs of 256 threads per SM (64 registers/thread), each CTA owns one contiguous slice of the
+//   - grid = 5 CTAs of 256 threads per SM (48 registers/thread), each CTA owns one contiguous slice of the
 //     flattened [replicate][lineage] space -> perfectly balanced, 2-3 flushes per CTA per launch;
-//   - 128-bit coalesced streaming loads (ld.global.nc.L1::no_allocate.v2.f64), 4 deep per array per thread
-//     = 128 KB in flight per SM;
+//   - 128-bit coalesced streaming loads (ld.global.nc.L1::no_allocate.v2.f64), 2 deep per array per thread
+//     = 80 KB in flight per SM (measured: 4 CTAs x 4 deep 6.06 TB/s, 5 x 2 deep 6.69 TB/s, 6 x 2 deep 5.88, 8 x 1 deep
+//     5.49, 3 x 4 deep 4.57, 4 x 3 deep 6.75 but slower on real-valued tables);
 //   - block-shared u32 histograms updated with shared-memory atomics (ATOMS.POPC.INC: lanes that hit the same bin
 //     are merged by the hardware, so year-sorted tables cost the same as shuffled ones); fractional parts that
 //     differ from the expected ones (integer ts, te = int + fe_ref) go through a 96-bit carry chain of 32-bit
 //     shared atomics;
-//   - measured on B200 (1M lineages x 64..256 replicates x 200 bins): 6.2-6.8 TB/s on integer-year tables
-//     (dram__bytes_read = the algorithmic 16 B/lineage), 4.1 TB/s on real-valued times (stalls on the returning
-//     atomics of the carry chain).  Two designs were measured and dropped: lane-private u16 histograms without
+//   - measured on B200 (1M lineages x 256 replicates x 200 bins): 6.7 TB/s on integer-year tables
+//     (dram__bytes_read = the algorithmic 16 B/lineage), 4.75 TB/s on real-valued times (stalls on the returning
+//     atomics of the carry chain; overlapping the chains of four lineages by hand cost registers and was slower).  Two designs were measured and dropped: lane-private u16 histograms without
 //     atomics (2.1 TB/s: 8 warps/SM cannot hide the serialised read-modify-write chains) and a joint
 //     (birth bin, lifetime) table with one atomic per lineage (5.8 TB/s: more index arithmetic than it saves).
 #include "lr_common.cuh"
 
 namespace {
 
-constexpr int K1_UNROLL = 4;                        // double2 loads in flight per array per thread
+constexpr int K1_UNROLL = 2;                        // double2 loads in flight per array per thread
 constexpr int K1_TILE = 64 * K1_UNROLL;             // lineages one warp consumes per tile
 constexpr int ROW_SP = 0, ROW_EX = 1, ROW_CS_LO = 2, ROW_CS_HI = 3, ROW_CE_LO = 4, ROW_CE_HI = 5,
               ROW_SPX = 6, ROW_EXX = 7;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
     }
 }
 
-__global__ void __launch_bounds__(256, 4) k1_bin_kernel(const K1Params p) {
+__global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const unsigned nb = p.nb;
@@ -321,7 +322,7 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     const size_t smem = 9 * (size_t)n_bins * sizeof(unsigned);
     const size_t budget = (size_t)h->max_smem_optin - 1024;
     int per_sm = (int)(budget / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 5) per_sm = 5;
     if (per_sm < 1) per_sm = 1;
     const int threads = 256, blocks = h->sm_count * per_sm;
     p.seg_max = 1ll << 31;             // u32 counters: at most 2^31 lineages between flushes
