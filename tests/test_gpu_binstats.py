@@ -153,3 +153,41 @@ def test_full_size_one_million(device):
     np.testing.assert_allclose(got.br[0], want.br, rtol=1e-11)
     again = device.bin_stats(tr, er, death_jitter=0.0)
     assert (again.br == got.br).all()          # run-to-run deterministic (integer accumulation)
+
+
+def test_empty_table_through_the_c_abi(device):
+    """n = 0: nothing is launched, the accumulators stay zero and finalise to empty bins; the host wrapper refuses it."""
+    import torch
+    acc = device.new_accumulators(1, 10, torch.device("cuda", 0))
+    e = torch.empty((1, 0), dtype=torch.float64, device="cuda")
+    device.bin_accumulate_device(e, e, 100, 10, acc)
+    sp, ex, br = device.bin_finalize_device(acc, 10)
+    torch.cuda.synchronize()
+    assert int(sp.sum()) == 0 and int(ex.sum()) == 0 and float(br.sum()) == 0.0
+    with pytest.raises(ValueError):
+        device.bin_stats(np.empty(0), np.empty(0))
+
+
+def test_full_size_hundred_million_lineages(device):
+    """BASELINE cfg5 size on one GPU: 1e8 lineages (1.6 GB) generated on the device; size-independent checks
+    (every lineage born once inside the window, total time at risk conserved exactly for half-integer data, the two
+    halves add up to the whole, a second pass gives the same integers)."""
+    import torch
+    n = 100_000_000
+    ts, te = synth.syn_int_device(n, 1, torch.device("cuda", 0))
+    ts, te = ts[:, :n], te[:, :n]
+    sp, ex, br = device.bin_stats_device(ts, te, 1800, 200)
+    torch.cuda.synchronize()
+    assert int(sp.sum()) == n
+    want = (torch.minimum(te, torch.tensor(2000.0, device="cuda", dtype=torch.float64)) - ts).sum()
+    assert float(br.sum()) == float(want)
+    alive_at_end = int((te > 2000.0).sum())
+    assert int(ex.sum()) == n - alive_at_end
+    h = n // 2
+    a = device.bin_stats_device(ts[:, :h], te[:, :h], 1800, 200)
+    b = device.bin_stats_device(ts[:, h:], te[:, h:], 1800, 200)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0] + b[0], sp) and torch.equal(a[1] + b[1], ex) and torch.equal(a[2] + b[2], br)
+    sp2, ex2, br2 = device.bin_stats_device(ts, te, 1800, 200)
+    torch.cuda.synchronize()
+    assert torch.equal(sp2, sp) and torch.equal(br2, br)

@@ -146,6 +146,30 @@ def test_many_rates_per_side_and_capacity(device, metal_path):
     assert r[E.REC_LIK] == pytest.approx(O.loglik_state(L, M, tL, tM, st, 0), rel=1e-10)
 
 
+def test_four_thousand_chains_shard_invariance(device, metal_path):
+    """BASELINE cfg4 population size (4096 chains, compact build): any shard of the population reproduces its slice bit for
+    bit, whatever build the shard size selects, and tempered swap rounds keyed by global ladder ids agree as well."""
+    lin, st, ds, whole = _setup(device, metal_path, n_chains=4096, seed=404)
+    parts = [(0, 256), (256, 1024), (1280, 2816)]              # specialised build, compact build, compact build
+    shards = [E.Chains(ds, n, 404, chain_id0=c0) for c0, n in parts]
+    from literate_b200 import parallel as P
+    beta = np.tile(P.temperature_ladder(8, 0.1), 512)
+    whole.set_beta(beta)
+    for (c0, n), s in zip(parts, shards):
+        s.set_beta(beta[c0:c0 + n])
+    rw = whole.run(1501, 500)
+    for (c0, n), s in zip(parts, shards):
+        assert np.array_equal(s.run(1501, 500), rw[:, c0:c0 + n])
+    for rnd in range(3):
+        whole.swap_step(8, rnd); whole.run(300)
+        for s in shards:
+            s.swap_step(8, rnd); s.run(300)
+    sw = whole.state()
+    for (c0, n), s in zip(parts, shards):
+        assert np.array_equal(s.state(), sw[c0:c0 + n])
+    assert whole.counters()[:, 9].sum() > 0
+
+
 def test_checkpoint_roundtrip(device):
     path = golden_input("example_dataTAD.txt")
     lin, st, ds, a = _setup(device, path, n_chains=4, seed=2)
