@@ -142,8 +142,10 @@ __device__ __forceinline__ double full_prior(const Side& L, const Side& M, const
 
 // (cold functions take their arguments BY VALUE: a reference into a __noinline__ callee would make the caller keep the
 // chain's state in local memory for the whole loop)
-__device__ __noinline__ void write_record(double* rec, long long it, const Side L, const Side M, const Hyper hp, const DataView d,
-                             double priorA, int poi_is_init, double beta, int lane, bool with_adequacy) {
+__device__ __noinline__ void write_record(double* rec, long long it, Side L, Side M, const Hyper hp, const DataView d,
+                                          double priorA, double poiA, int consistent, int poi_is_init, double beta, int lane, bool with_adequacy) {
+    side_sums(L, lane); side_sums(M, lane);
+    if (consistent) priorA = full_prior(L, M, hp, d, poiA);     // the stored prior IS the prior of the state (with the stale poiA, :300-304)
     double adq[3] = {0.0, 0.0, 0.0};
     if (with_adequacy) adequacy3(L, M, d, lane, adq);
     if (lane == 0) {
@@ -314,19 +316,8 @@ __device__ __forceinline__ Draws ring_load(const RingIter& S, int lane) {
 // ------------------------------------------------------------------------------------------------
 // proposals on one side (all warp-uniform control flow)
 // ------------------------------------------------------------------------------------------------
-// update_multiplier_freq (:165-176): q * m as the reference does; Hastings = sum log m.  The log-rate follows by
-// addition and is re-derived from the rate every LR_RESYNC iterations so that the two never drift apart.
-__device__ __forceinline__ void propose_rates(const Side& cur, Side& nw, const Draws& q, int lane, double& hasting) {
-    nw = cur;
-    const bool on = lane < cur.K;
-    nw.lr = cur.lr + (on ? q.dlt : 0.0);
-    nw.r = cur.r * (on ? q.m : 1.0);
-    side_sums(nw, lane);
-    hasting = nw.sumlr - cur.sumlr;
-}
-
 // add_shift_RJ_weighted_mean (:29-47).  Returns false if the proposal violates the spacing guard (:290).
-template <bool C>
+template <bool C, bool SUMS>
 __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
                                             const Draws& q, int lane, double& hasting) {
     const int K = cur.K;
@@ -355,13 +346,13 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
     else if (lane == i + 1) { nw.r = r2; nw.lr = lr2; nw.t = tp; }
     else if (lane > i + 1) { nw.r = ur; nw.lr = ulr; nw.t = ut; }
     side_stats(nw, d, tabA, tabB, lane);
-    side_sums(nw, lane);
+    if constexpr (SUMS) side_sums(nw, lane);
     return true;
 }
 
 // remove_shift_RJ_weighted_mean (:49-69); caller guarantees K > 1.  u = ra/(ra+rb): log u and log(1-u) come from the
 // stored log-rates and the one logarithm of (ra+rb) the Jacobian needs anyway.
-template <bool C>
+template <bool C, bool SUMS>
 __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
                                                const Draws& q, int lane, double& hasting) {
     const int K = cur.K;
@@ -390,11 +381,12 @@ __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const 
     if (lane == j - 1) { nw.r = merged; nw.lr = lm; }
     else if (lane >= j) { nw.r = dr; nw.lr = dlr; nw.t = dt; }
     side_stats(nw, d, tabA, tabB, lane);
-    side_sums(nw, lane);
+    if constexpr (SUMS) side_sums(nw, lane);
 }
 
 // opt-in real move-shift: reflected sliding window of width 1 on one interior shift (what
 // update_sliding_win :178-186 computes before it overwrites the result)
+template <bool SUMS>
 __device__ __forceinline__ bool propose_move(const Side& cur, Side& nw, const DataView& d, int tabA, int tabB,
                                              const Draws& q, int lane) {
     const int K = cur.K;
@@ -412,7 +404,7 @@ __device__ __forceinline__ bool propose_move(const Side& cur, Side& nw, const Da
     if (lane == j) nw.t = tp;
     if ((tp - t_a) <= LR_MIN_DT || (t_b - tp) <= LR_MIN_DT) return false;
     side_stats(nw, d, tabA, tabB, lane);
-    side_sums(nw, lane);
+    if constexpr (SUMS) side_sums(nw, lane);
     return true;
 }
 
@@ -446,80 +438,155 @@ __device__ __forceinline__ SideView side_view(const Hyper& hp, bool birth) {
     return v;
 }
 
-// birth block (:254-262) / death block (:264-272) on side `cur`; `oth` is the other side
+// ------------------------------------------------------------------------------------------------
+// The accept ratio in DELTA form.  With e_k = (beta A_k + 1) lr_k - (beta B_k + g) r_k summed over the K slots of a side,
+//     beta * lik_side + rates_prior_side = sum_k e_k + K * 2 log g            (:150-162 / :137-148, :201-202)
+// so every proposal's  beta (lik' - lik) + (prior' - prior) + hasting  is ONE warp reduction of per-lane differences plus a
+// few scalars; no sum of the current state is cached between iterations (nothing to keep consistent when the
+// hyper-parameters or the temperature change), and the difference of two 1e5-sized likelihoods is never formed.
+// This needs the stored prior to BE the prior of the current state (c.consistent), which holds from the first accepted
+// proposal on; before that -- the reference compares against the initial prior computed with Gamma rate 2, :227 -- and for
+// degenerate windows (every proposal rejected by the guard of :290) the absolute form below (slow_step) is used.
+// ------------------------------------------------------------------------------------------------
+
+// birth block (:254-262) / death block (:264-272) on side `cur`, delta form.  Returns false if the caller must use slow_step.
 template <bool C>
-__device__ __forceinline__ void block_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+__device__ __forceinline__ bool block_step(Side& cur, const SideView v, ChainRegs& c, const DataView& d,
                                            const lr_chain_config& cfg, const Draws& q, bool frozen, int lane) {
+    if (!c.consistent || frozen) return false;
     const bool rate = (q.kind >> 1) == DK_BLOCK_RATE || cur.K == 1;
-    if (!rate && !cfg.real_move_shift && c.consistent && !frozen) {
+    if (rate) {
+        // update_multiplier_freq (:165-176): q * m as the reference does; the log-rate follows by addition.
+        // x = sum_k (beta A_k + 1) dlt_k - (beta B_k + g)(r'_k - r_k)  +  hasting (= sum_k dlt_k)
+        c.cnt[3]++; c.cnt[2]++;
+        const bool on = lane < cur.K;
+        const double dl = on ? q.dlt : 0.0;
+        const double rn = cur.r * (on ? q.m : 1.0);
+        const double x = warp_sum((c.beta * cur.A + 2.0) * dl - (c.beta * cur.B + v.g_cur) * (rn - cur.r));
+        if (mh_accept(x, q)) { cur.r = rn; cur.lr += dl; c.cnt[1]++; }
+    } else if (!cfg.real_move_shift) {
         // The reference's move proposes the current state (:184-185): prior - priorA = 0, always accepted, nothing changes.
         c.cnt[4]++; c.cnt[2]++; c.cnt[1]++;
-        return;
-    }
-    const double p_oth = rates_prior(oth, v.g_oth, v.lg_oth) - d.log_span * (double)(cur.K + oth.K - 2) + c.poiA;   // :296-303
-    if (rate) {
-        c.cnt[3]++;
-        Side nw;
-        double hasting;
-        propose_rates(cur, nw, q, lane, hasting);
-        if (!frozen) {
-            c.cnt[2]++;
-            const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
-            if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, q)) {
-                cur.r = nw.r; cur.lr = nw.lr; cur.sumlr = nw.sumlr; cur.sumr = nw.sumr; cur.lik = nw.lik;
-                c.priorA = prior; c.consistent = 1; c.cnt[1]++;
-            }
-        }
     } else {
         c.cnt[4]++;
-        if (!cfg.real_move_shift) {
-            // same no-op move while priorA still is the initial prior of :227: only the prior bookkeeping can differ
-            if (!frozen) {
-                c.cnt[2]++;
-                const double prior = rates_prior(cur, v.g_cur, v.lg_cur) + p_oth;
-                if (mh_accept(prior - c.priorA, q)) { c.priorA = prior; c.consistent = 1; c.cnt[1]++; }
-            }
-        } else {
-            Side nw;
-            const bool ok = propose_move(cur, nw, d, v.tabA, v.tabB, q, lane);
-            if (ok && !frozen) {
-                c.cnt[2]++;
-                const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
-                if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA), q)) { cur = nw; c.priorA = prior; c.consistent = 1; c.cnt[1]++; }
-            }
+        Side nw;
+        if (propose_move<false>(cur, nw, d, v.tabA, v.tabB, q, lane)) {
+            c.cnt[2]++;
+            const bool on = lane < cur.K;
+            const double x = warp_sum(on ? c.beta * ((nw.A - cur.A) * cur.lr - (nw.B - cur.B) * cur.r) : 0.0);
+            if (mh_accept(x, q)) { cur.t = nw.t; cur.A = nw.A; cur.B = nw.B; cur.jb = nw.jb; c.cnt[1]++; }
         }
     }
+    return true;
 }
 
-// RJMCMC (:71-97, :274-279) on side `cur`
+// RJMCMC (:71-97, :274-279) on side `cur`, delta form.  Returns false if the caller must use slow_step.
 template <bool C>
-__device__ __forceinline__ void rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+__device__ __forceinline__ bool rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
                                         const Draws& q, bool frozen, int lane) {
+    if (!c.consistent || frozen) return false;
     Side nw = cur;
     double hasting = 0.0;
     bool ok = true;
     if ((q.kind >> 1) == DK_RJ_ADD) {
         if (cur.K >= LR_KMAX) { ok = false; c.cnt[7]++; }
-        else ok = propose_add<C>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
+        else ok = propose_add<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
     } else if (cur.K > 1) {
-        propose_remove<C>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
+        propose_remove<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
     }
-    if (ok && !frozen) {
+    if (ok) {
         c.cnt[2]++;
         const double poiN = poisson_prior(nw.K, c.hp.poi, c.hp.lpoi, c_lnfact) + poisson_prior(oth.K, c.hp.poi, c.hp.lpoi, c_lnfact);   // :279
-        const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + rates_prior(oth, v.g_oth, v.lg_oth)
-                             - d.log_span * (double)(nw.K + oth.K - 2) + poiN;
-        if (mh_accept(c.beta * (nw.lik - cur.lik) + (prior - c.priorA) + hasting, q)) {
-            cur = nw; c.priorA = prior; c.poiA = poiN; c.consistent = 1; c.cnt[1]++;
+        const double e_new = lane < nw.K ? (c.beta * nw.A + 1.0) * nw.lr - (c.beta * nw.B + v.g_cur) * nw.r : 0.0;
+        const double e_old = lane < cur.K ? (c.beta * cur.A + 1.0) * cur.lr - (c.beta * cur.B + v.g_cur) * cur.r : 0.0;
+        const double x = warp_sum(e_new - e_old) + (double)(nw.K - cur.K) * (2.0 * v.lg_cur - d.log_span) + (poiN - c.poiA) + hasting;
+        if (mh_accept(x, q)) { cur = nw; c.poiA = poiN; c.cnt[1]++; }
+    }
+    return true;
+}
+
+// Absolute form of one block / RJ iteration: the arithmetic of :296-313 term by term, on copies with freshly computed
+// sums.  Used while the stored prior is not the prior of the state (the first iterations of a chain) and for degenerate
+// windows; out of line and by value (see write_record).
+struct SlowOut {
+    Side cur;
+    double priorA, poiA;
+    int consistent, accepted, evaluated, cap_reject;
+};
+__device__ __noinline__ SlowOut slow_step(Side cur, Side oth, const SideView v, const Hyper hp, double priorA, double poiA, double beta,
+                                          int consistent, const DataView d, int real_move_shift, const Draws q, bool frozen, int lane) {
+    SlowOut o;
+    o.priorA = priorA; o.poiA = poiA; o.consistent = consistent; o.accepted = 0; o.evaluated = 0; o.cap_reject = 0;
+    side_sums(cur, lane); side_sums(oth, lane);
+    const int kind = q.kind >> 1;
+    if (kind <= DK_BLOCK_MOVE) {
+        const double p_oth = rates_prior(oth, v.g_oth, v.lg_oth) - d.log_span * (double)(cur.K + oth.K - 2) + poiA;   // :296-303
+        if (kind == DK_BLOCK_RATE || cur.K == 1) {
+            Side nw = cur;
+            const bool on = lane < cur.K;
+            nw.lr = cur.lr + (on ? q.dlt : 0.0);
+            nw.r = cur.r * (on ? q.m : 1.0);
+            side_sums(nw, lane);
+            const double hasting = nw.sumlr - cur.sumlr;
+            if (!frozen) {
+                o.evaluated = 1;
+                const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
+                if (mh_accept(beta * (nw.lik - cur.lik) + (prior - priorA) + hasting, q)) { cur = nw; o.priorA = prior; o.consistent = 1; o.accepted = 1; }
+            }
+        } else if (!real_move_shift) {
+            // the no-op move while priorA still is the initial prior of :227: only the prior bookkeeping can differ
+            if (!frozen) {
+                o.evaluated = 1;
+                const double prior = rates_prior(cur, v.g_cur, v.lg_cur) + p_oth;
+                if (mh_accept(prior - priorA, q)) { o.priorA = prior; o.consistent = 1; o.accepted = 1; }
+            }
+        } else {
+            Side nw;
+            const bool ok = propose_move<true>(cur, nw, d, v.tabA, v.tabB, q, lane);
+            if (ok && !frozen) {
+                o.evaluated = 1;
+                const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + p_oth;
+                if (mh_accept(beta * (nw.lik - cur.lik) + (prior - priorA), q)) { cur = nw; o.priorA = prior; o.consistent = 1; o.accepted = 1; }
+            }
+        }
+    } else {
+        Side nw = cur;
+        double hasting = 0.0;
+        bool ok = true;
+        if (kind == DK_RJ_ADD) {
+            if (cur.K >= LR_KMAX) { ok = false; o.cap_reject = 1; }
+            else ok = propose_add<true, true>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
+        } else if (cur.K > 1) {
+            propose_remove<true, true>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
+        }
+        if (ok && !frozen) {
+            o.evaluated = 1;
+            const double poiN = poisson_prior(nw.K, hp.poi, hp.lpoi, c_lnfact) + poisson_prior(oth.K, hp.poi, hp.lpoi, c_lnfact);   // :279
+            const double prior = rates_prior(nw, v.g_cur, v.lg_cur) + rates_prior(oth, v.g_oth, v.lg_oth)
+                                 - d.log_span * (double)(nw.K + oth.K - 2) + poiN;
+            if (mh_accept(beta * (nw.lik - cur.lik) + (prior - priorA) + hasting, q)) {
+                cur = nw; o.priorA = prior; o.poiA = poiN; o.consistent = 1; o.accepted = 1;
+            }
         }
     }
+    o.cur = cur;
+    return o;
+}
+__device__ __forceinline__ void run_slow(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+                                         const lr_chain_config& cfg, const Draws& q, bool frozen, int lane) {
+    const int kind = q.kind >> 1;
+    const SlowOut o = slow_step(cur, oth, v, c.hp, c.priorA, c.poiA, c.beta, c.consistent, d, cfg.real_move_shift, q, frozen, lane);
+    cur = o.cur; c.priorA = o.priorA; c.poiA = o.poiA; c.consistent = o.consistent;
+    if (kind <= DK_BLOCK_MOVE) c.cnt[(kind == DK_BLOCK_RATE || cur.K == 1) ? 3 : 4]++;
+    c.cnt[2] += o.evaluated; c.cnt[1] += o.accepted; c.cnt[7] += o.cap_reject;
 }
 
 // Gibbs on the hyper-priors (:281-287), always accepted (:313); one iteration in a thousand, kept out of line.
 // Arguments and result by value (see write_record).
 struct GibbsOut { Hyper hp; double priorA; int poi_is_init; };
-__device__ __noinline__ GibbsOut gibbs_step(const Side L, const Side M, Hyper hp, double poiA, int poi_is_init, const DataView d,
+__device__ __noinline__ GibbsOut gibbs_step(Side L, Side M, Hyper hp, double poiA, int poi_is_init, const DataView d,
                                             int sample_poisson, int use_rate_HP, const Rng rng, long long it, bool frozen, int lane) {
+    side_sums(L, lane); side_sums(M, lane);
     if (sample_poisson) {
         // get_post_rj_HP (:99-108): Gamma(2 + K_l + K_m, scale 1/3), integer shape
         double ga, gb;
@@ -552,10 +619,10 @@ __device__ __noinline__ GibbsOut gibbs_step(const Side L, const Side M, Hyper hp
 // log-rates follow the rates by addition inside the loop; every LR_RESYNC iterations they are re-derived from the rates
 // (at fixed iteration numbers, so that a chain does not depend on how a run is split into launches or sampled)
 // The COMPACT build calls the cold functions through these by-reference wrappers ON PURPOSE: the escaping addresses make
-// the compiler keep the two Sides and the ChainRegs in local memory (L1-resident, 368 B per thread) instead of registers,
-// 96 instead of 192 registers per thread.  With thousands of chains resident the extra warps hide more latency than the
-// local loads cost (B200, 16384 chains: 2.01 G it/s against 1.48-1.77 G it/s for register-resident builds at 168/128
-// registers); the SPECIALISED build wants the opposite and calls the by-value functions directly.
+// the compiler keep the two Sides and the ChainRegs in local memory (L1-resident) instead of registers, and the kernel is
+// capped at 128 registers (4 CTAs of 4 warps per SM).  With thousands of chains resident the extra warps hide more latency
+// than the local loads cost (B200, 4096 / 16384 chains: 1.67 / 1.87 G it/s at 128 registers, 1.42 / 1.67 at the 152 the
+// compiler would take, 1.62 / 1.92 at 96); the SPECIALISED build wants the opposite and calls the by-value functions.
 __device__ __noinline__ void gibbs_step_ref(const Side& L, const Side& M, ChainRegs& c, const DataView& d, int sample_poisson,
                                             int use_rate_HP, const Rng& rng, long long it, bool frozen, int lane) {
     const GibbsOut g = gibbs_step(L, M, c.hp, c.poiA, c.poi_is_init, d, sample_poisson, use_rate_HP, rng, it, frozen, lane);
@@ -563,7 +630,7 @@ __device__ __noinline__ void gibbs_step_ref(const Side& L, const Side& M, ChainR
 }
 __device__ __noinline__ void write_record_ref(double* rec, long long it, const Side& L, const Side& M, const ChainRegs& c, const DataView& d,
                                               int lane, bool with_adequacy) {
-    write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, with_adequacy);
+    write_record(rec, it, L, M, c.hp, d, c.priorA, c.poiA, c.consistent, c.poi_is_init, c.beta, lane, with_adequacy);
 }
 
 #define LR_RESYNC 1024
@@ -571,7 +638,6 @@ __device__ __forceinline__ void resync_log_rates(Side& L, Side& M, int lane) {
     const double a = ool_log(L.r), b = ool_log(M.r);      // inactive lanes hold 0: -inf, discarded
     L.lr = lane < L.K ? a : 0.0;
     M.lr = lane < M.K ? b : 0.0;
-    side_sums(L, lane); side_sums(M, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -579,7 +645,7 @@ __device__ __forceinline__ void resync_log_rates(Side& L, Side& M, int lane) {
 // otherwise compact build (one warp per chain, any blockDim that is a multiple of 32).
 // ------------------------------------------------------------------------------------------------
 template <bool SPEC>
-__global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
+__global__ void __launch_bounds__(128, SPEC ? 1 : 4) k3_run_kernel(const RunParams P) {
     constexpr bool C = !SPEC;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -622,8 +688,8 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
     const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
     Side L, M;
     load_sides(S, L, M, lane);
-    side_stats(L, d, T_AB, T_BB, lane); side_sums(L, lane);
-    side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
+    side_stats(L, d, T_AB, T_BB, lane);
+    side_stats(M, d, T_AD, T_BD, lane);
     ChainRegs c;
     c.hp.gL = S->gL; c.hp.gM = S->gM; c.hp.lgL = log(c.hp.gL); c.hp.lgM = log(c.hp.gM); c.hp.poi = S->poi; c.hp.lpoi = log(c.hp.poi);
     c.priorA = S->priorA; c.poiA = S->poiA; c.beta = S->beta; c.poi_is_init = S->poi_is_init; c.consistent = (int)S->consistent;
@@ -657,18 +723,23 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
         const bool birth = (q.kind & 1) != 0;
         if (kind <= DK_BLOCK_MOVE) {
             if constexpr (C) {
-                block_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, cfg, q, frozen, lane);
+                Side& cur = birth ? L : M;
+                if (!block_step<C>(cur, side_view(c.hp, birth), c, d, cfg, q, frozen, lane))
+                    run_slow(cur, birth ? M : L, side_view(c.hp, birth), c, d, cfg, q, frozen, lane);
             } else {
-                if (birth) block_step<C>(L, M, side_view(c.hp, true), c, d, cfg, q, frozen, lane);
-                else block_step<C>(M, L, side_view(c.hp, false), c, d, cfg, q, frozen, lane);
+                if (birth) { if (!block_step<C>(L, side_view(c.hp, true), c, d, cfg, q, frozen, lane)) run_slow(L, M, side_view(c.hp, true), c, d, cfg, q, frozen, lane); }
+                else { if (!block_step<C>(M, side_view(c.hp, false), c, d, cfg, q, frozen, lane)) run_slow(M, L, side_view(c.hp, false), c, d, cfg, q, frozen, lane); }
             }
         } else if (kind != DK_GIBBS) {
             c.cnt[5]++;
             if constexpr (C) {
-                rj_step<C>(birth ? L : M, birth ? M : L, side_view(c.hp, birth), c, d, q, frozen, lane);
+                Side& cur = birth ? L : M;
+                const Side& oth = birth ? M : L;
+                if (!rj_step<C>(cur, oth, side_view(c.hp, birth), c, d, q, frozen, lane))
+                    run_slow(cur, oth, side_view(c.hp, birth), c, d, cfg, q, frozen, lane);
             } else {
-                if (birth) rj_step<C>(L, M, side_view(c.hp, true), c, d, q, frozen, lane);
-                else rj_step<C>(M, L, side_view(c.hp, false), c, d, q, frozen, lane);
+                if (birth) { if (!rj_step<C>(L, M, side_view(c.hp, true), c, d, q, frozen, lane)) run_slow(L, M, side_view(c.hp, true), c, d, cfg, q, frozen, lane); }
+                else { if (!rj_step<C>(M, L, side_view(c.hp, false), c, d, q, frozen, lane)) run_slow(M, L, side_view(c.hp, false), c, d, cfg, q, frozen, lane); }
             }
         } else {
             c.cnt[6]++;
@@ -687,7 +758,7 @@ __global__ void __launch_bounds__(128) k3_run_kernel(const RunParams P) {
             if (it == next_resync) { resync_log_rates(L, M, lane); next_resync += LR_RESYNC; }
             if (it == next_sample) {                // it % sample_every == 0 (:321)
                 if constexpr (C) write_record_ref(rec, it, L, M, c, d, lane, P.with_adequacy != 0);
-                else write_record(rec, it, L, M, c.hp, d, c.priorA, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
+                else write_record(rec, it, L, M, c.hp, d, c.priorA, c.poiA, c.consistent, c.poi_is_init, c.beta, lane, P.with_adequacy != 0);
                 rec += (size_t)P.n_chains * LR_REC_DOUBLES;
                 next_sample += s_every;
             }
@@ -785,7 +856,7 @@ __global__ void k3_get_state_kernel(const ChainState* st, int n_chains, double* 
     side_stats(M, d, T_AD, T_BD, lane); side_sums(M, lane);
     Hyper hp;
     hp.gL = S->gL; hp.gM = S->gM; hp.poi = S->poi; hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.lpoi = log(hp.poi);
-    write_record(recs + (size_t)chain * LR_REC_DOUBLES, S->it, L, M, hp, d, S->priorA, S->poi_is_init, S->beta, lane, true);
+    write_record(recs + (size_t)chain * LR_REC_DOUBLES, S->it, L, M, hp, d, S->priorA, S->poiA, (int)S->consistent, S->poi_is_init, S->beta, lane, true);
 }
 
 // K2: one warp per state
