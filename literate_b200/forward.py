@@ -301,14 +301,8 @@ def run(args, device=None):
     per_launch = max(every, per_launch // every * every)
     done, rounds = 0, 0
     t_run = time.time()
-    while done < args.n:
-        n_it = min(per_launch, args.n - done)
-        if T > 1:
-            recs, r = chains.run_tempered(n_it, every, T, max(1, args.swap_every), round0=rounds)
-            rounds += r
-            recs = E.cold_records(recs, T)
-        else:
-            recs = chains.run(n_it, every)
+
+    def emit(recs):
         for r in range(recs.shape[0]):
             it = int(recs[r, 0, E.REC_IT])
             if it % s_freq == 0:
@@ -318,7 +312,42 @@ def run(args, device=None):
                 _print_state(recs[r, 0], float(end_time), args.calc_adequacy)
         for w in writers:
             w.flush()
-        done += n_it
+
+    if T > 1:
+        while done < args.n:
+            n_it = min(per_launch, args.n - done)
+            recs, r = chains.run_tempered(n_it, every, T, max(1, args.swap_every), round0=rounds)
+            rounds += r
+            emit(E.cold_records(recs, T))
+            done += n_it
+    else:
+        # Double-buffered: the text of launch k is formatted and written while launch k+1 runs on the device (formatting
+        # tens of millions of shortest-repr floats is the slower half for many chains).
+        import torch
+        tdev = torch.device("cuda", dev.index)
+        pending = None
+        while done < args.n or pending is not None:
+            nxt = None
+            if done < args.n:
+                n_it = min(per_launch, args.n - done)
+                n_rec = chains.records_per_run(n_it, every)              # waits for the previous launch
+                buf = torch.empty((n_rec, n_local, E.LR_REC_DOUBLES), dtype=torch.float64, device=tdev)
+                if pending is not None:
+                    host_prev = pending.cpu().numpy()
+                    pending = None
+                else:
+                    host_prev = None
+                chains.run_device(n_it, every, buf, stream="handle")     # asynchronous
+                done += n_it
+                nxt = buf
+                if host_prev is not None:
+                    emit(host_prev)
+            else:
+                dev.sync()
+                emit(pending.cpu().numpy())
+                pending = None
+            if nxt is not None:
+                pending = nxt
     t_run = time.time() - t_run
     for w in writers:
         w.close()
