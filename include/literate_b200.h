@@ -137,6 +137,15 @@ int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int
                        const double* gamma_rate, const double* poi_lambda,
                        double* lik, double* prior_rates, double* prior_poi, double* adequacy);
 
+/* Validation path: the Keiding log-likelihood (BD_lik_Keiding, :137-148; -model_BDI 2) of n_states states evaluated DIRECTLY
+ * over the lineages without binning -- the per-lineage formulation of the reference's ancestor
+ * (other/LiteRateBDI_ext.py:124-160, get_BDlik) -- to cross-check lr_bin_stats + lr_state_eval at full size.
+ *   d_lam, d_mu  [n_states][n_bins] per-bin rates (a state expanded with get_rate_index, :125-135)
+ *   d_out        [n_states]
+ * Reads the lineages once per group of 8 states (16 B per lineage per group); deterministic; asynchronous on `stream`. */
+int lr_loglik_direct(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t first_bin, int32_t n_bins,
+                     const double* d_lam, const double* d_mu, int32_t n_states, double* d_out, void* stream);
+
 /* ---------------------------------------------------------------- L4: the chains (runMCMC) */
 typedef struct lr_chain_config {
     int32_t model_BDI;          /* must equal the dataset's */

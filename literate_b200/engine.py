@@ -177,6 +177,17 @@ class Device:
                                            C.c_void_p(acc.data_ptr()), st), "lr_bin_accumulate")
         return acc
 
+    def loglik_direct_device(self, ts, te, first_bin, n_bins, lam, mu, stream=None):
+        """Validation path (lr_loglik_direct): Keiding log-likelihood of states given as per-bin rates, straight from the
+        lineages.  ts/te: float64 CUDA tensors [n]; lam/mu: float64 CUDA tensors [n_states, n_bins].  Returns [n_states]."""
+        import torch
+        assert ts.is_cuda and lam.is_cuda and lam.shape == mu.shape and lam.shape[1] == n_bins and lam.is_contiguous() and mu.is_contiguous()
+        out = torch.empty(lam.shape[0], dtype=torch.float64, device=lam.device)
+        N.check(self.lib.lr_loglik_direct(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), ts.numel(), int(first_bin), int(n_bins),
+                                          C.c_void_p(lam.data_ptr()), C.c_void_p(mu.data_ptr()), lam.shape[0], C.c_void_p(out.data_ptr()),
+                                          _stream_ptr(stream, lam.device)), "lr_loglik_direct")
+        return out
+
     def new_accumulators(self, n_rep, n_bins, device):
         import torch
         return torch.zeros((n_rep, N.LR_ACC_ROWS, int(self.lib.lr_acc_stride(int(n_bins)))), dtype=torch.int64, device=device)
