@@ -69,6 +69,8 @@ struct Side {
     double A, B;           // the segment's event count and exposure
     int jb;                // first bin of the segment
     int K;                 // number of rates (uniform)
+    // Filled by side_sums() where absolute values are needed (records, Gibbs, the slow path, K2); the loop itself works
+    // on per-lane differences and never reads them:
     double sumlr, sumr;    // sum of log-rates / rates over the K slots (uniform)
     double lik;            // sum_k A*lr - r*B (uniform)
 };

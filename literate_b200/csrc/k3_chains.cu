@@ -1,12 +1,13 @@
-// K2 (dataset tables + batched state evaluation) and K3 (persistent multi-chain RJMCMC).
+// K2 (dataset tables + batched state evaluation) and K3 (the multi-chain RJMCMC loop, whole loop on device).
 //
-// K3 replaces runMCMC (LiteRateForward.py:216-373): per iteration one warp = one chain draws its
-// randoms from a Philox-4x32-10 stream keyed by (seed, chain id), builds the proposal in
-// registers, evaluates likelihood/prior/Hastings-Jacobian terms and runs the Metropolis-Hastings
-// accept step -- no host round trip, no memory traffic besides the read-only prefix tables and
-// the sample records.  Reference quirks kept on purpose: no-op move-shift
-// (:184-185), stale priorPoiA (:300-304,:319), initial prior with Gamma rate 2 (:227), `>=`
-// accept test (:313), min-spacing guard (:290).
+// K3 replaces runMCMC (LiteRateForward.py:216-373).  A chain lives in the registers of one warp (lane k = slot k of the
+// birth and of the death side); per iteration it takes its random numbers from a Philox-4x32-10 stream keyed by
+// (seed, global chain id, iteration), builds the proposal with register shuffles, forms the Metropolis-Hastings ratio as
+// one warp reduction of per-lane differences and commits or not -- no host round trip, no memory traffic besides the
+// read-only prefix tables and the sample records.  Two builds of the loop (specialised: producer warps feed the chain
+// warp through a shared-memory ring; compact: one warp does everything) are described where they are defined.
+// Reference quirks kept on purpose: no-op move-shift (:184-185), stale priorPoiA (:300-304,:319),
+// initial prior with Gamma rate 2 (:227), `>=` accept test (:313), min-spacing guard (:290).
 #include "chain_device.cuh"
 
 namespace {
