@@ -156,9 +156,11 @@ typedef struct lr_chain_config {
     double  update_fraction;    /* -update_fraction    (:252, :399) */
     int32_t real_move_shift;    /* 0 = reference behaviour (move-shift proposes the current state, :184-185);
                                    1 = reflected sliding window d=1 (opt-in, deviates from the reference) */
-    int32_t loop_variant;       /* build of the chain loop: 0 choose by population size (1 up to two chains per SM, else 2),
-                                   1 warp-specialised (one CTA per chain: a chain warp fed by three producer warps),
-                                   2 compact (one warp per chain, for thousands of resident chains); results are identical */
+    int32_t loop_variant;       /* build of the chain loop: 0 choose by population size (1 up to two chains per SM, 3 up to
+                                   seven, else 2); 1 warp-specialised, one chain per CTA (a chain warp fed by three producer
+                                   warps); 3 warp-specialised, four chains per CTA (one producer each, registers re-balanced
+                                   with setmaxnreg); 2 compact (one warp per chain, thousands of resident chains).
+                                   Results are identical, bit for bit */
     double  beta;               /* likelihood tempering exponent of every chain unless set per chain; 1 = reference */
 } lr_chain_config;
 

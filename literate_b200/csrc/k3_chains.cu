@@ -276,21 +276,25 @@ __device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int la
 }
 
 // ---- shared-memory ring between the producer warps and the chain warp (SPECIALISED build).
-// The unit of hand-off is a BATCH of RING_BATCH consecutive iterations: batch b is produced by warp 1 + b % 3 into slot
-// b % RING_DEPTH and published with one release store; the chain warp acquires once per batch and releases the slot
+// The unit of hand-off is a BATCH of RING_BATCH consecutive iterations: batch b is produced by producer b % PPC of the
+// chain into slot b % DEPTH and published with one release store; the chain warp acquires once per batch and releases the slot
 // when it has taken the batch's last iteration.
-constexpr int RING_PRODUCERS = 3;
 constexpr int RING_BATCH = 8;
-constexpr int RING_DEPTH = 6;          // batches in flight: two per producer
 struct RingIter {
     double m[32], dlt[32];
     double sc[16];                     // u_acc u_idx u_t w ln_beta thr_hi thr_lo kind
 };
+template <int DEPTH>
 struct Ring {
-    RingIter it[RING_DEPTH][RING_BATCH];
-    unsigned long long full[RING_DEPTH];   // b + 1 once batch b is published
-    unsigned long long done[RING_DEPTH];   // b + 1 once batch b has been consumed
+    RingIter it[DEPTH][RING_BATCH];
+    unsigned long long full[DEPTH];        // b + 1 once batch b is published
+    unsigned long long done[DEPTH];        // b + 1 once batch b has been consumed
 };
+// register re-balancing between the warpgroups of the 4-chains-per-CTA build (PTX setmaxnreg, sm_90+): the kernel is
+// launched at 128 registers per thread (2 CTAs of 256 threads per SM); the producer warpgroup gives registers back, the
+// chain warpgroup takes them
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
 __device__ __forceinline__ unsigned long long ld_acquire_cta(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
@@ -645,33 +649,50 @@ __device__ __forceinline__ void resync_log_rates(Side& L, Side& M, int lane) {
 // K3: the chains.  SPEC = warp-specialised build (blockDim = 128: chain warp + 3 producer warps, one chain per CTA);
 // otherwise compact build (one warp per chain, any blockDim that is a multiple of 32).
 // ------------------------------------------------------------------------------------------------
-template <bool SPEC>
-__global__ void __launch_bounds__(128, SPEC ? 1 : 4) k3_run_kernel(const RunParams P) {
+// MODE 0  compact: one warp per chain, any blockDim that is a multiple of 32
+// MODE 1  specialised, one chain per CTA of 4 warps: chain warp + 3 producer warps (2 CTAs per SM at ~210 registers)
+// MODE 2  specialised, four chains per CTA of 8 warps: warpgroup 0 = 4 chain warps, warpgroup 1 = their 4 producers (one
+//         each, which keeps up: ~390 cycles per produced iteration against ~900 consumed); setmaxnreg moves registers from
+//         the producers (72) to the chain warps (184), 2 CTAs = 8 chains per SM
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) k3_run_kernel(const RunParams P) {
+    constexpr bool SPEC = MODE != 0;
     constexpr bool C = !SPEC;
+    constexpr int CPB = MODE == 2 ? 4 : 1;             // chains per CTA
+    constexpr int PPC = MODE == 2 ? 1 : 3;             // producer warps per chain
+    constexpr int DEPTH = MODE == 2 ? 3 : 6;           // ring slots (batches in flight) per chain
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int chain = SPEC ? (int)blockIdx.x : (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    if (chain >= P.n_chains) return;
-    ChainState* S = P.st + chain;
+    const bool producer = SPEC && warp >= CPB;
+    const int slot_in_cta = !SPEC ? 0 : (producer ? (warp - CPB) / PPC : warp);
+    const int chain = SPEC ? (int)blockIdx.x * CPB + slot_in_cta : (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+
+    extern __shared__ __align__(16) unsigned char ring_raw[];
+    Ring<DEPTH>* ring_p = nullptr;
     const lr_chain_config& cfg = P.cfg;
     const LoopConsts K = loop_consts(cfg);
-    Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
-    const long long it0 = S->it, it1 = it0 + P.n_iter;
-
-    Ring* ring_p = nullptr;
     if constexpr (SPEC) {
-        __shared__ Ring ring;
-        ring_p = &ring;
-        if (threadIdx.x < RING_DEPTH) { ring.full[threadIdx.x] = 0ull; ring.done[threadIdx.x] = 0ull; }
-        __syncthreads();                    // it0 was read above: the chain warp rewrites S->it only at the very end
-        if (warp > 0) {
-            // ---------------- producer warps: batches b = warp-1, warp-1+3, ... of RING_BATCH iterations each
+        Ring<DEPTH>* rings = reinterpret_cast<Ring<DEPTH>*>(ring_raw);
+        if (threadIdx.x < CPB * DEPTH) { rings[threadIdx.x / DEPTH].full[threadIdx.x % DEPTH] = 0ull; rings[threadIdx.x / DEPTH].done[threadIdx.x % DEPTH] = 0ull; }
+        __syncthreads();
+        ring_p = rings + slot_in_cta;
+        if (producer) {
+            // ---------------- producer warp `pid` of this chain: batches b = pid, pid + PPC, ... of RING_BATCH iterations each.
+            // (The whole producer role sits inside this branch and returns: the register re-balancing below applies to
+            // code that only one of the two warpgroups can reach.)
+            if constexpr (MODE == 2) reg_dealloc<72>();
+            if (chain >= P.n_chains) return;
+            const ChainState* S = P.st + chain;
+            Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
+            const long long it0 = S->it;                  // the chain warp rewrites S->it only at the very end
+            Ring<DEPTH>& ring = *ring_p;
+            const int pid = (warp - CPB) % PPC;
             const long long n_batches = (P.n_iter + RING_BATCH - 1) / RING_BATCH;
-            int s = warp - 1;                       // slot of batch b is b % RING_DEPTH, tracked without a division
-            for (long long b = warp - 1; b < n_batches; b += RING_PRODUCERS) {
-                // wait until the previous occupant of the slot (batch b - RING_DEPTH) has been consumed; back off while
+            int s = pid % DEPTH;                    // slot of batch b is b % DEPTH, tracked without a division
+            for (long long b = pid; b < n_batches; b += PPC) {
+                // wait until the previous occupant of the slot (batch b - DEPTH) has been consumed; back off while
                 // waiting so that the polling does not compete with the chain warp for the shared-memory pipe
-                while ((long long)ld_acquire_cta(&ring.done[s]) < b - RING_DEPTH + 1) __nanosleep(200);
+                while ((long long)ld_acquire_cta(&ring.done[s]) < b - DEPTH + 1) __nanosleep(200);
                 const long long j0 = b * RING_BATCH;
 #pragma unroll 1
                 for (int i = 0; i < RING_BATCH; ++i) {
@@ -679,11 +700,17 @@ __global__ void __launch_bounds__(128, SPEC ? 1 : 4) k3_run_kernel(const RunPara
                 }
                 __syncwarp();
                 if (lane == 0) st_release_cta(&ring.full[s], (unsigned long long)(b + 1));
-                s += RING_PRODUCERS; if (s >= RING_DEPTH) s -= RING_DEPTH;
+                s += PPC; if (s >= DEPTH) s -= DEPTH;
             }
             return;
+        } else {
+            if constexpr (MODE == 2) reg_alloc<184>();
         }
     }
+    if (chain >= P.n_chains) return;
+    ChainState* S = P.st + chain;
+    Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
+    const long long it0 = S->it, it1 = it0 + P.n_iter;
 
     // ---------------- the chain warp
     const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
@@ -709,13 +736,13 @@ __global__ void __launch_bounds__(128, SPEC ? 1 : 4) k3_run_kernel(const RunPara
     for (long long it = it0; it < it1; ++it) {
         Draws q;
         if constexpr (SPEC) {
-            Ring& R = *ring_p;
+            Ring<DEPTH>& R = *ring_p;
             if (in_batch == 0) { while (ld_acquire_cta(&R.full[slot]) != (unsigned long long)(batch + 1)) { } }
             q = ring_load(R.it[slot][in_batch], lane);
             if (++in_batch == RING_BATCH || it + 1 == it1) {
                 __syncwarp();
                 if (lane == 0) st_release_cta(&R.done[slot], (unsigned long long)(batch + 1));
-                in_batch = 0; ++batch; if (++slot == RING_DEPTH) slot = 0;
+                in_batch = 0; ++batch; if (++slot == DEPTH) slot = 0;
             }
         }
         else q = make_draws<true>(rng, it, lane, K);
@@ -1132,7 +1159,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
     LR_REQUIRE(cfg->model_BDI == ds->model, "lr_chains_create: cfg.model_BDI differs from the dataset's");
     LR_REQUIRE(cfg->update_fraction >= 0.0 && cfg->update_fraction <= 1.0, "lr_chains_create: update_fraction outside [0,1]");
     LR_REQUIRE(cfg->poisson_prior >= 0.0, "lr_chains_create: poisson_prior must be >= 0");
-    LR_REQUIRE(cfg->loop_variant >= 0 && cfg->loop_variant <= 2, "lr_chains_create: loop_variant must be 0, 1 or 2");
+    LR_REQUIRE(cfg->loop_variant >= 0 && cfg->loop_variant <= 3, "lr_chains_create: loop_variant must be 0..3");
     LR_REQUIRE(chain_id0 >= 0 && chain_id0 + n_chains <= 0xffffffffll, "lr_chains_create: chain ids must fit 32 bits");
     if (h_rep_of_chain)
         for (int i = 0; i < n_chains; ++i)
@@ -1199,12 +1226,21 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     const int blocks = chain_grid(c->n_chains, threads);
     // loop_variant: 0 = choose by population size (measured cross-over on B200), 1 = warp-specialised build
     // (one CTA of 4 warps per chain), 2 = compact build (one warp per chain)
-    // The specialised build holds 2 CTAs (= 2 chains) per SM; beyond one wave of it the compact build wins (B200, 148 SMs:
-    // 296 chains 545 M it/s specialised; 384 chains 372 M specialised vs 392 M compact; 512: 485 M vs 597 M).
+    // loop_variant 0 picks by population size (measured on B200, 148 SMs; M it/s for one-chain CTAs / four-chain CTAs / compact):
+    //   296 chains 572 / 506 / 325;  512: - / 873 / 557;  1024: - / 1094 / 1027;  1184: - / 1119 / 1161;  2048: - / 1051 / 1547
     int variant = c->cfg.loop_variant;
-    if (variant == 0) variant = c->n_chains <= 2 * h->sm_count ? 1 : 2;
-    if (variant == 1) k3_run_kernel<true><<<c->n_chains, 128, 0, st>>>(P);
-    else k3_run_kernel<false><<<blocks, threads, 0, st>>>(P);
+    if (variant == 0) variant = c->n_chains <= 2 * h->sm_count ? 1 : (c->n_chains <= 7 * h->sm_count ? 3 : 2);
+    if (variant == 1) {
+        const size_t smem = sizeof(Ring<6>);
+        LR_CUDA(cudaFuncSetAttribute(k3_run_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k3_run_kernel<1><<<c->n_chains, 128, smem, st>>>(P);
+    } else if (variant == 3) {
+        const size_t smem = 4 * sizeof(Ring<3>);
+        LR_CUDA(cudaFuncSetAttribute(k3_run_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k3_run_kernel<2><<<(c->n_chains + 3) / 4, 256, smem, st>>>(P);
+    } else {
+        k3_run_kernel<0><<<blocks, threads, 0, st>>>(P);
+    }
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;

@@ -98,11 +98,12 @@ def test_determinism_and_sharding_invariance(device):
 def test_loop_builds_give_identical_chains(device, metal_path):
     """The latency-optimised and the compact build of the chain loop (lr_chain_config.loop_variant) are the same
     arithmetic: identical records, bit for bit."""
-    lin, st, ds, a = _setup(device, metal_path, n_chains=24, seed=5, loop_variant=1)
-    b = E.Chains(ds, 24, 5, E.default_config(0, loop_variant=2))
-    ra, rb = a.run(30000, 250), b.run(30000, 250)
-    assert np.array_equal(ra, rb)
-    assert np.array_equal(a.counters(), b.counters())
+    lin, st, ds, a = _setup(device, metal_path, n_chains=22, seed=5, loop_variant=1)
+    b = E.Chains(ds, 22, 5, E.default_config(0, loop_variant=2))
+    c = E.Chains(ds, 22, 5, E.default_config(0, loop_variant=3))       # four chains per CTA: 22 leaves a ragged last CTA
+    ra, rb, rc = a.run(30000, 250), b.run(30000, 250), c.run(30000, 250)
+    assert np.array_equal(ra, rb) and np.array_equal(ra, rc)
+    assert np.array_equal(a.counters(), b.counters()) and np.array_equal(a.counters(), c.counters())
 
 
 def test_loop_builds_identical_for_ragged_launch_lengths(device):
@@ -110,13 +111,14 @@ def test_loop_builds_identical_for_ragged_launch_lengths(device):
     iterations (partial first/last batches, sampling on and off) must still be the compact build's chain, bit for bit."""
     lin, st, ds, a = _setup(device, golden_input("example_dataTAD.txt"), n_chains=9, seed=21, loop_variant=1)
     b = E.Chains(ds, 9, 21, E.default_config(0, loop_variant=2))
+    c = E.Chains(ds, 9, 21, E.default_config(0, loop_variant=3))
     for k, n in enumerate([1, 7, 8, 9, 23, 64, 65, 1000, 3, 1025, 4096, 5]):
         s = [0, 1, 5][k % 3]
-        ra, rb = a.run(n, s), b.run(n, s)
+        ra, rb, rc = a.run(n, s), b.run(n, s), c.run(n, s)
         if s:
-            assert np.array_equal(ra, rb), (k, n, s)
-        assert np.array_equal(a.state(), b.state()), (k, n)
-    assert np.array_equal(a.counters(), b.counters())
+            assert np.array_equal(ra, rb) and np.array_equal(ra, rc), (k, n, s)
+        assert np.array_equal(a.state(), b.state()) and np.array_equal(a.state(), c.state()), (k, n)
+    assert np.array_equal(a.counters(), b.counters()) and np.array_equal(a.counters(), c.counters())
 
 
 def test_many_rates_per_side_and_capacity(device, metal_path):
@@ -150,7 +152,7 @@ def test_four_thousand_chains_shard_invariance(device, metal_path):
     """BASELINE cfg4 population size (4096 chains, compact build): any shard of the population reproduces its slice bit for
     bit, whatever build the shard size selects, and tempered swap rounds keyed by global ladder ids agree as well."""
     lin, st, ds, whole = _setup(device, metal_path, n_chains=4096, seed=404)
-    parts = [(0, 256), (256, 1024), (1280, 2816)]              # specialised build, compact build, compact build
+    parts = [(0, 256), (256, 1024), (1280, 2816)]              # one chain per CTA, four chains per CTA, compact build
     shards = [E.Chains(ds, n, 404, chain_id0=c0) for c0, n in parts]
     from literate_b200 import parallel as P
     beta = np.tile(P.temperature_ladder(8, 0.1), 512)
