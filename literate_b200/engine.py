@@ -63,7 +63,7 @@ class Device:
     """One lr_handle_t: a B200 and its streams/workspace."""
 
     def __init__(self, index: int = 0):
-        self.lib = N.load(build_if_missing=False)
+        self.lib = N.load(build_if_missing=True)     # compiles the CUDA library with nvcc if it is not there; no other path exists
         h = C.c_void_p()
         N.check(self.lib.lr_create(int(index), C.byref(h)), "lr_create")
         self.h = h
