@@ -47,14 +47,18 @@ def load(build_if_missing=False):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if build_if_missing:
-            from . import build as _b
+    if build_if_missing:
+        # (re)build when the library is missing or older than its sources; a no-op when the digest stamp matches
+        from . import build as _b
+        try:
             _b.build()
-        else:
-            raise NativeError(
-                f"{LIB_PATH} is missing. Build it with `python -m literate_b200.build` (needs nvcc); "
-                "literate_b200 has no CPU fallback.")
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} is missing. Build it with `python -m literate_b200.build` (needs nvcc); "
+            "literate_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, u64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
     P = C.POINTER
