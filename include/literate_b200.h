@@ -218,6 +218,17 @@ int lr_chains_swap_apply(lr_chains_t c, const double* d_info_all, int64_t n_all,
 /* single-device convenience: swap_info + swap_apply on the handle's stream for ladders that live on this device */
 int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round);
 
+/* ---------------------------------------------------------------- posterior accumulators
+ * From device-resident sample records (any [n_records][LR_REC_DOUBLES] slice, e.g. the cold chains after the burn-in) the
+ * sums behind plotRJforward.v3.py's per-bin summaries (get_marginal_rates :92-139, get_r_plot :166-176, get_K_values :292-305):
+ *   d_sum_rate    [2][n_bins] fp64   sum over records of the marginal birth / death rate of every unit bin from first_edge
+ *                                     (np.histogram semantics: half-open bins, last one closed); mean = sum / n_records
+ *   d_shift_count [2][n_bins] int64  number of sampled shift times per bin (frequency = count / n_records)
+ *   d_k_count     [2][32]     int64  number of records with K = index + 1 rates
+ * Deterministic (fixed summation order); asynchronous on `stream`. */
+int lr_summarize_records(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
+                         double* d_sum_rate, int64_t* d_shift_count, int64_t* d_k_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

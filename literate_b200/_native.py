@@ -25,7 +25,7 @@ EXPORTS = [
     "lr_dataset_create", "lr_dataset_create_host", "lr_dataset_destroy", "lr_state_eval_host", "lr_loglik_direct",
     "lr_chains_create", "lr_chains_destroy", "lr_chains_records_per_run", "lr_chains_run", "lr_chains_run_host",
     "lr_chains_counters_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
-    "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step",
+    "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step", "lr_summarize_records",
 ]
 
 
@@ -96,6 +96,7 @@ def load(build_if_missing=False):
     sig("lr_chains_swap_info", C.c_int, vp, vp, vp)
     sig("lr_chains_swap_apply", C.c_int, vp, vp, i64, i64, i32, u64, vp)
     sig("lr_chains_swap_step", C.c_int, vp, i32, u64)
+    sig("lr_summarize_records", C.c_int, vp, vp, i64, f64, i32, vp, vp, vp, vp)
     if lib.lr_abi_version() != LR_ABI_VERSION:
         raise NativeError("libliterate_b200.so ABI version mismatch; rebuild with `python -m literate_b200.build --force`")
     _lib = lib

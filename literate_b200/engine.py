@@ -188,6 +188,20 @@ class Device:
                                           _stream_ptr(stream, lam.device)), "lr_loglik_direct")
         return out
 
+    def summarize_records_device(self, records, first_edge, n_bins, stream=None):
+        """Posterior accumulators of device-resident records (lr_summarize_records): `records` is a contiguous float64 CUDA
+        tensor [..., 144]; returns (sum_rate [2, n_bins] float64, shift_count [2, n_bins] int64, k_count [2, 32] int64, n_records)."""
+        import torch
+        assert records.is_cuda and records.dtype == torch.float64 and records.is_contiguous() and records.shape[-1] == LR_REC_DOUBLES
+        n = records.numel() // LR_REC_DOUBLES
+        sr = torch.empty((2, n_bins), dtype=torch.float64, device=records.device)
+        sc = torch.empty((2, n_bins), dtype=torch.int64, device=records.device)
+        kc = torch.empty((2, 32), dtype=torch.int64, device=records.device)
+        N.check(self.lib.lr_summarize_records(self.h, C.c_void_p(records.data_ptr()), n, float(first_edge), int(n_bins),
+                                              C.c_void_p(sr.data_ptr()), C.c_void_p(sc.data_ptr()), C.c_void_p(kc.data_ptr()),
+                                              _stream_ptr(stream, records.device)), "lr_summarize_records")
+        return sr, sc, kc, n
+
     def new_accumulators(self, n_rep, n_bins, device):
         import torch
         return torch.zeros((n_rep, N.LR_ACC_ROWS, int(self.lib.lr_acc_stride(int(n_bins)))), dtype=torch.int64, device=device)

@@ -165,6 +165,23 @@ def summarize_records(records, start_time, end_time, burnin=0.2, name="chains", 
     return _finish(name, float(start_time), float(end_time), b, d, bf_seed, div)
 
 
+def summarize_records_device(dev, records, start_time, end_time, burnin=0.2):
+    """Means, shift frequencies and number-of-rates counts of device-resident records (a float64 CUDA tensor
+    [n_samples, n_chains, 144]) without bringing them to the host (K5, lr_summarize_records).  HPD intervals need the
+    per-sample matrix and are left to summarize_records on a (thinned) host copy.  Returns a dict of NumPy arrays."""
+    b0 = burnin_index(records.shape[0], burnin)
+    post = records[b0:].contiguous()
+    nb = len(np.arange(start_time, end_time)) - 1
+    sr, sc, kc, n = dev.summarize_records_device(post, start_time, nb)
+    sr, sc, kc = sr.cpu().numpy(), sc.cpu().numpy(), kc.cpu().numpy()
+    out = {"n_samples": n, "time": (np.arange(start_time, end_time) - 0.5)[1:]}
+    for side, name in ((0, "birth"), (1, "death")):
+        k = np.nonzero(kc[side])[0]
+        out[name] = {"mean": sr[side] / n, "shift_freq": sc[side] / float(n), "k_values": (k + 1).astype(float), "k_counts": kc[side][k]}
+    out["net_mean"] = out["birth"]["mean"] - out["death"]["mean"]
+    return out
+
+
 def _read_ragged(path):
     """sp_rates.log / ex_rates.log: rows `rates... shifts...` -> padded (rates, shifts, K)."""
     rows = [np.array(l.split(), dtype=np.float64) for l in open(path) if l.strip()]

@@ -1,0 +1,74 @@
+"""GPU: K5 (lr_summarize_records), posterior accumulators straight from device-resident sample records, against the host
+summariser (literate_b200.summary, itself pinned to the unmodified plotRJforward.v3.py in tests/test_summary_host.py) and
+the oracle's per-row restatement."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_input
+from oracle import literate_oracle as O
+from literate_b200 import engine as E, summary as S
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_accumulators_match_host_summary(device, metal_path):
+    lin = O.read_lineages(metal_path)
+    st = device.bin_stats(lin.ts, lin.te)
+    ds = E.Dataset(device, st, 0, lin.start_time, lin.end_time)
+    ch = E.Chains(ds, 48, seed=31)
+    n_iter, s = 60001, 100
+    rec = torch.empty((ch.records_per_run(n_iter, s), 48, E.LR_REC_DOUBLES), dtype=torch.float64, device="cuda")
+    ch.run_device(n_iter, s, rec, stream="handle")
+    device.sync()
+    b0 = S.burnin_index(rec.shape[0], 0.2)
+    post = rec[b0:].contiguous()
+    nb = int(lin.end_time) - int(lin.start_time)
+    sr, sc, kc, n = device.summarize_records_device(post, lin.start_time, nb)
+    torch.cuda.synchronize()
+    sr, sc, kc = sr.cpu().numpy(), sc.cpu().numpy(), kc.cpu().numpy()
+    host = S.summarize_records(rec.cpu().numpy(), lin.start_time, lin.end_time, burnin=0.2, bf_seed=None)
+    assert n == host.birth.n_samples == post.shape[0] * 48
+    np.testing.assert_allclose(sr[0] / n, host.birth.mean, rtol=1e-12)
+    np.testing.assert_allclose(sr[1] / n, host.death.mean, rtol=1e-12)
+    assert np.array_equal(sc[0] / n, host.birth.shift_freq) and np.array_equal(sc[1] / n, host.death.shift_freq)
+    for side, hs in ((0, host.birth), (1, host.death)):
+        want = np.zeros(32, dtype=np.int64)
+        want[hs.k_values.astype(int) - 1] = hs.k_counts
+        assert np.array_equal(kc[side], want)
+    # oracle restatement on a few hundred rows
+    r = rec.cpu().numpy()[b0:, 0]
+    rows = [np.concatenate([x[E.REC_L:E.REC_L + int(x[E.REC_KL])], x[E.REC_TL + 1:E.REC_TL + int(x[E.REC_KL])]]) for x in r]
+    sr1, _, _, n1 = device.summarize_records_device(post[:, 0].contiguous(), lin.start_time, nb)
+    np.testing.assert_allclose(sr1[0].cpu().numpy() / n1, O.marginal_rates(rows, lin.end_time, lin.start_time, 0).mean(0), rtol=1e-12)
+    # the summary module's device entry point: same numbers, burn-in handled there
+    dv = S.summarize_records_device(device, rec, lin.start_time, lin.end_time, burnin=0.2)
+    np.testing.assert_allclose(dv["birth"]["mean"], host.birth.mean, rtol=1e-12)
+    np.testing.assert_allclose(dv["net_mean"], host.net_mean, rtol=1e-10, atol=1e-15)
+    assert np.array_equal(dv["death"]["k_values"], host.death.k_values) and np.array_equal(dv["death"]["k_counts"], host.death.k_counts)
+    assert np.array_equal(dv["time"], host.birth.time)
+    # deterministic
+    sr2, sc2, kc2, _ = device.summarize_records_device(post, lin.start_time, nb)
+    assert torch.equal(sr2.cpu(), torch.from_numpy(sr)) and torch.equal(sc2.cpu(), torch.from_numpy(sc))
+
+
+def test_more_than_256_bins_and_edge_shifts(device):
+    """Hand-made records: 300 bins (two passes), shift times on bin edges, on the closed last edge and outside the edges."""
+    nb, e0 = 300, 100.0
+    rec = np.zeros((5, E.LR_REC_DOUBLES))
+    cases = [([0.5], []), ([0.1, 0.2], [150.0]), ([1., 2., 3.], [100.0, 400.0]), ([1., 2., 3., 4.], [99.5, 250.25, 401.0]), ([5., 6.], [399.999])]
+    for r, (rates, shifts) in zip(rec, cases):
+        k = len(rates)
+        r[E.REC_KL], r[E.REC_KM] = k, 1
+        r[E.REC_L:E.REC_L + k] = rates; r[E.REC_TL + 1:E.REC_TL + k] = shifts
+        r[E.REC_M] = 0.25
+    sr, sc, kc, n = device.summarize_records_device(torch.from_numpy(rec).cuda(), e0, nb)
+    torch.cuda.synchronize()
+    edges = np.arange(e0, e0 + nb + 1)
+    want = np.zeros(nb); cnt = np.zeros(nb, dtype=np.int64)
+    for rates, shifts in cases:
+        h = np.histogram(shifts, bins=edges)[0]
+        want += np.array(rates)[np.cumsum(h)]; cnt += h
+    assert np.array_equal(sr[0].cpu().numpy(), want) and np.array_equal(sc[0].cpu().numpy(), cnt)
+    assert np.array_equal(sr[1].cpu().numpy(), np.full(nb, 5 * 0.25))
+    assert kc[0].cpu().numpy()[:4].tolist() == [1, 2, 1, 1] and kc[1].cpu().numpy()[0] == 5
