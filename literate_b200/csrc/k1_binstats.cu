@@ -304,8 +304,10 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     LR_REQUIRE(n_bins >= 1, "lr_bin_accumulate: n_bins must be >= 1");
     LR_REQUIRE(fe_ref > 0.0 && fe_ref <= 1.0, "lr_bin_accumulate: fe_ref must lie in (0, 1]");
     LR_REQUIRE(d_acc != nullptr && (n == 0 || (d_ts != nullptr && d_te != nullptr)), "lr_bin_accumulate: null pointer");
-    if (first_bin <= -(1ll << 30) || first_bin >= (1ll << 30) || n_bins > 24576) {
-        lr_set_error("lr_bin_accumulate: |first_bin| must be < 2^30 and n_bins <= 24576");
+    const size_t smem_need = 9 * (size_t)n_bins * sizeof(unsigned);
+    if (first_bin <= -(1ll << 30) || first_bin >= (1ll << 30) || smem_need + 1024 > (size_t)h->max_smem_optin) {
+        lr_set_error("lr_bin_accumulate: |first_bin| must be < 2^30 and the 9 x n_bins shared-memory counters must fit one SM (n_bins <= %d)",
+                     (int)(((size_t)h->max_smem_optin - 1024) / (9 * sizeof(unsigned))));
         return LR_ERR_UNSUPPORTED;
     }
     if (n == 0) return LR_OK;

@@ -110,6 +110,13 @@ def test_many_bins_and_single_bin(device):
         assert O.events_in_bin(ts, te, j, j + 1) == (got.sp[0, j], got.ex[0, j], got.br[0, j])
 
 
+def test_too_many_bins_is_refused_with_a_message(device):
+    from literate_b200.engine import NativeError
+    ts = np.array([0.0, 10.0]); te = np.array([7000.5, 20.5])
+    with pytest.raises(NativeError, match="n_bins <= "):
+        device.bin_stats(ts, te)
+
+
 def test_replicates_and_ragged_pitch(device):
     import torch
     n_rep, n = 5, 3001      # odd n: rows are not 16-byte aligned -> scalar load path for odd replicates
