@@ -428,8 +428,10 @@ struct ChainRegs {
     int poi_is_init;
     int consistent;                // priorA is the prior of the current state under the current hyper-parameters and poiA
                                    // (false only between the initial state of :227 and the first accepted proposal)
-    long long cnt[8];
 };
+// per-launch event counters (added to the chain's 64-bit counters when the launch ends; kept apart from ChainRegs so that
+// they stay in registers in both builds)
+struct Counters { unsigned v[8]; };
 // hyper-parameters and table ids as seen from the side a proposal works on
 struct SideView {
     double g_cur, lg_cur, g_oth, lg_oth;
@@ -456,30 +458,30 @@ __device__ __forceinline__ SideView side_view(const Hyper& hp, bool birth) {
 
 // birth block (:254-262) / death block (:264-272) on side `cur`, delta form.  Returns false if the caller must use slow_step.
 template <bool C>
-__device__ __forceinline__ bool block_step(Side& cur, const SideView v, ChainRegs& c, const DataView& d,
+__device__ __forceinline__ bool block_step(Side& cur, const SideView v, ChainRegs& c, Counters& n, const DataView& d,
                                            const lr_chain_config& cfg, const Draws& q, bool frozen, int lane) {
     if (!c.consistent || frozen) return false;
     const bool rate = (q.kind >> 1) == DK_BLOCK_RATE || cur.K == 1;
     if (rate) {
         // update_multiplier_freq (:165-176): q * m as the reference does; the log-rate follows by addition.
         // x = sum_k (beta A_k + 1) dlt_k - (beta B_k + g)(r'_k - r_k)  +  hasting (= sum_k dlt_k)
-        c.cnt[3]++; c.cnt[2]++;
+        n.v[3]++; n.v[2]++;
         const bool on = lane < cur.K;
         const double dl = on ? q.dlt : 0.0;
         const double rn = cur.r * (on ? q.m : 1.0);
         const double x = warp_sum((c.beta * cur.A + 2.0) * dl - (c.beta * cur.B + v.g_cur) * (rn - cur.r));
-        if (mh_accept(x, q)) { cur.r = rn; cur.lr += dl; c.cnt[1]++; }
+        if (mh_accept(x, q)) { cur.r = rn; cur.lr += dl; n.v[1]++; }
     } else if (!cfg.real_move_shift) {
         // The reference's move proposes the current state (:184-185): prior - priorA = 0, always accepted, nothing changes.
-        c.cnt[4]++; c.cnt[2]++; c.cnt[1]++;
+        n.v[4]++; n.v[2]++; n.v[1]++;
     } else {
-        c.cnt[4]++;
+        n.v[4]++;
         Side nw;
         if (propose_move<false>(cur, nw, d, v.tabA, v.tabB, q, lane)) {
-            c.cnt[2]++;
+            n.v[2]++;
             const bool on = lane < cur.K;
             const double x = warp_sum(on ? c.beta * ((nw.A - cur.A) * cur.lr - (nw.B - cur.B) * cur.r) : 0.0);
-            if (mh_accept(x, q)) { cur.t = nw.t; cur.A = nw.A; cur.B = nw.B; cur.jb = nw.jb; c.cnt[1]++; }
+            if (mh_accept(x, q)) { cur.t = nw.t; cur.A = nw.A; cur.B = nw.B; cur.jb = nw.jb; n.v[1]++; }
         }
     }
     return true;
@@ -487,25 +489,25 @@ __device__ __forceinline__ bool block_step(Side& cur, const SideView v, ChainReg
 
 // RJMCMC (:71-97, :274-279) on side `cur`, delta form.  Returns false if the caller must use slow_step.
 template <bool C>
-__device__ __forceinline__ bool rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+__device__ __forceinline__ bool rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, Counters& n, const DataView& d,
                                         const Draws& q, bool frozen, int lane) {
     if (!c.consistent || frozen) return false;
     Side nw = cur;
     double hasting = 0.0;
     bool ok = true;
     if ((q.kind >> 1) == DK_RJ_ADD) {
-        if (cur.K >= LR_KMAX) { ok = false; c.cnt[7]++; }
+        if (cur.K >= LR_KMAX) { ok = false; n.v[7]++; }
         else ok = propose_add<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
     } else if (cur.K > 1) {
         propose_remove<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
     }
     if (ok) {
-        c.cnt[2]++;
+        n.v[2]++;
         const double poiN = poisson_prior(nw.K, c.hp.poi, c.hp.lpoi, c_lnfact) + poisson_prior(oth.K, c.hp.poi, c.hp.lpoi, c_lnfact);   // :279
         const double e_new = lane < nw.K ? (c.beta * nw.A + 1.0) * nw.lr - (c.beta * nw.B + v.g_cur) * nw.r : 0.0;
         const double e_old = lane < cur.K ? (c.beta * cur.A + 1.0) * cur.lr - (c.beta * cur.B + v.g_cur) * cur.r : 0.0;
         const double x = warp_sum(e_new - e_old) + (double)(nw.K - cur.K) * (2.0 * v.lg_cur - d.log_span) + (poiN - c.poiA) + hasting;
-        if (mh_accept(x, q)) { cur = nw; c.poiA = poiN; c.cnt[1]++; }
+        if (mh_accept(x, q)) { cur = nw; c.poiA = poiN; n.v[1]++; }
     }
     return true;
 }
@@ -577,13 +579,13 @@ __device__ __noinline__ SlowOut slow_step(Side cur, Side oth, const SideView v, 
     o.cur = cur;
     return o;
 }
-__device__ __forceinline__ void run_slow(Side& cur, const Side& oth, const SideView v, ChainRegs& c, const DataView& d,
+__device__ __forceinline__ void run_slow(Side& cur, const Side& oth, const SideView v, ChainRegs& c, Counters& n, const DataView& d,
                                          const lr_chain_config& cfg, const Draws& q, bool frozen, int lane) {
     const int kind = q.kind >> 1;
     const SlowOut o = slow_step(cur, oth, v, c.hp, c.priorA, c.poiA, c.beta, c.consistent, d, cfg.real_move_shift, q, frozen, lane);
     cur = o.cur; c.priorA = o.priorA; c.poiA = o.poiA; c.consistent = o.consistent;
-    if (kind <= DK_BLOCK_MOVE) c.cnt[(kind == DK_BLOCK_RATE || cur.K == 1) ? 3 : 4]++;
-    c.cnt[2] += o.evaluated; c.cnt[1] += o.accepted; c.cnt[7] += o.cap_reject;
+    if (kind <= DK_BLOCK_MOVE) n.v[(kind == DK_BLOCK_RATE || cur.K == 1) ? 3 : 4]++;
+    n.v[2] += o.evaluated; n.v[1] += o.accepted; n.v[7] += o.cap_reject;
 }
 
 // Gibbs on the hyper-priors (:281-287), always accepted (:313); one iteration in a thousand, kept out of line.
@@ -721,8 +723,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     ChainRegs c;
     c.hp.gL = S->gL; c.hp.gM = S->gM; c.hp.lgL = log(c.hp.gL); c.hp.lgM = log(c.hp.gM); c.hp.poi = S->poi; c.hp.lpoi = log(c.hp.poi);
     c.priorA = S->priorA; c.poiA = S->poiA; c.beta = S->beta; c.poi_is_init = S->poi_is_init; c.consistent = (int)S->consistent;
+    Counters n;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) c.cnt[i] = S->counters[i];
+    for (int i = 0; i < 8; ++i) n.v[i] = 0u;
     const bool frozen = (d.end_time - d.start_time) <= LR_MIN_DT;      // guard :290 rejects everything
 
     const long long s_every = P.sample_every > 0 ? P.sample_every : 1;
@@ -752,25 +755,25 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
         if (kind <= DK_BLOCK_MOVE) {
             if constexpr (C) {
                 Side& cur = birth ? L : M;
-                if (!block_step<C>(cur, side_view(c.hp, birth), c, d, cfg, q, frozen, lane))
-                    run_slow(cur, birth ? M : L, side_view(c.hp, birth), c, d, cfg, q, frozen, lane);
+                if (!block_step<C>(cur, side_view(c.hp, birth), c, n, d, cfg, q, frozen, lane))
+                    run_slow(cur, birth ? M : L, side_view(c.hp, birth), c, n, d, cfg, q, frozen, lane);
             } else {
-                if (birth) { if (!block_step<C>(L, side_view(c.hp, true), c, d, cfg, q, frozen, lane)) run_slow(L, M, side_view(c.hp, true), c, d, cfg, q, frozen, lane); }
-                else { if (!block_step<C>(M, side_view(c.hp, false), c, d, cfg, q, frozen, lane)) run_slow(M, L, side_view(c.hp, false), c, d, cfg, q, frozen, lane); }
+                if (birth) { if (!block_step<C>(L, side_view(c.hp, true), c, n, d, cfg, q, frozen, lane)) run_slow(L, M, side_view(c.hp, true), c, n, d, cfg, q, frozen, lane); }
+                else { if (!block_step<C>(M, side_view(c.hp, false), c, n, d, cfg, q, frozen, lane)) run_slow(M, L, side_view(c.hp, false), c, n, d, cfg, q, frozen, lane); }
             }
         } else if (kind != DK_GIBBS) {
-            c.cnt[5]++;
+            n.v[5]++;
             if constexpr (C) {
                 Side& cur = birth ? L : M;
                 const Side& oth = birth ? M : L;
-                if (!rj_step<C>(cur, oth, side_view(c.hp, birth), c, d, q, frozen, lane))
-                    run_slow(cur, oth, side_view(c.hp, birth), c, d, cfg, q, frozen, lane);
+                if (!rj_step<C>(cur, oth, side_view(c.hp, birth), c, n, d, q, frozen, lane))
+                    run_slow(cur, oth, side_view(c.hp, birth), c, n, d, cfg, q, frozen, lane);
             } else {
-                if (birth) { if (!rj_step<C>(L, M, side_view(c.hp, true), c, d, q, frozen, lane)) run_slow(L, M, side_view(c.hp, true), c, d, cfg, q, frozen, lane); }
-                else { if (!rj_step<C>(M, L, side_view(c.hp, false), c, d, q, frozen, lane)) run_slow(M, L, side_view(c.hp, false), c, d, cfg, q, frozen, lane); }
+                if (birth) { if (!rj_step<C>(L, M, side_view(c.hp, true), c, n, d, q, frozen, lane)) run_slow(L, M, side_view(c.hp, true), c, n, d, cfg, q, frozen, lane); }
+                else { if (!rj_step<C>(M, L, side_view(c.hp, false), c, n, d, q, frozen, lane)) run_slow(M, L, side_view(c.hp, false), c, n, d, cfg, q, frozen, lane); }
             }
         } else {
-            c.cnt[6]++;
+            n.v[6]++;
             if constexpr (C) {
                 gibbs_step_ref(L, M, c, d, cfg.poisson_prior == 0.0 ? 1 : 0, cfg.use_rate_HP, rng, it, frozen, lane);
             } else {
@@ -778,9 +781,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
                 c.hp = g.hp; c.priorA = g.priorA; c.poi_is_init = g.poi_is_init;
             }
             c.consistent = 1;
-            c.cnt[1]++;
+            n.v[1]++;
         }
-        c.cnt[0]++;
 
         if (it == next_event) {                     // one comparison per iteration for the two rare events
             if (it == next_resync) { resync_log_rates(L, M, lane); next_resync += LR_RESYNC; }
@@ -798,8 +800,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     if (lane == 0) {
         S->it = it1;
         S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init; S->consistent = (unsigned)c.consistent;
+        S->counters[0] += P.n_iter;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) S->counters[i] = c.cnt[i];
+        for (int i = 1; i < 8; ++i) S->counters[i] += (long long)n.v[i];
     }
 }
 
@@ -1210,6 +1213,7 @@ extern "C" int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int6
 extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* d_records, void* stream) {
     LR_REQUIRE(c != nullptr, "lr_chains_run: null chains");
     LR_REQUIRE(n_iter >= 0 && sample_every >= 0, "lr_chains_run: negative count");
+    LR_REQUIRE(n_iter <= 2000000000ll, "lr_chains_run: at most 2e9 iterations per launch (32-bit per-launch counters); split the run");
     if (n_iter == 0) return LR_OK;
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
