@@ -7,6 +7,7 @@ everything it produces is committed so that no test reads /root/reference at run
     python oracle/make_golden.py kat         # seconds: exact log files of short reference runs
     python oracle/make_golden.py posterior   # minutes: 8 reference chains per data set -> summaries
     python oracle/make_golden.py posterior_flags   # ~10 min: 8 reference chains per non-default flag set (example TAD)
+    python oracle/make_golden.py prior_only   # ~2 min: 8 ORACLE chains on the example window with all statistics zero
     python oracle/make_golden.py plots       # ~30 s: the reference's plotRJforward.v3.py on two of the kat runs -> .r files
 
 The reference writes next to its input (LiteRateForward.py:479-491), so inputs are copied to
@@ -184,6 +185,34 @@ def posterior_flags(n_chains=8, n_it=200001, s=100):
         print(tag, "done:", [round(c["wall_s"]) for c in chains], flush=True)
 
 
+def _prior_chain(seed):
+    """One oracle chain (the restatement that reproduces the reference's logs byte for byte on real data) on the time window
+    of the example table with EVERY sufficient statistic set to zero: the likelihood is identically 0, so the chain samples
+    the prior the reference's proposals and acceptance rule define (number of shifts, shift times, rates, hyper-priors)."""
+    from oracle import literate_oracle as O
+    lin = O.read_lineages(os.path.join(GOLD, "inputs", "example_dataTAD.txt"))
+    nb = int(lin.end_time) - int(lin.start_time)
+    st = O.BinStats(int(lin.start_time), np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.int64), np.zeros(nb))
+    cfg = O.ChainConfig(n_iterations=300001, s_freq=100, calc_adequacy=0)
+    logs = O.run_chain(lin, st, cfg, seed)
+    mc = np.array([[float(x) for x in l.split("\t")] for l in logs.mcmc.getvalue().splitlines()])
+    b = int(0.2 * len(mc))
+    post = mc[b:]
+    return {"seed": seed, "K_l": O.k_pmf(mc[:, 6]), "K_m": O.k_pmf(mc[:, 7]), "lambda_avg": float(post[:, 4].mean()),
+            "mu_avg": float(post[:, 5].mean()), "prior_mean": float(post[:, 3].mean()), "gamma_hp_l": float(post[:, 10].mean()),
+            "poisson_hp": float(post[:, 12].mean()), "n_iterations": 300001, "s_freq": 100}
+
+
+def prior_only(n_chains=8):
+    from concurrent.futures import ProcessPoolExecutor
+    with ProcessPoolExecutor(n_chains) as ex:
+        chains = list(ex.map(_prior_chain, [501 + i for i in range(n_chains)]))
+    with open(os.path.join(GOLD, "posterior", "prior_only.json"), "w") as fh:
+        json.dump({"data": "example_tad window, all statistics zero", "generator": "oracle.run_chain (pinned to the reference)", "burnin": 0.2,
+                   "chains": chains}, fh, indent=1)
+    print("prior_only done")
+
+
 def posterior(n_chains=8):
     out = os.path.join(GOLD, "posterior")
     os.makedirs(out, exist_ok=True)
@@ -207,4 +236,4 @@ def posterior(n_chains=8):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "kat"
-    {"kat": kat, "posterior": posterior, "posterior_flags": posterior_flags, "plots": plots}[what]()
+    {"kat": kat, "posterior": posterior, "posterior_flags": posterior_flags, "prior_only": prior_only, "plots": plots}[what]()

@@ -266,3 +266,34 @@ def test_posterior_matches_reference_for_every_sampler_configuration(device, tag
     cnt = ch.counters().sum(0)
     if tag == "tad_constrates":
         assert cnt[5] == 0 and abs(cnt[6] / cnt[0] - 0.2) < 0.005          # every r0 >= .8 goes to the Gibbs branch (:281)
+
+
+def test_prior_only_matches_the_oracle_chain(device):
+    """All sufficient statistics zero: the likelihood vanishes and the chains sample the prior that the proposals, the
+    Hastings/Jacobian terms and the hyper-prior Gibbs steps define.  64 GPU chains against 8 oracle chains (the restatement
+    that reproduces the reference byte for byte; tests/golden/posterior/prior_only.json, `make_golden.py prior_only`):
+    number-of-rates distribution and the Poisson hyper-parameter agree within Monte-Carlo error."""
+    with open(os.path.join(GOLD, "posterior", "prior_only.json")) as fh:
+        ref = json.load(fh)["chains"]
+    lin = O.read_lineages(golden_input("example_dataTAD.txt"))
+    nb = int(lin.end_time) - int(lin.start_time)
+    z = np.zeros((1, nb))
+    ds = E.Dataset(device, E.BinStats(int(lin.start_time), z.astype(np.int64), z.astype(np.int64), z), 0, lin.start_time, lin.end_time)
+    ch = E.Chains(ds, 64, seed=606)
+    recs = ch.run(ref[0]["n_iterations"], ref[0]["s_freq"])
+    assert np.all(recs[:, :, E.REC_LIK] == 0.0)
+    post = recs[recs.shape[0] // 5:]
+
+    def frac(pmf, k):
+        return pmf.get(str(k), 0) / sum(pmf.values())
+
+    def close(name, a, b):
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) < 4.5 * se, (name, a.mean(), b.mean(), se)
+
+    for col, key in ((E.REC_KL, "K_l"), (E.REC_KM, "K_m")):
+        close(key + " mean", post[:, :, col].mean(0), [sum(int(k) * v for k, v in r[key].items()) / sum(r[key].values()) for r in ref])
+        for k in (1, 2, 3):
+            close("%s = %d" % (key, k), (post[:, :, col] == k).mean(0), [frac(r[key], k) for r in ref])
+    close("poisson_hp", post[:, :, E.REC_POI].mean(0), [r["poisson_hp"] for r in ref])
