@@ -194,6 +194,7 @@ def _summaries(recs, lin, burnin=0.2):
         rowsM = [np.concatenate([x[E.REC_M:E.REC_M + int(x[E.REC_KM])], x[E.REC_TM + 1:E.REC_TM + int(x[E.REC_KM])]]) for x in r]
         out.append({"K_l": r[:, E.REC_KL].mean(), "K_m": r[:, E.REC_KM].mean(), "lik": r[:, E.REC_LIK].mean(),
                     "lam": r[:, E.REC_LAVG].mean(), "mu": r[:, E.REC_MAVG].mean(),
+                    "gL": r[:, E.REC_GL].mean(), "gM": r[:, E.REC_GM].mean(), "poi": r[:, E.REC_POI].mean(),
                     "birth": O.marginal_rates(rowsL, lin.end_time, lin.start_time, 0).mean(0),
                     "death": O.marginal_rates(rowsM, lin.end_time, lin.start_time, 0).mean(0)})
     return out
@@ -207,6 +208,9 @@ def _compare_with_reference(mine, ref, what=("K_l", "K_m", "lik", "lambda_avg", 
     def compare(name, a, b, floor=0.0):
         a, b = np.asarray(a, float), np.asarray(b, float)
         se = np.sqrt(a.var(0, ddof=1) / len(a) + b.var(0, ddof=1) / len(b)) + floor
+        if np.all(se == 0):                      # a constant on both sides (hyper-parameters that are never resampled)
+            assert np.allclose(a.mean(0), b.mean(0), rtol=1e-12), (name, a.mean(0), b.mean(0))
+            return
         z = np.abs(a.mean(0) - b.mean(0)) / se
         assert np.all(z < 4.5), (name, float(np.max(z)), a.mean(0), b.mean(0))
 
@@ -219,6 +223,10 @@ def _compare_with_reference(mine, ref, what=("K_l", "K_m", "lik", "lambda_avg", 
     compare("mu_avg", [m["mu"] for m in mine], [r["mu_avg"] for r in ref])
     compare("birth", [m["birth"] for m in mine], [r["birth_rate_mean"] for r in ref], floor=1e-6)
     compare("death", [m["death"] for m in mine], [r["death_rate_mean"] for r in ref], floor=1e-6)
+    # hyper-parameters drawn by the Gibbs steps (:99-108, :210-213): integer-shape Gamma and Marsaglia-Tsang samplers
+    compare("gamma_rate_hp_BI", [m["gL"] for m in mine], [r["gamma_hp_l"] for r in ref])
+    compare("gamma_rate_hp_D", [m["gM"] for m in mine], [r["gamma_hp_m"] for r in ref])
+    compare("poisson_rate_hp", [m["poi"] for m in mine], [r["poisson_hp"] for r in ref])
 
 
 @pytest.mark.parametrize("data,n_iter,s", [("example_tad", 300000, 100), ("metal_bands", 400000, 200)])
@@ -297,3 +305,20 @@ def test_prior_only_matches_the_oracle_chain(device):
         for k in (1, 2, 3):
             close("%s = %d" % (key, k), (post[:, :, col] == k).mean(0), [frac(r[key], k) for r in ref])
     close("poisson_hp", post[:, :, E.REC_POI].mean(0), [r["poisson_hp"] for r in ref])
+
+
+def test_gibbs_poisson_rate_draws_are_gamma(device):
+    """With -const_rates 1 the dimension never changes (K_l = K_m = 1) and a fifth of the iterations redraw the Poisson rate
+    from Gamma(2 + K_l + K_m, scale 1/3) (get_post_rj_HP, :99-108): the logged values must be i.i.d. draws of Gamma(4, 1/3)
+    (Kolmogorov-Smirnov against scipy), which exercises the device's integer-shape Gamma sampler and the Philox streams."""
+    import scipy.stats
+    lin, st, ds, ch = _setup(device, golden_input("example_dataTAD.txt"), n_chains=32, seed=99, const_rates=1)
+    recs = ch.run(20001, 100)
+    x = recs[5:, :, E.REC_POI].ravel()                 # 50 samples apart: a fresh draw almost surely (1 - 0.8^100)
+    assert len(np.unique(x)) > 0.99 * len(x)
+    ks = scipy.stats.kstest(x, scipy.stats.gamma(4.0, scale=1.0 / 3.0).cdf)
+    assert ks.pvalue > 1e-3, ks
+    assert abs(x.mean() - 4.0 / 3.0) < 5 * np.sqrt((4.0 / 9.0) / len(x))
+    # independent streams: chains are uncorrelated
+    c = np.corrcoef(recs[5:, :8, E.REC_POI].T)
+    assert np.max(np.abs(c - np.eye(8))) < 0.25
