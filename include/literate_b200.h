@@ -137,6 +137,22 @@ int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int
                        const double* gamma_rate, const double* poi_lambda,
                        double* lik, double* prior_rates, double* prior_poi, double* adequacy);
 
+/* One reversible-jump proposal per explicit state with EXPLICIT draws, HOST buffers (parity entry point for the proposal
+ * arithmetic of add_shift_RJ_weighted_mean / remove_shift_RJ_weighted_mean, LiteRateForward.py:29-69, and the acceptance
+ * ratio of :296-313).  State arrays as lr_state_eval_host; additionally per state
+ *   beta (NULL: 1), poiA   inverse temperature and the stored (possibly stale) Poisson prior term priorPoiA (:300-304)
+ *   side                   1 birth side, 0 death side
+ *   kind, idx              2 add-shift inside segment idx (0-based); 3 remove interior shift idx (1..K-1)
+ *   u_t, u_beta            add-shift: position inside the segment as a fraction, Beta(10,10) variate
+ * Outputs: ok (0 = rejected by the spacing guard :290 or at capacity), K_new, rates_new / times_new [n][LR_KMAX] of the proposed
+ * side, hasting = log q-ratio + log Jacobian (:47, :69), x = beta (lik' - lik) + (prior' - prior) + hasting with the new
+ * Poisson prior term against poiA (:279, :313). */
+int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int32_t* K_l, const int32_t* K_m,
+                          const double* L, const double* M, const double* tL, const double* tM,
+                          const double* gamma_rate, const double* poi_lambda, const double* beta, const double* poiA,
+                          const int32_t* side, const int32_t* kind, const int32_t* idx, const double* u_t, const double* u_beta,
+                          int32_t* ok, int32_t* K_new, double* rates_new, double* times_new, double* hasting, double* x);
+
 /* Validation path: the Keiding log-likelihood (BD_lik_Keiding, :137-148; -model_BDI 2) of n_states states evaluated DIRECTLY
  * over the lineages without binning -- the per-lineage formulation of the reference's ancestor
  * (other/LiteRateBDI_ext.py:124-160, get_BDlik) -- to cross-check lr_bin_stats + lr_state_eval at full size.

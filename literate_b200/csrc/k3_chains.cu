@@ -487,27 +487,44 @@ __device__ __forceinline__ bool block_step(Side& cur, const SideView v, ChainReg
     return true;
 }
 
+// One RJ proposal in delta form: the proposed side `nw`, its Hastings/Jacobian term, the new Poisson prior and the log
+// acceptance ratio x.  Shared by the loop (rj_step) and by the parity entry point lr_proposal_eval_host.
+// Returns false if nothing is to be evaluated (capacity reached: *cap set; or spacing guard :290).
+template <bool C>
+__device__ __forceinline__ bool rj_propose(const Side& cur, const Side& oth, const SideView v, const Hyper& hp, double beta, double poiA,
+                                           const DataView& d, const Draws& q, int lane, Side& nw, double& hasting, double& poiN, double& x,
+                                           bool& cap) {
+    nw = cur;
+    hasting = 0.0;
+    cap = false;
+    bool ok = true;
+    if ((q.kind >> 1) == DK_RJ_ADD) {
+        if (cur.K >= LR_KMAX) { ok = false; cap = true; }
+        else ok = propose_add<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
+    } else if (cur.K > 1) {
+        propose_remove<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
+    }
+    if (!ok) return false;
+    poiN = poisson_prior(nw.K, hp.poi, hp.lpoi, c_lnfact) + poisson_prior(oth.K, hp.poi, hp.lpoi, c_lnfact);   // :279
+    const double e_new = lane < nw.K ? (beta * nw.A + 1.0) * nw.lr - (beta * nw.B + v.g_cur) * nw.r : 0.0;
+    const double e_old = lane < cur.K ? (beta * cur.A + 1.0) * cur.lr - (beta * cur.B + v.g_cur) * cur.r : 0.0;
+    x = warp_sum(e_new - e_old) + (double)(nw.K - cur.K) * (2.0 * v.lg_cur - d.log_span) + (poiN - poiA) + hasting;
+    return true;
+}
+
 // RJMCMC (:71-97, :274-279) on side `cur`, delta form.  Returns false if the caller must use slow_step.
 template <bool C>
 __device__ __forceinline__ bool rj_step(Side& cur, const Side& oth, const SideView v, ChainRegs& c, Counters& n, const DataView& d,
                                         const Draws& q, bool frozen, int lane) {
     if (!c.consistent || frozen) return false;
-    Side nw = cur;
-    double hasting = 0.0;
-    bool ok = true;
-    if ((q.kind >> 1) == DK_RJ_ADD) {
-        if (cur.K >= LR_KMAX) { ok = false; n.v[7]++; }
-        else ok = propose_add<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
-    } else if (cur.K > 1) {
-        propose_remove<C, false>(cur, nw, d, v.tabA, v.tabB, q, lane, hasting);
-    }
-    if (ok) {
+    Side nw;
+    double hasting, poiN, x;
+    bool cap;
+    if (rj_propose<C>(cur, oth, v, c.hp, c.beta, c.poiA, d, q, lane, nw, hasting, poiN, x, cap)) {
         n.v[2]++;
-        const double poiN = poisson_prior(nw.K, c.hp.poi, c.hp.lpoi, c_lnfact) + poisson_prior(oth.K, c.hp.poi, c.hp.lpoi, c_lnfact);   // :279
-        const double e_new = lane < nw.K ? (c.beta * nw.A + 1.0) * nw.lr - (c.beta * nw.B + v.g_cur) * nw.r : 0.0;
-        const double e_old = lane < cur.K ? (c.beta * cur.A + 1.0) * cur.lr - (c.beta * cur.B + v.g_cur) * cur.r : 0.0;
-        const double x = warp_sum(e_new - e_old) + (double)(nw.K - cur.K) * (2.0 * v.lg_cur - d.log_span) + (poiN - c.poiA) + hasting;
         if (mh_accept(x, q)) { cur = nw; c.poiA = poiN; n.v[1]++; }
+    } else if (cap) {
+        n.v[7]++;
     }
     return true;
 }
@@ -925,6 +942,58 @@ __global__ void k2_state_eval_kernel(int n, const int* __restrict__ rep, const i
     }
 }
 
+// K2b: one RJ proposal per explicit state with explicit draws (parity entry point; one warp per state).
+// kind 2 = add-shift on segment idx at t_idx + u_t * gap with Beta variate u_beta; kind 3 = remove interior shift idx.
+__global__ void k2_proposal_eval_kernel(int n, const int* __restrict__ rep, const int* __restrict__ K_l, const int* __restrict__ K_m,
+                                        const double* __restrict__ Lr, const double* __restrict__ Mr,
+                                        const double* __restrict__ tL, const double* __restrict__ tM,
+                                        const double* __restrict__ gamma_rate, const double* __restrict__ poi_lambda,
+                                        const double* __restrict__ beta_in, const double* __restrict__ poiA_in,
+                                        const int* __restrict__ side, const int* __restrict__ kind, const int* __restrict__ idx,
+                                        const double* __restrict__ u_t, const double* __restrict__ u_beta,
+                                        const double* tab, const double* cst, int nb, int s0f, double start_time, double end_time,
+                                        int* __restrict__ ok_out, int* __restrict__ K_new, double* __restrict__ rates_new,
+                                        double* __restrict__ times_new, double* __restrict__ hasting_out, double* __restrict__ x_out) {
+    const int lane = threadIdx.x & 31;
+    const int i = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (i >= n) return;
+    const DataView d = make_view(tab, cst, rep ? rep[i] : 0, nb, s0f, start_time, end_time);
+    Side L, M;
+    L.K = K_l[i]; M.K = K_m[i];
+    const bool inL = lane < L.K && lane < LR_KMAX, inM = lane < M.K && lane < LR_KMAX;
+    L.r = inL ? Lr[(size_t)i * LR_KMAX + lane] : 0.0; L.lr = inL ? log(L.r) : 0.0;
+    L.t = lane == 0 ? start_time : (inL ? tL[(size_t)i * LR_KMAX + lane] : 0.0);
+    M.r = inM ? Mr[(size_t)i * LR_KMAX + lane] : 0.0; M.lr = inM ? log(M.r) : 0.0;
+    M.t = lane == 0 ? start_time : (inM ? tM[(size_t)i * LR_KMAX + lane] : 0.0);
+    side_stats(L, d, T_AB, T_BB, lane);
+    side_stats(M, d, T_AD, T_BD, lane);
+    Hyper hp;
+    hp.gL = gamma_rate ? gamma_rate[2 * i] : 1.0; hp.gM = gamma_rate ? gamma_rate[2 * i + 1] : 1.0;
+    hp.poi = poi_lambda ? poi_lambda[i] : 1.0;
+    hp.lgL = log(hp.gL); hp.lgM = log(hp.gM); hp.lpoi = log(hp.poi);
+    const bool birth = side[i] != 0;
+    const Side& cur = birth ? L : M;
+    const Side& oth = birth ? M : L;
+    Draws q;
+    q.u_acc = 0.5; q.thr_hi = 0.0; q.thr_lo = 0.0; q.m = 1.0; q.dlt = 0.0;
+    q.kind = ((kind[i] == 2 ? DK_RJ_ADD : DK_RJ_REMOVE) << 1) | (birth ? 1 : 0);
+    // the index draws that select exactly segment / shift idx (propose_add: (int)(u K); propose_remove: 1 + (int)(u (K-1)))
+    q.u_idx = kind[i] == 2 ? ((double)idx[i] + 0.5) / (double)cur.K : ((double)(idx[i] - 1) + 0.5) / (double)(cur.K > 1 ? cur.K - 1 : 1);
+    q.u_t = u_t[i];
+    const double ub = u_beta[i];
+    q.w = log((1.0 - ub) / ub);                                                           // :41-42
+    q.ln_beta = (LR_SHAPE_BETA - 1.0) * (log(ub) + log1p(-ub)) - LR_BETA_NORM;            // beta.logpdf(u; 10, 10), :22-23
+    Side nw;
+    double hasting = 0.0, poiN = 0.0, x = 0.0;
+    bool cap = false;
+    const bool ok = rj_propose<false>(cur, oth, side_view(hp, birth), hp, beta_in ? beta_in[i] : 1.0, poiA_in[i], d, q, lane, nw, hasting, poiN, x, cap);
+    if (lane == 0) { ok_out[i] = ok ? 1 : 0; K_new[i] = ok ? nw.K : cur.K; hasting_out[i] = ok ? hasting : 0.0; x_out[i] = ok ? x : 0.0; }
+    if (lane < LR_KMAX) {
+        rates_new[(size_t)i * LR_KMAX + lane] = (ok && lane < nw.K) ? nw.r : 0.0;
+        times_new[(size_t)i * LR_KMAX + lane] = (ok && lane < nw.K) ? (lane == 0 ? start_time : nw.t) : 0.0;
+    }
+}
+
 __global__ void k3_set_beta_kernel(ChainState* st, int n, const double* beta) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st[i].beta = beta[i];
@@ -1143,6 +1212,60 @@ extern "C" int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep
     if (prior_rates) LR_CUDA(cudaMemcpyAsync(prior_rates, w + o_pr, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     if (prior_poi) LR_CUDA(cudaMemcpyAsync(prior_poi, w + o_pp, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     if (adequacy) LR_CUDA(cudaMemcpyAsync(adequacy, w + o_ad, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+    return LR_OK;
+}
+
+extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int32_t* K_l, const int32_t* K_m,
+                                     const double* L, const double* M, const double* tL, const double* tM,
+                                     const double* gamma_rate, const double* poi_lambda, const double* beta, const double* poiA,
+                                     const int32_t* side, const int32_t* kind, const int32_t* idx, const double* u_t, const double* u_beta,
+                                     int32_t* ok, int32_t* K_new, double* rates_new, double* times_new, double* hasting, double* x) {
+    LR_REQUIRE(ds && K_l && K_m && L && M && tL && tM && poiA && side && kind && idx && u_t && u_beta && ok && K_new && rates_new && times_new && hasting && x,
+               "lr_proposal_eval_host: null pointer");
+    LR_REQUIRE(n >= 0, "lr_proposal_eval_host: n < 0");
+    if (n == 0) return LR_OK;
+    for (int i = 0; i < n; ++i) {
+        LR_REQUIRE(K_l[i] >= 1 && K_l[i] <= LR_KMAX && K_m[i] >= 1 && K_m[i] <= LR_KMAX, "lr_proposal_eval_host: K out of 1..%d at state %d", LR_KMAX, i);
+        LR_REQUIRE(!rep || (rep[i] >= 0 && rep[i] < ds->n_rep), "lr_proposal_eval_host: replicate index out of range at state %d", i);
+        const int K = side[i] ? K_l[i] : K_m[i];
+        LR_REQUIRE(kind[i] == 2 || kind[i] == 3, "lr_proposal_eval_host: kind must be 2 (add-shift) or 3 (remove-shift) at state %d", i);
+        LR_REQUIRE(kind[i] == 2 ? (idx[i] >= 0 && idx[i] < K) : (K > 1 && idx[i] >= 1 && idx[i] <= K - 1), "lr_proposal_eval_host: index out of range at state %d", i);
+        LR_REQUIRE(u_beta[i] > 0.0 && u_beta[i] < 1.0 && u_t[i] >= 0.0 && u_t[i] <= 1.0, "lr_proposal_eval_host: draws outside (0,1) at state %d", i);
+    }
+    lr_handle_t h = ds->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t nK = (size_t)n * LR_KMAX * 8, n4 = (size_t)n * 4, n8 = (size_t)n * 8;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
+    const size_t o_rep = take(n4), o_kl = take(n4), o_km = take(n4), o_L = take(nK), o_M = take(nK), o_tL = take(nK), o_tM = take(nK);
+    const size_t o_g = take(2 * n8), o_p = take(n8), o_b = take(n8), o_pa = take(n8), o_sd = take(n4), o_kd = take(n4), o_ix = take(n4);
+    const size_t o_ut = take(n8), o_ub = take(n8), o_ok = take(n4), o_kn = take(n4), o_rn = take(nK), o_tn = take(nK), o_h = take(n8), o_x = take(n8);
+    int rc = lr_ws_reserve(h, off);
+    if (rc != LR_OK) return rc;
+    char* w = (char*)h->ws;
+    cudaStream_t st = h->stream;
+    auto up = [&](size_t o, const void* src, size_t b) { return src ? cudaMemcpyAsync(w + o, src, b, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    LR_CUDA(up(o_rep, rep, n4)); LR_CUDA(up(o_kl, K_l, n4)); LR_CUDA(up(o_km, K_m, n4));
+    LR_CUDA(up(o_L, L, nK)); LR_CUDA(up(o_M, M, nK)); LR_CUDA(up(o_tL, tL, nK)); LR_CUDA(up(o_tM, tM, nK));
+    LR_CUDA(up(o_g, gamma_rate, 2 * n8)); LR_CUDA(up(o_p, poi_lambda, n8)); LR_CUDA(up(o_b, beta, n8)); LR_CUDA(up(o_pa, poiA, n8));
+    LR_CUDA(up(o_sd, side, n4)); LR_CUDA(up(o_kd, kind, n4)); LR_CUDA(up(o_ix, idx, n4)); LR_CUDA(up(o_ut, u_t, n8)); LR_CUDA(up(o_ub, u_beta, n8));
+    const int wpb = 4;
+    k2_proposal_eval_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        n, rep ? (const int*)(w + o_rep) : nullptr, (const int*)(w + o_kl), (const int*)(w + o_km), (const double*)(w + o_L), (const double*)(w + o_M),
+        (const double*)(w + o_tL), (const double*)(w + o_tM), gamma_rate ? (const double*)(w + o_g) : nullptr,
+        poi_lambda ? (const double*)(w + o_p) : nullptr, beta ? (const double*)(w + o_b) : nullptr, (const double*)(w + o_pa),
+        (const int*)(w + o_sd), (const int*)(w + o_kd), (const int*)(w + o_ix), (const double*)(w + o_ut), (const double*)(w + o_ub),
+        ds->tab, ds->cst, ds->n_bins, ds->s0f, ds->start_time, ds->end_time,
+        (int*)(w + o_ok), (int*)(w + o_kn), (double*)(w + o_rn), (double*)(w + o_tn), (double*)(w + o_h), (double*)(w + o_x));
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    LR_CUDA(cudaMemcpyAsync(ok, w + o_ok, n4, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(K_new, w + o_kn, n4, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(rates_new, w + o_rn, nK, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(times_new, w + o_tn, nK, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(hasting, w + o_h, n8, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(x, w + o_x, n8, cudaMemcpyDeviceToHost, st));
     LR_CUDA(cudaStreamSynchronize(st));
     return LR_OK;
 }

@@ -296,6 +296,43 @@ class Dataset:
         return {"lik": lik, "prior_rates": pr, "prior_poi": pp, "adequacy": ad}
 
 
+def _pack_states(states):
+    n = len(states)
+    K_l = np.zeros(n, np.int32); K_m = np.zeros(n, np.int32)
+    L = np.zeros((n, LR_KMAX)); M = np.zeros((n, LR_KMAX)); tL = np.zeros((n, LR_KMAX)); tM = np.zeros((n, LR_KMAX))
+    for i, (l, m, tl, tm) in enumerate(states):
+        l, m, tl, tm = (np.asarray(x, dtype=np.float64) for x in (l, m, tl, tm))
+        if len(tl) != len(l) + 1 or len(tm) != len(m) + 1:
+            raise ValueError("times must hold one more entry than rates")
+        K_l[i], K_m[i] = len(l), len(m)
+        L[i, :len(l)], M[i, :len(m)] = l, m
+        tL[i, :len(l)], tM[i, :len(m)] = tl[:-1], tm[:-1]
+    return K_l, K_m, L, M, tL, tM
+
+
+def evaluate_proposals(ds: "Dataset", states, side, kind, idx, u_t, u_beta, gamma_rate=None, poi_lambda=None, beta=None, poiA=None, rep=None):
+    """One reversible-jump proposal per state with explicit draws (lr_proposal_eval_host; parity entry point).
+    kind: 2 add-shift inside segment idx, 3 remove interior shift idx.  Returns dict: ok, K_new, rates, times (lists of
+    arrays: the proposed side in the reference's layout [start, shifts..., end]), hasting, x."""
+    n = len(states)
+    K_l, K_m, L, M, tL, tM = _pack_states(states)
+    b = lambda a, dt, shape: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, dt), shape))
+    g, p, be = b(gamma_rate, np.float64, (n, 2)), b(poi_lambda, np.float64, (n,)), b(beta, np.float64, (n,))
+    pa = b(0.0 if poiA is None else poiA, np.float64, (n,))
+    r = b(rep, np.int32, (n,))
+    sd, kd, ix = b(side, np.int32, (n,)), b(kind, np.int32, (n,)), b(idx, np.int32, (n,))
+    ut, ub = b(u_t, np.float64, (n,)), b(u_beta, np.float64, (n,))
+    ok = np.empty(n, np.int32); kn = np.empty(n, np.int32)
+    rn = np.empty((n, LR_KMAX)); tn = np.empty((n, LR_KMAX)); hs = np.empty(n); x = np.empty(n)
+    N.check(ds.dev.lib.lr_proposal_eval_host(ds.ds, n, N.np_ptr(r), N.np_ptr(K_l), N.np_ptr(K_m), N.np_ptr(L), N.np_ptr(M), N.np_ptr(tL),
+                                             N.np_ptr(tM), N.np_ptr(g), N.np_ptr(p), N.np_ptr(be), N.np_ptr(pa), N.np_ptr(sd), N.np_ptr(kd),
+                                             N.np_ptr(ix), N.np_ptr(ut), N.np_ptr(ub), N.np_ptr(ok), N.np_ptr(kn), N.np_ptr(rn), N.np_ptr(tn),
+                                             N.np_ptr(hs), N.np_ptr(x)), "lr_proposal_eval_host")
+    rates = [rn[i, :kn[i]].copy() for i in range(n)]
+    times = [np.concatenate([tn[i, :kn[i]], [ds.end_time]]) for i in range(n)]
+    return {"ok": ok.astype(bool), "K_new": kn, "rates": rates, "times": times, "hasting": hs, "x": x}
+
+
 # field offsets of a sample record (include/literate_b200.h)
 REC_IT, REC_LIK, REC_PRIOR, REC_LAVG, REC_MAVG, REC_KL, REC_KM, REC_GL, REC_GM, REC_POI = range(10)
 REC_ADQ, REC_POI_INIT, REC_BETA = 10, 13, 14

@@ -354,17 +354,13 @@ def propose_move_shift(times, start_time, end_time):
     return np.sort(out)
 
 
-def propose_add_shift(rates, times, exact_scipy=False):
-    """add_shift_RJ_weighted_mean (:29-47)."""
-    gaps = np.diff(times)
-    i = np.random.choice(range(len(gaps)))
-    gap = gaps[i]
-    t_new = times[i] + np.random.uniform(0, gap)
+def add_shift_given(rates, times, i, t_new, u, exact_scipy=False):
+    """add_shift_RJ_weighted_mean (:29-47) for given draws: segment i, new shift time t_new, Beta(10,10) variate u."""
+    gap = times[i + 1] - times[i]
     times_new = np.sort(np.array(list(times) + [t_new]))
     ta, tb = times[i], times[i + 1]
     p1 = (ta - t_new) / (ta - tb)
     p2 = (t_new - tb) / (ta - tb)
-    u = np.random.beta(SHAPE_BETA_RJ, SHAPE_BETA_RJ)
     r = rates[i]
     r1 = np.exp(np.log(r) - p2 * np.log((1 - u) / u))
     r2 = np.exp(np.log(r) + p1 * np.log((1 - u) / u))
@@ -375,9 +371,17 @@ def propose_add_shift(rates, times, exact_scipy=False):
     return rates_new, times_new, log_q + jac
 
 
-def propose_remove_shift(rates, times, exact_scipy=False):
-    """remove_shift_RJ_weighted_mean (:49-69)."""
-    j = np.random.choice(range(1, len(times) - 1))
+def propose_add_shift(rates, times, exact_scipy=False):
+    """add_shift_RJ_weighted_mean (:29-47) with the reference's draws from the global stream, in its order."""
+    gaps = np.diff(times)
+    i = np.random.choice(range(len(gaps)))
+    t_new = times[i] + np.random.uniform(0, gaps[i])
+    u = np.random.beta(SHAPE_BETA_RJ, SHAPE_BETA_RJ)
+    return add_shift_given(rates, times, i, t_new, u, exact_scipy)
+
+
+def remove_shift_given(rates, times, j, exact_scipy=False):
+    """remove_shift_RJ_weighted_mean (:49-69) for a given interior shift j (1 <= j <= len(times) - 2)."""
     t_rm, ta, tb = times[j], times[j - 1], times[j + 1]
     span = abs(tb - ta)
     times_new = times[times != t_rm]
@@ -391,6 +395,12 @@ def propose_remove_shift(rates, times, exact_scipy=False):
     log_q = -np.log(span) + _sym_beta_logpdf(u, exact_scipy)
     jac = np.log(merged) - (2 * np.log(ra + rb))
     return rates_new, times_new, log_q + jac
+
+
+def propose_remove_shift(rates, times, exact_scipy=False):
+    """remove_shift_RJ_weighted_mean (:49-69) with the reference's draw."""
+    j = np.random.choice(range(1, len(times) - 1))
+    return remove_shift_given(rates, times, j, exact_scipy)
 
 
 def propose_rj(L, M, tL, tM, sample_shift_mu, exact_scipy=False):

@@ -94,3 +94,63 @@ def test_replicates_select_their_own_tables(device):
     for i, (L, M, tL, tM) in enumerate(states):
         st = O.BinStats(0, sp[rep[i]], ex[rep[i]], br[rep[i]])
         assert out["lik"][i] == pytest.approx(O.loglik_state(L, M, tL, tM, st, 0), rel=RTOL)
+
+
+@pytest.mark.parametrize("model", [0, 2])
+def test_rj_proposals_match_the_oracle(device, model, metal_path):
+    """add_shift_RJ_weighted_mean / remove_shift_RJ_weighted_mean (LiteRateForward.py:29-69) on explicit states with explicit
+    draws: proposed rates and times, the Hastings + Jacobian term and the whole acceptance ratio of :296-313 against the
+    oracle's restatement (the functions its byte-for-byte pinned chain calls); add followed by the matching remove returns
+    to the start with opposite log-ratios."""
+    from literate_b200.engine import evaluate_proposals
+    lin = O.read_lineages(metal_path)
+    st, ds = _dataset(device, lin, model)
+    rng = np.random.default_rng(40 + model)
+    span = lin.end_time - lin.start_time
+    states = random_states(rng, 96, lin.start_time, lin.end_time, kmax=8, rate_scale=0.3)
+    n = len(states)
+    side = rng.integers(0, 2, n)
+    g = rng.gamma(2.0, 1.0, (n, 2)) + 0.05
+    lam = rng.gamma(2.0, 1.0, n) + 0.05
+    poiA = rng.normal(-3, 1, n)
+    Ks = np.array([len(s[0]) if sd else len(s[1]) for s, sd in zip(states, side)])
+    kind = np.where((rng.random(n) < 0.5) & (Ks > 1), 3, 2)
+    idx = np.array([rng.integers(0, k) if kd == 2 else rng.integers(1, k) for k, kd in zip(Ks, kind)])
+    u_t, u_b = rng.uniform(0.02, 0.98, n), rng.beta(10, 10, n)
+    out = evaluate_proposals(ds, states, side, kind, idx, u_t, u_b, gamma_rate=g, poi_lambda=lam, poiA=poiA)
+
+    def lik_prior(L, M, tL, tM, i, poi_term):
+        return O.loglik_state(L, M, tL, tM, st, model), O.state_prior(L, M, g[i], span, poi_term)
+
+    n_checked = 0
+    for i, (L, M, tL, tM) in enumerate(states):
+        r, t = (L, tL) if side[i] else (M, tM)
+        if kind[i] == 2:
+            t_new = t[idx[i]] + u_t[i] * (t[idx[i] + 1] - t[idx[i]])
+            guard = min(t_new - t[idx[i]], t[idx[i] + 1] - t_new) <= 1
+            assert bool(out["ok"][i]) == (not guard), i
+            if guard:
+                continue
+            rn, tn, h = O.add_shift_given(r, t, idx[i], t_new, u_b[i])
+        else:
+            rn, tn, h = O.remove_shift_given(r, t, idx[i])
+            assert out["ok"][i]
+        np.testing.assert_allclose(out["rates"][i], rn, rtol=1e-12)
+        np.testing.assert_allclose(out["times"][i], tn, rtol=1e-14)
+        assert out["hasting"][i] == pytest.approx(h, rel=1e-11, abs=1e-12)
+        L2, M2, tL2, tM2 = (rn, M, tn, tM) if side[i] else (L, rn, tL, tn)
+        poiN = O.poisson_prior(len(L2), lam[i]) + O.poisson_prior(len(M2), lam[i])
+        l0, p0 = lik_prior(L, M, tL, tM, i, poiA[i])
+        l1, p1 = lik_prior(L2, M2, tL2, tM2, i, poiN)
+        assert out["x"][i] == pytest.approx((l1 - l0) + (p1 - p0) + h, rel=1e-9, abs=1e-8), (i, kind[i])
+        n_checked += 1
+    assert n_checked > 60
+    # round trip: remove the shift an add just inserted
+    adds = [i for i in range(n) if kind[i] == 2 and out["ok"][i]]
+    st2 = [((out["rates"][i], states[i][1], out["times"][i], states[i][3]) if side[i] else
+            (states[i][0], out["rates"][i], states[i][2], out["times"][i])) for i in adds]
+    back = evaluate_proposals(ds, st2, side[adds], 3, idx[adds] + 1, 0.5, 0.5, gamma_rate=g[adds], poi_lambda=lam[adds], poiA=poiA[adds])
+    for k, i in enumerate(adds):
+        r0 = states[i][0] if side[i] else states[i][1]
+        np.testing.assert_allclose(back["rates"][k], r0, rtol=1e-11)
+        assert back["hasting"][k] == pytest.approx(-out["hasting"][i], rel=1e-9, abs=1e-9)
