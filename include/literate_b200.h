@@ -142,8 +142,10 @@ int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const int
  * ratio of :296-313).  State arrays as lr_state_eval_host; additionally per state
  *   beta (NULL: 1), poiA   inverse temperature and the stored (possibly stale) Poisson prior term priorPoiA (:300-304)
  *   side                   1 birth side, 0 death side
- *   kind, idx              2 add-shift inside segment idx (0-based); 3 remove interior shift idx (1..K-1)
+ *   kind, idx              0 rate multiplier (update_multiplier_freq, :165-176); 2 add-shift inside segment idx (0-based);
+ *                          3 remove interior shift idx (1..K-1)
  *   u_t, u_beta            add-shift: position inside the segment as a fraction, Beta(10,10) variate
+ *   mult_on, mult_u        kind 0: [n][LR_KMAX] Bernoulli mask and uniforms of the multipliers (may be NULL otherwise)
  * Outputs: ok (0 = rejected by the spacing guard :290 or at capacity), K_new, rates_new / times_new [n][LR_KMAX] of the proposed
  * side, hasting = log q-ratio + log Jacobian (:47, :69), x = beta (lik' - lik) + (prior' - prior) + hasting with the new
  * Poisson prior term against poiA (:279, :313). */
@@ -151,6 +153,7 @@ int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep, const 
                           const double* L, const double* M, const double* tL, const double* tM,
                           const double* gamma_rate, const double* poi_lambda, const double* beta, const double* poiA,
                           const int32_t* side, const int32_t* kind, const int32_t* idx, const double* u_t, const double* u_beta,
+                          const int32_t* mult_on, const double* mult_u,
                           int32_t* ok, int32_t* K_new, double* rates_new, double* times_new, double* hasting, double* x);
 
 /* Validation path: the Keiding log-likelihood (BD_lik_Keiding, :137-148; -model_BDI 2) of n_states states evaluated DIRECTLY

@@ -83,7 +83,7 @@ def load(build_if_missing=False):
     sig("lr_dataset_create_host", C.c_int, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, P(vp))
     sig("lr_dataset_destroy", C.c_int, vp)
     sig("lr_state_eval_host", C.c_int, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
-    sig("lr_proposal_eval_host", C.c_int, vp, i32, *([vp] * 22))
+    sig("lr_proposal_eval_host", C.c_int, vp, i32, *([vp] * 24))
     sig("lr_loglik_direct", C.c_int, vp, vp, vp, i64, i64, i32, vp, vp, i32, vp, vp)
     sig("lr_chains_create", C.c_int, vp, vp, i32, P(ChainConfig), u64, i64, vp, P(vp))
     sig("lr_chains_destroy", C.c_int, vp)

@@ -951,6 +951,7 @@ __global__ void k2_proposal_eval_kernel(int n, const int* __restrict__ rep, cons
                                         const double* __restrict__ beta_in, const double* __restrict__ poiA_in,
                                         const int* __restrict__ side, const int* __restrict__ kind, const int* __restrict__ idx,
                                         const double* __restrict__ u_t, const double* __restrict__ u_beta,
+                                        const int* __restrict__ mult_on, const double* __restrict__ mult_u,
                                         const double* tab, const double* cst, int nb, int s0f, double start_time, double end_time,
                                         int* __restrict__ ok_out, int* __restrict__ K_new, double* __restrict__ rates_new,
                                         double* __restrict__ times_new, double* __restrict__ hasting_out, double* __restrict__ x_out) {
@@ -976,17 +977,31 @@ __global__ void k2_proposal_eval_kernel(int n, const int* __restrict__ rep, cons
     const Side& oth = birth ? M : L;
     Draws q;
     q.u_acc = 0.5; q.thr_hi = 0.0; q.thr_lo = 0.0; q.m = 1.0; q.dlt = 0.0;
-    q.kind = ((kind[i] == 2 ? DK_RJ_ADD : DK_RJ_REMOVE) << 1) | (birth ? 1 : 0);
-    // the index draws that select exactly segment / shift idx (propose_add: (int)(u K); propose_remove: 1 + (int)(u (K-1)))
-    q.u_idx = kind[i] == 2 ? ((double)idx[i] + 0.5) / (double)cur.K : ((double)(idx[i] - 1) + 0.5) / (double)(cur.K > 1 ? cur.K - 1 : 1);
-    q.u_t = u_t[i];
-    const double ub = u_beta[i];
-    q.w = log((1.0 - ub) / ub);                                                           // :41-42
-    q.ln_beta = (LR_SHAPE_BETA - 1.0) * (log(ub) + log1p(-ub)) - LR_BETA_NORM;            // beta.logpdf(u; 10, 10), :22-23
     Side nw;
     double hasting = 0.0, poiN = 0.0, x = 0.0;
-    bool cap = false;
-    const bool ok = rj_propose<false>(cur, oth, side_view(hp, birth), hp, beta_in ? beta_in[i] : 1.0, poiA_in[i], d, q, lane, nw, hasting, poiN, x, cap);
+    bool cap = false, ok = true;
+    if (kind[i] == 0) {
+        // update_multiplier_freq (:165-176) with the given Bernoulli mask and uniforms: m = exp(2 ln(1.1) (u - .5)) on the
+        // touched rates, Hastings = sum log m; the acceptance ratio exactly as block_step forms it
+        const bool on = lane < cur.K && lane < LR_KMAX;
+        const bool touched = on && mult_on[(size_t)i * LR_KMAX + lane] != 0;
+        const double dl = touched ? LR_LN_MULT * (mult_u[(size_t)i * LR_KMAX + lane] - 0.5) : 0.0;
+        const double rn = cur.r * exp(dl);
+        const SideView v = side_view(hp, birth);
+        const double b = beta_in ? beta_in[i] : 1.0;
+        x = warp_sum((b * cur.A + 2.0) * dl - (b * cur.B + v.g_cur) * (rn - cur.r));
+        hasting = warp_sum(dl);
+        nw = cur; nw.r = rn; nw.lr = cur.lr + dl;
+    } else {
+        q.kind = ((kind[i] == 2 ? DK_RJ_ADD : DK_RJ_REMOVE) << 1) | (birth ? 1 : 0);
+        // the index draws that select exactly segment / shift idx (propose_add: (int)(u K); propose_remove: 1 + (int)(u (K-1)))
+        q.u_idx = kind[i] == 2 ? ((double)idx[i] + 0.5) / (double)cur.K : ((double)(idx[i] - 1) + 0.5) / (double)(cur.K > 1 ? cur.K - 1 : 1);
+        q.u_t = u_t[i];
+        const double ub = u_beta[i];
+        q.w = log((1.0 - ub) / ub);                                                           // :41-42
+        q.ln_beta = (LR_SHAPE_BETA - 1.0) * (log(ub) + log1p(-ub)) - LR_BETA_NORM;            // beta.logpdf(u; 10, 10), :22-23
+        ok = rj_propose<false>(cur, oth, side_view(hp, birth), hp, beta_in ? beta_in[i] : 1.0, poiA_in[i], d, q, lane, nw, hasting, poiN, x, cap);
+    }
     if (lane == 0) { ok_out[i] = ok ? 1 : 0; K_new[i] = ok ? nw.K : cur.K; hasting_out[i] = ok ? hasting : 0.0; x_out[i] = ok ? x : 0.0; }
     if (lane < LR_KMAX) {
         rates_new[(size_t)i * LR_KMAX + lane] = (ok && lane < nw.K) ? nw.r : 0.0;
@@ -1220,6 +1235,7 @@ extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* 
                                      const double* L, const double* M, const double* tL, const double* tM,
                                      const double* gamma_rate, const double* poi_lambda, const double* beta, const double* poiA,
                                      const int32_t* side, const int32_t* kind, const int32_t* idx, const double* u_t, const double* u_beta,
+                                     const int32_t* mult_on, const double* mult_u,
                                      int32_t* ok, int32_t* K_new, double* rates_new, double* times_new, double* hasting, double* x) {
     LR_REQUIRE(ds && K_l && K_m && L && M && tL && tM && poiA && side && kind && idx && u_t && u_beta && ok && K_new && rates_new && times_new && hasting && x,
                "lr_proposal_eval_host: null pointer");
@@ -1229,7 +1245,9 @@ extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* 
         LR_REQUIRE(K_l[i] >= 1 && K_l[i] <= LR_KMAX && K_m[i] >= 1 && K_m[i] <= LR_KMAX, "lr_proposal_eval_host: K out of 1..%d at state %d", LR_KMAX, i);
         LR_REQUIRE(!rep || (rep[i] >= 0 && rep[i] < ds->n_rep), "lr_proposal_eval_host: replicate index out of range at state %d", i);
         const int K = side[i] ? K_l[i] : K_m[i];
-        LR_REQUIRE(kind[i] == 2 || kind[i] == 3, "lr_proposal_eval_host: kind must be 2 (add-shift) or 3 (remove-shift) at state %d", i);
+        LR_REQUIRE(kind[i] == 0 || kind[i] == 2 || kind[i] == 3, "lr_proposal_eval_host: kind must be 0 (rate multiplier), 2 (add-shift) or 3 (remove-shift) at state %d", i);
+        LR_REQUIRE(kind[i] != 0 || (mult_on && mult_u), "lr_proposal_eval_host: kind 0 needs mult_on and mult_u");
+        if (kind[i] == 0) continue;
         LR_REQUIRE(kind[i] == 2 ? (idx[i] >= 0 && idx[i] < K) : (K > 1 && idx[i] >= 1 && idx[i] <= K - 1), "lr_proposal_eval_host: index out of range at state %d", i);
         LR_REQUIRE(u_beta[i] > 0.0 && u_beta[i] < 1.0 && u_t[i] >= 0.0 && u_t[i] <= 1.0, "lr_proposal_eval_host: draws outside (0,1) at state %d", i);
     }
@@ -1240,6 +1258,7 @@ extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* 
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
     const size_t o_rep = take(n4), o_kl = take(n4), o_km = take(n4), o_L = take(nK), o_M = take(nK), o_tL = take(nK), o_tM = take(nK);
     const size_t o_g = take(2 * n8), o_p = take(n8), o_b = take(n8), o_pa = take(n8), o_sd = take(n4), o_kd = take(n4), o_ix = take(n4);
+    const size_t o_mo = take((size_t)n * LR_KMAX * 4), o_mu = take(nK);
     const size_t o_ut = take(n8), o_ub = take(n8), o_ok = take(n4), o_kn = take(n4), o_rn = take(nK), o_tn = take(nK), o_h = take(n8), o_x = take(n8);
     int rc = lr_ws_reserve(h, off);
     if (rc != LR_OK) return rc;
@@ -1250,12 +1269,14 @@ extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* 
     LR_CUDA(up(o_L, L, nK)); LR_CUDA(up(o_M, M, nK)); LR_CUDA(up(o_tL, tL, nK)); LR_CUDA(up(o_tM, tM, nK));
     LR_CUDA(up(o_g, gamma_rate, 2 * n8)); LR_CUDA(up(o_p, poi_lambda, n8)); LR_CUDA(up(o_b, beta, n8)); LR_CUDA(up(o_pa, poiA, n8));
     LR_CUDA(up(o_sd, side, n4)); LR_CUDA(up(o_kd, kind, n4)); LR_CUDA(up(o_ix, idx, n4)); LR_CUDA(up(o_ut, u_t, n8)); LR_CUDA(up(o_ub, u_beta, n8));
+    LR_CUDA(up(o_mo, mult_on, (size_t)n * LR_KMAX * 4)); LR_CUDA(up(o_mu, mult_u, nK));
     const int wpb = 4;
     k2_proposal_eval_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(
         n, rep ? (const int*)(w + o_rep) : nullptr, (const int*)(w + o_kl), (const int*)(w + o_km), (const double*)(w + o_L), (const double*)(w + o_M),
         (const double*)(w + o_tL), (const double*)(w + o_tM), gamma_rate ? (const double*)(w + o_g) : nullptr,
         poi_lambda ? (const double*)(w + o_p) : nullptr, beta ? (const double*)(w + o_b) : nullptr, (const double*)(w + o_pa),
         (const int*)(w + o_sd), (const int*)(w + o_kd), (const int*)(w + o_ix), (const double*)(w + o_ut), (const double*)(w + o_ub),
+        mult_on ? (const int*)(w + o_mo) : nullptr, mult_u ? (const double*)(w + o_mu) : nullptr,
         ds->tab, ds->cst, ds->n_bins, ds->s0f, ds->start_time, ds->end_time,
         (int*)(w + o_ok), (int*)(w + o_kn), (double*)(w + o_rn), (double*)(w + o_tn), (double*)(w + o_h), (double*)(w + o_x));
     LR_CUDA(cudaGetLastError());

@@ -310,9 +310,10 @@ def _pack_states(states):
     return K_l, K_m, L, M, tL, tM
 
 
-def evaluate_proposals(ds: "Dataset", states, side, kind, idx, u_t, u_beta, gamma_rate=None, poi_lambda=None, beta=None, poiA=None, rep=None):
+def evaluate_proposals(ds: "Dataset", states, side, kind, idx, u_t, u_beta, gamma_rate=None, poi_lambda=None, beta=None, poiA=None, rep=None,
+                       mult_on=None, mult_u=None):
     """One reversible-jump proposal per state with explicit draws (lr_proposal_eval_host; parity entry point).
-    kind: 2 add-shift inside segment idx, 3 remove interior shift idx.  Returns dict: ok, K_new, rates, times (lists of
+    kind: 0 rate multiplier with mask mult_on / uniforms mult_u [n, LR_KMAX]; 2 add-shift inside segment idx; 3 remove interior shift idx.  Returns dict: ok, K_new, rates, times (lists of
     arrays: the proposed side in the reference's layout [start, shifts..., end]), hasting, x."""
     n = len(states)
     K_l, K_m, L, M, tL, tM = _pack_states(states)
@@ -322,11 +323,12 @@ def evaluate_proposals(ds: "Dataset", states, side, kind, idx, u_t, u_beta, gamm
     r = b(rep, np.int32, (n,))
     sd, kd, ix = b(side, np.int32, (n,)), b(kind, np.int32, (n,)), b(idx, np.int32, (n,))
     ut, ub = b(u_t, np.float64, (n,)), b(u_beta, np.float64, (n,))
+    mo, mu = b(mult_on, np.int32, (n, LR_KMAX)), b(mult_u, np.float64, (n, LR_KMAX))
     ok = np.empty(n, np.int32); kn = np.empty(n, np.int32)
     rn = np.empty((n, LR_KMAX)); tn = np.empty((n, LR_KMAX)); hs = np.empty(n); x = np.empty(n)
     N.check(ds.dev.lib.lr_proposal_eval_host(ds.ds, n, N.np_ptr(r), N.np_ptr(K_l), N.np_ptr(K_m), N.np_ptr(L), N.np_ptr(M), N.np_ptr(tL),
                                              N.np_ptr(tM), N.np_ptr(g), N.np_ptr(p), N.np_ptr(be), N.np_ptr(pa), N.np_ptr(sd), N.np_ptr(kd),
-                                             N.np_ptr(ix), N.np_ptr(ut), N.np_ptr(ub), N.np_ptr(ok), N.np_ptr(kn), N.np_ptr(rn), N.np_ptr(tn),
+                                             N.np_ptr(ix), N.np_ptr(ut), N.np_ptr(ub), N.np_ptr(mo), N.np_ptr(mu), N.np_ptr(ok), N.np_ptr(kn), N.np_ptr(rn), N.np_ptr(tn),
                                              N.np_ptr(hs), N.np_ptr(x)), "lr_proposal_eval_host")
     rates = [rn[i, :kn[i]].copy() for i in range(n)]
     times = [np.concatenate([tn[i, :kn[i]], [ds.end_time]]) for i in range(n)]

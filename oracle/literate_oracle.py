@@ -335,14 +335,19 @@ def _sym_beta_logpdf(u, exact_scipy):
     return ln_sym_beta_pdf(u, SHAPE_BETA_RJ)
 
 
+def rate_multiplier_given(q, touched, u, d=1.1):
+    """update_multiplier_freq (:165-176) for a given Bernoulli mask and uniforms."""
+    m = np.exp(2 * np.log(d) * (np.asarray(u, float) - .5))
+    m[np.asarray(touched) == 0] = 1.
+    return q * m, np.sum(np.log(m))
+
+
 def propose_rate_multiplier(q, f, d=1.1):
-    """update_multiplier_freq (:165-176)."""
+    """update_multiplier_freq (:165-176) with the reference's draws."""
     shape = np.shape(q)
     touched = np.random.binomial(1, f, shape)
     u = np.random.uniform(0, 1, shape)
-    m = np.exp(2 * np.log(d) * (u - .5))
-    m[touched == 0] = 1.
-    return q * m, np.sum(np.log(m))
+    return rate_multiplier_given(q, touched, u, d)
 
 
 def propose_move_shift(times, start_time, end_time):

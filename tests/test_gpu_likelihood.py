@@ -154,3 +154,30 @@ def test_rj_proposals_match_the_oracle(device, model, metal_path):
         r0 = states[i][0] if side[i] else states[i][1]
         np.testing.assert_allclose(back["rates"][k], r0, rtol=1e-11)
         assert back["hasting"][k] == pytest.approx(-out["hasting"][i], rel=1e-9, abs=1e-9)
+
+
+def test_rate_multiplier_proposal_matches_the_oracle(device, metal_path):
+    """update_multiplier_freq (:165-176) with an explicit mask and uniforms: proposed rates, Hastings term and the acceptance
+    ratio the loop forms from per-lane differences against the oracle's absolute form, also for a heated chain (beta < 1)."""
+    from literate_b200.engine import evaluate_proposals, LR_KMAX
+    lin = O.read_lineages(metal_path)
+    st, ds = _dataset(device, lin, 0)
+    rng = np.random.default_rng(77)
+    span = lin.end_time - lin.start_time
+    states = random_states(rng, 64, lin.start_time, lin.end_time, kmax=9, rate_scale=0.3)
+    n = len(states)
+    side = rng.integers(0, 2, n)
+    g = rng.gamma(2.0, 1.0, (n, 2)) + 0.05
+    beta = np.where(rng.random(n) < 0.5, 1.0, rng.uniform(0.3, 1.0, n))
+    on = (rng.random((n, LR_KMAX)) < 0.75).astype(np.int32)
+    u = rng.random((n, LR_KMAX))
+    out = evaluate_proposals(ds, states, side, 0, 0, 0.5, 0.5, gamma_rate=g, poi_lambda=1.0, beta=beta, poiA=0.0, mult_on=on, mult_u=u)
+    for i, (L, M, tL, tM) in enumerate(states):
+        r = L if side[i] else M
+        rn, h = O.rate_multiplier_given(r, on[i, :len(r)], u[i, :len(r)])
+        np.testing.assert_allclose(out["rates"][i], rn, rtol=1e-13)
+        assert out["hasting"][i] == pytest.approx(h, rel=1e-11, abs=1e-13)
+        L2, M2 = (rn, M) if side[i] else (L, rn)
+        dl = O.loglik_state(L2, M2, tL, tM, st, 0) - O.loglik_state(L, M, tL, tM, st, 0)
+        dp = O.state_prior(L2, M2, g[i], span, 0.0) - O.state_prior(L, M, g[i], span, 0.0)
+        assert out["x"][i] == pytest.approx(beta[i] * dl + dp + h, rel=1e-9, abs=1e-8)
