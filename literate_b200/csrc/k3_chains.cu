@@ -231,8 +231,10 @@ __device__ __forceinline__ LoopConsts loop_consts(const lr_chain_config& cfg) {
     return k;
 }
 
+// K_l / K_m: the chain's current numbers of rates if the caller knows them (compact build), -1 otherwise (producers): a
+// block iteration that will be a move-shift (r1 >= .5 on a side with more than one rate) does not need the multipliers.
 template <bool C>
-__device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int lane, const LoopConsts& k) {
+__device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int lane, const LoopConsts& k, int K_l = -1, int K_m = -1) {
     Draws q;
     double ua, ub;
     rng.draw(it, 0, lane, ua, ub);
@@ -248,9 +250,12 @@ __device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int la
         // update_multiplier_freq (:165-176): each rate w.p. f times exp(2 ln(1.1) (u - .5))
         const bool birth = r0 < k.b_freq;
         const double f = birth ? k.fL : k.fM;
-        const bool touched = ua < f;
-        q.dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
-        q.m = xexp<C>(q.dlt);                               // exp(0) = 1 exactly
+        const int K_side = birth ? K_l : K_m;
+        if (r1 < 0.5 || K_side <= 1) {
+            const bool touched = ua < f;
+            q.dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
+            q.m = xexp<C>(q.dlt);                           // exp(0) = 1 exactly
+        }
         q.kind = ((r1 < 0.5 ? DK_BLOCK_RATE : DK_BLOCK_MOVE) << 1) | (birth ? 1 : 0);
         if (k.real_move_shift) { q.u_idx = __shfl_sync(0xffffffffu, ua, 28); q.u_t = __shfl_sync(0xffffffffu, ub, 28); }
     } else if (r0 < 0.999 && !k.const_rates) {
@@ -765,7 +770,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
                 in_batch = 0; ++batch; if (++slot == DEPTH) slot = 0;
             }
         }
-        else q = make_draws<true>(rng, it, lane, K);
+        else q = make_draws<true>(rng, it, lane, K, L.K, M.K);
 
         const int kind = q.kind >> 1;
         const bool birth = (q.kind & 1) != 0;
