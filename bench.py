@@ -316,6 +316,8 @@ def run_cuda(a):
             "gpu_launches": int(tot[1]),
             "lik_evals_per_s": float(tot[0]) / (total_ms * 1e-3),
             "kernels": {"k1_bin_kernel_ms": k1, "k3_run_kernel_ms": statistics.mean(k3_ms),
+                        "k3_ns_per_iteration_per_chain": 1e6 * statistics.mean(k3_ms) / a.iters,
+                        "k3_bound": "dependent-instruction latency of one chain warp per chain (no DRAM traffic in the loop; see profiles/)",
                         "k1_share_of_step": k1 * a.steps / total_ms, "k3_share_of_step": sum(k3_ms) / total_ms},
             "roofline": {"kernel": "k1_bin_kernel (lineages -> per-bin births/deaths/time at risk)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(a),
