@@ -248,6 +248,54 @@ int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round);
 int lr_summarize_records(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
                          double* d_sum_rate, int64_t* d_shift_count, int64_t* d_k_count, void* stream);
 
+/* ---------------------------------------------------------------- TrendRate: fixed-dimension chains on the same statistics
+ *
+ * Replaces the Metropolis-Hastings loop of trend_rate.py:102-196 (likelihood_function :73-91, calc_prior :93-100) and the
+ * literate_library.py functions it calls (update_normal_nobound_vec :140-146, update_multiplier_proposal_vec :156-165,
+ * prior_gamma/prior_norm :182-187, calculate_r_squared :268-279).  Rates follow an exogenous trend,
+ *   lambda_j = l_min + alpha * trend_j ** delta,   mu_j = m_min + beta * trend_j ** gamma   (values <= 0 become 1e-15),
+ * and the likelihood is the Keiding form over the bins of literate_library.create_bins (:231-257: unit bins from the
+ * first birth time, the last one dropped) -- the statistics lr_bin_stats delivers for n_bins = that count.
+ *
+ *   sp, ex, br   [n_rep][n_bins]  statistics (device pointers: the outputs of lr_bin_stats; host pointers for *_host)
+ *   h_trend      [n_bins] HOST    the min-max normalised trend with zeros replaced by 1e-15 (trend_rate.py:61-69)
+ *   const_birth / const_death     -const_B / -const_D (-no_death implies -const_D, :44); both together are refused
+ *                                 (the reference stops in np.random.binomial(p = nan), :129-134)
+ * Chain c uses replicate h_rep_of_chain[c] (NULL: 0) and the Philox-4x32-10 stream keyed by (seed, chain_id0 + c).  The
+ * initial state is :141-147; as in the reference the proposal of iteration 0 is always accepted (:176). */
+typedef struct lr_trend_s* lr_trend_t;
+int lr_trend_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, const int64_t* d_sp, const int64_t* d_ex,
+                    const double* d_br, const double* h_trend, int32_t const_birth, int32_t const_death,
+                    int32_t n_chains, uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain,
+                    void* stream, lr_trend_t* out);
+int lr_trend_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, const int64_t* h_sp, const int64_t* h_ex,
+                         const double* h_br, const double* h_trend, int32_t const_birth, int32_t const_death,
+                         int32_t n_chains, uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain,
+                         lr_trend_t* out);
+int lr_trend_destroy(lr_trend_t t);
+/* One sample record = lr_trend_record_doubles(n_bins) = LR_TREND_REC_HEAD + 2 n_bins doubles (the row of :191):
+ *   [0] iteration  [1] likelihood  [2] likelihood_birth  [3] likelihood_death  [4] prior
+ *   [5..10] l_min, m_min, alpha, beta, delta, gamma  [11..13] adequacy (coeff, r2, gelman_r2)
+ *   [14] proposals accepted so far  [15] reserved  [16 .. 16+n_bins) birth rates  [16+n_bins .. 16+2 n_bins) death rates */
+#define LR_TREND_REC_HEAD 16
+int64_t lr_trend_record_doubles(int32_t n_bins);
+/* A record is written after every iteration `it` with it % sample_every == 0 (:184: the sample follows the accept step, so
+ * the record of iteration 0 already holds the first proposal).  Layout [sample][chain][record]; asynchronous on `stream`. */
+int64_t lr_trend_records_per_run(lr_trend_t t, int64_t n_iter, int64_t sample_every);
+int lr_trend_run(lr_trend_t t, int64_t n_iter, int64_t sample_every, double* d_records, void* stream);
+int lr_trend_run_host(lr_trend_t t, int64_t n_iter, int64_t sample_every, double* h_records);
+/* Parity entry point, HOST buffers: evaluates n explicit parameter vectors params[n][6] on replicate rep[n] (NULL: 0).
+ * With kind != NULL one proposal with EXPLICIT draws is applied first: kind[n] 0 multiplier (draw = uniform) / 1 additive
+ * normal (draw = standard normal), on[n][6] the Bernoulli mask, draw[n][6]; out_params[n][6], out_hast[n] receive it.
+ * Outputs (any may be NULL): lik[n][2] birth and death log-likelihood, prior[n], rates[n][2][n_bins], adequacy[n][3]. */
+int lr_trend_eval_host(lr_trend_t t, int32_t n, const int32_t* rep, const double* params, const int32_t* kind,
+                       const int32_t* on, const double* draw, double* out_params, double* out_hast, double* lik,
+                       double* prior, double* rates, double* adequacy);
+/* current state of every chain: [n_chains][LR_TREND_STATE_DOUBLES] = six parameters, likelihood_birth, likelihood_death,
+ * prior, iterations done, proposals accepted, replicate */
+#define LR_TREND_STATE_DOUBLES 12
+int lr_trend_state_host(lr_trend_t t, double* h_state);
+
 #ifdef __cplusplus
 }
 #endif
