@@ -136,7 +136,7 @@ def test_chain_bookkeeping(device, tmp_path):
     recs = ch.run(20001, 500)
     assert recs.shape == (41, 16, 16 + 2 * bins.n_bins)
     assert np.all(recs[0, :, 14] == 1)                                       # iteration 0 is always accepted (:176)
-    assert not np.array_equal(recs[0, 0, 5:11], [.1, .1, 0, 0, 1, 1])
+    assert not np.all(recs[0, :, 5:11] == np.array([.1, .1, 0, 0, 1, 1]))
     emp_b, emp_d = bins.n_spec / bins.dt, bins.n_exti / bins.dt
     for si in range(0, 41, 4):
         for c in (0, 7, 15):
