@@ -1,0 +1,263 @@
+"""CPU oracle for DDRate: fixed-dimension Metropolis-Hastings on the binned statistics with
+diversity-dependent birth and death rates against a constant or logistic carrying capacity.  TEST INFRASTRUCTURE ONLY.
+
+NumPy restatement of ``DDRatev3.py`` and of the ``literate_library.py`` functions it calls.  Only ``tests/`` may import
+this module, as the checker -- never the product path.
+
+What of the reference runs: as shipped ``DDRatev3.py`` stops with NameError at :48 (``GN_SPEC`` exists only with
+``-m_birth 3``) and, with ``-m_birth -1`` / ``-m_death -1``, at :192/:194 (``init_death`` / ``init_birth``); ``DDRatev2.py``
+stops at ``out_div`` (:153).  The only runnable configurations are ``-m_birth 3 -g <genre table>`` with ``-m_death`` 0, 1
+or 2, and these are the parity pin: ``oracle/make_golden_ddrate.py`` runs them unmodified and ``run_chain`` below, same seed
+and legacy ``np.random`` draw order, reproduces both log files byte for byte (``tests/golden/ddrate/``,
+``tests/test_oracle_ddrate_golden.py``).  ``m_birth`` 0/1/2 follow the same functions (the ``M_BIRTH>=2`` branch is the one
+the pinned runs execute; the ``M_BIRTH`` 0/1 branches are restated from :86-93 and have no runnable reference: "parity
+unpinned" for those two).
+
+All ``file:line`` citations are relative to the reference checkout.
+"""
+from __future__ import annotations
+
+import csv
+import math
+import os
+
+import numpy as np
+
+from oracle.trendrate_oracle import Bins, adequacy, create_bins, parse_ts_te, precompute_events  # noqa: F401  (same library functions)
+
+SMALL_NUMBER = 0.000000000000001      # DDRatev3.py:54
+PARAMS = ["l_f", "l_mul", "k", "x0", "div_0", "L", "m_mul", "nuB", "nuD", "g_lambda1", "g_lambda2"]      # :83
+NPAR = 11
+
+
+class Setup:
+    """Module-level globals of DDRatev3.py (:33-56)."""
+
+    def __init__(self, bins: Bins, m_birth=2, m_death=2, gts=None, gte=None):
+        self.bins = bins
+        self.origin, self.present = bins.origin, bins.present
+        self.m_birth, self.m_death = m_birth, m_death
+        self.n = bins.n_bins
+        self.time_range = np.arange(self.n).astype(float)          # literate_library.py:255
+        self.prior_k0_l = float(np.max(bins.dt))                   # :53
+        self.gts, self.gte = gts, gte
+
+
+def get_logistic(x, L, k, x0, div_0, nu):                          # :64-65
+    return div_0 + L / ((1 + np.exp(-k * (x - x0))) ** (1 / nu))
+
+
+def get_brates(rate_f, rate_mul, niche_frac):                      # :70-74
+    rate_max = rate_f + rate_f * rate_mul
+    rate = rate_max - (rate_max - rate_f) * niche_frac
+    rate[rate <= 0] = SMALL_NUMBER
+    return rate
+
+
+def get_drates(rate_f, rate_mul, niche_frac):                      # :76-80
+    rate_min = rate_f - rate_f * rate_mul
+    rate = rate_min + (rate_f - rate_min) * niche_frac
+    rate[rate <= 0] = SMALL_NUMBER
+    return rate
+
+
+def genre_stats(S: Setup, x0):
+    """The two precompute_events calls of :100-101 -> (spec1, br1, spec2, br2)."""
+    s1, _, b1 = precompute_events(S.gts, S.gte, S.origin, S.origin + x0)
+    s2, _, b2 = precompute_events(S.gts, S.gte, S.origin + x0, S.present)
+    return s1, b1, s2, b2
+
+
+def likelihood(args, S: Setup):
+    """likelihood_function (:82-124) -> (lik[3], birth_rates, death_rates, niche, niche_frac)."""
+    l_f, l_mul, k, x0, div_0, L, m_mul, nuB, nuD, g1, g2 = args
+    DT, n = S.bins.dt, S.n
+    g_birth_lik = 1
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if S.m_birth == 0:                                         # :86-89
+            birth = np.ones(n) * l_f * l_mul
+            niche = np.ones(n)
+            niche_frac = np.ones(n)
+        elif S.m_birth == 1:                                       # :90-93
+            niche = np.ones(n) * (L + div_0)
+            niche_frac = DT / niche
+            birth = get_brates(l_f, l_mul, niche_frac ** nuB)
+        else:                                                      # :94-97
+            niche = get_logistic(S.time_range, L, k, x0, div_0, 1)
+            niche_frac = DT / niche
+            birth = get_brates(l_f, l_mul, niche_frac ** nuB)
+        birth_lik = np.sum(np.log(birth) * S.bins.n_spec - birth * DT)          # :98
+        if S.m_birth == 3:                                         # :99-102
+            s1, b1, s2, b2 = genre_stats(S, x0)
+            g_birth_lik = (np.log(g1) * s1 - g1 * b1) + (np.log(g2) * s2 - g2 * b2)
+        if S.m_death <= 0:                                         # :105-106
+            death = np.ones(n)
+        elif S.m_death == 1:                                       # :109-112
+            niche = np.ones(n) * (L + div_0)
+            niche_frac = DT / niche
+            death = get_drates(l_f, m_mul, niche_frac ** nuD)
+        else:                                                      # :113-116
+            niche = get_logistic(S.time_range, L, k, x0, div_0, 1)
+            niche_frac = DT / niche
+            death = get_drates(l_f, m_mul, niche_frac ** nuD)
+        death_lik = np.sum(np.log(death) * S.bins.n_exti - death * DT)          # :118
+    return np.array([birth_lik, death_lik, g_birth_lik]), birth, death, niche, niche_frac
+
+
+def _ln_gamma1(x, scale):
+    """scipy.stats.gamma.logpdf(x, 1, scale=scale, loc=0)"""
+    return -math.inf if x < 0 else -x / scale - math.log(scale)
+
+
+def _ln_gamma3(x, scale):
+    y = x / scale
+    return -math.inf if y <= 0 else 2.0 * math.log(y) - y - math.lgamma(3.0) - math.log(scale)
+
+
+def prior(args, S: Setup, exact_scipy=False):
+    """calc_prior (:127-141)."""
+    if exact_scipy:
+        import scipy.stats as st
+        g = lambda x, a, s: st.gamma.logpdf(x, a, scale=s, loc=0)
+        p = g(args[0], 1, 10)
+        p += g(args[1], 1, 1)
+        p += st.beta.logpdf(args[6], 1, 1.2)
+        p += g(args[2], 1, 10)
+        p += g(args[4], 1, S.prior_k0_l)
+        p += g(args[5], 1, S.prior_k0_l)
+        p += g(args[7], 3, .5)
+        p += g(args[8], 3, .5)
+        p += g(args[9], 1, 10)
+        p += g(args[10], 1, 10)
+    else:
+        m = args[6]
+        p = _ln_gamma1(args[0], 10) + _ln_gamma1(args[1], 1)
+        p += (math.log(1.2) + 0.2 * math.log1p(-m)) if 0 <= m < 1 else -math.inf
+        p += _ln_gamma1(args[2], 10) + _ln_gamma1(args[4], S.prior_k0_l) + _ln_gamma1(args[5], S.prior_k0_l)
+        p += _ln_gamma3(args[7], .5) + _ln_gamma3(args[8], .5) + _ln_gamma1(args[9], 10) + _ln_gamma1(args[10], 10)
+    if S.origin + args[3] >= S.present:                            # :139-140
+        p = -np.inf
+    return p
+
+
+def move_weights(m_birth, m_death):
+    """update_multiplier (:208-225)."""
+    if m_birth == 0 and m_death <= 0:
+        w = np.array([1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0], dtype=float)
+    elif m_birth == 2 or m_death == 2:
+        w = np.array([1, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0], dtype=float)
+    else:
+        w = np.array([1, 1, 0, 0, 0, 1, 0, 1, 1, 0, 0], dtype=float)
+    if m_birth == 3:
+        w = np.array([1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1], dtype=float)
+    return w / np.sum(w)
+
+
+def initial_args(S: Setup):
+    """:187-201"""
+    x0 = S.present - np.mean([S.origin, S.present])
+    return np.array([0.5, 1.01, 1.5, x0, 10, 20000, .99, 1., 1., 1., 1.])
+
+
+def sliding_window_given(i, u, M, d, m=0):
+    """update_sliding_win (literate_library.py:124-128) with a given uniform."""
+    ii = i + (u - .5) * d
+    if ii > M:
+        ii = M - (ii - M)
+    if m == 0:
+        ii = abs(ii)
+    return ii
+
+
+def multiplier_given(q, on, u, d=1.1):
+    """update_multiplier_proposal_vec with given mask and uniforms (literate_library.py:156-165)."""
+    m = np.exp(2 * np.log(d) * (np.asarray(u) - .5))
+    m[np.asarray(on) == 0] = 1.
+    return np.asarray(q) * m, float(np.sum(np.log(m)))
+
+
+def log_stem(path, seed, m_birth, m_death):
+    out = {0: "_LL", 1: "_LDD", 2: "_LDDN", 3: "_GLDDN"}.get(m_birth, "")         # :146-153
+    out += "_ML" if m_death <= 0 else ("_MDD" if m_death == 1 else "_MDDN")
+    return "%s_%s%s" % (os.path.splitext(path)[0], seed, out)
+
+
+def header(n_bins, m_birth):
+    head = ["it", "posterior", "likelihood", "likelihood_death", "likelihood_genre", "prior", "l_f", "l_mul", "steepness_k",
+            "midpoint_x0", "initCarryingCap", "maxCarryingCap", "m_mul", "nuB", "nuD", "g_l1", "g_l2"]       # :159-161
+    if m_birth == 3:
+        head += ["genre_lik"]
+    for tag in ("l_", "m_", "niche_", "nicheFrac_"):
+        head += ["%s%s" % (tag, i) for i in range(n_bins)]
+    return head + ["corr_coeff", "rsquared", "gelman_r2"]
+
+
+def write_div_log(fh, bins: Bins, gbins: Bins = None):
+    """:170-183 (the csv rows end with \\r\\n, the header with \\n; zip stops at the shorter table)."""
+    if gbins is None:
+        fh.write('sp_events\tex_events\tbr_length\n')
+        rows = zip(bins.n_spec, bins.n_exti, bins.dt)
+    else:
+        fh.write('sp_events\tex_events\tbr_length\tg_sp_events\tg_ex_events\tg_br_length\n')
+        rows = zip(bins.n_spec, bins.n_exti, bins.dt, gbins.n_spec, gbins.n_exti, gbins.dt)
+    w = csv.writer(fh, delimiter='\t')
+    for row in rows:
+        w.writerow(row)
+
+
+def run_chain(S: Setup, n_iter, sample_every, seed, fh=None, exact_scipy=True, collect=False):
+    """The reference chain (:187-292) on the legacy global np.random stream."""
+    np.random.seed(seed)
+    bins = S.bins
+    with np.errstate(divide="ignore", invalid="ignore"):
+        emp_b, emp_d = bins.n_spec / bins.dt, bins.n_exti / bins.dt
+    wlog = None
+    if fh is not None:
+        wlog = csv.writer(fh, delimiter="\t")
+        wlog.writerow(header(bins.n_bins, S.m_birth))
+    f = move_weights(S.m_birth, S.m_death)
+    argsA = initial_args(S)
+    lk, birth, death, niche, nfrac = likelihood(argsA, S)
+    likA, likB, likD, likG = np.sum(lk), lk[0], lk[1], lk[2]
+    priorA = prior(argsA, S, exact_scipy)
+    rows = []
+    it = 0
+    while it != n_iter:
+        args = argsA + 0.
+        rr = np.random.random(3)                                                  # :247
+        if rr[1] < 0.1 and (S.m_birth >= 1 or S.m_death >= 1):                    # :248-256
+            res = argsA + 0
+            if rr[2] < .5:
+                res[3] = sliding_window_given(res[3], np.random.random(), S.present, 1.5)
+            else:
+                res[6] = sliding_window_given(res[6], np.random.random(), 1, .05)
+            args, hast = res, 0
+        else:                                                                     # :258
+            shp = np.shape(args)
+            ff = np.random.binomial(1, f, shp)
+            u = np.random.uniform(0, 1, shp)
+            m = np.exp(2 * np.log(1.1) * (u - .5))
+            m[ff == 0] = 1.
+            args, hast = args * m, np.sum(np.log(m))
+        lk2, b2, d2, n2, nf2 = likelihood(args, S)
+        lik = np.sum(lk2)
+        pr = prior(args, S, exact_scipy)
+        if (lik - likA) + (pr - priorA) + hast > np.log(np.random.random()) or it == 0:        # :263
+            argsA, priorA, likA, likB, likD, likG = args, pr, lik, lk2[0], lk2[1], lk2[2]
+            birth, death, niche, nfrac = b2, d2, n2, nf2
+        if it % sample_every == 0:                                                # :274-290
+            argsO = argsA.copy()
+            argsO[3] += S.origin
+            argsO[5] += argsO[4]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                adq = adequacy(emp_b, emp_d, birth, death)
+            row = [it, likA + priorA, likA, likB, likD, priorA] + list(argsO)
+            if S.m_birth == 3:
+                row += [likG]
+            row += list(birth) + list(death) + list(niche) + list(nfrac) + list(adq)
+            if wlog is not None:
+                wlog.writerow(row)
+            if collect:
+                rows.append(np.array(row, dtype=float))
+        it += 1
+    return np.array(rows) if collect else None
