@@ -18,6 +18,9 @@ LR_REC_DOUBLES = 144
 LR_NCOUNTERS = 10
 LR_TREND_REC_HEAD = 16
 LR_TREND_STATE_DOUBLES = 12
+LR_DD_NPAR = 11
+LR_DD_REC_HEAD = 24
+LR_DD_STATE_DOUBLES = 24
 LR_OK = 0
 
 # every symbol include/literate_b200.h declares (checked by the CPU tests)
@@ -30,6 +33,8 @@ EXPORTS = [
     "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step", "lr_summarize_records",
     "lr_trend_create", "lr_trend_create_host", "lr_trend_destroy", "lr_trend_record_doubles", "lr_trend_records_per_run",
     "lr_trend_run", "lr_trend_run_host", "lr_trend_eval_host", "lr_trend_state_host",
+    "lr_dd_create", "lr_dd_create_host", "lr_dd_destroy", "lr_dd_record_doubles", "lr_dd_records_per_run",
+    "lr_dd_run", "lr_dd_run_host", "lr_dd_eval_host", "lr_dd_state_host",
 ]
 
 
@@ -111,6 +116,15 @@ def load(build_if_missing=False):
     sig("lr_trend_run_host", C.c_int, vp, i64, i64, vp)
     sig("lr_trend_eval_host", C.c_int, vp, i32, *([vp] * 11))
     sig("lr_trend_state_host", C.c_int, vp, vp)
+    sig("lr_dd_create", C.c_int, vp, i32, vp, vp, vp, f64, f64, i32, i32, vp, vp, i32, i32, u64, i64, vp, P(vp))
+    sig("lr_dd_create_host", C.c_int, vp, i32, vp, vp, vp, f64, f64, i32, i32, vp, vp, i32, i32, u64, i64, P(vp))
+    sig("lr_dd_destroy", C.c_int, vp)
+    sig("lr_dd_record_doubles", i64, i32)
+    sig("lr_dd_records_per_run", i64, vp, i64, i64)
+    sig("lr_dd_run", C.c_int, vp, i64, i64, vp, vp)
+    sig("lr_dd_run_host", C.c_int, vp, i64, i64, vp)
+    sig("lr_dd_eval_host", C.c_int, vp, i32, *([vp] * 11))
+    sig("lr_dd_state_host", C.c_int, vp, vp)
     if lib.lr_abi_version() != LR_ABI_VERSION:
         raise NativeError("libliterate_b200.so ABI version mismatch; rebuild with `python -m literate_b200.build --force`")
     _lib = lib

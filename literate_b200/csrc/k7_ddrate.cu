@@ -1,0 +1,638 @@
+// K7: DDRate -- fixed-dimension Metropolis-Hastings chains on the binned statistics of K1 with
+// diversity-dependent birth and death rates against a constant or logistic carrying capacity.  Replaces the loop of
+// DDRatev3.py:242-292 with likelihood_function (:82-124), calc_prior (:127-141) and the literate_library.py proposals
+// (update_sliding_win :124-128, update_multiplier_proposal_vec :156-165).
+//
+//   niche_j  = div_0 + L / (1 + exp(-k (j - x0)))   (-m_birth >= 2 / -m_death 2)   or   L + div_0   (-m_* 1)
+//   lambda_j = l_max - (l_max - l_f) (br_j / niche_j) ** nuB,   l_max = l_f + l_f l_mul               (:70-74)
+//   mu_j     = m_min + (l_f - m_min) (br_j / niche_j) ** nuD,   m_min = l_f - l_f m_mul               (:76-80)
+//   log-lik  = sum_j log(lambda_j) sp_j - lambda_j br_j + sum_j log(mu_j) ex_j - mu_j br_j  [+ genre term, -m_birth 3, :99-102]
+//
+// One warp = one chain, whole loop on device (the layout of K6): lane p < 11 owns parameter p (Philox draw, multiplier,
+// prior term), lane 11 draws the two branch uniforms, lane 12 the sliding-window and the acceptance uniform; bins are
+// strided over the lanes.  A term none of whose parameters was touched keeps its stored value.  The genre term of
+// -m_birth 3 needs births and time at risk of the genre table inside [origin, origin + x0) and [origin + x0, present):
+// one strided pass over the (small, L1-resident) genre table whenever x0 is proposed, cached otherwise.
+#include "lr_common.cuh"
+
+#define DD_NPAR LR_DD_NPAR
+#define DD_ROWS 6
+#define DD_SP 0
+#define DD_EX 1
+#define DD_BR 2
+#define DD_LNBR 3          // log(br): niche_frac ** nu = exp(nu (log br - log niche))
+#define DD_XB 4
+#define DD_XD 5
+#define DD_SMALL 0.000000000000001      // SMALL_NUMBER, DDRatev3.py:54
+#define DD_LN_MULT 0.19062035960864987  // 2 log(1.1)
+// parameter indices (:83)
+#define P_LF 0
+#define P_LMUL 1
+#define P_K 2
+#define P_X0 3
+#define P_DIV0 4
+#define P_L 5
+#define P_MMUL 6
+#define P_NUB 7
+#define P_NUD 8
+#define P_G1 9
+#define P_G2 10
+
+struct DDChain {
+    double p[DD_NPAR];
+    double likB, likD, likG, prior;
+    double g[4];           // genre statistics of the current x0: births and time at risk in the two windows
+    long long it, accepted;
+    unsigned chain;
+    int pad;
+};
+
+struct lr_dd_s {
+    lr_handle_t h;
+    int n_bins, nbp, m_birth, m_death, n_genre;
+    double origin, present, k0l;
+    double* tab;           // device [DD_ROWS][nbp]
+    double* cst;           // device [4]: sum x, sum x^2 (adequacy), -sum br (death likelihood of -m_death <= 0), max br
+    double cst_host[4];    // the same on the host (they parameterise every launch)
+    double* genre;         // device [2][n_genre] (ts, te) or null
+    int n_chains;
+    uint64_t seed;
+    DDChain* st;
+    double f[DD_NPAR];     // Bernoulli probability of every parameter in the multiplier move (:208-225)
+    unsigned depB, depD;   // parameters the birth side / the death side depend on
+};
+
+namespace {
+
+struct DDView {
+    const double* tab;
+    const double* genre;
+    int nb, nbp, mb, md, ng;
+    double origin, present, ln_k0l, k0l, Sx, Sxx, likD_const;
+};
+
+__device__ __forceinline__ double dd_floor(double r) { return r > 0.0 ? r : DD_SMALL; }
+
+// niche of bin j for the two kinds of carrying capacity (:64-68)
+__device__ __forceinline__ double dd_niche_logistic(const double* p, int j) {
+    return p[P_DIV0] + p[P_L] / (1.0 + exp(-p[P_K] * ((double)j - p[P_X0])));
+}
+
+// rates, niche and niche fraction of bin j as likelihood_function leaves them (:86-116)
+__device__ __forceinline__ void dd_bin(const DDView& v, const double* p, int j, double br, double lnbr, bool doB, bool doD,
+                                       double& lam, double& mu, double& niche_out, double& nf_out) {
+    const bool needL = (doB && v.mb >= 2) || (doD && v.md == 2), needC = (doB && v.mb == 1) || (doD && v.md == 1);
+    const double nicheC = p[P_L] + p[P_DIV0];
+    const double nicheL = needL ? dd_niche_logistic(p, j) : 1.0;
+    const double ln_nicheL = needL ? log(nicheL) : 0.0, ln_nicheC = needC ? log(nicheC) : 0.0;
+    lam = 0.0; mu = 1.0; niche_out = 1.0; nf_out = 1.0;
+    if (doB) {
+        if (v.mb == 0) {
+            lam = p[P_LF] * p[P_LMUL];                                   // :87 (no floor in the reference)
+        } else {
+            const double x = exp(p[P_NUB] * (lnbr - (v.mb == 1 ? ln_nicheC : ln_nicheL)));
+            const double rmax = p[P_LF] + p[P_LF] * p[P_LMUL];
+            lam = dd_floor(rmax - (rmax - p[P_LF]) * x);
+            niche_out = v.mb == 1 ? nicheC : nicheL;
+            nf_out = br / niche_out;
+        }
+    }
+    if (doD && v.md >= 1) {
+        const double x = exp(p[P_NUD] * (lnbr - (v.md == 1 ? ln_nicheC : ln_nicheL)));
+        const double rmin = p[P_LF] - p[P_LF] * p[P_MMUL];
+        mu = dd_floor(rmin + (p[P_LF] - rmin) * x);
+        niche_out = v.md == 1 ? nicheC : nicheL;
+        nf_out = br / niche_out;
+    }
+}
+
+__device__ __forceinline__ void dd_lik(const DDView& v, const double* p, int lane, bool doB, bool doD, double& likB, double& likD) {
+    const bool evalD = doD && v.md >= 1;
+    double sB = 0.0, sD = 0.0;
+    if (doB || evalD) {
+        for (int j = lane; j < v.nb; j += 32) {
+            const double br = __ldg(v.tab + DD_BR * v.nbp + j), lnbr = __ldg(v.tab + DD_LNBR * v.nbp + j);
+            double lam, mu, ni, nf;
+            dd_bin(v, p, j, br, lnbr, doB, evalD, lam, mu, ni, nf);
+            if (doB) sB += log(lam) * __ldg(v.tab + DD_SP * v.nbp + j) - lam * br;
+            if (evalD) sD += log(mu) * __ldg(v.tab + DD_EX * v.nbp + j) - mu * br;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sB += __shfl_xor_sync(0xffffffffu, sB, o);
+            sD += __shfl_xor_sync(0xffffffffu, sD, o);
+        }
+    }
+    if (doB) likB = sB;
+    if (doD) likD = v.md >= 1 ? sD : v.likD_const;                   // death rate 1 in every bin (:105-106)
+}
+
+// births and time at risk of the genre table in [origin, c) and [c, present)   (precompute_events, :100-101)
+__device__ __forceinline__ void dd_genre_stats(const DDView& v, double x0, int lane, double g[4]) {
+    const double O = v.origin, c = v.origin + x0, Pn = v.present;
+    double s1 = 0, b1 = 0, s2 = 0, b2 = 0;
+    for (int i = lane; i < v.ng; i += 32) {
+        const double ts = __ldg(v.genre + i), te = __ldg(v.genre + v.ng + i);
+        if (ts >= O && ts < c) s1 += 1.0;
+        if (ts >= c && ts < Pn) s2 += 1.0;
+        const double d1 = fmin(te, c) - fmax(ts, O), d2 = fmin(te, Pn) - fmax(ts, c);
+        if (d1 > 0.0) b1 += d1;
+        if (d2 > 0.0) b2 += d2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o); b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    }
+    g[0] = s1; g[1] = b1; g[2] = s2; g[3] = b2;
+}
+
+__device__ __forceinline__ double dd_genre_lik(const double* p, const double g[4]) {
+    return (log(p[P_G1]) * g[0] - p[P_G1] * g[1]) + (log(p[P_G2]) * g[2] - p[P_G2] * g[3]);     // :102
+}
+
+// prior term of parameter `lane` (calc_prior :127-141; closed forms of scipy's gamma / beta logpdf)
+__device__ __forceinline__ double dd_prior_term(const DDView& v, int lane, double x) {
+    switch (lane) {
+        case P_LF: case P_K: case P_G1: case P_G2: return x < 0.0 ? -INFINITY : -x / 10.0 - 2.302585092994046;      // Gamma(1, scale 10)
+        case P_LMUL: return x < 0.0 ? -INFINITY : -x;                                                                  // Gamma(1, scale 1)
+        case P_X0: return (v.origin + x >= v.present) ? -INFINITY : 0.0;                                               // :139-140
+        case P_DIV0: case P_L: return x < 0.0 ? -INFINITY : -x / v.k0l - v.ln_k0l;                                     // Gamma(1, scale max br)
+        case P_MMUL: return (x >= 0.0 && x < 1.0) ? 0.1823215567939546 + 0.2 * log1p(-x) : -INFINITY;                  // Beta(1, 1.2)
+        case P_NUB: case P_NUD: return x > 0.0 ? 2.0 * log(2.0 * x) - 2.0 * x : -INFINITY;                            // Gamma(3, scale .5)
+        default: return 0.0;
+    }
+}
+
+// update_sliding_win (literate_library.py:124-128) with m = 0
+__device__ __forceinline__ double dd_slide(double x, double u, double M, double d) {
+    double y = x + (u - 0.5) * d;
+    if (y > M) y = M - (y - M);
+    return fabs(y);
+}
+
+__device__ __forceinline__ void dd_bcast(double mine, double* p) {
+#pragma unroll
+    for (int k = 0; k < DD_NPAR; ++k) p[k] = __shfl_sync(0xffffffffu, mine, k);
+}
+
+// kind: 0 multiplier move (mask `on`, uniform `draw`), 1 sliding window on x0, 2 sliding window on m_mul (uniform `draw`)
+__device__ __forceinline__ double dd_propose(const DDView& v, int lane, int kind, double x, bool on, double draw, double& hast) {
+    hast = 0.0;
+    if (kind == 1) return lane == P_X0 ? dd_slide(x, draw, v.present, 1.5) : x;        // :251
+    if (kind == 2) return lane == P_MMUL ? dd_slide(x, draw, 1.0, 0.05) : x;           // :253
+    if (!on) return x;
+    const double lm = DD_LN_MULT * (draw - 0.5);
+    hast = lm;
+    return x * exp(lm);
+}
+
+__device__ __forceinline__ void dd_adequacy(const DDView& v, const double* p, int lane, double out[3]) {
+    double sy = 0, syy = 0, sxy = 0;
+    for (int j = lane; j < v.nb; j += 32) {
+        double lam, mu, ni, nf;
+        dd_bin(v, p, j, __ldg(v.tab + DD_BR * v.nbp + j), __ldg(v.tab + DD_LNBR * v.nbp + j), true, true, lam, mu, ni, nf);
+        const double xb = __ldg(v.tab + DD_XB * v.nbp + j), xd = __ldg(v.tab + DD_XD * v.nbp + j);
+        sy += lam + mu; syy += lam * lam + mu * mu; sxy += lam * xb + mu * xd;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        syy += __shfl_xor_sync(0xffffffffu, syy, o);
+        sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+    }
+    const double n = 2.0 * v.nb;
+    const double c = sxy / v.Sxx;
+    const double ssres = syy - c * sxy;
+    const double var_f = c * c * (v.Sxx - v.Sx * v.Sx / n) / (n - 1.0);
+    const double sres = sy - c * v.Sx;
+    const double var_r = (ssres - sres * sres / n) / (n - 1.0);
+    out[0] = c; out[1] = 1.0 - ssres / syy; out[2] = var_f / (var_f + var_r);
+}
+
+// the four per-bin series of the log row (:287): birth rates, death rates, niche, niche fraction
+__device__ __forceinline__ void dd_series(double* out, const DDView& v, const double* p, int lane) {
+    for (int j = lane; j < v.nb; j += 32) {
+        const double br = __ldg(v.tab + DD_BR * v.nbp + j);
+        double lam, mu, ni, nf;
+        dd_bin(v, p, j, br, __ldg(v.tab + DD_LNBR * v.nbp + j), true, true, lam, mu, ni, nf);
+        out[j] = lam; out[v.nb + j] = mu; out[2 * v.nb + j] = ni; out[3 * v.nb + j] = nf;
+    }
+}
+
+__device__ __forceinline__ void dd_record(double* rec, const DDView& v, const double* p, double likB, double likD, double likG,
+                                          double prior, long long it, long long accepted, int lane) {
+    double adq[3];
+    dd_adequacy(v, p, lane, adq);
+    if (lane == 0) {
+        rec[0] = (double)it; rec[1] = likB + likD + likG; rec[2] = likB; rec[3] = likD; rec[4] = prior; rec[16] = likG;
+        rec[17] = adq[0]; rec[18] = adq[1]; rec[19] = adq[2]; rec[20] = (double)accepted; rec[21] = 0.0; rec[22] = 0.0; rec[23] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < DD_NPAR; ++k)
+        if (lane == k) rec[5 + k] = p[k];
+    dd_series(rec + LR_DD_REC_HEAD, v, p, lane);
+}
+
+struct DDRun {
+    DDChain* st;
+    int n_chains;
+    DDView v;
+    uint32_t k0, k1;
+    long long n_iter, sample_every;
+    double* records;
+    int rec_doubles;
+    double f[DD_NPAR];
+    unsigned depB, depD;
+};
+
+__global__ void __launch_bounds__(128) k7_dd_kernel(const DDRun P) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= P.n_chains) return;
+    DDChain* S = P.st + c;
+    const DDView v = P.v;
+    const unsigned chain = S->chain;
+    double mine = lane < DD_NPAR ? S->p[lane] : 0.0;
+    double p[DD_NPAR];
+    dd_bcast(mine, p);
+    double likB = S->likB, likD = S->likD, likG = S->likG, prior = S->prior;
+    double g[4] = {S->g[0], S->g[1], S->g[2], S->g[3]};
+    long long it = S->it, accepted = S->accepted;
+    const long long it_end = it + P.n_iter;
+    double fmine = 0.0;
+#pragma unroll
+    for (int k = 0; k < DD_NPAR; ++k)
+        if (lane == k) fmine = P.f[k];
+    const bool can_slide = v.mb >= 1 || v.md >= 1;
+    long long next_sample = (it + P.sample_every - 1) / P.sample_every * P.sample_every;
+    long long rec_idx = 0;
+
+    for (; it < it_end; ++it) {
+        const Philox4 r = philox4x32_10((uint32_t)it, (uint32_t)((unsigned long long)it >> 32), (uint32_t)lane | (0x70u << 8), chain, P.k0, P.k1);
+        const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
+        const double rr1 = __shfl_sync(0xffffffffu, ua, 11), rr2 = __shfl_sync(0xffffffffu, ub, 11);
+        const double us = __shfl_sync(0xffffffffu, ua, 12);
+        const double log_u = log(__shfl_sync(0xffffffffu, ub, 12));
+        const int kind = (rr1 < 0.1 && can_slide) ? (rr2 < 0.5 ? 1 : 2) : 0;                  // :248-258
+        const bool on = kind == 0 && (((double)r.x + 0.5) * 2.3283064365386963e-10) < fmine;
+        double h;
+        const double prop = dd_propose(v, lane, kind, mine, on, kind == 0 ? u01(r.y, r.z) : us, h);
+        unsigned touched = __ballot_sync(0xffffffffu, on);
+        if (kind == 1) touched = 1u << P_X0;
+        if (kind == 2) touched = 1u << P_MMUL;
+        double q[DD_NPAR];
+        dd_bcast(prop, q);
+        double hs = h, pr = dd_prior_term(v, lane, prop);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {       // lanes 0..15 carry terms
+            hs += __shfl_xor_sync(0xffffffffu, hs, o);
+            pr += __shfl_xor_sync(0xffffffffu, pr, o);
+        }
+        hs = __shfl_sync(0xffffffffu, hs, 0);
+        pr = __shfl_sync(0xffffffffu, pr, 0);
+        double nB = likB, nD = likD, nG = likG;
+        double ng[4] = {g[0], g[1], g[2], g[3]};
+        dd_lik(v, q, lane, (touched & P.depB) != 0, (touched & P.depD) != 0, nB, nD);
+        if (v.mb == 3) {
+            if (touched & (1u << P_X0)) dd_genre_stats(v, q[P_X0], lane, ng);
+            if (touched & ((1u << P_X0) | (1u << P_G1) | (1u << P_G2))) nG = dd_genre_lik(q, ng);
+        }
+        const double x = ((nB + nD + nG) - (likB + likD + likG)) + (pr - prior) + hs;
+        if (x > log_u || it == 0) {                                                              // :263
+#pragma unroll
+            for (int k = 0; k < DD_NPAR; ++k) p[k] = q[k];
+            mine = prop;
+            likB = nB; likD = nD; likG = nG; prior = pr;
+            g[0] = ng[0]; g[1] = ng[1]; g[2] = ng[2]; g[3] = ng[3];
+            ++accepted;
+        }
+        if (it == next_sample) {                                                                 // :274
+            if (P.records) dd_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v, p, likB, likD, likG, prior, it, accepted, lane);
+            ++rec_idx;
+            next_sample += P.sample_every;
+        }
+    }
+    if (lane < DD_NPAR) S->p[lane] = mine;
+    if (lane == 0) {
+        S->likB = likB; S->likD = likD; S->likG = likG; S->prior = prior; S->it = it; S->accepted = accepted;
+        S->g[0] = g[0]; S->g[1] = g[1]; S->g[2] = g[2]; S->g[3] = g[3];
+    }
+}
+
+__device__ __forceinline__ void dd_eval_all(const DDView& v, const double* p, double mine, int lane, double& likB, double& likD,
+                                            double& likG, double& prior, double g[4]) {
+    likB = 0; likD = 0;
+    dd_lik(v, p, lane, true, true, likB, likD);
+    likG = 1.0;                                                    // g_birth_lik = 1 unless -m_birth 3 (:84)
+    g[0] = g[1] = g[2] = g[3] = 0.0;
+    if (v.mb == 3) { dd_genre_stats(v, p[P_X0], lane, g); likG = dd_genre_lik(p, g); }
+    prior = warp_sum(dd_prior_term(v, lane, mine));
+}
+
+// initial state (:187-201, :229-240)
+__global__ void k7_init_kernel(DDChain* st, int n_chains, long long chain_id0, const DDView v) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_chains) return;
+    const double init[DD_NPAR] = {0.5, 1.01, 1.5, v.present - (v.origin + v.present) / 2.0, 10.0, 20000.0, 0.99, 1.0, 1.0, 1.0, 1.0};
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < DD_NPAR; ++k)
+        if (lane == k) mine = init[k];
+    double p[DD_NPAR];
+    dd_bcast(mine, p);
+    double likB, likD, likG, prior, g[4];
+    dd_eval_all(v, p, mine, lane, likB, likD, likG, prior, g);
+    if (lane < DD_NPAR) st[c].p[lane] = mine;
+    if (lane == 0) {
+        st[c].likB = likB; st[c].likD = likD; st[c].likG = likG; st[c].prior = prior;
+        st[c].g[0] = g[0]; st[c].g[1] = g[1]; st[c].g[2] = g[2]; st[c].g[3] = g[3];
+        st[c].it = 0; st[c].accepted = 0; st[c].chain = (unsigned)(chain_id0 + c); st[c].pad = 0;
+    }
+}
+
+__global__ void k7_build_tables(const long long* __restrict__ sp, const long long* __restrict__ ex, const double* __restrict__ br,
+                                int nb, int nbp, double* __restrict__ tab, double* __restrict__ cst) {
+    for (int j = threadIdx.x; j < nbp; j += blockDim.x) {
+        const bool in = j < nb;
+        const double U = in ? (double)sp[j] : 0.0, D = in ? (double)ex[j] : 0.0, K = in ? br[j] : 0.0;
+        tab[DD_SP * nbp + j] = U; tab[DD_EX * nbp + j] = D; tab[DD_BR * nbp + j] = K;
+        tab[DD_LNBR * nbp + j] = in ? log(K) : 0.0;
+        tab[DD_XB * nbp + j] = in ? U / K : 0.0;
+        tab[DD_XD * nbp + j] = in ? D / K : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sx = 0, sxx = 0, sk = 0, mx = 0;
+        for (int j = 0; j < nb; ++j) {
+            const double xb = tab[DD_XB * nbp + j], xd = tab[DD_XD * nbp + j];
+            sx += xb + xd; sxx += xb * xb + xd * xd;
+            sk += log(1.0) * tab[DD_EX * nbp + j] - 1.0 * tab[DD_BR * nbp + j];      // death rate 1 (:105-106, :118)
+            mx = fmax(mx, tab[DD_BR * nbp + j]);
+        }
+        cst[0] = sx; cst[1] = sxx; cst[2] = sk; cst[3] = mx;        // mx = PRIOR_K0_L (:53)
+    }
+}
+
+__global__ void k7_eval_kernel(const DDView v, int n, const double* params, const int* kind, const int* on, const double* draw,
+                               double* out_params, double* out_hast, double* lik, double* prior, double* series, double* adequacy,
+                               double* genre) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n) return;
+    double mine = lane < DD_NPAR ? params[s * DD_NPAR + lane] : 0.0, h = 0.0;
+    if (kind) mine = dd_propose(v, lane, kind[s], mine, lane < DD_NPAR && on[s * DD_NPAR + lane] != 0,
+                                lane < DD_NPAR ? draw[s * DD_NPAR + lane] : 0.0, h);
+    h = warp_sum(h);
+    double p[DD_NPAR];
+    dd_bcast(mine, p);
+    double likB, likD, likG, pr, g[4];
+    dd_eval_all(v, p, mine, lane, likB, likD, likG, pr, g);
+    double adq[3];
+    dd_adequacy(v, p, lane, adq);
+    if (lane == 0) {
+        if (lik) { lik[3 * s] = likB; lik[3 * s + 1] = likD; lik[3 * s + 2] = likG; }
+        if (prior) prior[s] = pr;
+        if (out_hast) out_hast[s] = h;
+        if (adequacy) { adequacy[3 * s] = adq[0]; adequacy[3 * s + 1] = adq[1]; adequacy[3 * s + 2] = adq[2]; }
+        if (genre) { genre[4 * s] = g[0]; genre[4 * s + 1] = g[1]; genre[4 * s + 2] = g[2]; genre[4 * s + 3] = g[3]; }
+    }
+    if (out_params && lane < DD_NPAR) out_params[s * DD_NPAR + lane] = mine;
+    if (series) dd_series(series + (size_t)s * 4 * v.nb, v, p, lane);
+}
+
+inline int dd_grid(int n, int& threads) {
+    const int wpb = n <= 1024 ? 1 : 4;
+    threads = wpb * 32;
+    return (n + wpb - 1) / wpb;
+}
+
+// update_multiplier (:208-225) and the parameters every term depends on
+void dd_model_tables(int mb, int md, double* f, unsigned& depB, unsigned& depD) {
+    double w[DD_NPAR];
+    const double w0[DD_NPAR] = {1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0}, w2[DD_NPAR] = {1, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0},
+                 w1[DD_NPAR] = {1, 1, 0, 0, 0, 1, 0, 1, 1, 0, 0}, w3[DD_NPAR] = {1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1};
+    const double* src = (mb == 0 && md <= 0) ? w0 : ((mb == 2 || md == 2) ? w2 : w1);
+    if (mb == 3) src = w3;
+    double s = 0;
+    for (int k = 0; k < DD_NPAR; ++k) { w[k] = src[k]; s += w[k]; }
+    for (int k = 0; k < DD_NPAR; ++k) f[k] = w[k] / s;
+    const unsigned logistic = (1u << P_K) | (1u << P_X0) | (1u << P_DIV0) | (1u << P_L), constK = (1u << P_DIV0) | (1u << P_L);
+    depB = (1u << P_LF) | (1u << P_LMUL);
+    if (mb >= 1) depB |= (1u << P_NUB) | (mb == 1 ? constK : logistic);
+    depD = 0;
+    if (md >= 1) depD = (1u << P_LF) | (1u << P_MMUL) | (1u << P_NUD) | (md == 1 ? constK : logistic);
+}
+
+DDView dd_view(lr_dd_t t, const double* h_cst) {
+    DDView v;
+    v.tab = t->tab; v.genre = t->genre; v.nb = t->n_bins; v.nbp = t->nbp; v.mb = t->m_birth; v.md = t->m_death; v.ng = t->n_genre;
+    v.origin = t->origin; v.present = t->present; v.k0l = t->k0l; v.ln_k0l = log(t->k0l);
+    v.Sx = h_cst[0]; v.Sxx = h_cst[1]; v.likD_const = h_cst[2];
+    return v;
+}
+
+}  // namespace
+
+extern "C" int64_t lr_dd_record_doubles(int32_t n_bins) { return LR_DD_REC_HEAD + 4 * (int64_t)n_bins; }
+
+// the constants of the table live on the host too (they parameterise every launch)
+static int dd_fetch_cst(lr_dd_t t, cudaStream_t st, double* h_cst) {
+    LR_CUDA(cudaMemcpyAsync(h_cst, t->cst, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+    return LR_OK;
+}
+
+extern "C" int lr_dd_create(lr_handle_t h, int32_t n_bins, const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
+                            double origin, double present, int32_t m_birth, int32_t m_death,
+                            const double* h_gts, const double* h_gte, int32_t n_genre,
+                            int32_t n_chains, uint64_t seed, int64_t chain_id0, void* stream, lr_dd_t* out) {
+    LR_REQUIRE(h && d_sp && d_ex && d_br && out, "lr_dd_create: null pointer");
+    LR_REQUIRE(n_bins >= 1 && n_chains >= 1, "lr_dd_create: n_bins and n_chains must be >= 1");
+    LR_REQUIRE(present > origin, "lr_dd_create: present must be later than origin");
+    LR_REQUIRE(chain_id0 >= 0 && chain_id0 + n_chains <= 0xffffffffll, "lr_dd_create: chain ids must fit 32 bits");
+    if (m_birth < 0 || m_birth > 3 || m_death < 0 || m_death > 2) {
+        lr_set_error("lr_dd_create: -m_birth must be 0..3 and -m_death 0..2 (the fixed-rate models -1 stop with NameError in the "
+                     "reference, DDRatev3.py:192-195)");
+        return LR_ERR_UNSUPPORTED;
+    }
+    LR_REQUIRE(m_birth != 3 || (h_gts && h_gte && n_genre >= 1), "lr_dd_create: -m_birth 3 needs the genre table (DDRatev3.py:36-38)");
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    lr_dd_t t = new lr_dd_s();
+    memset(t, 0, sizeof(*t));
+    t->h = h; t->n_bins = n_bins; t->nbp = (n_bins + 3) & ~3; t->m_birth = m_birth; t->m_death = m_death;
+    t->n_genre = m_birth == 3 ? n_genre : 0; t->origin = origin; t->present = present; t->n_chains = n_chains; t->seed = seed;
+    dd_model_tables(m_birth, m_death, t->f, t->depB, t->depD);
+    cudaError_t e = cudaMallocAsync((void**)&t->tab, (size_t)DD_ROWS * t->nbp * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&t->cst, 4 * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&t->st, (size_t)n_chains * sizeof(DDChain), st);
+    if (e == cudaSuccess && t->n_genre) e = cudaMallocAsync((void**)&t->genre, (size_t)2 * t->n_genre * sizeof(double), st);
+    if (e != cudaSuccess) { lr_set_error("lr_dd_create: cudaMallocAsync: %s", cudaGetErrorString(e)); lr_dd_destroy(t); return LR_ERR_NOMEM; }
+    if (t->n_genre) {
+        LR_CUDA(cudaMemcpyAsync(t->genre, h_gts, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st));
+        LR_CUDA(cudaMemcpyAsync(t->genre + t->n_genre, h_gte, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    k7_build_tables<<<1, 128, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, n_bins, t->nbp, t->tab, t->cst);
+    LR_CUDA(cudaGetLastError());
+    double h_cst[4];
+    int rc = dd_fetch_cst(t, st, h_cst);
+    if (rc != LR_OK) { lr_dd_destroy(t); return rc; }
+    t->k0l = h_cst[3];
+    if (!(t->k0l > 0.0)) { lr_set_error("lr_dd_create: no time at risk in any bin (max br = %g)", t->k0l); lr_dd_destroy(t); return LR_ERR_INVALID; }
+    t->cst_host[0] = h_cst[0]; t->cst_host[1] = h_cst[1]; t->cst_host[2] = h_cst[2]; t->cst_host[3] = h_cst[3];
+    int threads;
+    const int blocks = dd_grid(n_chains, threads);
+    k7_init_kernel<<<blocks, threads, 0, st>>>(t->st, n_chains, chain_id0, dd_view(t, t->cst_host));
+    LR_CUDA(cudaGetLastError());
+    h->launches += 2;
+    LR_CUDA(cudaStreamSynchronize(st));
+    *out = t;
+    return LR_OK;
+}
+
+extern "C" int lr_dd_create_host(lr_handle_t h, int32_t n_bins, const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
+                                 double origin, double present, int32_t m_birth, int32_t m_death,
+                                 const double* h_gts, const double* h_gte, int32_t n_genre,
+                                 int32_t n_chains, uint64_t seed, int64_t chain_id0, lr_dd_t* out) {
+    LR_REQUIRE(h && h_sp && h_ex && h_br, "lr_dd_create_host: null pointer");
+    LR_REQUIRE(n_bins >= 1, "lr_dd_create_host: bad sizes");
+    LR_CUDA(cudaSetDevice(h->device));
+    const size_t cnt = (size_t)n_bins;
+    int rc = lr_ws_reserve(h, cnt * 24);
+    if (rc != LR_OK) return rc;
+    int64_t* d_sp = (int64_t*)h->ws;
+    int64_t* d_ex = d_sp + cnt;
+    double* d_br = (double*)(d_ex + cnt);
+    LR_CUDA(cudaMemcpyAsync(d_sp, h_sp, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaMemcpyAsync(d_ex, h_ex, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaMemcpyAsync(d_br, h_br, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    return lr_dd_create(h, n_bins, d_sp, d_ex, d_br, origin, present, m_birth, m_death, h_gts, h_gte, n_genre, n_chains, seed,
+                        chain_id0, h->stream, out);
+}
+
+extern "C" int lr_dd_destroy(lr_dd_t t) {
+    if (!t) return LR_OK;
+    cudaSetDevice(t->h->device);
+    if (t->tab) cudaFreeAsync(t->tab, t->h->stream);
+    if (t->cst) cudaFreeAsync(t->cst, t->h->stream);
+    if (t->st) cudaFreeAsync(t->st, t->h->stream);
+    if (t->genre) cudaFreeAsync(t->genre, t->h->stream);
+    delete t;
+    return LR_OK;
+}
+
+extern "C" int64_t lr_dd_records_per_run(lr_dd_t t, int64_t n_iter, int64_t sample_every) {
+    if (!t || n_iter <= 0 || sample_every <= 0) return 0;
+    long long it0 = 0;
+    cudaSetDevice(t->h->device);
+    cudaStreamSynchronize(t->h->stream);
+    if (cudaMemcpy(&it0, &t->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    const long long first = (it0 + sample_every - 1) / sample_every * sample_every;
+    const long long it1 = it0 + n_iter;
+    return first < it1 ? (it1 - 1 - first) / sample_every + 1 : 0;
+}
+
+extern "C" int lr_dd_run(lr_dd_t t, int64_t n_iter, int64_t sample_every, double* d_records, void* stream) {
+    LR_REQUIRE(t != nullptr, "lr_dd_run: null chains");
+    LR_REQUIRE(n_iter >= 0 && sample_every >= 0, "lr_dd_run: negative count");
+    if (n_iter == 0) return LR_OK;
+    lr_handle_t h = t->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    DDRun P;
+    P.st = t->st; P.n_chains = t->n_chains; P.v = dd_view(t, t->cst_host);
+    P.k0 = (uint32_t)t->seed; P.k1 = (uint32_t)(t->seed >> 32);
+    P.n_iter = n_iter; P.sample_every = sample_every > 0 ? sample_every : (int64_t)1 << 62;
+    P.records = sample_every > 0 ? d_records : nullptr;
+    P.rec_doubles = (int)lr_dd_record_doubles(t->n_bins);
+    for (int k = 0; k < DD_NPAR; ++k) P.f[k] = t->f[k];
+    P.depB = t->depB; P.depD = t->depD;
+    int threads;
+    const int blocks = dd_grid(t->n_chains, threads);
+    k7_dd_kernel<<<blocks, threads, 0, st>>>(P);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_dd_run_host(lr_dd_t t, int64_t n_iter, int64_t sample_every, double* h_records) {
+    LR_REQUIRE(t != nullptr, "lr_dd_run_host: null chains");
+    lr_handle_t h = t->h;
+    const int64_t nrec = (h_records && sample_every > 0) ? lr_dd_records_per_run(t, n_iter, sample_every) : 0;
+    LR_REQUIRE(nrec >= 0, "lr_dd_run_host: could not read the iteration counter");
+    const size_t bytes = (size_t)nrec * t->n_chains * lr_dd_record_doubles(t->n_bins) * sizeof(double);
+    double* d_rec = nullptr;
+    if (bytes) {
+        int rc = lr_ws_reserve(h, bytes);
+        if (rc != LR_OK) return rc;
+        d_rec = (double*)h->ws;
+    }
+    int rc = lr_dd_run(t, n_iter, bytes ? sample_every : 0, d_rec, h->stream);
+    if (rc != LR_OK) return rc;
+    if (bytes) LR_CUDA(cudaMemcpyAsync(h_records, d_rec, bytes, cudaMemcpyDeviceToHost, h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const double* params, const int32_t* kind, const int32_t* on,
+                               const double* draw, double* out_params, double* out_hast, double* lik, double* prior,
+                               double* series, double* adequacy, double* genre) {
+    LR_REQUIRE(t && params, "lr_dd_eval_host: null pointer");
+    LR_REQUIRE(n >= 1, "lr_dd_eval_host: n must be >= 1");
+    LR_REQUIRE(!kind || (on && draw), "lr_dd_eval_host: kind needs on and draw");
+    lr_handle_t h = t->h;
+    LR_CUDA(cudaSetDevice(h->device));
+    const int nb = t->n_bins;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_par = take((size_t)n * DD_NPAR * 8), o_kind = take((size_t)n * 4), o_on = take((size_t)n * DD_NPAR * 4),
+                 o_draw = take((size_t)n * DD_NPAR * 8), o_np = take((size_t)n * DD_NPAR * 8), o_h = take((size_t)n * 8),
+                 o_lik = take((size_t)n * 24), o_pr = take((size_t)n * 8), o_ser = take((size_t)n * 4 * nb * 8),
+                 o_adq = take((size_t)n * 24), o_g = take((size_t)n * 32);
+    int rc = lr_ws_reserve(h, off);
+    if (rc != LR_OK) return rc;
+    char* W = (char*)h->ws;
+    cudaStream_t st = h->stream;
+    LR_CUDA(cudaMemcpyAsync(W + o_par, params, (size_t)n * DD_NPAR * 8, cudaMemcpyHostToDevice, st));
+    if (kind) {
+        LR_CUDA(cudaMemcpyAsync(W + o_kind, kind, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        LR_CUDA(cudaMemcpyAsync(W + o_on, on, (size_t)n * DD_NPAR * 4, cudaMemcpyHostToDevice, st));
+        LR_CUDA(cudaMemcpyAsync(W + o_draw, draw, (size_t)n * DD_NPAR * 8, cudaMemcpyHostToDevice, st));
+    }
+    k7_eval_kernel<<<(n + 3) / 4, 128, 0, st>>>(dd_view(t, t->cst_host), n, (const double*)(W + o_par), kind ? (const int*)(W + o_kind) : nullptr,
+                                                (const int*)(W + o_on), (const double*)(W + o_draw), (double*)(W + o_np), (double*)(W + o_h),
+                                                (double*)(W + o_lik), (double*)(W + o_pr), (double*)(W + o_ser), (double*)(W + o_adq),
+                                                (double*)(W + o_g));
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (out_params) LR_CUDA(cudaMemcpyAsync(out_params, W + o_np, (size_t)n * DD_NPAR * 8, cudaMemcpyDeviceToHost, st));
+    if (out_hast) LR_CUDA(cudaMemcpyAsync(out_hast, W + o_h, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (lik) LR_CUDA(cudaMemcpyAsync(lik, W + o_lik, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    if (prior) LR_CUDA(cudaMemcpyAsync(prior, W + o_pr, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (series) LR_CUDA(cudaMemcpyAsync(series, W + o_ser, (size_t)n * 4 * nb * 8, cudaMemcpyDeviceToHost, st));
+    if (adequacy) LR_CUDA(cudaMemcpyAsync(adequacy, W + o_adq, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+    if (genre) LR_CUDA(cudaMemcpyAsync(genre, W + o_g, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+    return LR_OK;
+}
+
+extern "C" int lr_dd_state_host(lr_dd_t t, double* h_state) {
+    LR_REQUIRE(t && h_state, "lr_dd_state_host: null pointer");
+    LR_CUDA(cudaSetDevice(t->h->device));
+    LR_CUDA(cudaStreamSynchronize(t->h->stream));
+    DDChain* tmp = new DDChain[t->n_chains];
+    cudaError_t e = cudaMemcpy(tmp, t->st, (size_t)t->n_chains * sizeof(DDChain), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete[] tmp; lr_set_error("lr_dd_state_host: %s", cudaGetErrorString(e)); return LR_ERR_CUDA; }
+    for (int c = 0; c < t->n_chains; ++c) {
+        double* o = h_state + (size_t)c * LR_DD_STATE_DOUBLES;
+        for (int k = 0; k < DD_NPAR; ++k) o[k] = tmp[c].p[k];
+        o[11] = tmp[c].likB; o[12] = tmp[c].likD; o[13] = tmp[c].likG; o[14] = tmp[c].prior;
+        o[15] = (double)tmp[c].it; o[16] = (double)tmp[c].accepted;
+        for (int k = 0; k < 4; ++k) o[17 + k] = tmp[c].g[k];
+        o[21] = 0.0; o[22] = 0.0; o[23] = 0.0;
+    }
+    delete[] tmp;
+    return LR_OK;
+}

@@ -1,0 +1,197 @@
+"""GPU: K7 (DDRate chains) through the C ABI against the oracle pinned to the unmodified DDRatev3.py.
+
+Deterministic parity (1e-10 relative, the north star's tolerance): the three likelihood terms, prior, per-bin rates / niche
+/ niche fraction, genre-window statistics (exact counts), the multiplier move and both sliding-window moves with explicit
+draws, for every (m_birth, m_death) the functions of the reference define.  Chain-level parity is distributional: 64 device
+chains against the committed summaries of 8 unmodified reference chains (-m_birth 3, the configuration that runs as shipped).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ddrate_oracle as D
+from literate_b200 import ddrate as DD
+from literate_b200 import trend as TR
+from test_oracle_ddrate_golden import DG, _jobs, stage
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _job(tag):
+    return [j for j in _jobs() if j["tag"] == tag][0]
+
+
+def _setup(device, tmp_path, tag="ex_g_mddn", mb=3, md=2, n_chains=8, seed=1, rm=0):
+    job = _job(tag)
+    data, genre = stage(job, tmp_path)
+    ts, te, present, origin = TR.parse_ts_te(data)
+    first, nb = TR.bin_window(origin, present, rm)
+    st = device.bin_stats(ts, te, first_bin=first, n_bins=nb)
+    gts, gte, _, _ = TR.parse_ts_te(genre)
+    bins = D.create_bins(origin, present, ts, te, rm)
+    assert np.array_equal(st.sp[0], bins.n_spec) and np.array_equal(st.ex[0], bins.n_exti) and np.array_equal(st.br[0], bins.dt)
+    S = D.Setup(bins, mb, md, gts, gte)
+    ch = DD.DDChains(device, st.sp[0], st.ex[0], st.br[0], bins.origin, present, mb, md, gts if mb == 3 else None,
+                     gte if mb == 3 else None, n_chains, seed)
+    return S, ch
+
+
+def _random_params(rng, n, S):
+    span = S.present - S.origin
+    return np.stack([rng.gamma(2, .2, n), rng.gamma(2, .5, n), rng.gamma(2, .5, n), rng.uniform(0, span * .98, n), rng.gamma(2, 5, n),
+                     rng.gamma(2, 30, n), rng.uniform(0, 1, n), rng.gamma(3, .5, n), rng.gamma(3, .5, n), rng.gamma(2, .5, n),
+                     rng.gamma(2, .5, n)], axis=1)
+
+
+@pytest.mark.parametrize("mb,md", [(3, 2), (3, 1), (3, 0), (2, 2), (2, 1), (1, 2), (1, 1), (0, 0), (0, 2), (1, 0)])
+def test_state_evaluation_matches_the_oracle(device, tmp_path, mb, md):
+    S, ch = _setup(device, tmp_path, mb=mb, md=md)
+    rng = np.random.default_rng(100 + 10 * mb + md)
+    P = _random_params(rng, 120, S)
+    P[0] = D.initial_args(S)
+    P[1, 6] = 1.7                  # m_mul > 1: death rates floored at SMALL_NUMBER where they turn negative (:79)
+    out = ch.evaluate(P)
+    emp_b, emp_d = S.bins.n_spec / S.bins.dt, S.bins.n_exti / S.bins.dt
+    for i, p in enumerate(P):
+        lk, birth, death, niche, nf = D.likelihood(p, S)
+        np.testing.assert_allclose(out["lik"][i], lk, rtol=RTOL)
+        want = D.prior(p, S, exact_scipy=True)
+        assert out["prior"][i] == (pytest.approx(want, rel=RTOL) if np.isfinite(want) else want)
+        np.testing.assert_allclose(out["series"][i], [birth, death, niche, nf], rtol=RTOL)
+        np.testing.assert_allclose(out["adequacy"][i], D.adequacy(emp_b, emp_d, birth, death), rtol=1e-8)
+        if mb == 3:
+            assert tuple(out["genre"][i]) == pytest.approx(D.genre_stats(S, p[3]), rel=1e-13)
+            assert out["genre"][i][0] == D.genre_stats(S, p[3])[0] and out["genre"][i][2] == D.genre_stats(S, p[3])[2]   # counts exact
+    bad = np.tile(D.initial_args(S), (5, 1))
+    bad[0, 0] = -.1; bad[1, 3] = S.present - S.origin; bad[2, 6] = 1.0; bad[3, 7] = 0.0; bad[4, 5] = -1.0
+    assert np.all(np.isneginf(ch.evaluate(bad)["prior"]))
+
+
+def test_proposals_with_explicit_draws_match_the_oracle(device, tmp_path):
+    S, ch = _setup(device, tmp_path)
+    rng = np.random.default_rng(12)
+    n = 300
+    P = _random_params(rng, n, S)
+    kind = rng.integers(0, 3, n).astype(np.int32)
+    on = (rng.uniform(size=(n, 11)) < .4).astype(np.int32)
+    draw = rng.uniform(size=(n, 11))
+    P[:20, 6] = rng.uniform(0, .02, 20); P[20:40, 6] = rng.uniform(.98, 1, 20)     # m_mul near both reflecting ends
+    P[40:50, 3] = rng.uniform(0, .7, 10)                                             # x0 near 0: the abs() branch
+    out = ch.evaluate(P, kind=kind, on=on, draw=draw)
+    for i in range(n):
+        q, h = P[i].copy(), 0.0
+        if kind[i] == 0:
+            q, h = D.multiplier_given(P[i], on[i], draw[i])
+        elif kind[i] == 1:
+            q[3] = D.sliding_window_given(q[3], draw[i, 3], S.present, 1.5)
+        else:
+            q[6] = D.sliding_window_given(q[6], draw[i, 6], 1, .05)
+        np.testing.assert_allclose(out["params"][i], q, rtol=1e-13)
+        assert out["hastings"][i] == pytest.approx(h, rel=1e-11, abs=1e-15)
+        lk, _, _, _, _ = D.likelihood(q, S)
+        np.testing.assert_allclose(out["lik"][i], lk, rtol=RTOL)
+        want = D.prior(q, S, exact_scipy=True)
+        assert out["prior"][i] == (pytest.approx(want, rel=RTOL) if np.isfinite(want) else want)
+
+
+@pytest.mark.parametrize("mb,md", [(3, 2), (2, 1), (1, 0)])
+def test_chain_bookkeeping(device, tmp_path, mb, md):
+    """Initial state, forced acceptance of iteration 0, stored terms = terms of the stored parameters (the cached sides and
+    the cached genre statistics), records on the sampling grid."""
+    S, ch = _setup(device, tmp_path, mb=mb, md=md, n_chains=16, seed=3)
+    s0 = ch.state()
+    init = D.initial_args(S)
+    lk, _, _, _, _ = D.likelihood(init, S)
+    for s in s0:
+        assert np.array_equal(s[:11], init) and s[15] == 0
+        np.testing.assert_allclose(s[11:14], lk, rtol=RTOL)
+        assert s[14] == pytest.approx(D.prior(init, S, exact_scipy=True), rel=RTOL)
+    recs = ch.run(20001, 500)
+    nb = S.n
+    assert recs.shape == (41, 16, 24 + 4 * nb) and np.all(recs[0, :, 20] == 1)
+    emp_b, emp_d = S.bins.n_spec / S.bins.dt, S.bins.n_exti / S.bins.dt
+    for si in range(0, 41, 4):
+        for c in (0, 7, 15):
+            r = recs[si, c]
+            assert r[0] == si * 500
+            p = r[5:16]
+            lk, birth, death, niche, nf = D.likelihood(p, S)
+            np.testing.assert_allclose([r[2], r[3], r[16]], lk, rtol=RTOL)
+            assert r[1] == pytest.approx(r[2] + r[3] + r[16], rel=1e-15)
+            assert r[4] == pytest.approx(D.prior(p, S, exact_scipy=True), rel=RTOL)
+            np.testing.assert_allclose(r[24:].reshape(4, nb), [birth, death, niche, nf], rtol=RTOL)
+            np.testing.assert_allclose(r[17:20], D.adequacy(emp_b, emp_d, birth, death), rtol=1e-8)
+    fin = ch.state()
+    assert np.all(fin[:, 15] == 20001) and np.all(fin[:, 16] == recs[-1, :, 20])
+    if mb == 3:
+        for s in fin[:4]:
+            assert tuple(s[17:21]) == pytest.approx(D.genre_stats(S, s[3]), rel=1e-13)
+    assert 0.05 < fin[:, 16].mean() / 20001 < 0.95
+
+
+def test_determinism_split_runs_and_sharding(device, tmp_path):
+    S, a = _setup(device, tmp_path, n_chains=32, seed=11)
+    ra = a.run(3000, 100)
+    mk = lambda n, seed, c0=0: DD.DDChains(device, S.bins.n_spec, S.bins.n_exti, S.bins.dt, S.origin, S.present, 3, 2, S.gts, S.gte,
+                                           n, seed, chain_id0=c0)
+    b = mk(32, 11)
+    rb = np.concatenate([b.run(1000, 100), b.run(1501, 100), b.run(499, 100)])
+    assert np.array_equal(ra, rb) and np.array_equal(a.state(), b.state())
+    assert np.array_equal(mk(8, 11, 16).run(3000, 100), ra[:, 16:24])
+    assert not np.array_equal(mk(32, 12).run(3000, 100), ra)
+    assert np.array_equal(mk(2048, 11).run(3000, 100)[:, :32], ra)
+
+
+def test_unsupported_models_are_refused(device, tmp_path):
+    from literate_b200._native import NativeError
+    with pytest.raises(NativeError, match="NameError"):
+        _setup(device, tmp_path, mb=2, md=-1)
+
+
+@pytest.mark.parametrize("tag,md", [("ex_g_mddn", 2), ("ex_g_mdd", 1)])
+def test_posterior_matches_reference_chains(device, tmp_path, tag, md):
+    """64 device chains against 8 unmodified reference chains of the same length: every posterior mean within 4.5 standard
+    errors (between-chain variance of both sides)."""
+    with open(os.path.join(DG, "posterior", tag + ".json")) as fh:
+        ref = json.load(fh)
+    S, ch = _setup(device, tmp_path, "ex_g_mddn", mb=3, md=md, n_chains=64, seed=2027)
+    recs = ch.run(ref["n_iter"], ref["sample_every"])
+    r = recs[int(ref["burnin"] * recs.shape[0]):]
+    nb = S.n
+    cols = {"likelihood": r[:, :, 1], "likelihood_birth": r[:, :, 2], "likelihood_death": r[:, :, 3], "prior": r[:, :, 4],
+            "l_f": r[:, :, 5], "l_mul": r[:, :, 6], "k": r[:, :, 7], "x0_abs": r[:, :, 8] + S.origin, "div_0": r[:, :, 9],
+            "K_max": r[:, :, 10] + r[:, :, 9], "m_mul": r[:, :, 11], "nuB": r[:, :, 12], "nuD": r[:, :, 13], "g_l1": r[:, :, 14],
+            "g_l2": r[:, :, 15], "likelihood_genre": r[:, :, 16]}
+    mine = {k + "_mean": v.mean(0) for k, v in cols.items()}
+    for i, k in enumerate(["birth_rate", "death_rate", "niche", "niche_frac"]):
+        mine[k + "_mean"] = r[:, :, 24 + i * nb:24 + (i + 1) * nb].mean(0)
+    for key, a in mine.items():
+        b = np.array([c[key] for c in ref["chains"]], dtype=float)
+        a = np.asarray(a, dtype=float)
+        se = np.sqrt(a.var(0, ddof=1) / len(a) + b.var(0, ddof=1) / len(b))
+        z = np.abs(a.mean(0) - b.mean(0)) / se
+        assert np.all(z < 4.5), (key, float(np.max(z)), a.mean(0), b.mean(0))
+
+
+def test_command_line_end_to_end(device, tmp_path):
+    job = _job("ex_g_mddn")
+    data, genre = stage(job, tmp_path)
+    paths = DD.run(DD.build_parser().parse_args(["-d", data, "-m_birth", "3", "-g", genre, "-n", "3001", "-s", "50", "-seed", "1",
+                                                 "-chains", "2", "-quiet", "1"]), device=device)
+    assert [os.path.basename(p) for p in paths] == ["example3_%d_GLDDN_MDDN.log" % s for s in (1, 2)]
+    files = {f: open(os.path.join(DG, "ex_g_mddn", f), "rb").read() for f in job["files"]}
+    want = files["example3_1_GLDDN_MDDN.log"].split(b"\r\n")
+    for p in paths:
+        got = open(p, "rb").read().split(b"\r\n")
+        assert got[0] == want[0] and len(got) == len(want)
+        rows = np.array([l.split(b"\t") for l in got[1:-1]], dtype=float)
+        assert rows.shape[1] == len(want[1].split(b"\t")) and np.array_equal(rows[:, 0], np.arange(0, 3001, 50))
+        assert open(p[:-4] + ".div.log", "rb").read() == files["example3_1_GLDDN_MDDN.div.log"]      # statistics: byte-identical
+    # a model the reference cannot start (NameError at :48) but whose functions are defined
+    paths = DD.run(DD.build_parser().parse_args(["-d", data, "-m_birth", "2", "-m_death", "1", "-n", "501", "-s", "100", "-seed", "4",
+                                                 "-quiet", "1"]), device=device)
+    assert os.path.basename(paths[0]) == "example3_4_LDDN_MDD.log"
+    assert len(open(paths[0]).read().splitlines()) == 7
