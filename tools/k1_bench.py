@@ -17,8 +17,10 @@ tdev = torch.device("cuda:0")
 n, nb = 1_000_000, 200
 res = {}
 for kind in kinds:
-    if kind == "real":
+    if kind in ("real", "realsorted"):
         ts, te = synth.syn_real_device(n, n_rep, tdev); fe = 1.0
+        if kind == "realsorted":
+            ts, idx = torch.sort(ts, dim=1); te = torch.gather(te, 1, idx)
     else:
         ts, te = synth.syn_int_device(n, n_rep, tdev); fe = 0.5
         if kind == "sorted":
