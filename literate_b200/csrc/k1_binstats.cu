@@ -70,10 +70,10 @@ __device__ __forceinline__ void add96(unsigned* arr, unsigned nb, unsigned idx, 
 
 struct K1Smem {
     unsigned* hs32;       // [nb] births
-    unsigned* he32;       // [nb] deaths
+    unsigned* he32;       // [nb] deaths whose fraction is the expected one (fe == fe_ref)
     unsigned* cS;         // [3][nb]
     unsigned* cE;         // [3][nb]
-    unsigned* exC;        // [nb]
+    unsigned* exC;        // [nb] deaths with any other fraction: every death takes exactly ONE of the two counters
 };
 
 // Lineages that are not (alive for a positive time, born inside the window): rare, global atomics.
@@ -124,11 +124,12 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
         const double fr = ts - (double)ti;
         if (fr != 0.0) add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
         if (b < p.nb) {
-            atomicAdd(&s.he32[b], 1u);
             const double fe = te - (double)(ci - 1);
             if (fe != p.fe_ref) {
                 atomicAdd(&s.exC[b], 1u);
                 add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
+            } else {
+                atomicAdd(&s.he32[b], 1u);
             }
         }
     } else {
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
         unsigned long long* g = (unsigned long long*)acc;
         for (unsigned i = tid; i < nb; i += blockDim.x) {
             if (s.hs32[i]) atomicAdd(&g[ROW_SP * p.acc_stride + i], (unsigned long long)s.hs32[i]);
-            if (s.he32[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.he32[i]);
+            if (s.he32[i] | s.exC[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.he32[i] + (unsigned long long)s.exC[i]);
         }
         for (unsigned i = tid; i < nb; i += blockDim.x) {
             const unsigned a0 = s.cS[i], a1 = s.cS[nb + i], a2 = s.cS[2 * nb + i];
