@@ -7,7 +7,8 @@
 //
 // One warp = one chain, whole loop on device.  Lane p < 6 owns parameter p: it draws the parameter's Bernoulli mask and
 // its multiplier / normal step from one Philox call keyed by (seed, chain, iteration, lane), evaluates the parameter's
-// prior term, and the six values are broadcast by shuffles; lane 6 draws the branch uniform and the acceptance uniform.
+// prior difference (no logarithm: the Gamma(3) parameters only move by multipliers), and the six values are broadcast by
+// shuffles; lane 6 draws the branch uniform and the acceptance uniform (accept test through a single-precision bracket of log u).
 // Bins are strided over the 32 lanes (bin j lives in lane j % 32; the first 32 bins' statistics stay in registers), the
 // two side sums come out of one butterfly.  A side none of whose parameters was touched keeps its stored likelihood (the
 // reference recomputes the identical number).  Nothing but the read-only per-bin table (L1-resident) is read inside the
@@ -78,15 +79,30 @@ __device__ __forceinline__ double trend_rate(double a, double b, double c, doubl
     return r > 0.0 ? r : TR_SMALL;
 }
 
-// both side likelihoods (uniform over the warp); a side with do_* == false keeps the value passed in
-__device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, int lane, bool doB, bool doD, double& likB, double& likD) {
+// T**delta and T**gamma of the first 32 bins (one per lane): they change only when delta / gamma are proposed
+struct PowCache { double b, d; };
+
+// both side likelihoods (uniform over the warp); a side with do_* == false keeps the value passed in.  newPowB/newPowD: the
+// exponent of that side differs from the one `pc` was computed for (pc is updated in place)
+__device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, int lane, bool doB, bool doD, bool newPowB, bool newPowD,
+                                          PowCache& pc, double& likB, double& likD) {
     double sB = 0.0, sD = 0.0;
     if (doB) {
-        const double lam = trend_rate(p[0], p[2], p[4], v.lnT0, v.const_b);
+        double lam = p[0];
+        if (!v.const_b) {
+            if (newPowB) pc.b = exp(p[4] * v.lnT0);
+            lam = p[0] + p[2] * pc.b;
+            lam = lam > 0.0 ? lam : TR_SMALL;
+        }
         sB = log(lam) * v.sp0 - lam * v.br0;
     }
     if (doD) {
-        const double mu = trend_rate(p[1], p[3], p[5], v.lnT0, v.const_d);
+        double mu = p[1];
+        if (!v.const_d) {
+            if (newPowD) pc.d = exp(p[5] * v.lnT0);
+            mu = p[1] + p[3] * pc.d;
+            mu = mu > 0.0 ? mu : TR_SMALL;
+        }
         sD = log(mu) * v.ex0 - mu * v.br0;
     }
     for (int j = lane + 32; j < v.nb; j += 32) {
@@ -122,6 +138,16 @@ __device__ __forceinline__ double trend_prior_term(int lane, double x) {
     return 0.0;
 }
 
+// prior(x') - prior(x) of parameter `lane` inside the loop, without logarithms: the Gamma(3) parameters (delta, gamma) only move
+// by multipliers, where log x' - log x is the log-multiplier `lm` itself.  `x` lies in the support (it is an accepted state).
+__device__ __forceinline__ double trend_prior_delta(int lane, double x, double xn, double lm) {
+    const double d = xn - x;
+    if (lane < 2) return xn < 0.001 ? -INFINITY : -d / 10.0;
+    if (lane < 4) return -(d * (xn + x)) / 50.0;
+    if (lane < 6) return xn > 0.0 ? 2.0 * lm - 2.0 * d : -INFINITY;
+    return 0.0;
+}
+
 // One proposal (trend_rate.py:166-171).  Lane p < 6 returns the proposed value of parameter p given the parameter's own
 // value `x`, its mask bit and its draw (uniform for the multiplier, standard normal for the additive step); `hast` receives
 // the lane's share of the Hastings ratio.
@@ -131,7 +157,7 @@ __device__ __forceinline__ double trend_propose(int kind_normal, double x, bool 
     if (kind_normal) return x + TR_NORM_SD * draw;          // literate_library.py:140-146
     const double lm = TR_LN_MULT * (draw - 0.5);            // literate_library.py:156-165: m = exp(l (u - .5)), U = sum log m
     hast = lm;
-    return x * exp(lm);
+    return x * exp_small(lm);
 }
 
 __device__ __forceinline__ void bcast6(double mine, double* p) {
@@ -165,10 +191,11 @@ __device__ __forceinline__ void trend_adequacy(const TrendView& v, const double*
 
 // record: [0] it [1] likelihood [2] likelihood_birth [3] likelihood_death [4] prior [5..10] parameters [11..13] adequacy
 //         [14] accepted so far [15] reserved [16 .. 16+nb) birth rates [16+nb .. 16+2nb) death rates
-__device__ __forceinline__ void trend_record(double* rec, const TrendView& v, const double* p, double likB, double likD,
-                                             double prior, long long it, long long accepted, int lane) {
+__device__ __forceinline__ void trend_record(double* rec, const TrendView& v, const double* p, double mine, double likB, double likD,
+                                             long long it, long long accepted, int lane) {
     double adq[3];
     trend_adequacy(v, p, lane, adq);
+    const double prior = warp_sum(trend_prior_term(lane, mine));
     if (lane == 0) {
         rec[0] = (double)it; rec[1] = likB + likD; rec[2] = likB; rec[3] = likD; rec[4] = prior;
         rec[11] = adq[0]; rec[12] = adq[1]; rec[13] = adq[2]; rec[14] = (double)accepted; rec[15] = 0.0;
@@ -196,7 +223,7 @@ struct TrendRun {
     double fd_mult[TR_NPAR], fd_norm[TR_NPAR];  // Bernoulli probability of every parameter under the two proposal kinds
 };
 
-__global__ void __launch_bounds__(128) k6_trend_kernel(const TrendRun P) {
+__global__ void __launch_bounds__(128, 4) k6_trend_kernel(const TrendRun P) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= P.n_chains) return;
@@ -206,7 +233,10 @@ __global__ void __launch_bounds__(128) k6_trend_kernel(const TrendRun P) {
     double mine = lane < TR_NPAR ? S->p[lane] : 0.0;       // this lane's parameter; p[] = the broadcast copies
     double p[TR_NPAR];
     bcast6(mine, p);
-    double likB = S->likB, likD = S->likD, prior = S->prior;
+    double likB = S->likB, likD = S->likD;
+    PowCache pc;
+    pc.b = v.const_b ? 1.0 : exp(p[4] * v.lnT0);
+    pc.d = v.const_d ? 1.0 : exp(p[5] * v.lnT0);
     long long it = S->it, accepted = S->accepted;
     const long long it_end = it + P.n_iter;
     // this lane's Bernoulli probabilities (lanes >= 6: never on)
@@ -219,43 +249,45 @@ __global__ void __launch_bounds__(128) k6_trend_kernel(const TrendRun P) {
         // lane 6: branch and acceptance uniforms
         const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
         const double rr = __shfl_sync(0xffffffffu, ua, 6);
-        const double log_u = log(__shfl_sync(0xffffffffu, ub, 6));
+        const double u_acc = __shfl_sync(0xffffffffu, ub, 6);
         const int kind_normal = rr < 0.33;                                  // trend_rate.py:167
-        // lanes 0..5: mask from 32 bits, draw from 52 bits (+ 32 bits for the angle of Box-Muller)
+        // lanes 0..5: mask from 32 bits, draw from 52 bits (+ 24 bits for the angle of Box-Muller)
         const double um = ((double)r.x + 0.5) * 2.3283064365386963e-10;
         const bool on = um < (kind_normal ? fn : fm);
         double draw = u01(r.y, r.z);
-        if (kind_normal) draw = sqrt(-2.0 * log(draw)) * cospi(2.0 * (((double)r.w + 0.5) * 2.3283064365386963e-10));
+        if (kind_normal) draw = normal_f32(draw, r.w);
         double h;
         const double prop = trend_propose(kind_normal, mine, on, draw, h);
         const unsigned touched = __ballot_sync(0xffffffffu, on);
         double q[TR_NPAR];
         bcast6(prop, q);
-        // Hastings ratio and prior: one butterfly for both
-        double hs = h, pr = trend_prior_term(lane, prop);
+        // Hastings ratio and prior difference: one butterfly for both
+        double hs = h, dpr = trend_prior_delta(lane, mine, prop, h);
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {       // only lanes 0..7 carry terms
             hs += __shfl_xor_sync(0xffffffffu, hs, o);
-            pr += __shfl_xor_sync(0xffffffffu, pr, o);
+            dpr += __shfl_xor_sync(0xffffffffu, dpr, o);
         }
         hs = __shfl_sync(0xffffffffu, hs, 0);
-        pr = __shfl_sync(0xffffffffu, pr, 0);
+        dpr = __shfl_sync(0xffffffffu, dpr, 0);
         double nB = likB, nD = likD;
-        trend_lik(v, q, lane, (touched & 0x15u) != 0, (touched & 0x2au) != 0, nB, nD);
-        const double x = ((nB + nD) - (likB + likD)) + (pr - prior) + hs;
-        if (x > log_u || it == 0) {                                          // trend_rate.py:176
+        PowCache npc = pc;
+        trend_lik(v, q, lane, (touched & 0x15u) != 0, (touched & 0x2au) != 0, (touched & 0x10u) != 0, (touched & 0x20u) != 0, npc, nB, nD);
+        const double x = ((nB + nD) - (likB + likD)) + dpr + hs;
+        if (it == 0 || mh_accept_gt(x, u_acc)) {                            // trend_rate.py:176
 #pragma unroll
             for (int k = 0; k < TR_NPAR; ++k) p[k] = q[k];
             mine = prop;
-            likB = nB; likD = nD; prior = pr;
+            likB = nB; likD = nD; pc = npc;
             ++accepted;
         }
         if (it == next_sample) {                                             // trend_rate.py:184
-            if (P.records) trend_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v, p, likB, likD, prior, it, accepted, lane);
+            if (P.records) trend_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v, p, mine, likB, likD, it, accepted, lane);
             ++rec_idx;
             next_sample += P.sample_every;
         }
     }
+    const double prior = warp_sum(trend_prior_term(lane, mine));
     if (lane < TR_NPAR) S->p[lane] = mine;
     if (lane == 0) { S->likB = likB; S->likD = likD; S->prior = prior; S->it = it; S->accepted = accepted; }
 }
@@ -272,7 +304,8 @@ __global__ void k6_init_kernel(TrendChain* st, int n_chains, const int* rep_of_c
     double p[TR_NPAR];
     bcast6(mine, p);
     double likB = 0, likD = 0;
-    trend_lik(v, p, lane, true, true, likB, likD);
+    PowCache pc;
+    trend_lik(v, p, lane, true, true, true, true, pc, likB, likD);
     double pr = trend_prior_term(lane, mine);
     pr = warp_sum(pr);
     if (lane < TR_NPAR) st[c].p[lane] = mine;
@@ -321,7 +354,8 @@ __global__ void k6_eval_kernel(const double* tab, const double* cst, int nb, int
     double p[TR_NPAR];
     bcast6(mine, p);
     double likB = 0, likD = 0;
-    trend_lik(v, p, lane, true, true, likB, likD);
+    PowCache pc;
+    trend_lik(v, p, lane, true, true, true, true, pc, likB, likD);
     const double pr = warp_sum(trend_prior_term(lane, mine));
     double adq[3];
     trend_adequacy(v, p, lane, adq);

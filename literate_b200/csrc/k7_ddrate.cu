@@ -9,8 +9,9 @@
 //   log-lik  = sum_j log(lambda_j) sp_j - lambda_j br_j + sum_j log(mu_j) ex_j - mu_j br_j  [+ genre term, -m_birth 3, :99-102]
 //
 // One warp = one chain, whole loop on device (the layout of K6): lane p < 11 owns parameter p (Philox draw, multiplier,
-// prior term), lane 11 draws the two branch uniforms, lane 12 the sliding-window and the acceptance uniform; bins are
-// strided over the lanes.  A term none of whose parameters was touched keeps its stored value.  The genre term of
+// prior difference without logarithms), lane 11 draws the two branch uniforms, lane 12 the sliding-window and the acceptance
+// uniform (accept test through a single-precision bracket of log u); bins are strided over the lanes.  A term none of whose
+// parameters was touched keeps its stored value, and so do the logarithms of the niche of the first 32 bins.  The genre term of
 // -m_birth 3 needs births and time at risk of the genre table inside [origin, origin + x0) and [origin + x0, present):
 // one strided pass over the (small, L1-resident) genre table whenever x0 is proposed, cached otherwise.
 #include "lr_common.cuh"
@@ -106,11 +107,49 @@ __device__ __forceinline__ void dd_bin(const DDView& v, const double* p, int j, 
     }
 }
 
-__device__ __forceinline__ void dd_lik(const DDView& v, const double* p, int lane, bool doB, bool doD, double& likB, double& likD) {
+// Logarithms that survive from one iteration to the next: log niche of bin `lane` (the first 32 bins, one per lane) for the
+// logistic carrying capacity, log(L + div_0) for the constant one, log g_lambda1/2.  They are recomputed only when one of the
+// parameters they depend on is proposed.
+struct DDCache { double lnL0, lnC, lg1, lg2; };
+
+// this lane's bin of the first 32: statistics held in registers for the whole launch
+struct DDBin0 { double sp, ex, br, lnbr; };
+
+__device__ __forceinline__ DDBin0 dd_bin0(const DDView& v, int lane) {
+    DDBin0 b;
+    const bool in = lane < v.nb;
+    b.sp = in ? v.tab[DD_SP * v.nbp + lane] : 0.0;
+    b.ex = in ? v.tab[DD_EX * v.nbp + lane] : 0.0;
+    b.br = in ? v.tab[DD_BR * v.nbp + lane] : 0.0;
+    b.lnbr = in ? v.tab[DD_LNBR * v.nbp + lane] : 0.0;
+    return b;
+}
+
+// newL / newC: a parameter of the logistic / constant carrying capacity differs from the one `c` was computed for
+__device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const double* p, int lane, bool doB, bool doD, bool newL,
+                                       bool newC, DDCache& c, double& likB, double& likD) {
     const bool evalD = doD && v.md >= 1;
     double sB = 0.0, sD = 0.0;
     if (doB || evalD) {
-        for (int j = lane; j < v.nb; j += 32) {
+        const bool needL = (doB && v.mb >= 2) || (evalD && v.md == 2), needC = (doB && v.mb == 1) || (evalD && v.md == 1);
+        if (needL && newL) c.lnL0 = log(dd_niche_logistic(p, lane));
+        if (needC && newC) c.lnC = log(p[P_L] + p[P_DIV0]);
+        if (doB) {
+            double lam = p[P_LF] * p[P_LMUL];                            // :87 (no floor in the reference)
+            if (v.mb >= 1) {
+                const double x = exp(p[P_NUB] * (b0.lnbr - (v.mb == 1 ? c.lnC : c.lnL0)));
+                const double rmax = p[P_LF] + p[P_LF] * p[P_LMUL];
+                lam = dd_floor(rmax - (rmax - p[P_LF]) * x);
+            }
+            sB = log(lam) * b0.sp - lam * b0.br;
+        }
+        if (evalD) {
+            const double x = exp(p[P_NUD] * (b0.lnbr - (v.md == 1 ? c.lnC : c.lnL0)));
+            const double rmin = p[P_LF] - p[P_LF] * p[P_MMUL];
+            const double mu = dd_floor(rmin + (p[P_LF] - rmin) * x);
+            sD = log(mu) * b0.ex - mu * b0.br;
+        }
+        for (int j = lane + 32; j < v.nb; j += 32) {
             const double br = __ldg(v.tab + DD_BR * v.nbp + j), lnbr = __ldg(v.tab + DD_LNBR * v.nbp + j);
             double lam, mu, ni, nf;
             dd_bin(v, p, j, br, lnbr, doB, evalD, lam, mu, ni, nf);
@@ -147,8 +186,10 @@ __device__ __forceinline__ void dd_genre_stats(const DDView& v, double x0, int l
     g[0] = s1; g[1] = b1; g[2] = s2; g[3] = b2;
 }
 
-__device__ __forceinline__ double dd_genre_lik(const double* p, const double g[4]) {
-    return (log(p[P_G1]) * g[0] - p[P_G1] * g[1]) + (log(p[P_G2]) * g[2] - p[P_G2] * g[3]);     // :102
+__device__ __forceinline__ double dd_genre_lik(const double* p, const double g[4], bool new1, bool new2, DDCache& c) {
+    if (new1) c.lg1 = log(p[P_G1]);
+    if (new2) c.lg2 = log(p[P_G2]);
+    return (c.lg1 * g[0] - p[P_G1] * g[1]) + (c.lg2 * g[2] - p[P_G2] * g[3]);                    // :102
 }
 
 // prior term of parameter `lane` (calc_prior :127-141; closed forms of scipy's gamma / beta logpdf)
@@ -162,6 +203,33 @@ __device__ __forceinline__ double dd_prior_term(const DDView& v, int lane, doubl
         case P_NUB: case P_NUD: return x > 0.0 ? 2.0 * log(2.0 * x) - 2.0 * x : -INFINITY;                            // Gamma(3, scale .5)
         default: return 0.0;
     }
+}
+
+// Per-lane constants of the prior difference used inside the loop (no logarithm except for the rare m_mul window move):
+// prior(x') - prior(x) = -coef (x' - x) [+ 2 lm for the Gamma(3) parameters, which only move by multipliers with log-multiplier lm]
+struct DDPriorLane { double coef; int cls; };      // cls 0 Gamma(1, .), 1 Gamma(3, .5), 2 x0, 3 m_mul, 4 none
+__device__ __forceinline__ DDPriorLane dd_prior_lane(const DDView& v, int lane) {
+    DDPriorLane r; r.coef = 0.0; r.cls = 4;
+    if (lane == P_LF || lane == P_K || lane == P_G1 || lane == P_G2) { r.coef = 0.1; r.cls = 0; }
+    if (lane == P_LMUL) { r.coef = 1.0; r.cls = 0; }
+    if (lane == P_DIV0 || lane == P_L) { r.coef = 1.0 / v.k0l; r.cls = 0; }
+    if (lane == P_NUB || lane == P_NUD) { r.coef = 2.0; r.cls = 1; }
+    if (lane == P_X0) r.cls = 2;
+    if (lane == P_MMUL) r.cls = 3;
+    return r;
+}
+__device__ __forceinline__ double dd_prior_delta(const DDView& v, const DDPriorLane& pl, double x, double xn, double lm) {
+    double d = -pl.coef * (xn - x);
+    if (pl.cls == 1) d += 2.0 * lm;
+    bool bad = false;
+    if (pl.cls == 0) bad = xn < 0.0;
+    if (pl.cls == 1) bad = !(xn > 0.0);
+    if (pl.cls == 2) bad = v.origin + xn >= v.present;                                     // :139-140
+    if (pl.cls == 3) {
+        bad = !(xn >= 0.0 && xn < 1.0);
+        if (!bad && xn != x) d = 0.2 * (log1p(-xn) - log1p(-x));                           // Beta(1, 1.2)
+    }
+    return bad ? -INFINITY : d;
 }
 
 // update_sliding_win (literate_library.py:124-128) with m = 0
@@ -184,7 +252,7 @@ __device__ __forceinline__ double dd_propose(const DDView& v, int lane, int kind
     if (!on) return x;
     const double lm = DD_LN_MULT * (draw - 0.5);
     hast = lm;
-    return x * exp(lm);
+    return x * exp_small(lm);
 }
 
 __device__ __forceinline__ void dd_adequacy(const DDView& v, const double* p, int lane, double out[3]) {
@@ -220,10 +288,11 @@ __device__ __forceinline__ void dd_series(double* out, const DDView& v, const do
     }
 }
 
-__device__ __forceinline__ void dd_record(double* rec, const DDView& v, const double* p, double likB, double likD, double likG,
-                                          double prior, long long it, long long accepted, int lane) {
+__device__ __forceinline__ void dd_record(double* rec, const DDView& v, const double* p, double mine, double likB, double likD,
+                                          double likG, long long it, long long accepted, int lane) {
     double adq[3];
     dd_adequacy(v, p, lane, adq);
+    const double prior = warp_sum(dd_prior_term(v, lane, mine));
     if (lane == 0) {
         rec[0] = (double)it; rec[1] = likB + likD + likG; rec[2] = likB; rec[3] = likD; rec[4] = prior; rec[16] = likG;
         rec[17] = adq[0]; rec[18] = adq[1]; rec[19] = adq[2]; rec[20] = (double)accepted; rec[21] = 0.0; rec[22] = 0.0; rec[23] = 0.0;
@@ -246,7 +315,7 @@ struct DDRun {
     unsigned depB, depD;
 };
 
-__global__ void __launch_bounds__(128) k7_dd_kernel(const DDRun P) {
+__global__ void __launch_bounds__(128, 3) k7_dd_kernel(const DDRun P) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= P.n_chains) return;
@@ -256,8 +325,15 @@ __global__ void __launch_bounds__(128) k7_dd_kernel(const DDRun P) {
     double mine = lane < DD_NPAR ? S->p[lane] : 0.0;
     double p[DD_NPAR];
     dd_bcast(mine, p);
-    double likB = S->likB, likD = S->likD, likG = S->likG, prior = S->prior;
+    double likB = S->likB, likD = S->likD, likG = S->likG;
     double g[4] = {S->g[0], S->g[1], S->g[2], S->g[3]};
+    const DDBin0 b0 = dd_bin0(v, lane);
+    const DDPriorLane pl = dd_prior_lane(v, lane);
+    const unsigned maskL = (1u << P_K) | (1u << P_X0) | (1u << P_DIV0) | (1u << P_L), maskC = (1u << P_DIV0) | (1u << P_L);
+    DDCache cache;
+    cache.lnL0 = log(dd_niche_logistic(p, lane));
+    cache.lnC = log(p[P_L] + p[P_DIV0]);
+    cache.lg1 = log(p[P_G1]); cache.lg2 = log(p[P_G2]);
     long long it = S->it, accepted = S->accepted;
     const long long it_end = it + P.n_iter;
     double fmine = 0.0;
@@ -273,7 +349,7 @@ __global__ void __launch_bounds__(128) k7_dd_kernel(const DDRun P) {
         const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
         const double rr1 = __shfl_sync(0xffffffffu, ua, 11), rr2 = __shfl_sync(0xffffffffu, ub, 11);
         const double us = __shfl_sync(0xffffffffu, ua, 12);
-        const double log_u = log(__shfl_sync(0xffffffffu, ub, 12));
+        const double u_acc = __shfl_sync(0xffffffffu, ub, 12);
         const int kind = (rr1 < 0.1 && can_slide) ? (rr2 < 0.5 ? 1 : 2) : 0;                  // :248-258
         const bool on = kind == 0 && (((double)r.x + 0.5) * 2.3283064365386963e-10) < fmine;
         double h;
@@ -283,36 +359,39 @@ __global__ void __launch_bounds__(128) k7_dd_kernel(const DDRun P) {
         if (kind == 2) touched = 1u << P_MMUL;
         double q[DD_NPAR];
         dd_bcast(prop, q);
-        double hs = h, pr = dd_prior_term(v, lane, prop);
+        double hs = h, dpr = dd_prior_delta(v, pl, mine, prop, h);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {       // lanes 0..15 carry terms
             hs += __shfl_xor_sync(0xffffffffu, hs, o);
-            pr += __shfl_xor_sync(0xffffffffu, pr, o);
+            dpr += __shfl_xor_sync(0xffffffffu, dpr, o);
         }
         hs = __shfl_sync(0xffffffffu, hs, 0);
-        pr = __shfl_sync(0xffffffffu, pr, 0);
+        dpr = __shfl_sync(0xffffffffu, dpr, 0);
         double nB = likB, nD = likD, nG = likG;
         double ng[4] = {g[0], g[1], g[2], g[3]};
-        dd_lik(v, q, lane, (touched & P.depB) != 0, (touched & P.depD) != 0, nB, nD);
+        DDCache nc = cache;
+        dd_lik(v, b0, q, lane, (touched & P.depB) != 0, (touched & P.depD) != 0, (touched & maskL) != 0, (touched & maskC) != 0, nc, nB, nD);
         if (v.mb == 3) {
             if (touched & (1u << P_X0)) dd_genre_stats(v, q[P_X0], lane, ng);
-            if (touched & ((1u << P_X0) | (1u << P_G1) | (1u << P_G2))) nG = dd_genre_lik(q, ng);
+            if (touched & ((1u << P_X0) | (1u << P_G1) | (1u << P_G2)))
+                nG = dd_genre_lik(q, ng, (touched & (1u << P_G1)) != 0, (touched & (1u << P_G2)) != 0, nc);
         }
-        const double x = ((nB + nD + nG) - (likB + likD + likG)) + (pr - prior) + hs;
-        if (x > log_u || it == 0) {                                                              // :263
+        const double x = ((nB + nD + nG) - (likB + likD + likG)) + dpr + hs;
+        if (it == 0 || mh_accept_gt(x, u_acc)) {                                                 // :263
 #pragma unroll
             for (int k = 0; k < DD_NPAR; ++k) p[k] = q[k];
             mine = prop;
-            likB = nB; likD = nD; likG = nG; prior = pr;
+            likB = nB; likD = nD; likG = nG; cache = nc;
             g[0] = ng[0]; g[1] = ng[1]; g[2] = ng[2]; g[3] = ng[3];
             ++accepted;
         }
         if (it == next_sample) {                                                                 // :274
-            if (P.records) dd_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v, p, likB, likD, likG, prior, it, accepted, lane);
+            if (P.records) dd_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v, p, mine, likB, likD, likG, it, accepted, lane);
             ++rec_idx;
             next_sample += P.sample_every;
         }
     }
+    const double prior = warp_sum(dd_prior_term(v, lane, mine));
     if (lane < DD_NPAR) S->p[lane] = mine;
     if (lane == 0) {
         S->likB = likB; S->likD = likD; S->likG = likG; S->prior = prior; S->it = it; S->accepted = accepted;
@@ -323,10 +402,12 @@ __global__ void __launch_bounds__(128) k7_dd_kernel(const DDRun P) {
 __device__ __forceinline__ void dd_eval_all(const DDView& v, const double* p, double mine, int lane, double& likB, double& likD,
                                             double& likG, double& prior, double g[4]) {
     likB = 0; likD = 0;
-    dd_lik(v, p, lane, true, true, likB, likD);
+    DDCache c;
+    c.lnL0 = c.lnC = c.lg1 = c.lg2 = 0.0;
+    dd_lik(v, dd_bin0(v, lane), p, lane, true, true, true, true, c, likB, likD);
     likG = 1.0;                                                    // g_birth_lik = 1 unless -m_birth 3 (:84)
     g[0] = g[1] = g[2] = g[3] = 0.0;
-    if (v.mb == 3) { dd_genre_stats(v, p[P_X0], lane, g); likG = dd_genre_lik(p, g); }
+    if (v.mb == 3) { dd_genre_stats(v, p[P_X0], lane, g); likG = dd_genre_lik(p, g, true, true, c); }
     prior = warp_sum(dd_prior_term(v, lane, mine));
 }
 

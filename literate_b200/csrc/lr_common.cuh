@@ -102,3 +102,37 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
     const double x = __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
     return (x - 1.0) + 1.1102230246251565e-16;
 }
+
+// exp(x) for |x| <= 0.1 (the log-multipliers of update_multiplier_proposal_vec: |2 log(1.1) (u - .5)| <= 0.0954): Taylor series to
+// x^11, truncation error < 2e-21, i.e. rounding only
+__device__ __forceinline__ double exp_small(double x) {
+    double p = 2.505210838544172e-8;            // 1/11!
+    p = fma(p, x, 2.755731922398589e-7);        // 1/10!
+    p = fma(p, x, 2.755731922398589e-6);        // 1/9!
+    p = fma(p, x, 2.48015873015873e-5);         // 1/8!
+    p = fma(p, x, 1.984126984126984e-4);        // 1/7!
+    p = fma(p, x, 1.388888888888889e-3);        // 1/6!
+    p = fma(p, x, 8.333333333333333e-3);        // 1/5!
+    p = fma(p, x, 4.166666666666666e-2);        // 1/4!
+    p = fma(p, x, 1.666666666666667e-1);        // 1/3!
+    p = fma(p, x, 0.5);
+    p = fma(p, x, 1.0);
+    return fma(p, x, 1.0);
+}
+
+// Metropolis-Hastings test `x > log(u)` with the double-precision logarithm evaluated only when a single-precision bracket of
+// log(u) cannot decide (error bound: __logf <= 2^-21.4 absolute on [.5, 2], 3 ulp elsewhere, plus the rounding of u to float);
+// the decision is always the one the exact comparison gives.  NaN and -inf are rejected.
+__device__ __forceinline__ bool mh_accept_gt(double x, double u) {
+    const float lf = __logf((float)u);
+    const float err = 2e-6f * (1.0f + fabsf(lf));
+    if (x > (double)(lf + err)) return true;
+    if (!(x >= (double)(lf - err))) return false;
+    return x > log(u);
+}
+
+// standard normal from two uniforms in single precision (Box-Muller); a proposal step, not a likelihood term: 24 bits suffice
+__device__ __forceinline__ double normal_f32(double u1, uint32_t bits) {
+    const float r = sqrtf(-2.0f * __logf((float)u1));
+    return (double)(r * cospif(((float)(bits >> 8) + 0.5f) * 1.1920929e-7f));     // angle 2 pi k / 2^24 as cospi(2 k / 2^24)
+}
