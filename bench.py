@@ -297,6 +297,26 @@ def run_cuda(a):
             del hts, hte, hrec
         cl = clocks.stop(t_wall0, t_wall1)
 
+        # ---------------- the sibling samplers of SURVEY 8 f-4 on the statistics of replicate 0 (reported beside the metric, not part of it)
+        siblings = None
+        if rank == 0:
+            from literate_b200 import trend as TR, ddrate as DD
+            sp, ex, br = (x[0].cpu().numpy() for x in dev.bin_finalize_device(acc, nb, fe_ref=fe_ref, stream=stream.cuda_stream))
+            trend = np.clip(np.linspace(0.0, 1.0, nb), 1e-15, 1.0)
+            sib_iters = 20000
+            siblings = {"chains": chains, "bins": nb, "iterations": sib_iters}
+            for name, mk in (("k6_trend_it_per_s", lambda: TR.TrendChains(dev, sp, ex, br, trend, chains, 7)),
+                             ("k7_ddrate_it_per_s", lambda: DD.DDChains(dev, sp, ex, br, float(FIRST_BIN), end_time, 2, 2, None, None, chains, 7))):
+                sc = mk()
+                sc.run(2000)
+                srec = torch.empty((sc.records_per_run(sib_iters, SAMPLE), chains, sc.rec_doubles), dtype=torch.float64, device=tdev)
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(); sc.run_device(sib_iters, SAMPLE, srec, stream=stream.cuda_stream); s1.record()
+                torch.cuda.synchronize()
+                siblings[name] = chains * sib_iters / (s0.elapsed_time(s1) * 1e-3)
+                assert bool(torch.isfinite(srec[:, :, 1]).all())
+                sc.close()
+
     t = torch.tensor([total_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=tdev)
     tot = torch.tensor([float(lik_evals), float(launches)], dtype=torch.float64, device=tdev)
     if world > 1:
@@ -323,6 +343,8 @@ def run_cuda(a):
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(a),
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src, "ms_per_launch": k1},
         }
+        if siblings:
+            line["siblings"] = siblings
         if e2e:
             line["e2e"] = {"value": n_gpus * chains * a.iters / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": e2e[1],
                            "d2h_bytes_per_step": e2e[2], "ms_per_step": 1e3 * e2e_step_s}

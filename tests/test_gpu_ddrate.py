@@ -70,6 +70,26 @@ def test_state_evaluation_matches_the_oracle(device, tmp_path, mb, md):
     assert np.all(np.isneginf(ch.evaluate(bad)["prior"]))
 
 
+def test_first_bin_removed_and_metal_bands(device, tmp_path):
+    """-rm_first_bin moves the origin (create_bins, literate_library.py:247-252): midpoint prior, initial x0 and the genre
+    windows follow; the metal-band table has 32 bins (one per lane) and counts in the thousands."""
+    for tag, rm in (("ex_g_rmfirst", 1), ("metal_g_mddn", 0)):
+        S, ch = _setup(device, tmp_path, tag, rm=rm, n_chains=4)
+        assert np.array_equal(ch.state()[0, :11], D.initial_args(S))
+        rng = np.random.default_rng(77)
+        P = _random_params(rng, 40, S)
+        out = ch.evaluate(P)
+        for i, p in enumerate(P):
+            lk, birth, death, niche, nf = D.likelihood(p, S)
+            np.testing.assert_allclose(out["lik"][i], lk, rtol=RTOL)
+            want = D.prior(p, S, exact_scipy=True)
+            assert out["prior"][i] == (pytest.approx(want, rel=RTOL) if np.isfinite(want) else want)
+            assert tuple(out["genre"][i]) == pytest.approx(D.genre_stats(S, p[3]), rel=1e-13)
+        r = ch.run(3001, 1000)[-1, 0]
+        lk, _, _, _, _ = D.likelihood(r[5:16], S)
+        np.testing.assert_allclose([r[2], r[3], r[16]], lk, rtol=RTOL)
+
+
 def test_proposals_with_explicit_draws_match_the_oracle(device, tmp_path):
     S, ch = _setup(device, tmp_path)
     rng = np.random.default_rng(12)

@@ -100,6 +100,29 @@ def test_two_hundred_bins_strided_over_the_lanes(device):
         np.testing.assert_allclose(r[16 + nb:], mu, rtol=RTOL)
 
 
+def test_replicates_of_the_statistics(device):
+    """Imputation replicates: chain c runs on replicate rep_of_chain[c]; states are evaluated on the replicate asked for."""
+    rng = np.random.default_rng(9)
+    nb, n_rep = 40, 3
+    sp = rng.integers(0, 300, (n_rep, nb)); ex = rng.integers(0, 200, (n_rep, nb)); br = rng.uniform(100, 3000, (n_rep, nb))
+    trend = np.clip(rng.uniform(0, 1, nb), T.SMALL_NUMBER, 1.0)
+    rep_of_chain = np.arange(12) % n_rep
+    ch = TR.TrendChains(device, sp, ex, br, trend, 12, 5, rep_of_chain=rep_of_chain)
+    P = _random_params(rng, 30)
+    rep = rng.integers(0, n_rep, 30)
+    out = ch.evaluate(P, rep=rep)
+    for i, p in enumerate(P):
+        lk, lam, mu = T.likelihood(p, T.Bins(0.0, nb + 1.5, sp[rep[i]], ex[rep[i]], br[rep[i]]), trend)
+        np.testing.assert_allclose(out["lik"][i], lk, rtol=RTOL)
+    recs = ch.run(1501, 500)
+    for c in range(12):
+        r = recs[-1, c]
+        k = rep_of_chain[c]
+        lk, _, _ = T.likelihood(r[5:11], T.Bins(0.0, nb + 1.5, sp[k], ex[k], br[k]), trend)
+        np.testing.assert_allclose(r[2:4], lk, rtol=RTOL)
+    assert np.array_equal(ch.state()[:, 11], rep_of_chain)
+
+
 def test_proposals_with_explicit_draws_match_the_oracle(device, tmp_path):
     st, bins, trend, otrend, ch = _setup(device, tmp_path)
     rng = np.random.default_rng(11)
