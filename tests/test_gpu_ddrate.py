@@ -90,6 +90,33 @@ def test_first_bin_removed_and_metal_bands(device, tmp_path):
         np.testing.assert_allclose([r[2], r[3], r[16]], lk, rtol=RTOL)
 
 
+@pytest.mark.parametrize("nb,mb,md", [(200, 3, 2), (200, 1, 1), (33, 2, 2), (1, 2, 2), (5, 3, 0)])
+def test_bin_counts_from_one_to_two_hundred(device, nb, mb, md):
+    """n_bins > 32: every lane owns several bins (the first 32 go through the cached logarithms, the rest through dd_bin);
+    n_bins = 1: a single lane carries the whole likelihood."""
+    rng = np.random.default_rng(1000 + nb + mb)
+    t = np.arange(nb)
+    br = 20 + 400 / (1 + np.exp(-0.3 * (t - nb / 2))) + rng.uniform(0, 5, nb)
+    sp = rng.poisson(br * 0.2); ex = rng.poisson(br * 0.1)
+    gts = np.sort(rng.uniform(0, nb * .7, 40)).round(); gte = np.minimum(gts + rng.integers(1, nb + 1, 40), nb) + .5
+    bins = D.Bins(0.0, nb + 1.5, sp, ex, br)
+    S = D.Setup(bins, mb, md, gts, gte)
+    ch = DD.DDChains(device, sp, ex, br, 0.0, nb + 1.5, mb, md, gts if mb == 3 else None, gte if mb == 3 else None, 6, 3)
+    P = _random_params(rng, 40, S)
+    out = ch.evaluate(P)
+    for i, p in enumerate(P):
+        lk, birth, death, niche, nf = D.likelihood(p, S)
+        np.testing.assert_allclose(out["lik"][i], lk, rtol=RTOL)
+        np.testing.assert_allclose(out["series"][i], [birth, death, niche, nf], rtol=RTOL)
+    recs = ch.run(6001, 1000)
+    assert recs.shape == (7, 6, 24 + 4 * nb)
+    for r in recs[1:, ::2].reshape(-1, recs.shape[-1]):
+        lk, birth, death, niche, nf = D.likelihood(r[5:16], S)
+        np.testing.assert_allclose([r[2], r[3], r[16]], lk, rtol=RTOL)
+        np.testing.assert_allclose(r[24:].reshape(4, nb), [birth, death, niche, nf], rtol=RTOL)
+        assert r[4] == pytest.approx(D.prior(r[5:16], S, exact_scipy=True), rel=RTOL)
+
+
 def test_proposals_with_explicit_draws_match_the_oracle(device, tmp_path):
     S, ch = _setup(device, tmp_path)
     rng = np.random.default_rng(12)

@@ -100,6 +100,21 @@ def test_two_hundred_bins_strided_over_the_lanes(device):
         np.testing.assert_allclose(r[16 + nb:], mu, rtol=RTOL)
 
 
+@pytest.mark.parametrize("nb", [1, 2, 33])
+def test_few_bins(device, nb):
+    rng = np.random.default_rng(40 + nb)
+    sp = rng.integers(1, 50, nb); ex = rng.integers(1, 40, nb); br = rng.uniform(50, 500, nb)
+    trend = np.clip(rng.uniform(0, 1, nb), T.SMALL_NUMBER, 1.0)
+    bins = T.Bins(0.0, nb + 1.5, sp, ex, br)
+    ch = TR.TrendChains(device, sp, ex, br, trend, 4, 2)
+    recs = ch.run(4001, 1000)
+    for r in recs[1:].reshape(-1, recs.shape[-1]):
+        lk, lam, mu = T.likelihood(r[5:11], bins, trend)
+        np.testing.assert_allclose(r[2:4], lk, rtol=RTOL)
+        np.testing.assert_allclose(r[16:], np.concatenate([lam, mu]), rtol=RTOL)
+        assert r[4] == pytest.approx(T.prior(r[5:11], exact_scipy=True), rel=RTOL)
+
+
 def test_replicates_of_the_statistics(device):
     """Imputation replicates: chain c runs on replicate rep_of_chain[c]; states are evaluated on the replicate asked for."""
     rng = np.random.default_rng(9)
