@@ -254,7 +254,7 @@ __device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int la
         if (r1 < 0.5 || K_side <= 1) {
             const bool touched = ua < f;
             q.dlt = touched ? LR_LN_MULT * (ub - 0.5) : 0.0;
-            q.m = xexp<C>(q.dlt);                           // exp(0) = 1 exactly
+            q.m = exp_small(q.dlt);                         // |dlt| <= 0.0954: 11-term polynomial, inline; exp_small(0) = 1 exactly
         }
         q.kind = ((r1 < 0.5 ? DK_BLOCK_RATE : DK_BLOCK_MOVE) << 1) | (birth ? 1 : 0);
         if (k.real_move_shift) { q.u_idx = __shfl_sync(0xffffffffu, ua, 28); q.u_t = __shfl_sync(0xffffffffu, ub, 28); }
@@ -991,7 +991,7 @@ __global__ void k2_proposal_eval_kernel(int n, const int* __restrict__ rep, cons
         const bool on = lane < cur.K && lane < LR_KMAX;
         const bool touched = on && mult_on[(size_t)i * LR_KMAX + lane] != 0;
         const double dl = touched ? LR_LN_MULT * (mult_u[(size_t)i * LR_KMAX + lane] - 0.5) : 0.0;
-        const double rn = cur.r * exp(dl);
+        const double rn = cur.r * exp_small(dl);
         const SideView v = side_view(hp, birth);
         const double b = beta_in ? beta_in[i] : 1.0;
         x = warp_sum((b * cur.A + 2.0) * dl - (b * cur.B + v.g_cur) * (rn - cur.r));
