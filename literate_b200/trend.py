@@ -6,8 +6,10 @@ name, header and row layout (trend_rate.py:110-118, :191).  The statistics come 
 K6 (`lr_trend_*`); this module parses, launches and writes text.  There is no CPU path.
 
 New flags: -chains (independent chains, one warp each; chain k is named like a reference run with seed + k), -device,
--quiet.  Under torchrun the chains are block-partitioned over the ranks; a chain keeps its name and its Philox stream
-whatever the number of GPUs.
+-quiet.  -d may name a directory of tables (stochastic imputations of one data set, as for literate_b200.forward): every
+table is a replicate binned in the same K1 launch over the common window, chain k runs on table k % n_tables and writes
+next to that table.  Under torchrun the chains are block-partitioned over the ranks; a chain keeps its name and its Philox
+stream whatever the number of GPUs.
 
   python -m literate_b200.trend -d table.tsv -trend_data trend.tsv -trend_index 1 -n 1000000 -s 1000 -seed 1 -chains 256
 """
@@ -16,6 +18,7 @@ from __future__ import annotations
 import argparse
 import csv
 import ctypes as C
+import glob
 import os
 import time
 from warnings import warn
@@ -253,28 +256,47 @@ def run(args, device=None):
     if const_birth and const_death:
         raise SystemExit("-const_B with -const_D / -no_death leaves the additive move without a parameter: the reference stops "
                          "with ValueError in np.random.binomial (trend_rate.py:129-134, :168)")
-    ts, te, present, origin = parse_ts_te(args.d, args.TBP, args.first_year, args.last_year, args.death_jitter)
+    # -d may name a DIRECTORY of tables (stochastic imputations of one data set): one replicate each, common window
+    if os.path.isdir(args.d):
+        tables = sorted(f for f in glob.glob(os.path.join(args.d, "*")) if os.path.isfile(f) and f.lower().endswith((".tsv", ".txt"))
+                        and os.path.abspath(f) != os.path.abspath(args.trend_data))
+        if not tables:
+            raise SystemExit("no .tsv/.txt table in " + args.d)
+    else:
+        tables = [args.d]
+    parsed = [parse_ts_te(f, args.TBP, args.first_year, args.last_year, args.death_jitter) for f in tables]
+    n_tab = len(parsed)
+    if args.chains == 1 and n_tab > 1:
+        args.chains = n_tab
+    if args.chains % n_tab:
+        raise SystemExit("-chains must be a multiple of the number of tables (%d)" % n_tab)
+    present, origin = max(p[2] for p in parsed), min(p[3] for p in parsed)
     first_bin, n_bins = bin_window(origin, present, args.rm_first_bin)
     trend = parse_trend_data(args.trend_data, args.trend_index, args.rm_first_bin)
     if len(trend) != n_bins:
         raise SystemExit("the trend table must hold one row per unit bin from the first birth time plus one (%d rows); it has %d"
                          % (n_bins + 1 + (1 if args.rm_first_bin else 0), len(trend) + 1 + (1 if args.rm_first_bin else 0)))
+    n_max = max(len(p[0]) for p in parsed)
+    ts = np.full((n_tab, n_max), np.nan); te = np.full((n_tab, n_max), np.nan)      # NaN rows carry no event and no time at risk
+    for i, p in enumerate(parsed):
+        ts[i, :len(p[0])], te[i, :len(p[1])] = p[0], p[1]
     dev = device if device is not None else E.Device(local_rank if world > 1 else args.device)
     t0 = time.time()
     stats = dev.bin_stats(ts, te, first_bin=first_bin, n_bins=n_bins, death_jitter=args.death_jitter)
     t_bin = time.time() - t0
-    sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
+    sp, ex, br = stats.sp, stats.ex, stats.br
     if lead:                                                           # print_empirical_rates, literate_library.py:260-265
         with np.errstate(divide="ignore", invalid="ignore"), np.printoptions(suppress=True, precision=3):
-            print("EMPIRICAL BIRTH RATES:"); print(sp / br)
-            print("EMPIRICAL DEATH RATES:"); print(ex / br)
+            print("EMPIRICAL BIRTH RATES:"); print(sp[0] / br[0])
+            print("EMPIRICAL DEATH RATES:"); print(ex[0] / br[0])
             print("TREND", trend)
 
     c0, n_local = P.shard_range(args.chains, world, rank)
-    chains = TrendChains(dev, sp, ex, br, trend, n_local, seed, const_birth, const_death, chain_id0=c0)
+    rep_of_chain = (np.arange(c0, c0 + n_local) % n_tab).astype(np.int32)
+    chains = TrendChains(dev, sp, ex, br, trend, n_local, seed, const_birth, const_death, chain_id0=c0, rep_of_chain=rep_of_chain)
     paths, files, writers = [], [], []
     for k in range(c0, c0 + n_local):
-        path = log_name(args.d, seed + k, args.trend_index, const_birth, const_death, no_death)
+        path = log_name(tables[k % n_tab], seed + k // n_tab, args.trend_index, const_birth, const_death, no_death)
         fh = open(path, "w", newline="")
         w = csv.writer(fh, delimiter="\t")
         w.writerow(header(n_bins))

@@ -260,3 +260,38 @@ def test_command_line_end_to_end(device, tmp_path, capsys):
         np.testing.assert_allclose(rows[:, 1], rows[:, 2] + rows[:, 5], rtol=1e-15)
     a, b = open(paths[0], "rb").read(), open(paths[1], "rb").read()
     assert a != b
+
+
+def test_directory_of_imputations(device, tmp_path):
+    """-d <directory>: every table is a replicate of one K1 launch; chain k runs on table k % n_tables and logs next to it."""
+    job = _job("ex_ramp")
+    data, trend_path = stage(job, tmp_path)
+    rows = [l.split("\t") for l in open(data).read().splitlines()[1:]]
+    d = os.path.join(str(tmp_path), "imputations")
+    os.makedirs(d)
+    rng = np.random.default_rng(3)
+    tables = []
+    for i in range(3):
+        path = os.path.join(d, "imp_%d.tsv" % i)
+        with open(path, "w") as fh:
+            fh.write("id\tts\tte\n")
+            for j, r in enumerate(rows):
+                ts, te = int(r[1]), int(r[2])
+                if i and 1996 < ts < 2010 and te - ts > 2 and rng.uniform() < .3:
+                    ts += 1                                     # another imputation of the same record, window unchanged
+                fh.write("%s\t%d\t%d\n" % (r[0], ts, te))
+            if i == 2:
+                fh.write("999\t2001\t2005\n")                  # ragged: one more lineage than the others
+        tables.append(path)
+    paths = TR.run(TR.build_parser().parse_args(["-d", d, "-trend_data", trend_path, "-trend_index", "1", "-n", "2001", "-s", "500",
+                                                 "-seed", "5", "-chains", "6", "-quiet", "1"]), device=device)
+    assert [os.path.basename(p) for p in paths] == ["imp_%d_%d_EXPB_EXPD_1.trendrate.log" % (k % 3, 5 + k // 3) for k in range(6)]
+    otrend = T.normalise_trend(T.read_trend_column(trend_path, 1))
+    for k, p in enumerate(paths):
+        ts, te, present, origin = T.parse_ts_te(tables[k % 3])
+        bins = T.create_bins(origin, present, ts, te)
+        got = np.loadtxt(p, skiprows=1)
+        assert got.shape[0] == 5
+        for row in got:
+            lk, lam, mu = T.likelihood(row[6:12], bins, otrend)
+            np.testing.assert_allclose(row[3:5], lk, rtol=RTOL)
