@@ -345,7 +345,8 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
     const double lr_i = __shfl_sync(0xffffffffu, cur.lr, i);
     const double lr1 = lr_i - p2 * q.w, lr2 = lr_i + p1 * q.w;
     const double r1 = xexp<C>(lr1), r2 = xexp<C>(lr2);
-    hasting = xlog<C>(fabs(gap)) - q.ln_beta + 2.0 * xlog<C>(r1 + r2) - lr_i;
+    const double rs = r1 + r2;
+    hasting = xlog<C>(fabs(gap) * rs * rs) - q.ln_beta - lr_i;            // log|gap| + 2 log(r1 + r2): one logarithm
     // shift slots above i up by one
     const double ur = __shfl_up_sync(0xffffffffu, cur.r, 1);
     const double ulr = __shfl_up_sync(0xffffffffu, cur.lr, 1);
@@ -380,9 +381,10 @@ __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const 
     const double ra = __shfl_sync(0xffffffffu, cur.r, j - 1), rb = __shfl_sync(0xffffffffu, cur.r, j);
     const double lm = p1 * lra + p2 * lrb;
     const double merged = xexp<C>(lm);
-    const double ls = xlog<C>(ra + rb);
-    const double ln_beta = (LR_SHAPE_BETA - 1.0) * (lra + lrb - 2.0 * ls) - LR_BETA_NORM;
-    hasting = -xlog<C>(dT) + ln_beta + lm - 2.0 * ls;
+    // -log dT + lnBeta(u) + lm - 2 log(ra + rb), lnBeta(u) = 9 (lra + lrb - 2 log(ra + rb)) - norm: the three logarithms of
+    // the reference collapse into  -log(dT (ra + rb)^20)  (rates within 1e-15 .. 1e15 keep the power inside fp64)
+    const double s1 = ra + rb, s2 = s1 * s1, s4 = s2 * s2, s8 = s4 * s4, s16 = s8 * s8;
+    hasting = (LR_SHAPE_BETA - 1.0) * (lra + lrb) - LR_BETA_NORM + lm - xlog<C>(dT * (s16 * s4));
     const double dr = __shfl_down_sync(0xffffffffu, cur.r, 1);
     const double dlr = __shfl_down_sync(0xffffffffu, cur.lr, 1);
     const double dt = __shfl_down_sync(0xffffffffu, cur.t, 1);
