@@ -110,7 +110,13 @@ __device__ __forceinline__ void dd_bin(const DDView& v, const double* p, int j, 
 // Logarithms that survive from one iteration to the next: log niche of bin `lane` (the first 32 bins, one per lane) for the
 // logistic carrying capacity, log(L + div_0) for the constant one, log g_lambda1/2.  They are recomputed only when one of the
 // parameters they depend on is proposed.
-struct DDCache { double lnL0, lnC, lg1, lg2; };
+struct DDCache {
+    double lnL0, lnC, lg1, lg2;
+    // log logistic niche of the bins beyond the first 32 (bin j lives in lane j % 32, which alone reads and writes entry j - 32):
+    // per warp in shared memory, two buffers; sel = the buffer that holds the values of the accepted state.  Null: no cache.
+    double* tail;          // [2][nt]
+    int nt, sel;
+};
 
 // this lane's bin of the first 32: statistics held in registers for the whole launch
 struct DDBin0 { double sp, ex, br, lnbr; };
@@ -151,11 +157,29 @@ __device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const 
         }
         for (int j = lane + 32; j < v.nb; j += 32) {
             const double br = __ldg(v.tab + DD_BR * v.nbp + j), lnbr = __ldg(v.tab + DD_LNBR * v.nbp + j);
-            double lam, mu, ni, nf;
-            dd_bin(v, p, j, br, lnbr, doB, evalD, lam, mu, ni, nf);
-            if (doB) sB += log(lam) * __ldg(v.tab + DD_SP * v.nbp + j) - lam * br;
-            if (evalD) sD += log(mu) * __ldg(v.tab + DD_EX * v.nbp + j) - mu * br;
+            double lnL = 0.0;
+            if (needL) {
+                if (c.tail == nullptr) lnL = log(dd_niche_logistic(p, j));
+                else if (newL) { lnL = log(dd_niche_logistic(p, j)); c.tail[(c.sel ^ 1) * c.nt + j - 32] = lnL; }
+                else lnL = c.tail[c.sel * c.nt + j - 32];
+            }
+            if (doB) {
+                double lam = p[P_LF] * p[P_LMUL];
+                if (v.mb >= 1) {
+                    const double x = exp(p[P_NUB] * (lnbr - (v.mb == 1 ? c.lnC : lnL)));
+                    const double rmax = p[P_LF] + p[P_LF] * p[P_LMUL];
+                    lam = dd_floor(rmax - (rmax - p[P_LF]) * x);
+                }
+                sB += log(lam) * __ldg(v.tab + DD_SP * v.nbp + j) - lam * br;
+            }
+            if (evalD) {
+                const double x = exp(p[P_NUD] * (lnbr - (v.md == 1 ? c.lnC : lnL)));
+                const double rmin = p[P_LF] - p[P_LF] * p[P_MMUL];
+                const double mu = dd_floor(rmin + (p[P_LF] - rmin) * x);
+                sD += log(mu) * __ldg(v.tab + DD_EX * v.nbp + j) - mu * br;
+            }
         }
+        if (c.tail != nullptr && needL && newL) c.sel ^= 1;       // the recomputed values sit in the other buffer
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             sB += __shfl_xor_sync(0xffffffffu, sB, o);
@@ -313,6 +337,7 @@ struct DDRun {
     int rec_doubles;
     double f[DD_NPAR];
     unsigned depB, depD;
+    int tail_n;            // entries per buffer of the shared-memory log-niche cache of the bins beyond the first 32 (0: none)
 };
 
 __global__ void __launch_bounds__(128, 3) k7_dd_kernel(const DDRun P) {
@@ -330,7 +355,12 @@ __global__ void __launch_bounds__(128, 3) k7_dd_kernel(const DDRun P) {
     const DDBin0 b0 = dd_bin0(v, lane);
     const DDPriorLane pl = dd_prior_lane(v, lane);
     const unsigned maskL = (1u << P_K) | (1u << P_X0) | (1u << P_DIV0) | (1u << P_L), maskC = (1u << P_DIV0) | (1u << P_L);
+    extern __shared__ double tail_s[];
     DDCache cache;
+    cache.nt = P.tail_n; cache.sel = 0;
+    cache.tail = P.tail_n > 0 ? tail_s + (size_t)(threadIdx.x >> 5) * 2 * P.tail_n : nullptr;
+    if (cache.tail != nullptr)
+        for (int j = lane + 32; j < v.nb; j += 32) cache.tail[j - 32] = log(dd_niche_logistic(p, j));
     cache.lnL0 = log(dd_niche_logistic(p, lane));
     cache.lnC = log(p[P_L] + p[P_DIV0]);
     cache.lg1 = log(p[P_G1]); cache.lg2 = log(p[P_G2]);
@@ -404,6 +434,7 @@ __device__ __forceinline__ void dd_eval_all(const DDView& v, const double* p, do
     likB = 0; likD = 0;
     DDCache c;
     c.lnL0 = c.lnC = c.lg1 = c.lg2 = 0.0;
+    c.tail = nullptr; c.nt = 0; c.sel = 0;
     dd_lik(v, dd_bin0(v, lane), p, lane, true, true, true, true, c, likB, likD);
     likG = 1.0;                                                    // g_birth_lik = 1 unless -m_birth 3 (:84)
     g[0] = g[1] = g[2] = g[3] = 0.0;
@@ -632,7 +663,11 @@ extern "C" int lr_dd_run(lr_dd_t t, int64_t n_iter, int64_t sample_every, double
     P.depB = t->depB; P.depD = t->depD;
     int threads;
     const int blocks = dd_grid(t->n_chains, threads);
-    k7_dd_kernel<<<blocks, threads, 0, st>>>(P);
+    // log-niche cache of the bins beyond the first 32: [warp][2 buffers][tail_n] doubles of shared memory, if it fits 48 KB
+    P.tail_n = t->n_bins > 32 ? t->nbp - 32 : 0;
+    size_t smem = (size_t)(threads / 32) * 2 * P.tail_n * sizeof(double);
+    if (smem > 48 * 1024) { P.tail_n = 0; smem = 0; }
+    k7_dd_kernel<<<blocks, threads, smem, st>>>(P);
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;
