@@ -12,6 +12,8 @@
  *         -> lr_dataset_create + lr_state_eval
  *   L4  runMCMC()                                LiteRateForward.py:216-373
  *         -> lr_chains_create / lr_chains_run / lr_chains_get_state / lr_chains_destroy
+ *   and, on the same statistics, the loops of the two sibling fixed-dimension samplers:
+ *       trend_rate.py:102-196 -> lr_trend_*          DDRatev3.py:242-292 -> lr_dd_*
  *
  * Conventions
  *   - plain C, no torch / CUDA types in signatures; `stream` is a cudaStream_t passed as void*
