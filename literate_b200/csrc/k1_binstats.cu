@@ -68,6 +68,27 @@ __device__ __forceinline__ void add96(unsigned* arr, unsigned nb, unsigned idx, 
     }
 }
 
+// Fraction of one lineage into the 96-bit accumulator of its bin.  `merge` (warp-uniform, decided once per segment from the
+// first lineages the warp sees): the table looks sorted by year, i.e. the lanes of a warp mostly hit ONE bin and 32 carry chains
+// on one word would serialise (measured 1.8 TB/s).  Then, when every lane that carries a fraction here does hit the same bin,
+// the 52-bit values are summed across the warp as three 18-bit parts with REDUX and a single lane runs the carry chain.
+__device__ __forceinline__ void add_frac(unsigned* arr, unsigned nb, unsigned idx, long long v, bool merge) {
+    if (merge) {
+        const unsigned m = __activemask();
+        int same;
+        __match_all_sync(m, idx, &same);
+        if (same) {
+            const unsigned long long u = (unsigned long long)v;
+            const unsigned long long t = (unsigned long long)__reduce_add_sync(m, (unsigned)u & 0x3ffffu) +
+                                         ((unsigned long long)__reduce_add_sync(m, (unsigned)(u >> 18) & 0x3ffffu) << 18) +
+                                         ((unsigned long long)__reduce_add_sync(m, (unsigned)(u >> 36)) << 36);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) add96(arr, nb, idx, (long long)t);
+            return;
+        }
+    }
+    add96(arr, nb, idx, v);
+}
+
 struct K1Smem {
     unsigned* hs32;       // [nb] births
     unsigned* he32;       // [nb] deaths whose fraction is the expected one (fe == fe_ref)
@@ -111,7 +132,8 @@ __device__ __noinline__ void k1_irregular(const K1Params& p, long long* acc, dou
     }
 }
 
-__device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te) {
+template <bool MERGE>
+__device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te, bool mergeS, bool mergeE) {
     if (p.dead_only) {
         if (!(te < p.end_time)) return;      // :531-532
     }
@@ -122,18 +144,52 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
     if ((te > ts) && (a < p.nb)) {
         atomicAdd(&s.hs32[a], 1u);
         const double fr = ts - (double)ti;
-        if (fr != 0.0) add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
+        if (fr != 0.0) {
+            if constexpr (MERGE) add_frac(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE), mergeS);
+            else add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
+        }
         if (b < p.nb) {
             const double fe = te - (double)(ci - 1);
             if (fe != p.fe_ref) {
                 atomicAdd(&s.exC[b], 1u);
-                add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
+                if constexpr (MERGE) add_frac(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE), mergeE);
+                else add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
             } else {
                 atomicAdd(&s.he32[b], 1u);
             }
         }
     } else {
         k1_irregular(p, acc, ts, te);
+    }
+}
+
+// the full tiles of one segment; MERGE = false is the plain stream (no per-lineage test of the merge flags)
+template <bool MERGE>
+__device__ __forceinline__ void k1_tiles(const K1Params& p, const K1Smem& s, long long* acc, const double* ts, const double* te,
+                                         long long A, long long ntiles, int warp, int W, int lane, bool mergeS, bool mergeE) {
+        if (p.vec_ok) {
+        for (long long k = warp; k < ntiles; k += W) {
+            const double2* t2 = (const double2*)(ts + A + k * K1_TILE) + lane;
+            const double2* e2 = (const double2*)(te + A + k * K1_TILE) + lane;
+            double2 sv[K1_UNROLL], ev[K1_UNROLL];
+#pragma unroll
+            for (int u = 0; u < K1_UNROLL; ++u) { sv[u] = ld_stream_f64x2(t2 + u * 32); ev[u] = ld_stream_f64x2(e2 + u * 32); }
+#pragma unroll
+            for (int u = 0; u < K1_UNROLL; ++u) {
+                k1_lineage<MERGE>(p, s, acc, sv[u].x, ev[u].x, mergeS, mergeE);
+                k1_lineage<MERGE>(p, s, acc, sv[u].y, ev[u].y, mergeS, mergeE);
+            }
+        }
+    } else {
+        for (long long k = warp; k < ntiles; k += W) {
+            const double* t1 = ts + A + k * K1_TILE + lane;
+            const double* e1 = te + A + k * K1_TILE + lane;
+            double sv[2 * K1_UNROLL], ev[2 * K1_UNROLL];
+#pragma unroll
+            for (int u = 0; u < 2 * K1_UNROLL; ++u) { sv[u] = ld_stream_f64(t1 + u * 32); ev[u] = ld_stream_f64(e1 + u * 32); }
+#pragma unroll
+            for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage<MERGE>(p, s, acc, sv[u], ev[u], mergeS, mergeE);
+        }
     }
 }
 
@@ -178,32 +234,23 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
         if (A > s1) A = s1;
         const long long ntiles = (s1 - A) / K1_TILE;
         const long long B = A + ntiles * K1_TILE;
-        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
-        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
-        if (p.vec_ok) {
-            for (long long k = warp; k < ntiles; k += W) {
-                const double2* t2 = (const double2*)(ts + A + k * K1_TILE) + lane;
-                const double2* e2 = (const double2*)(te + A + k * K1_TILE) + lane;
-                double2 sv[K1_UNROLL], ev[K1_UNROLL];
-#pragma unroll
-                for (int u = 0; u < K1_UNROLL; ++u) { sv[u] = ld_stream_f64x2(t2 + u * 32); ev[u] = ld_stream_f64x2(e2 + u * 32); }
-#pragma unroll
-                for (int u = 0; u < K1_UNROLL; ++u) {
-                    k1_lineage(p, s, acc, sv[u].x, ev[u].x);
-                    k1_lineage(p, s, acc, sv[u].y, ev[u].y);
-                }
-            }
-        } else {
-            for (long long k = warp; k < ntiles; k += W) {
-                const double* t1 = ts + A + k * K1_TILE + lane;
-                const double* e1 = te + A + k * K1_TILE + lane;
-                double sv[2 * K1_UNROLL], ev[2 * K1_UNROLL];
-#pragma unroll
-                for (int u = 0; u < 2 * K1_UNROLL; ++u) { sv[u] = ld_stream_f64(t1 + u * 32); ev[u] = ld_stream_f64(e1 + u * 32); }
-#pragma unroll
-                for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage(p, s, acc, sv[u], ev[u]);
-            }
+        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage<false>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i), false, false);
+        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage<false>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i), false, false);
+        // Sorted-looking table?  One probe per warp and segment: the first lineage of each lane's first tile.
+        bool mergeS = false, mergeE = false;
+        if (warp < ntiles) {
+            const long long i0 = A + (long long)warp * K1_TILE + lane;
+            const double t0 = ld_stream_f64(ts + i0), e0 = ld_stream_f64(te + i0);
+            int sameS, sameE;
+            __match_all_sync(0xffffffffu, __double2int_rd(t0), &sameS);
+            __match_all_sync(0xffffffffu, __double2int_ru(e0), &sameE);
+            // only tables that carry fractions reach the carry chains at all: integer-year tables keep the plain stream
+            const bool fracS = __any_sync(0xffffffffu, t0 != floor(t0));
+            const bool fracE = __any_sync(0xffffffffu, e0 - (ceil(e0) - 1.0) != p.fe_ref);
+            mergeS = sameS != 0 && fracS; mergeE = sameE != 0 && fracE;
         }
+        if (mergeS || mergeE) k1_tiles<true>(p, s, acc, ts, te, A, ntiles, warp, W, lane, mergeS, mergeE);
+        else k1_tiles<false>(p, s, acc, ts, te, A, ntiles, warp, W, lane, false, false);
         __syncthreads();
 
         // ---- flush this segment into the replicate's global accumulators

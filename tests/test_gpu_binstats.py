@@ -63,6 +63,27 @@ def test_random_integer_and_real(device):
     _check(device, ts, te, 0.0)
 
 
+def test_sorted_real_valued_tables_take_the_warp_merge(device):
+    """Tables sorted by birth (or death) time: the lanes of a warp hit one bin, the fractions are summed across the warp
+    (MATCH.ALL + REDUX) before one carry chain.  The sums are integers: the result must be the SAME BITS as for the shuffled
+    table, whatever mix of merged and per-lane updates a warp ends up doing (bin boundaries, half-sorted tables)."""
+    rng = np.random.default_rng(17)
+    n = 300_000
+    ts, te = synth.syn_real(n, replicate=3)
+    ref = device.bin_stats(ts, te, death_jitter=0.0)
+    want = O.bin_stats_fast(ts, te)
+    assert (ref.sp[0] == want.sp).all() and (ref.ex[0] == want.ex).all()
+    np.testing.assert_allclose(ref.br[0], want.br, rtol=1e-12)
+    orders = {"by birth": np.argsort(ts), "by death": np.argsort(te), "first half by birth": np.r_[np.argsort(ts[:n // 2]), n // 2 + rng.permutation(n - n // 2)],
+              "runs of 40": np.argsort(np.floor(ts) * 1e6 + np.arange(n) // 40 % 7)}
+    for name, o in orders.items():
+        got = device.bin_stats(ts[o], te[o], death_jitter=0.0)
+        assert (got.sp == ref.sp).all() and (got.ex == ref.ex).all() and (got.br == ref.br).all(), name
+    # quarter-year data sorted by birth: fractional, dyadic -> bit-exact against the reference arithmetic
+    ts = np.sort(1900 + rng.integers(0, 400, 50_000) / 4.0); te = ts + rng.integers(1, 200, 50_000) / 4.0
+    _check(device, ts, te, 0.0)
+
+
 def test_degenerate_inputs(device):
     # all extant, single bin
     ts = np.array([10.0, 10.0, 10.0]); te = np.array([11.5, 11.5, 11.5])
