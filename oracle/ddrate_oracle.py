@@ -1,8 +1,8 @@
 """CPU oracle for DDRate: fixed-dimension Metropolis-Hastings on the binned statistics with
 diversity-dependent birth and death rates against a constant or logistic carrying capacity.  TEST INFRASTRUCTURE ONLY.
 
-NumPy restatement of ``DDRatev3.py`` and of the ``literate_library.py`` functions it calls.  Only ``tests/`` may import
-this module, as the checker -- never the product path.
+NumPy restatement of ``DDRatev3.py`` and of the ``literate_library.py`` functions it calls.  Only ``tests/`` and
+``__graft_entry__.smoke()`` may import this module, as the checker -- never the product path.
 
 What of the reference runs: as shipped ``DDRatev3.py`` stops with NameError at :48 (``GN_SPEC`` exists only with
 ``-m_birth 3``) and, with ``-m_birth -1`` / ``-m_death -1``, at :192/:194 (``init_death`` / ``init_birth``); ``DDRatev2.py``

@@ -2,8 +2,8 @@
 death rates that follow an exogenous trend.  TEST INFRASTRUCTURE ONLY.
 
 NumPy restatement of ``trend_rate.py`` and of the ``literate_library.py`` functions it calls.  The script cannot be
-imported (it parses ``sys.argv`` and runs the chain at module level).  Only ``tests/`` may import this module, as the
-checker -- never the product path.
+imported (it parses ``sys.argv`` and runs the chain at module level).  Only ``tests/`` and ``__graft_entry__.smoke()`` may import this
+module, as the checker -- never the product path.
 
 Parity pin: ``oracle/make_golden_trend.py`` runs the *unmodified* ``trend_rate.py`` in the build container (the tree
 ships no trend table, so the script writes a small synthetic one next to a three-column copy of the example table) and
