@@ -58,6 +58,18 @@ def main():
         mine.run(400); whole.run(400)
     assert np.array_equal(mine.state(), whole.state()[c0:c0 + nl])
     acc = whole.counters()[:, 9].sum()
+
+    # ---- 4. the sibling samplers: a chain shard reproduces its slice of the population
+    from literate_b200 import trend as TR, ddrate as DD
+    hsp, hex_, hbr = sp.cpu().numpy()[0], ex.cpu().numpy()[0], br.cpu().numpy()[0]
+    nbin = hsp.shape[0]
+    trend = np.clip(np.linspace(0.0, 1.0, nbin), 1e-15, 1.0)
+    t_mine = TR.TrendChains(dev, hsp, hex_, hbr, trend, nl, 9, chain_id0=c0)
+    t_all = TR.TrendChains(dev, hsp, hex_, hbr, trend, n_chains, 9)
+    assert np.array_equal(t_mine.run(2001, 100), t_all.run(2001, 100)[:, c0:c0 + nl]), "TrendRate shard differs"
+    d_mine = DD.DDChains(dev, hsp, hex_, hbr, float(ts.min()), float(te.max()), 2, 2, None, None, nl, 9, chain_id0=c0)
+    d_all = DD.DDChains(dev, hsp, hex_, hbr, float(ts.min()), float(te.max()), 2, 2, None, None, n_chains, 9)
+    assert np.array_equal(d_mine.run(2001, 100), d_all.run(2001, 100)[:, c0:c0 + nl]), "DDRate shard differs"
     dist.barrier()
     if rank == 0:
         print("MULTIGPU OK world=%d swaps_accepted=%d" % (world, acc), flush=True)
