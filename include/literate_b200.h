@@ -249,6 +249,13 @@ int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round);
  * Deterministic (fixed summation order); asynchronous on `stream`. */
 int lr_summarize_records(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
                          double* d_sum_rate, int64_t* d_shift_count, int64_t* d_k_count, void* stream);
+/* The per-sample matrix behind the 95 % HPD intervals (get_marginal_rates :92-139, calcHPD :12-28): the marginal birth and death
+ * rate of every record in the unit bins [bin_lo, bin_lo + bin_cnt) of the n_bins from first_edge, record-major:
+ *   d_birth, d_death  [n_records][bin_cnt] fp64
+ * (sort the columns and take the narrowest window holding 95 % of the rows: literate_b200.summary.hpd_device does it with
+ * torch.sort on the device, a bin range at a time so that the matrix of a large ensemble need not exist as a whole). */
+int lr_marginal_rates(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
+                      int32_t bin_lo, int32_t bin_cnt, double* d_birth, double* d_death, void* stream);
 
 /* ---------------------------------------------------------------- TrendRate: fixed-dimension chains on the same statistics
  *

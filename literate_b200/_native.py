@@ -30,7 +30,7 @@ EXPORTS = [
     "lr_dataset_create", "lr_dataset_create_host", "lr_dataset_destroy", "lr_state_eval_host", "lr_proposal_eval_host", "lr_loglik_direct",
     "lr_chains_create", "lr_chains_destroy", "lr_chains_records_per_run", "lr_chains_run", "lr_chains_run_host",
     "lr_chains_counters_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
-    "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step", "lr_summarize_records",
+    "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step", "lr_summarize_records", "lr_marginal_rates",
     "lr_trend_create", "lr_trend_create_host", "lr_trend_destroy", "lr_trend_record_doubles", "lr_trend_records_per_run",
     "lr_trend_run", "lr_trend_run_host", "lr_trend_eval_host", "lr_trend_state_host",
     "lr_dd_create", "lr_dd_create_host", "lr_dd_destroy", "lr_dd_record_doubles", "lr_dd_records_per_run",
@@ -107,6 +107,7 @@ def load(build_if_missing=False):
     sig("lr_chains_swap_apply", C.c_int, vp, vp, i64, i64, i32, u64, vp)
     sig("lr_chains_swap_step", C.c_int, vp, i32, u64)
     sig("lr_summarize_records", C.c_int, vp, vp, i64, f64, i32, vp, vp, vp, vp)
+    sig("lr_marginal_rates", C.c_int, vp, vp, i64, f64, i32, i32, i32, vp, vp, vp)
     sig("lr_trend_create", C.c_int, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, u64, i64, vp, vp, P(vp))
     sig("lr_trend_create_host", C.c_int, vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, u64, i64, vp, P(vp))
     sig("lr_trend_destroy", C.c_int, vp)

@@ -51,16 +51,15 @@ __device__ __forceinline__ K5Rec k5_load(const double* r, int lane) {
     return x;
 }
 
-__device__ __forceinline__ void k5_side(double k_raw, double rate_raw, double t_raw, double e0, int nb, int bin0, int lane,
-                                        const K5Warp& w, double (&acc)[K5_BINS_PER_LANE], int (&cnt)[K5_BINS_PER_LANE], int& kcnt) {
-    const int K = (int)k_raw;
+// One side of one record: v[q] = marginal rate and m[q] = number of shift times of the lane's bin bin0 + 8 lane + q.
+__device__ __forceinline__ void k5_eval(double k_raw, double rate_raw, double t_raw, double e0, int nb, int bin0, int lane,
+                                        const K5Warp& w, double (&v)[K5_BINS_PER_LANE], int (&m)[K5_BINS_PER_LANE], int& K) {
+    K = (int)k_raw;
     const double rate = lane < K ? rate_raw : 0.0;
-    if (bin0 == 0 && lane == K - 1) kcnt++;
     if (K == 1) {                                   // no shift: one rate everywhere
         const double r0 = __shfl_sync(0xffffffffu, rate, 0);
 #pragma unroll
-        for (int q = 0; q < K5_BINS_PER_LANE; ++q)
-            if (bin0 + K5_BINS_PER_LANE * lane + q < nb) acc[q] += r0;
+        for (int q = 0; q < K5_BINS_PER_LANE; ++q) { v[q] = r0; m[q] = 0; }
         return;
     }
     // slot k >= 1 holds shift k-1; its histogram bin (np.histogram: half-open unit bins, the last one closed, outside ignored)
@@ -79,7 +78,7 @@ __device__ __forceinline__ void k5_side(double k_raw, double rate_raw, double t_
     __syncwarp();
     const int4 m0 = *reinterpret_cast<const int4*>(w.mark + K5_BINS_PER_LANE * lane);
     const int4 m1 = *reinterpret_cast<const int4*>(w.mark + K5_BINS_PER_LANE * lane + 4);
-    const int m[K5_BINS_PER_LANE] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
     int tot = 0;
 #pragma unroll
     for (int q = 0; q < K5_BINS_PER_LANE; ++q) tot += m[q];
@@ -93,11 +92,95 @@ __device__ __forceinline__ void k5_side(double k_raw, double rate_raw, double t_
 #pragma unroll
     for (int q = 0; q < K5_BINS_PER_LANE; ++q) {
         run += m[q];
+        v[q] = w.rate[run & 31];
+    }
+}
+
+// The accumulating twin of k5_eval (kept fused: going through v[] / m[] costs the accumulate kernel 10 % at its 128 registers).
+__device__ __forceinline__ void k5_side(double k_raw, double rate_raw, double t_raw, double e0, int nb, int bin0, int lane,
+                                        const K5Warp& w, double (&acc)[K5_BINS_PER_LANE], int (&cnt)[K5_BINS_PER_LANE], int& kcnt) {
+    const int K = (int)k_raw;
+    const double rate = lane < K ? rate_raw : 0.0;
+    if (bin0 == 0 && lane == K - 1) kcnt++;
+    if (K == 1) {                                   // no shift: one rate everywhere
+        const double r0 = __shfl_sync(0xffffffffu, rate, 0);
+#pragma unroll
+        for (int q = 0; q < K5_BINS_PER_LANE; ++q)
+            if (bin0 + K5_BINS_PER_LANE * lane + q < nb) acc[q] += r0;
+        return;
+    }
+    int sb = 0x7fffffff;
+    if (lane >= 1 && lane < K) {
+        const double s = t_raw;
+        if (s >= e0 && s <= e0 + (double)nb) { sb = __double2int_rd(s - e0); if (sb > nb - 1) sb = nb - 1; }
+    }
+    __syncwarp();
+    *reinterpret_cast<int4*>(w.mark + K5_BINS_PER_LANE * lane) = make_int4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(w.mark + K5_BINS_PER_LANE * lane + 4) = make_int4(0, 0, 0, 0);
+    w.rate[lane] = rate;
+    __syncwarp();
+    const int before = __popc(__ballot_sync(0xffffffffu, sb < bin0));
+    if (sb >= bin0 && sb < bin0 + 256) atomicAdd(w.mark + (sb - bin0), 1);
+    __syncwarp();
+    const int4 m0 = *reinterpret_cast<const int4*>(w.mark + K5_BINS_PER_LANE * lane);
+    const int4 m1 = *reinterpret_cast<const int4*>(w.mark + K5_BINS_PER_LANE * lane + 4);
+    const int m[K5_BINS_PER_LANE] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    int tot = 0;
+#pragma unroll
+    for (int q = 0; q < K5_BINS_PER_LANE; ++q) tot += m[q];
+    int run = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += t;
+    }
+    run += before - tot;
+#pragma unroll
+    for (int q = 0; q < K5_BINS_PER_LANE; ++q) {
+        run += m[q];
         if (bin0 + K5_BINS_PER_LANE * lane + q < nb) { acc[q] += w.rate[run & 31]; cnt[q] += m[q]; }
     }
 }
 
-__global__ void __launch_bounds__(K5_WARPS_PER_CTA * 32) k5_accumulate_kernel(const K5Params p) {
+// The per-sample matrix behind the HPD intervals (get_marginal_rates, plotRJforward.v3.py:92-139): row = record, column = bin of
+// [bin_lo, bin_lo + bin_cnt), record-major so that a warp writes its record's row in one piece.
+struct K5Expand {
+    const double* rec;
+    long long n_rec;
+    double first_edge;
+    int nb, bin_lo, bin_cnt;
+    double* birth;              // [n_rec][bin_cnt]
+    double* death;
+};
+
+__global__ void __launch_bounds__(K5_WARPS_PER_CTA * 32) k5_expand_kernel(const K5Expand p) {
+    __shared__ __align__(16) int mark_s[K5_WARPS_PER_CTA][256];
+    __shared__ double rate_s[K5_WARPS_PER_CTA][32];
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    K5Warp w;
+    w.mark = mark_s[threadIdx.x >> 5]; w.rate = rate_s[threadIdx.x >> 5];
+    for (long long i = warp; i < p.n_rec; i += n_warps) {
+        const K5Rec cur = k5_load(p.rec + (size_t)i * REC_W, lane);
+        for (int bin0 = p.bin_lo; bin0 < p.bin_lo + p.bin_cnt; bin0 += 256) {
+            double v[K5_BINS_PER_LANE];
+            int m[K5_BINS_PER_LANE], K;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                k5_eval(side ? cur.km : cur.kl, side ? cur.rm : cur.rl, side ? cur.tm : cur.tl, p.first_edge, p.nb, bin0, lane, w, v, m, K);
+                double* row = (side ? p.death : p.birth) + (size_t)i * p.bin_cnt;
+#pragma unroll
+                for (int q = 0; q < K5_BINS_PER_LANE; ++q) {
+                    const int j = bin0 + K5_BINS_PER_LANE * lane + q;
+                    if (j < p.bin_lo + p.bin_cnt && j < p.nb) row[j - p.bin_lo] = v[q];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K5_WARPS_PER_CTA * 32, 2) k5_accumulate_kernel(const K5Params p) {
     __shared__ __align__(16) int mark_s[K5_WARPS_PER_CTA][256];
     __shared__ double rate_s[K5_WARPS_PER_CTA][32];
     const int lane = threadIdx.x & 31;
@@ -162,6 +245,22 @@ __global__ void __launch_bounds__(1024) k5_reduce_kernel(const double* __restric
 }
 
 }  // namespace
+
+extern "C" int lr_marginal_rates(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
+                                 int32_t bin_lo, int32_t bin_cnt, double* d_birth, double* d_death, void* stream) {
+    LR_REQUIRE(h && d_birth && d_death && (n_records == 0 || d_records), "lr_marginal_rates: null pointer");
+    LR_REQUIRE(n_records >= 0 && n_bins >= 1 && bin_lo >= 0 && bin_cnt >= 1 && bin_lo + bin_cnt <= n_bins, "lr_marginal_rates: bad sizes");
+    if (n_records == 0) return LR_OK;
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    K5Expand p;
+    p.rec = d_records; p.n_rec = n_records; p.first_edge = first_edge; p.nb = n_bins; p.bin_lo = bin_lo; p.bin_cnt = bin_cnt;
+    p.birth = d_birth; p.death = d_death;
+    k5_expand_kernel<<<h->sm_count * 4, K5_WARPS_PER_CTA * 32, 0, st>>>(p);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
 
 extern "C" int lr_summarize_records(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
                                     double* d_sum_rate, int64_t* d_shift_count, int64_t* d_k_count, void* stream) {

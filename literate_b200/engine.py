@@ -202,6 +202,21 @@ class Device:
                                               _stream_ptr(stream, records.device)), "lr_summarize_records")
         return sr, sc, kc, n
 
+    def marginal_rates_device(self, records, first_edge, n_bins, bin_lo=0, bin_cnt=None, stream=None):
+        """Per-sample marginal rates of device-resident records (lr_marginal_rates): `records` a contiguous float64 CUDA tensor
+        [..., 144]; returns (birth, death), float64 CUDA tensors [n_records, bin_cnt] for the bins [bin_lo, bin_lo + bin_cnt)."""
+        import torch
+        assert records.is_cuda and records.dtype == torch.float64 and records.is_contiguous() and records.shape[-1] == LR_REC_DOUBLES
+        n = records.numel() // LR_REC_DOUBLES
+        if bin_cnt is None:
+            bin_cnt = n_bins - bin_lo
+        b = torch.empty((n, bin_cnt), dtype=torch.float64, device=records.device)
+        d = torch.empty((n, bin_cnt), dtype=torch.float64, device=records.device)
+        N.check(self.lib.lr_marginal_rates(self.h, C.c_void_p(records.data_ptr()), n, float(first_edge), int(n_bins), int(bin_lo), int(bin_cnt),
+                                           C.c_void_p(b.data_ptr()), C.c_void_p(d.data_ptr()), _stream_ptr(stream, records.device)),
+                "lr_marginal_rates")
+        return b, d
+
     def new_accumulators(self, n_rep, n_bins, device):
         import torch
         return torch.zeros((n_rep, N.LR_ACC_ROWS, int(self.lib.lr_acc_stride(int(n_bins)))), dtype=torch.int64, device=device)

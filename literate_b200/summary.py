@@ -165,10 +165,26 @@ def summarize_records(records, start_time, end_time, burnin=0.2, name="chains", 
     return _finish(name, float(start_time), float(end_time), b, d, bf_seed, div)
 
 
-def summarize_records_device(dev, records, start_time, end_time, burnin=0.2):
+def hpd_device(x, level=0.95):
+    """hpd_columns on the device: x a CUDA tensor [n, m] -> (lo [m], hi [m]) CUDA tensors.  Same rule as calcHPD
+    (plotRJforward.v3.py:12-28): the FIRST narrowest window of round(level n) sorted values (torch.argmin returns the first
+    minimum).  Sorting is torch's (device plumbing); the values are the kernel's."""
+    import torch
+    s, _ = torch.sort(x, dim=0)
+    n = s.shape[0]
+    n_in = int(round(level * n))
+    if n_in < 2:
+        raise RuntimeError("not enough data")
+    width = s[n_in - 1:] - s[:n - n_in + 1]
+    i = torch.argmin(width, dim=0, keepdim=True)
+    return s.gather(0, i)[0], s.gather(0, i + (n_in - 1))[0]
+
+
+def summarize_records_device(dev, records, start_time, end_time, burnin=0.2, hpd=False, hpd_bytes=1 << 30):
     """Means, shift frequencies and number-of-rates counts of device-resident records (a float64 CUDA tensor
-    [n_samples, n_chains, 144]) without bringing them to the host (K5, lr_summarize_records).  HPD intervals need the
-    per-sample matrix and are left to summarize_records on a (thinned) host copy.  Returns a dict of NumPy arrays."""
+    [n_samples, n_chains, 144]) without bringing them to the host (K5, lr_summarize_records).  With ``hpd`` the 95 % HPD
+    intervals of the birth, death and net rates as well: the per-sample matrix is expanded on the device a range of bins at a
+    time (lr_marginal_rates; at most ``hpd_bytes`` per matrix) and its columns are sorted there.  Returns a dict of NumPy arrays."""
     b0 = burnin_index(records.shape[0], burnin)
     post = records[b0:].contiguous()
     nb = len(np.arange(start_time, end_time)) - 1
@@ -179,6 +195,19 @@ def summarize_records_device(dev, records, start_time, end_time, burnin=0.2):
         k = np.nonzero(kc[side])[0]
         out[name] = {"mean": sr[side] / n, "shift_freq": sc[side] / float(n), "k_values": (k + 1).astype(float), "k_counts": kc[side][k]}
     out["net_mean"] = out["birth"]["mean"] - out["death"]["mean"]
+    if hpd:
+        import torch
+        step = max(1, min(nb, int(hpd_bytes // (8 * max(n, 1)))))
+        parts = {"birth": [], "death": [], "net": []}
+        for lo in range(0, nb, step):
+            mb, md = dev.marginal_rates_device(post, start_time, nb, lo, min(step, nb - lo))
+            for name, m in (("birth", mb), ("death", md), ("net", mb - md)):
+                parts[name].append(torch.stack(hpd_device(m)))
+            del mb, md
+        for name in parts:
+            lohi = torch.cat(parts[name], dim=1).cpu().numpy()
+            tgt = out[name] if name != "net" else out
+            tgt["hpd_lo" if name != "net" else "net_lo"], tgt["hpd_hi" if name != "net" else "net_hi"] = lohi[0], lohi[1]
     return out
 
 

@@ -72,3 +72,29 @@ def test_more_than_256_bins_and_edge_shifts(device):
     assert np.array_equal(sr[0].cpu().numpy(), want) and np.array_equal(sc[0].cpu().numpy(), cnt)
     assert np.array_equal(sr[1].cpu().numpy(), np.full(nb, 5 * 0.25))
     assert kc[0].cpu().numpy()[:4].tolist() == [1, 2, 1, 1] and kc[1].cpu().numpy()[0] == 5
+
+
+def test_hpd_intervals_on_the_device(device, metal_path):
+    """The per-sample matrix (lr_marginal_rates) equals the host's marginal_matrix element for element, and the HPD intervals
+    of birth, death and net rate computed on the device (sorted there, a few bins at a time) are the host's, bit for bit."""
+    lin = O.read_lineages(metal_path)
+    st = device.bin_stats(lin.ts, lin.te)
+    ds = E.Dataset(device, st, 0, lin.start_time, lin.end_time)
+    ch = E.Chains(ds, 24, seed=7)
+    n_iter, s = 40001, 100
+    rec = torch.empty((ch.records_per_run(n_iter, s), 24, E.LR_REC_DOUBLES), dtype=torch.float64, device="cuda")
+    ch.run_device(n_iter, s, rec, stream="handle")
+    device.sync()
+    host = S.summarize_records(rec.cpu().numpy(), lin.start_time, lin.end_time, burnin=0.2, bf_seed=None)
+    b0 = S.burnin_index(rec.shape[0], 0.2)
+    post = rec[b0:].contiguous()
+    nb = int(lin.end_time) - int(lin.start_time)
+    mb, md = device.marginal_rates_device(post, lin.start_time, nb)
+    torch.cuda.synchronize()
+    assert np.array_equal(mb.cpu().numpy(), host.birth.marginal) and np.array_equal(md.cpu().numpy(), host.death.marginal)
+    mb2, md2 = device.marginal_rates_device(post, lin.start_time, nb, 5, 9)          # a range of bins
+    assert torch.equal(mb2, mb[:, 5:14]) and torch.equal(md2, md[:, 5:14])
+    dv = S.summarize_records_device(device, rec, lin.start_time, lin.end_time, burnin=0.2, hpd=True, hpd_bytes=8 * post.shape[0] * post.shape[1] * 7)
+    for name, hs in (("birth", host.birth), ("death", host.death)):
+        assert np.array_equal(dv[name]["hpd_lo"], hs.hpd_lo) and np.array_equal(dv[name]["hpd_hi"], hs.hpd_hi)
+    assert np.array_equal(dv["net_lo"], host.net_lo) and np.array_equal(dv["net_hi"], host.net_hi)

@@ -23,3 +23,14 @@ b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 5
 n = rec.shape[0] * rec.shape[1]
 print("K5: %d records (%.2f GB) in %.3f ms = %.3g records/s, %.0f GB/s of records" % (n, n * 1152 / 1e9, ms, n / (ms * 1e-3), n * 1152 / (ms * 1e-3) / 1e9))
+# HPD intervals on the device: the per-sample matrix a range of bins at a time (lr_marginal_rates) + torch.sort of its columns
+from literate_b200 import summary as S
+S.summarize_records_device(dev, rec, 1800.0, 2000.5, burnin=0.0, hpd=True)
+torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+out = S.summarize_records_device(dev, rec, 1800.0, 2000.5, burnin=0.0, hpd=True)
+torch.cuda.synchronize()
+print("means + HPD of birth, death, net rate for %d records x 200 bins on the device: %.1f ms" % (n, 1e3 * (time.perf_counter() - t0)))
+a.record(); mb, md = dev.marginal_rates_device(rec, 1800.0, 200, 0, 64); b.record(); torch.cuda.synchronize()
+print("lr_marginal_rates, 64 bins: %.3f ms (%.0f GB/s written)" % (a.elapsed_time(b), 2 * n * 64 * 8 / (a.elapsed_time(b) * 1e-3) / 1e9))
