@@ -312,18 +312,19 @@ int lr_trend_state_host(lr_trend_t t, double* h_state);
  * g_lambda2.  m_birth: 0 constant, 1 constant carrying capacity, 2 logistic carrying capacity, 3 = 2 plus the genre-birth term of
  * :99-102 (needs the genre table h_gts/h_gte[n_genre], HOST, as parse_ts_te leaves it); m_death: 0 death rate 1 (:105-106),
  * 1 constant, 2 logistic carrying capacity.  -m_birth -1 / -m_death -1 stop with NameError in the reference (:192-195) and are
- * refused.  sp, ex, br [n_bins] are the statistics of literate_library.create_bins' window (as for lr_trend_create);
- * origin/present = min ts / max te (:35).  Chain c draws from the Philox-4x32-10 stream keyed by (seed, chain_id0 + c). */
+ * refused.  sp, ex, br [n_rep][n_bins] are the statistics of literate_library.create_bins' window (as for lr_trend_create; replicates =
+ * stochastic imputations of one data set over a common window); origin/present = min ts / max te (:35).  Chain c runs on replicate
+ * h_rep_of_chain[c] (NULL: 0) and draws from the Philox-4x32-10 stream keyed by (seed, chain_id0 + c). */
 typedef struct lr_dd_s* lr_dd_t;
 #define LR_DD_NPAR 11
-int lr_dd_create(lr_handle_t h, int32_t n_bins, const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
+int lr_dd_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
                  double origin, double present, int32_t m_birth, int32_t m_death,
                  const double* h_gts, const double* h_gte, int32_t n_genre,
-                 int32_t n_chains, uint64_t seed, int64_t chain_id0, void* stream, lr_dd_t* out);
-int lr_dd_create_host(lr_handle_t h, int32_t n_bins, const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
+                 int32_t n_chains, uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain, void* stream, lr_dd_t* out);
+int lr_dd_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
                       double origin, double present, int32_t m_birth, int32_t m_death,
                       const double* h_gts, const double* h_gte, int32_t n_genre,
-                      int32_t n_chains, uint64_t seed, int64_t chain_id0, lr_dd_t* out);
+                      int32_t n_chains, uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain, lr_dd_t* out);
 int lr_dd_destroy(lr_dd_t t);
 /* One sample record = lr_dd_record_doubles(n_bins) = LR_DD_REC_HEAD + 4 n_bins doubles (the row of :285-287):
  *   [0] iteration  [1] likelihood (sum of the three terms; the genre term is the constant 1 unless m_birth = 3, :84)
@@ -335,16 +336,16 @@ int64_t lr_dd_record_doubles(int32_t n_bins);
 int64_t lr_dd_records_per_run(lr_dd_t t, int64_t n_iter, int64_t sample_every);
 int lr_dd_run(lr_dd_t t, int64_t n_iter, int64_t sample_every, double* d_records, void* stream);
 int lr_dd_run_host(lr_dd_t t, int64_t n_iter, int64_t sample_every, double* h_records);
-/* Parity entry point, HOST buffers: n explicit parameter vectors params[n][11]; with kind != NULL one proposal with EXPLICIT
+/* Parity entry point, HOST buffers: n explicit parameter vectors params[n][11] on replicate rep[n] (NULL: 0); with kind != NULL one proposal with EXPLICIT
  * draws is applied first: kind[n] 0 multiplier move (on[n][11] mask, draw[n][11] uniforms), 1 sliding window on x0 (uniform
  * draw[n][3]), 2 sliding window on m_mul (uniform draw[n][6]).  Outputs (any may be NULL): out_params[n][11], out_hast[n],
  * lik[n][3] (birth, death, genre), prior[n], series[n][4][n_bins], adequacy[n][3], genre[n][4] (births and time at risk of the
  * genre table before / after origin + x0). */
-int lr_dd_eval_host(lr_dd_t t, int32_t n, const double* params, const int32_t* kind, const int32_t* on, const double* draw,
+int lr_dd_eval_host(lr_dd_t t, int32_t n, const int32_t* rep, const double* params, const int32_t* kind, const int32_t* on, const double* draw,
                     double* out_params, double* out_hast, double* lik, double* prior, double* series, double* adequacy,
                     double* genre);
 /* [n_chains][LR_DD_STATE_DOUBLES]: 11 parameters, the three likelihood terms, prior, iterations done, proposals accepted,
- * the four cached genre statistics, 3 reserved */
+ * the four cached genre statistics, replicate, 2 reserved */
 #define LR_DD_STATE_DOUBLES 24
 int lr_dd_state_host(lr_dd_t t, double* h_state);
 

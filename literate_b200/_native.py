@@ -117,14 +117,14 @@ def load(build_if_missing=False):
     sig("lr_trend_run_host", C.c_int, vp, i64, i64, vp)
     sig("lr_trend_eval_host", C.c_int, vp, i32, *([vp] * 11))
     sig("lr_trend_state_host", C.c_int, vp, vp)
-    sig("lr_dd_create", C.c_int, vp, i32, vp, vp, vp, f64, f64, i32, i32, vp, vp, i32, i32, u64, i64, vp, P(vp))
-    sig("lr_dd_create_host", C.c_int, vp, i32, vp, vp, vp, f64, f64, i32, i32, vp, vp, i32, i32, u64, i64, P(vp))
+    sig("lr_dd_create", C.c_int, vp, i32, i32, vp, vp, vp, f64, f64, i32, i32, vp, vp, i32, i32, u64, i64, vp, vp, P(vp))
+    sig("lr_dd_create_host", C.c_int, vp, i32, i32, vp, vp, vp, f64, f64, i32, i32, vp, vp, i32, i32, u64, i64, vp, P(vp))
     sig("lr_dd_destroy", C.c_int, vp)
     sig("lr_dd_record_doubles", i64, i32)
     sig("lr_dd_records_per_run", i64, vp, i64, i64)
     sig("lr_dd_run", C.c_int, vp, i64, i64, vp, vp)
     sig("lr_dd_run_host", C.c_int, vp, i64, i64, vp)
-    sig("lr_dd_eval_host", C.c_int, vp, i32, *([vp] * 11))
+    sig("lr_dd_eval_host", C.c_int, vp, i32, *([vp] * 12))
     sig("lr_dd_state_host", C.c_int, vp, vp)
     if lib.lr_abi_version() != LR_ABI_VERSION:
         raise NativeError("libliterate_b200.so ABI version mismatch; rebuild with `python -m literate_b200.build --force`")

@@ -45,16 +45,15 @@ struct DDChain {
     double g[4];           // genre statistics of the current x0: births and time at risk in the two windows
     long long it, accepted;
     unsigned chain;
-    int pad;
+    int rep;
 };
 
 struct lr_dd_s {
     lr_handle_t h;
-    int n_bins, nbp, m_birth, m_death, n_genre;
-    double origin, present, k0l;
-    double* tab;           // device [DD_ROWS][nbp]
-    double* cst;           // device [4]: sum x, sum x^2 (adequacy), -sum br (death likelihood of -m_death <= 0), max br
-    double cst_host[4];    // the same on the host (they parameterise every launch)
+    int n_rep, n_bins, nbp, m_birth, m_death, n_genre;
+    double origin, present;
+    double* tab;           // device [n_rep][DD_ROWS][nbp]
+    double* cst;           // device [n_rep][4]: sum x, sum x^2 (adequacy), -sum br (death likelihood of -m_death <= 0), max br
     double* genre;         // device [2][n_genre] (ts, te) or null
     int n_chains;
     uint64_t seed;
@@ -66,11 +65,20 @@ struct lr_dd_s {
 namespace {
 
 struct DDView {
-    const double* tab;
+    const double* tab;         // as a kernel argument: the tables of all replicates; after dd_select(): this chain's replicate
+    const double* cst;
     const double* genre;
     int nb, nbp, mb, md, ng;
-    double origin, present, ln_k0l, k0l, Sx, Sxx, likD_const;
+    double origin, present, ln_k0l, k0l, Sx, Sxx, likD_const;      // the last five are filled by dd_select()
 };
+
+// the view of one replicate (statistics table and its constants; PRIOR_K0_L = max br of that replicate, DDRatev3.py:53)
+__device__ __forceinline__ DDView dd_select(DDView v, int rep) {
+    v.tab += (size_t)rep * DD_ROWS * v.nbp;
+    const double* c = v.cst + 4 * rep;
+    v.Sx = c[0]; v.Sxx = c[1]; v.likD_const = c[2]; v.k0l = c[3]; v.ln_k0l = log(c[3]);
+    return v;
+}
 
 __device__ __forceinline__ double dd_floor(double r) { return r > 0.0 ? r : DD_SMALL; }
 
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(128, 3) k7_dd_kernel(const DDRun P) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= P.n_chains) return;
     DDChain* S = P.st + c;
-    const DDView v = P.v;
+    const DDView v = dd_select(P.v, S->rep);
     const unsigned chain = S->chain;
     double mine = lane < DD_NPAR ? S->p[lane] : 0.0;
     double p[DD_NPAR];
@@ -443,10 +451,12 @@ __device__ __forceinline__ void dd_eval_all(const DDView& v, const double* p, do
 }
 
 // initial state (:187-201, :229-240)
-__global__ void k7_init_kernel(DDChain* st, int n_chains, long long chain_id0, const DDView v) {
+__global__ void k7_init_kernel(DDChain* st, int n_chains, const int* rep_of_chain, long long chain_id0, const DDView v_all) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_chains) return;
+    const int rep = rep_of_chain ? rep_of_chain[c] : 0;
+    const DDView v = dd_select(v_all, rep);
     const double init[DD_NPAR] = {0.5, 1.01, 1.5, v.present - (v.origin + v.present) / 2.0, 10.0, 20000.0, 0.99, 1.0, 1.0, 1.0, 1.0};
     double mine = 0.0;
 #pragma unroll
@@ -460,12 +470,18 @@ __global__ void k7_init_kernel(DDChain* st, int n_chains, long long chain_id0, c
     if (lane == 0) {
         st[c].likB = likB; st[c].likD = likD; st[c].likG = likG; st[c].prior = prior;
         st[c].g[0] = g[0]; st[c].g[1] = g[1]; st[c].g[2] = g[2]; st[c].g[3] = g[3];
-        st[c].it = 0; st[c].accepted = 0; st[c].chain = (unsigned)(chain_id0 + c); st[c].pad = 0;
+        st[c].it = 0; st[c].accepted = 0; st[c].chain = (unsigned)(chain_id0 + c); st[c].rep = rep;
     }
 }
 
-__global__ void k7_build_tables(const long long* __restrict__ sp, const long long* __restrict__ ex, const double* __restrict__ br,
-                                int nb, int nbp, double* __restrict__ tab, double* __restrict__ cst) {
+__global__ void k7_build_tables(const long long* __restrict__ sp_all, const long long* __restrict__ ex_all, const double* __restrict__ br_all,
+                                int nb, int nbp, double* __restrict__ tab_all, double* __restrict__ cst_all) {
+    const int rep = blockIdx.x;
+    const long long* sp = sp_all + (size_t)rep * nb;
+    const long long* ex = ex_all + (size_t)rep * nb;
+    const double* br = br_all + (size_t)rep * nb;
+    double* tab = tab_all + (size_t)rep * DD_ROWS * nbp;
+    double* cst = cst_all + 4 * rep;
     for (int j = threadIdx.x; j < nbp; j += blockDim.x) {
         const bool in = j < nb;
         const double U = in ? (double)sp[j] : 0.0, D = in ? (double)ex[j] : 0.0, K = in ? br[j] : 0.0;
@@ -487,12 +503,13 @@ __global__ void k7_build_tables(const long long* __restrict__ sp, const long lon
     }
 }
 
-__global__ void k7_eval_kernel(const DDView v, int n, const double* params, const int* kind, const int* on, const double* draw,
+__global__ void k7_eval_kernel(const DDView v_all, int n, const int* rep, const double* params, const int* kind, const int* on, const double* draw,
                                double* out_params, double* out_hast, double* lik, double* prior, double* series, double* adequacy,
                                double* genre) {
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (s >= n) return;
+    const DDView v = dd_select(v_all, rep ? rep[s] : 0);
     double mine = lane < DD_NPAR ? params[s * DD_NPAR + lane] : 0.0, h = 0.0;
     if (kind) mine = dd_propose(v, lane, kind[s], mine, lane < DD_NPAR && on[s * DD_NPAR + lane] != 0,
                                 lane < DD_NPAR ? draw[s * DD_NPAR + lane] : 0.0, h);
@@ -537,11 +554,11 @@ void dd_model_tables(int mb, int md, double* f, unsigned& depB, unsigned& depD) 
     if (md >= 1) depD = (1u << P_LF) | (1u << P_MMUL) | (1u << P_NUD) | (md == 1 ? constK : logistic);
 }
 
-DDView dd_view(lr_dd_t t, const double* h_cst) {
+DDView dd_view(lr_dd_t t) {
     DDView v;
-    v.tab = t->tab; v.genre = t->genre; v.nb = t->n_bins; v.nbp = t->nbp; v.mb = t->m_birth; v.md = t->m_death; v.ng = t->n_genre;
-    v.origin = t->origin; v.present = t->present; v.k0l = t->k0l; v.ln_k0l = log(t->k0l);
-    v.Sx = h_cst[0]; v.Sxx = h_cst[1]; v.likD_const = h_cst[2];
+    v.tab = t->tab; v.cst = t->cst; v.genre = t->genre; v.nb = t->n_bins; v.nbp = t->nbp; v.mb = t->m_birth; v.md = t->m_death;
+    v.ng = t->n_genre; v.origin = t->origin; v.present = t->present;
+    v.k0l = 0.0; v.ln_k0l = 0.0; v.Sx = 0.0; v.Sxx = 0.0; v.likD_const = 0.0;
     return v;
 }
 
@@ -549,19 +566,13 @@ DDView dd_view(lr_dd_t t, const double* h_cst) {
 
 extern "C" int64_t lr_dd_record_doubles(int32_t n_bins) { return LR_DD_REC_HEAD + 4 * (int64_t)n_bins; }
 
-// the constants of the table live on the host too (they parameterise every launch)
-static int dd_fetch_cst(lr_dd_t t, cudaStream_t st, double* h_cst) {
-    LR_CUDA(cudaMemcpyAsync(h_cst, t->cst, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    LR_CUDA(cudaStreamSynchronize(st));
-    return LR_OK;
-}
-
-extern "C" int lr_dd_create(lr_handle_t h, int32_t n_bins, const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
+extern "C" int lr_dd_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, const int64_t* d_sp, const int64_t* d_ex, const double* d_br,
                             double origin, double present, int32_t m_birth, int32_t m_death,
                             const double* h_gts, const double* h_gte, int32_t n_genre,
-                            int32_t n_chains, uint64_t seed, int64_t chain_id0, void* stream, lr_dd_t* out) {
+                            int32_t n_chains, uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain,
+                            void* stream, lr_dd_t* out) {
     LR_REQUIRE(h && d_sp && d_ex && d_br && out, "lr_dd_create: null pointer");
-    LR_REQUIRE(n_bins >= 1 && n_chains >= 1, "lr_dd_create: n_bins and n_chains must be >= 1");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1 && n_chains >= 1, "lr_dd_create: n_rep, n_bins and n_chains must be >= 1");
     LR_REQUIRE(present > origin, "lr_dd_create: present must be later than origin");
     LR_REQUIRE(chain_id0 >= 0 && chain_id0 + n_chains <= 0xffffffffll, "lr_dd_create: chain ids must fit 32 bits");
     if (m_birth < 0 || m_birth > 3 || m_death < 0 || m_death > 2) {
@@ -570,48 +581,59 @@ extern "C" int lr_dd_create(lr_handle_t h, int32_t n_bins, const int64_t* d_sp, 
         return LR_ERR_UNSUPPORTED;
     }
     LR_REQUIRE(m_birth != 3 || (h_gts && h_gte && n_genre >= 1), "lr_dd_create: -m_birth 3 needs the genre table (DDRatev3.py:36-38)");
+    if (h_rep_of_chain)
+        for (int i = 0; i < n_chains; ++i)
+            LR_REQUIRE(h_rep_of_chain[i] >= 0 && h_rep_of_chain[i] < n_rep, "lr_dd_create: replicate of chain %d out of range", i);
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     lr_dd_t t = new lr_dd_s();
     memset(t, 0, sizeof(*t));
-    t->h = h; t->n_bins = n_bins; t->nbp = (n_bins + 3) & ~3; t->m_birth = m_birth; t->m_death = m_death;
+    t->h = h; t->n_rep = n_rep; t->n_bins = n_bins; t->nbp = (n_bins + 3) & ~3; t->m_birth = m_birth; t->m_death = m_death;
     t->n_genre = m_birth == 3 ? n_genre : 0; t->origin = origin; t->present = present; t->n_chains = n_chains; t->seed = seed;
     dd_model_tables(m_birth, m_death, t->f, t->depB, t->depD);
-    cudaError_t e = cudaMallocAsync((void**)&t->tab, (size_t)DD_ROWS * t->nbp * sizeof(double), st);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&t->cst, 4 * sizeof(double), st);
+    int* d_rep = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&t->tab, (size_t)n_rep * DD_ROWS * t->nbp * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&t->cst, (size_t)n_rep * 4 * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&t->st, (size_t)n_chains * sizeof(DDChain), st);
     if (e == cudaSuccess && t->n_genre) e = cudaMallocAsync((void**)&t->genre, (size_t)2 * t->n_genre * sizeof(double), st);
+    if (e == cudaSuccess && h_rep_of_chain) e = cudaMallocAsync((void**)&d_rep, (size_t)n_chains * sizeof(int), st);
     if (e != cudaSuccess) { lr_set_error("lr_dd_create: cudaMallocAsync: %s", cudaGetErrorString(e)); lr_dd_destroy(t); return LR_ERR_NOMEM; }
     if (t->n_genre) {
         LR_CUDA(cudaMemcpyAsync(t->genre, h_gts, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st));
         LR_CUDA(cudaMemcpyAsync(t->genre + t->n_genre, h_gte, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    k7_build_tables<<<1, 128, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, n_bins, t->nbp, t->tab, t->cst);
+    if (d_rep) LR_CUDA(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * sizeof(int), cudaMemcpyHostToDevice, st));
+    k7_build_tables<<<n_rep, 128, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, n_bins, t->nbp, t->tab, t->cst);
     LR_CUDA(cudaGetLastError());
-    double h_cst[4];
-    int rc = dd_fetch_cst(t, st, h_cst);
-    if (rc != LR_OK) { lr_dd_destroy(t); return rc; }
-    t->k0l = h_cst[3];
-    if (!(t->k0l > 0.0)) { lr_set_error("lr_dd_create: no time at risk in any bin (max br = %g)", t->k0l); lr_dd_destroy(t); return LR_ERR_INVALID; }
-    t->cst_host[0] = h_cst[0]; t->cst_host[1] = h_cst[1]; t->cst_host[2] = h_cst[2]; t->cst_host[3] = h_cst[3];
+    // every replicate needs some time at risk: its largest br is the scale of two priors (PRIOR_K0_L, DDRatev3.py:53)
+    double* h_cst = new double[(size_t)n_rep * 4];
+    cudaError_t ce = cudaMemcpyAsync(h_cst, t->cst, (size_t)n_rep * 4 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    int bad = -1;
+    for (int r = 0; ce == cudaSuccess && r < n_rep; ++r)
+        if (!(h_cst[4 * r + 3] > 0.0)) { bad = r; break; }
+    delete[] h_cst;
+    if (ce != cudaSuccess) { lr_set_error("lr_dd_create: %s", cudaGetErrorString(ce)); lr_dd_destroy(t); return LR_ERR_CUDA; }
+    if (bad >= 0) { lr_set_error("lr_dd_create: replicate %d has no time at risk in any bin", bad); lr_dd_destroy(t); return LR_ERR_INVALID; }
     int threads;
     const int blocks = dd_grid(n_chains, threads);
-    k7_init_kernel<<<blocks, threads, 0, st>>>(t->st, n_chains, chain_id0, dd_view(t, t->cst_host));
+    k7_init_kernel<<<blocks, threads, 0, st>>>(t->st, n_chains, d_rep, chain_id0, dd_view(t));
     LR_CUDA(cudaGetLastError());
     h->launches += 2;
     LR_CUDA(cudaStreamSynchronize(st));
+    if (d_rep) cudaFreeAsync(d_rep, st);
     *out = t;
     return LR_OK;
 }
 
-extern "C" int lr_dd_create_host(lr_handle_t h, int32_t n_bins, const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
+extern "C" int lr_dd_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
                                  double origin, double present, int32_t m_birth, int32_t m_death,
                                  const double* h_gts, const double* h_gte, int32_t n_genre,
-                                 int32_t n_chains, uint64_t seed, int64_t chain_id0, lr_dd_t* out) {
+                                 int32_t n_chains, uint64_t seed, int64_t chain_id0, const int32_t* h_rep_of_chain, lr_dd_t* out) {
     LR_REQUIRE(h && h_sp && h_ex && h_br, "lr_dd_create_host: null pointer");
-    LR_REQUIRE(n_bins >= 1, "lr_dd_create_host: bad sizes");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_dd_create_host: bad sizes");
     LR_CUDA(cudaSetDevice(h->device));
-    const size_t cnt = (size_t)n_bins;
+    const size_t cnt = (size_t)n_rep * n_bins;
     int rc = lr_ws_reserve(h, cnt * 24);
     if (rc != LR_OK) return rc;
     int64_t* d_sp = (int64_t*)h->ws;
@@ -620,8 +642,8 @@ extern "C" int lr_dd_create_host(lr_handle_t h, int32_t n_bins, const int64_t* h
     LR_CUDA(cudaMemcpyAsync(d_sp, h_sp, cnt * 8, cudaMemcpyHostToDevice, h->stream));
     LR_CUDA(cudaMemcpyAsync(d_ex, h_ex, cnt * 8, cudaMemcpyHostToDevice, h->stream));
     LR_CUDA(cudaMemcpyAsync(d_br, h_br, cnt * 8, cudaMemcpyHostToDevice, h->stream));
-    return lr_dd_create(h, n_bins, d_sp, d_ex, d_br, origin, present, m_birth, m_death, h_gts, h_gte, n_genre, n_chains, seed,
-                        chain_id0, h->stream, out);
+    return lr_dd_create(h, n_rep, n_bins, d_sp, d_ex, d_br, origin, present, m_birth, m_death, h_gts, h_gte, n_genre, n_chains, seed,
+                        chain_id0, h_rep_of_chain, h->stream, out);
 }
 
 extern "C" int lr_dd_destroy(lr_dd_t t) {
@@ -654,7 +676,7 @@ extern "C" int lr_dd_run(lr_dd_t t, int64_t n_iter, int64_t sample_every, double
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     DDRun P;
-    P.st = t->st; P.n_chains = t->n_chains; P.v = dd_view(t, t->cst_host);
+    P.st = t->st; P.n_chains = t->n_chains; P.v = dd_view(t);
     P.k0 = (uint32_t)t->seed; P.k1 = (uint32_t)(t->seed >> 32);
     P.n_iter = n_iter; P.sample_every = sample_every > 0 ? sample_every : (int64_t)1 << 62;
     P.records = sample_every > 0 ? d_records : nullptr;
@@ -692,18 +714,20 @@ extern "C" int lr_dd_run_host(lr_dd_t t, int64_t n_iter, int64_t sample_every, d
     return LR_OK;
 }
 
-extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const double* params, const int32_t* kind, const int32_t* on,
+extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const int32_t* rep, const double* params, const int32_t* kind, const int32_t* on,
                                const double* draw, double* out_params, double* out_hast, double* lik, double* prior,
                                double* series, double* adequacy, double* genre) {
     LR_REQUIRE(t && params, "lr_dd_eval_host: null pointer");
     LR_REQUIRE(n >= 1, "lr_dd_eval_host: n must be >= 1");
     LR_REQUIRE(!kind || (on && draw), "lr_dd_eval_host: kind needs on and draw");
+    if (rep)
+        for (int i = 0; i < n; ++i) LR_REQUIRE(rep[i] >= 0 && rep[i] < t->n_rep, "lr_dd_eval_host: replicate of state %d out of range", i);
     lr_handle_t h = t->h;
     LR_CUDA(cudaSetDevice(h->device));
     const int nb = t->n_bins;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_par = take((size_t)n * DD_NPAR * 8), o_kind = take((size_t)n * 4), o_on = take((size_t)n * DD_NPAR * 4),
+    const size_t o_par = take((size_t)n * DD_NPAR * 8), o_rep = take((size_t)n * 4), o_kind = take((size_t)n * 4), o_on = take((size_t)n * DD_NPAR * 4),
                  o_draw = take((size_t)n * DD_NPAR * 8), o_np = take((size_t)n * DD_NPAR * 8), o_h = take((size_t)n * 8),
                  o_lik = take((size_t)n * 24), o_pr = take((size_t)n * 8), o_ser = take((size_t)n * 4 * nb * 8),
                  o_adq = take((size_t)n * 24), o_g = take((size_t)n * 32);
@@ -712,12 +736,13 @@ extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const double* params, const
     char* W = (char*)h->ws;
     cudaStream_t st = h->stream;
     LR_CUDA(cudaMemcpyAsync(W + o_par, params, (size_t)n * DD_NPAR * 8, cudaMemcpyHostToDevice, st));
+    if (rep) LR_CUDA(cudaMemcpyAsync(W + o_rep, rep, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     if (kind) {
         LR_CUDA(cudaMemcpyAsync(W + o_kind, kind, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         LR_CUDA(cudaMemcpyAsync(W + o_on, on, (size_t)n * DD_NPAR * 4, cudaMemcpyHostToDevice, st));
         LR_CUDA(cudaMemcpyAsync(W + o_draw, draw, (size_t)n * DD_NPAR * 8, cudaMemcpyHostToDevice, st));
     }
-    k7_eval_kernel<<<(n + 3) / 4, 128, 0, st>>>(dd_view(t, t->cst_host), n, (const double*)(W + o_par), kind ? (const int*)(W + o_kind) : nullptr,
+    k7_eval_kernel<<<(n + 3) / 4, 128, 0, st>>>(dd_view(t), n, rep ? (const int*)(W + o_rep) : nullptr, (const double*)(W + o_par), kind ? (const int*)(W + o_kind) : nullptr,
                                                 (const int*)(W + o_on), (const double*)(W + o_draw), (double*)(W + o_np), (double*)(W + o_h),
                                                 (double*)(W + o_lik), (double*)(W + o_pr), (double*)(W + o_ser), (double*)(W + o_adq),
                                                 (double*)(W + o_g));
@@ -747,7 +772,7 @@ extern "C" int lr_dd_state_host(lr_dd_t t, double* h_state) {
         o[11] = tmp[c].likB; o[12] = tmp[c].likD; o[13] = tmp[c].likG; o[14] = tmp[c].prior;
         o[15] = (double)tmp[c].it; o[16] = (double)tmp[c].accepted;
         for (int k = 0; k < 4; ++k) o[17 + k] = tmp[c].g[k];
-        o[21] = 0.0; o[22] = 0.0; o[23] = 0.0;
+        o[21] = (double)tmp[c].rep; o[22] = 0.0; o[23] = 0.0;
     }
     delete[] tmp;
     return LR_OK;

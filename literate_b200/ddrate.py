@@ -7,13 +7,15 @@ this module parses, launches and writes text.  There is no CPU path.
 
 As shipped the reference only starts with ``-m_birth 3 -g <genre table>`` (NameError at :48 otherwise); here -m_birth 0, 1
 and 2 run what its functions define for them.  -m_birth -1 / -m_death -1 (NameError at :192-195) are refused.
-New flags: -chains (chain k is named like a reference run with seed + k), -device, -quiet.
+New flags: -chains (chain k is named like a reference run with seed + k), -device, -quiet.  -d may name a directory of tables
+(stochastic imputations of one data set): one replicate each over the common window, chain k on table k % n_tables.
 """
 from __future__ import annotations
 
 import argparse
 import csv
 import ctypes as C
+import glob
 import os
 import time
 
@@ -59,23 +61,28 @@ class DDChains:
     """lr_dd_t: the per-bin table, the genre table and a population of independent DDRate chains on one device."""
 
     def __init__(self, dev: E.Device, sp, ex, br, origin, present, m_birth=2, m_death=2, gts=None, gte=None, n_chains=1, seed=1,
-                 chain_id0=0):
-        sp = np.ascontiguousarray(sp, dtype=np.int64).ravel()
-        ex = np.ascontiguousarray(ex, dtype=np.int64).ravel()
-        br = np.ascontiguousarray(br, dtype=np.float64).ravel()
+                 chain_id0=0, rep_of_chain=None):
+        sp = np.ascontiguousarray(np.atleast_2d(sp), dtype=np.int64)
+        ex = np.ascontiguousarray(np.atleast_2d(ex), dtype=np.int64)
+        br = np.ascontiguousarray(np.atleast_2d(br), dtype=np.float64)
         if not (sp.shape == ex.shape == br.shape):
-            raise ValueError("sp, ex, br must be [n_bins]")
-        self.dev, self.n_chains, self.n_bins = dev, int(n_chains), sp.shape[0]
+            raise ValueError("sp, ex, br must be [n_bins] or [n_rep, n_bins]")
+        self.dev, self.n_chains, self.n_rep, self.n_bins = dev, int(n_chains), sp.shape[0], sp.shape[1]
         self.m_birth, self.m_death, self.origin = int(m_birth), int(m_death), float(origin)
+        rep = None
+        if rep_of_chain is not None:
+            rep = np.ascontiguousarray(rep_of_chain, dtype=np.int32)
+            if rep.shape != (self.n_chains,):
+                raise ValueError("rep_of_chain must have one entry per chain")
         ng = 0
         if gts is not None:
             gts = np.ascontiguousarray(gts, dtype=np.float64)
             gte = np.ascontiguousarray(gte, dtype=np.float64)
             ng = len(gts)
         t = C.c_void_p()
-        N.check(dev.lib.lr_dd_create_host(dev.h, self.n_bins, N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br), float(origin), float(present),
-                                          self.m_birth, self.m_death, N.np_ptr(gts), N.np_ptr(gte), ng, self.n_chains,
-                                          C.c_uint64(int(seed) & (2**64 - 1)), int(chain_id0), C.byref(t)), "lr_dd_create_host")
+        N.check(dev.lib.lr_dd_create_host(dev.h, self.n_rep, self.n_bins, N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br), float(origin),
+                                          float(present), self.m_birth, self.m_death, N.np_ptr(gts), N.np_ptr(gte), ng, self.n_chains,
+                                          C.c_uint64(int(seed) & (2**64 - 1)), int(chain_id0), N.np_ptr(rep), C.byref(t)), "lr_dd_create_host")
         self.t = t
         self.rec_doubles = int(dev.lib.lr_dd_record_doubles(self.n_bins))
 
@@ -112,11 +119,12 @@ class DDChains:
         N.check(self.dev.lib.lr_dd_state_host(self.t, N.np_ptr(out)), "lr_dd_state_host")
         return out
 
-    def evaluate(self, params, kind=None, on=None, draw=None):
+    def evaluate(self, params, kind=None, on=None, draw=None, rep=None):
         """Parity entry point: the three likelihood terms, prior, per-bin series, adequacy and genre statistics of explicit
         parameter vectors [n, 11], optionally after one proposal with explicit draws."""
         params = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
         n = params.shape[0]
+        rep_a = None if rep is None else np.ascontiguousarray(rep, dtype=np.int32)
         kind_a = on_a = draw_a = None
         if kind is not None:
             kind_a = np.ascontiguousarray(kind, dtype=np.int32)
@@ -125,7 +133,7 @@ class DDChains:
             assert kind_a.shape == (n,) and on_a.shape == (n, NPAR) and draw_a.shape == (n, NPAR)
         out = {"params": np.empty((n, NPAR)), "hastings": np.empty(n), "lik": np.empty((n, 3)), "prior": np.empty(n),
                "series": np.empty((n, 4, self.n_bins)), "adequacy": np.empty((n, 3)), "genre": np.empty((n, 4))}
-        N.check(self.dev.lib.lr_dd_eval_host(self.t, n, N.np_ptr(params), N.np_ptr(kind_a), N.np_ptr(on_a), N.np_ptr(draw_a),
+        N.check(self.dev.lib.lr_dd_eval_host(self.t, n, N.np_ptr(rep_a), N.np_ptr(params), N.np_ptr(kind_a), N.np_ptr(on_a), N.np_ptr(draw_a),
                                              N.np_ptr(out["params"]), N.np_ptr(out["hastings"]), N.np_ptr(out["lik"]),
                                              N.np_ptr(out["prior"]), N.np_ptr(out["series"]), N.np_ptr(out["adequacy"]),
                                              N.np_ptr(out["genre"])), "lr_dd_eval_host")
@@ -195,12 +203,30 @@ def run(args, device=None):
         seed = args.seed
     if args.chains < max(1, world):
         raise SystemExit("-chains must be >= 1 and at least the number of GPUs")
-    ts, te, present, origin = parse_ts_te(args.d, args.TBP, args.first_year, args.last_year, args.death_jitter)
+    # -d may name a DIRECTORY of tables (stochastic imputations of one data set): one replicate each, common window
+    if os.path.isdir(args.d):
+        tables = sorted(f for f in glob.glob(os.path.join(args.d, "*")) if os.path.isfile(f) and f.lower().endswith((".tsv", ".txt"))
+                        and os.path.abspath(f) != os.path.abspath(args.genre_times or "-"))
+        if not tables:
+            raise SystemExit("no .tsv/.txt table in " + args.d)
+    else:
+        tables = [args.d]
+    parsed = [parse_ts_te(f, args.TBP, args.first_year, args.last_year, args.death_jitter) for f in tables]
+    n_tab = len(parsed)
+    if args.chains == 1 and n_tab > 1:
+        args.chains = n_tab
+    if args.chains % n_tab:
+        raise SystemExit("-chains must be a multiple of the number of tables (%d)" % n_tab)
+    present, origin = max(p[2] for p in parsed), min(p[3] for p in parsed)
     first_bin, n_bins = bin_window(origin, present, args.rm_first_bin)
+    n_max = max(len(p[0]) for p in parsed)
+    ts = np.full((n_tab, n_max), np.nan); te = np.full((n_tab, n_max), np.nan)      # NaN rows carry no event and no time at risk
+    for i, p in enumerate(parsed):
+        ts[i, :len(p[0])], te[i, :len(p[1])] = p[0], p[1]
     dev = device if device is not None else E.Device(local_rank if world > 1 else args.device)
     t0 = time.time()
     stats = dev.bin_stats(ts, te, first_bin=first_bin, n_bins=n_bins, death_jitter=args.death_jitter)
-    sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
+    sp, ex, br = stats.sp, stats.ex, stats.br
     gts = gte = gstats = None
     if args.m_birth == 3:
         gts, gte, gpresent, gorigin = parse_ts_te(args.genre_times, args.TBP, args.first_year, args.last_year, args.death_jitter)
@@ -212,22 +238,25 @@ def run(args, device=None):
     if lead:
         print(origin, present)
         with np.errstate(divide="ignore", invalid="ignore"), np.printoptions(suppress=True, precision=3):
-            print("EMPIRICAL BIRTH RATES:"); print(sp / br)
-            print("EMPIRICAL DEATH RATES:"); print(ex / br)
+            print("EMPIRICAL BIRTH RATES:"); print(sp[0] / br[0])
+            print("EMPIRICAL DEATH RATES:"); print(ex[0] / br[0])
 
     c0, n_local = P.shard_range(args.chains, world, rank)
-    chains = DDChains(dev, sp, ex, br, origin, present, args.m_birth, args.m_death, gts, gte, n_local, seed, chain_id0=c0)
+    rep_of_chain = (np.arange(c0, c0 + n_local) % n_tab).astype(np.int32)
+    chains = DDChains(dev, sp, ex, br, origin, present, args.m_birth, args.m_death, gts, gte, n_local, seed, chain_id0=c0,
+                      rep_of_chain=rep_of_chain)
     paths, files, writers = [], [], []
     for k in range(c0, c0 + n_local):
-        stem = log_stem(args.d, seed + k, args.m_birth, args.m_death)
+        r = k % n_tab
+        stem = log_stem(tables[r], seed + k // n_tab, args.m_birth, args.m_death)
         fh = open(stem + ".log", "w", newline="")
         w = csv.writer(fh, delimiter="\t")
         w.writerow(header(n_bins, args.m_birth))
         paths.append(stem + ".log"); files.append(fh); writers.append(w)
         if gstats is None:
-            write_div_log(stem + ".div.log", sp, ex, br)
+            write_div_log(stem + ".div.log", sp[r], ex[r], br[r])
         else:
-            write_div_log(stem + ".div.log", sp, ex, br, gstats.sp[0], gstats.ex[0], gstats.br[0])
+            write_div_log(stem + ".div.log", sp[r], ex[r], br[r], gstats.sp[0], gstats.ex[0], gstats.br[0])
 
     s_freq = max(1, args.s)
     max_rec = max(1, (256 << 20) // (n_local * chains.rec_doubles * 8))

@@ -242,3 +242,57 @@ def test_command_line_end_to_end(device, tmp_path):
                                                  "-quiet", "1"]), device=device)
     assert os.path.basename(paths[0]) == "example3_4_LDDN_MDD.log"
     assert len(open(paths[0]).read().splitlines()) == 7
+
+
+def test_replicates_and_directory_of_imputations(device, tmp_path):
+    """Replicate axis of K7 (PRIOR_K0_L = the replicate's own max br) and -d <directory> of the command line."""
+    rng = np.random.default_rng(21)
+    nb, n_rep = 40, 3
+    t = np.arange(nb)
+    br = np.stack([20 + (300 + 60 * r) / (1 + np.exp(-0.3 * (t - nb / 2))) + rng.uniform(0, 5, nb) for r in range(n_rep)])
+    sp = rng.poisson(br * 0.2); ex = rng.poisson(br * 0.1)
+    rep_of_chain = np.arange(9) % n_rep
+    ch = DD.DDChains(device, sp, ex, br, 0.0, nb + 1.5, 2, 2, None, None, 9, 4, rep_of_chain=rep_of_chain)
+    setups = [D.Setup(D.Bins(0.0, nb + 1.5, sp[r], ex[r], br[r]), 2, 2) for r in range(n_rep)]
+    P = _random_params(rng, 30, setups[0])
+    rep = rng.integers(0, n_rep, 30)
+    out = ch.evaluate(P, rep=rep)
+    for i, p in enumerate(P):
+        lk, birth, death, niche, nf = D.likelihood(p, setups[rep[i]])
+        np.testing.assert_allclose(out["lik"][i], lk, rtol=RTOL)
+        assert out["prior"][i] == pytest.approx(D.prior(p, setups[rep[i]], exact_scipy=True), rel=RTOL)
+    recs = ch.run(3001, 1000)
+    for c in range(9):
+        r = recs[-1, c]
+        S = setups[rep_of_chain[c]]
+        lk, _, _, _, _ = D.likelihood(r[5:16], S)
+        np.testing.assert_allclose([r[2], r[3], r[16]], lk, rtol=RTOL)
+        assert r[4] == pytest.approx(D.prior(r[5:16], S, exact_scipy=True), rel=RTOL)
+    assert np.array_equal(ch.state()[:, 21], rep_of_chain)
+    # the command line on a directory: two imputations of the example table
+    job = _job("ex_g_mddn")
+    data, genre = stage(job, tmp_path)
+    rows = [l.split("\t") for l in open(data).read().splitlines()[1:]]
+    d = os.path.join(str(tmp_path), "imputations")
+    os.makedirs(d)
+    for i in range(2):
+        with open(os.path.join(d, "imp_%d.tsv" % i), "w") as fh:
+            fh.write("id\tts\tte\n")
+            for r in rows:
+                ts_, te_ = int(r[1]), int(r[2])
+                if i and 1996 < ts_ < 2010 and te_ - ts_ > 2 and rng.uniform() < .3:
+                    ts_ += 1
+                fh.write("%s\t%d\t%d\n" % (r[0], ts_, te_))
+    paths = DD.run(DD.build_parser().parse_args(["-d", d, "-m_birth", "3", "-g", genre, "-n", "1001", "-s", "500", "-seed", "3", "-chains", "4",
+                                                 "-quiet", "1"]), device=device)
+    assert [os.path.basename(p) for p in paths] == ["imp_%d_%d_GLDDN_MDDN.log" % (k % 2, 3 + k // 2) for k in range(4)]
+    gts, gte, _, _ = TR.parse_ts_te(genre)
+    for k, p in enumerate(paths):
+        ts, te, present, origin = TR.parse_ts_te(os.path.join(d, "imp_%d.tsv" % (k % 2)))
+        S = D.Setup(D.create_bins(origin, present, ts, te), 3, 2, gts, gte)
+        got = np.loadtxt(p, skiprows=1)
+        assert got.shape[0] == 3
+        for row in got:
+            args = row[6:17].copy(); args[3] -= S.origin; args[5] -= args[4]
+            lk, _, _, _, _ = D.likelihood(args, S)
+            np.testing.assert_allclose([row[3], row[4], row[17]], lk, rtol=1e-9)
