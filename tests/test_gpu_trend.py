@@ -11,7 +11,6 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLD
 from oracle import trendrate_oracle as T
 from literate_b200 import trend as TR
 from test_oracle_trend_golden import TG, _jobs, stage
