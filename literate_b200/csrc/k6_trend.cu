@@ -430,16 +430,17 @@ extern "C" int lr_trend_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, con
     e = cudaMallocAsync((void**)&d_trend, (size_t)n_bins * sizeof(double), st);
     if (e == cudaSuccess && h_rep_of_chain) e = cudaMallocAsync((void**)&d_rep, (size_t)n_chains * sizeof(int), st);
     if (e != cudaSuccess) { lr_set_error("lr_trend_create: cudaMallocAsync: %s", cudaGetErrorString(e)); lr_trend_destroy(t); return LR_ERR_NOMEM; }
-    LR_CUDA(cudaMemcpyAsync(d_trend, h_trend, (size_t)n_bins * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (d_rep) LR_CUDA(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * sizeof(int), cudaMemcpyHostToDevice, st));
+    auto undo = [&]() { if (d_trend) cudaFreeAsync(d_trend, st); if (d_rep) cudaFreeAsync(d_rep, st); lr_trend_destroy(t); };
+    LR_CUDA_CLEAN(cudaMemcpyAsync(d_trend, h_trend, (size_t)n_bins * sizeof(double), cudaMemcpyHostToDevice, st), undo());
+    if (d_rep) LR_CUDA_CLEAN(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * sizeof(int), cudaMemcpyHostToDevice, st), undo());
     k6_build_tables<<<n_rep, 128, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, d_trend, n_bins, t->nbp, t->tab, t->cst);
-    LR_CUDA(cudaGetLastError());
+    LR_CUDA_CLEAN(cudaGetLastError(), undo());
     int threads;
     const int blocks = trend_grid(n_chains, threads);
     k6_init_kernel<<<blocks, threads, 0, st>>>(t->st, n_chains, d_rep, chain_id0, t->tab, t->cst, n_bins, t->nbp, t->const_b, t->const_d);
-    LR_CUDA(cudaGetLastError());
+    LR_CUDA_CLEAN(cudaGetLastError(), undo());
     h->launches += 2;
-    LR_CUDA(cudaStreamSynchronize(st));       // h_trend / h_rep_of_chain may be pageable: they are consumed when this returns
+    LR_CUDA_CLEAN(cudaStreamSynchronize(st), undo());       // h_trend / h_rep_of_chain may be pageable: they are consumed when this returns
     cudaFreeAsync(d_trend, st);
     if (d_rep) cudaFreeAsync(d_rep, st);
     *out = t;

@@ -598,13 +598,14 @@ extern "C" int lr_dd_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, const 
     if (e == cudaSuccess && t->n_genre) e = cudaMallocAsync((void**)&t->genre, (size_t)2 * t->n_genre * sizeof(double), st);
     if (e == cudaSuccess && h_rep_of_chain) e = cudaMallocAsync((void**)&d_rep, (size_t)n_chains * sizeof(int), st);
     if (e != cudaSuccess) { lr_set_error("lr_dd_create: cudaMallocAsync: %s", cudaGetErrorString(e)); lr_dd_destroy(t); return LR_ERR_NOMEM; }
+    auto undo = [&]() { if (d_rep) cudaFreeAsync(d_rep, st); lr_dd_destroy(t); };
     if (t->n_genre) {
-        LR_CUDA(cudaMemcpyAsync(t->genre, h_gts, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st));
-        LR_CUDA(cudaMemcpyAsync(t->genre + t->n_genre, h_gte, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st));
+        LR_CUDA_CLEAN(cudaMemcpyAsync(t->genre, h_gts, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st), undo());
+        LR_CUDA_CLEAN(cudaMemcpyAsync(t->genre + t->n_genre, h_gte, (size_t)t->n_genre * sizeof(double), cudaMemcpyHostToDevice, st), undo());
     }
-    if (d_rep) LR_CUDA(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (d_rep) LR_CUDA_CLEAN(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * sizeof(int), cudaMemcpyHostToDevice, st), undo());
     k7_build_tables<<<n_rep, 128, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, n_bins, t->nbp, t->tab, t->cst);
-    LR_CUDA(cudaGetLastError());
+    LR_CUDA_CLEAN(cudaGetLastError(), undo());
     // every replicate needs some time at risk: its largest br is the scale of two priors (PRIOR_K0_L, DDRatev3.py:53)
     double* h_cst = new double[(size_t)n_rep * 4];
     cudaError_t ce = cudaMemcpyAsync(h_cst, t->cst, (size_t)n_rep * 4 * sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -613,14 +614,14 @@ extern "C" int lr_dd_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, const 
     for (int r = 0; ce == cudaSuccess && r < n_rep; ++r)
         if (!(h_cst[4 * r + 3] > 0.0)) { bad = r; break; }
     delete[] h_cst;
-    if (ce != cudaSuccess) { lr_set_error("lr_dd_create: %s", cudaGetErrorString(ce)); lr_dd_destroy(t); return LR_ERR_CUDA; }
-    if (bad >= 0) { lr_set_error("lr_dd_create: replicate %d has no time at risk in any bin", bad); lr_dd_destroy(t); return LR_ERR_INVALID; }
+    if (ce != cudaSuccess) { lr_set_error("lr_dd_create: %s", cudaGetErrorString(ce)); undo(); return LR_ERR_CUDA; }
+    if (bad >= 0) { lr_set_error("lr_dd_create: replicate %d has no time at risk in any bin", bad); undo(); return LR_ERR_INVALID; }
     int threads;
     const int blocks = dd_grid(n_chains, threads);
     k7_init_kernel<<<blocks, threads, 0, st>>>(t->st, n_chains, d_rep, chain_id0, dd_view(t));
-    LR_CUDA(cudaGetLastError());
+    LR_CUDA_CLEAN(cudaGetLastError(), undo());
     h->launches += 2;
-    LR_CUDA(cudaStreamSynchronize(st));
+    LR_CUDA_CLEAN(cudaStreamSynchronize(st), undo());
     if (d_rep) cudaFreeAsync(d_rep, st);
     *out = t;
     return LR_OK;

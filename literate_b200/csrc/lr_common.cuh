@@ -25,6 +25,16 @@ void lr_set_error(const char* fmt, ...);
             return LR_ERR_CUDA;                                                              \
         }                                                                                    \
     } while (0)
+// same, running `cleanup` (free what the function has allocated so far) before returning
+#define LR_CUDA_CLEAN(call, cleanup)                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            lr_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            cleanup;                                                                         \
+            return LR_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
 #define LR_REQUIRE(cond, ...)                                                                \
     do {                                                                                     \
         if (!(cond)) {                                                                       \
