@@ -476,7 +476,7 @@ __device__ __forceinline__ bool block_step(Side& cur, const SideView v, ChainReg
         const bool on = lane < cur.K;
         const double dl = on ? q.dlt : 0.0;
         const double rn = cur.r * (on ? q.m : 1.0);
-        const double x = warp_sum((c.beta * cur.A + 2.0) * dl - (c.beta * cur.B + v.g_cur) * (rn - cur.r));
+        const double x = warp_sum_first((c.beta * cur.A + 2.0) * dl - (c.beta * cur.B + v.g_cur) * (rn - cur.r), cur.K);
         if (mh_accept(x, q)) { cur.r = rn; cur.lr += dl; n.v[1]++; }
     } else if (!cfg.real_move_shift) {
         // The reference's move proposes the current state (:184-185): prior - priorA = 0, always accepted, nothing changes.
@@ -515,7 +515,7 @@ __device__ __forceinline__ bool rj_propose(const Side& cur, const Side& oth, con
     poiN = poisson_prior(nw.K, hp.poi, hp.lpoi, c_lnfact) + poisson_prior(oth.K, hp.poi, hp.lpoi, c_lnfact);   // :279
     const double e_new = lane < nw.K ? (beta * nw.A + 1.0) * nw.lr - (beta * nw.B + v.g_cur) * nw.r : 0.0;
     const double e_old = lane < cur.K ? (beta * cur.A + 1.0) * cur.lr - (beta * cur.B + v.g_cur) * cur.r : 0.0;
-    x = warp_sum(e_new - e_old) + (double)(nw.K - cur.K) * (2.0 * v.lg_cur - d.log_span) + (poiN - poiA) + hasting;
+    x = warp_sum_first(e_new - e_old, nw.K > cur.K ? nw.K : cur.K) + (double)(nw.K - cur.K) * (2.0 * v.lg_cur - d.log_span) + (poiN - poiA) + hasting;
     return true;
 }
 

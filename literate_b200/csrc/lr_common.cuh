@@ -77,6 +77,17 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// warp_sum of a value that is zero in every lane >= K (the slots a side does not use), K warp-uniform: the butterfly steps that
+// would only add zeros are skipped -- the bits are those of warp_sum -- and lane 0's total is broadcast.  One shuffle for a
+// single-rate side instead of five.
+__device__ __forceinline__ double warp_sum_first(double v, int K) {
+    if (K > 8) return warp_sum(v);
+    if (K > 1) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return __shfl_sync(0xffffffffu, v, 0);
+}
 __device__ __forceinline__ double warp_prod(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
