@@ -84,8 +84,10 @@ struct PowCache { double b, d; };
 
 // both side likelihoods (uniform over the warp); a side with do_* == false keeps the value passed in.  newPowB/newPowD: the
 // exponent of that side differs from the one `pc` was computed for (pc is updated in place)
+// `extra`: a per-lane term (Hastings share + prior difference of the lane's parameter) that rides the same butterfly; its
+// warp total comes back in place.
 __device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, int lane, bool doB, bool doD, bool newPowB, bool newPowD,
-                                          PowCache& pc, double& likB, double& likD) {
+                                          PowCache& pc, double& likB, double& likD, double& extra) {
     double sB = 0.0, sD = 0.0;
     if (doB) {
         double lam = p[0];
@@ -116,12 +118,11 @@ __device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, i
             sD += log(mu) * __ldg(v.tab + TR_EX * v.nbp + j) - mu * br;
         }
     }
-    if (doB | doD) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sB += __shfl_xor_sync(0xffffffffu, sB, o);
-            sD += __shfl_xor_sync(0xffffffffu, sD, o);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        sB += __shfl_xor_sync(0xffffffffu, sB, o);
+        sD += __shfl_xor_sync(0xffffffffu, sD, o);
+        extra += __shfl_xor_sync(0xffffffffu, extra, o);
     }
     if (doB) likB = sB;
     if (doD) likD = sD;
@@ -261,19 +262,12 @@ __global__ void __launch_bounds__(128, 4) k6_trend_kernel(const TrendRun P) {
         const unsigned touched = __ballot_sync(0xffffffffu, on);
         double q[TR_NPAR];
         bcast6(prop, q);
-        // Hastings ratio and prior difference: one butterfly for both
-        double hs = h, dpr = trend_prior_delta(lane, mine, prop, h);
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {       // only lanes 0..7 carry terms
-            hs += __shfl_xor_sync(0xffffffffu, hs, o);
-            dpr += __shfl_xor_sync(0xffffffffu, dpr, o);
-        }
-        hs = __shfl_sync(0xffffffffu, hs, 0);
-        dpr = __shfl_sync(0xffffffffu, dpr, 0);
+        // Hastings share and prior difference of this lane's parameter: summed in the butterfly of the likelihood
+        double hp = h + trend_prior_delta(lane, mine, prop, h);
         double nB = likB, nD = likD;
         PowCache npc = pc;
-        trend_lik(v, q, lane, (touched & 0x15u) != 0, (touched & 0x2au) != 0, (touched & 0x10u) != 0, (touched & 0x20u) != 0, npc, nB, nD);
-        const double x = ((nB + nD) - (likB + likD)) + dpr + hs;
+        trend_lik(v, q, lane, (touched & 0x15u) != 0, (touched & 0x2au) != 0, (touched & 0x10u) != 0, (touched & 0x20u) != 0, npc, nB, nD, hp);
+        const double x = ((nB + nD) - (likB + likD)) + hp;
         if (it == 0 || mh_accept_gt(x, u_acc)) {                            // trend_rate.py:176
 #pragma unroll
             for (int k = 0; k < TR_NPAR; ++k) p[k] = q[k];
@@ -305,7 +299,8 @@ __global__ void k6_init_kernel(TrendChain* st, int n_chains, const int* rep_of_c
     bcast6(mine, p);
     double likB = 0, likD = 0;
     PowCache pc;
-    trend_lik(v, p, lane, true, true, true, true, pc, likB, likD);
+    double unused = 0.0;
+    trend_lik(v, p, lane, true, true, true, true, pc, likB, likD, unused);
     double pr = trend_prior_term(lane, mine);
     pr = warp_sum(pr);
     if (lane < TR_NPAR) st[c].p[lane] = mine;
@@ -355,7 +350,8 @@ __global__ void k6_eval_kernel(const double* tab, const double* cst, int nb, int
     bcast6(mine, p);
     double likB = 0, likD = 0;
     PowCache pc;
-    trend_lik(v, p, lane, true, true, true, true, pc, likB, likD);
+    double unused = 0.0;
+    trend_lik(v, p, lane, true, true, true, true, pc, likB, likD, unused);
     const double pr = warp_sum(trend_prior_term(lane, mine));
     double adq[3];
     trend_adequacy(v, p, lane, adq);

@@ -140,8 +140,10 @@ __device__ __forceinline__ DDBin0 dd_bin0(const DDView& v, int lane) {
 }
 
 // newL / newC: a parameter of the logistic / constant carrying capacity differs from the one `c` was computed for
+// `extra`: a per-lane term (Hastings share + prior difference of the lane's parameter) that rides the same butterfly; its warp
+// total comes back in place.
 __device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const double* p, int lane, bool doB, bool doD, bool newL,
-                                       bool newC, DDCache& c, double& likB, double& likD) {
+                                       bool newC, DDCache& c, double& likB, double& likD, double& extra) {
     const bool evalD = doD && v.md >= 1;
     double sB = 0.0, sD = 0.0;
     if (doB || evalD) {
@@ -188,11 +190,12 @@ __device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const 
             }
         }
         if (c.tail != nullptr && needL && newL) c.sel ^= 1;       // the recomputed values sit in the other buffer
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sB += __shfl_xor_sync(0xffffffffu, sB, o);
-            sD += __shfl_xor_sync(0xffffffffu, sD, o);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        sB += __shfl_xor_sync(0xffffffffu, sB, o);
+        sD += __shfl_xor_sync(0xffffffffu, sD, o);
+        extra += __shfl_xor_sync(0xffffffffu, extra, o);
     }
     if (doB) likB = sB;
     if (doD) likD = v.md >= 1 ? sD : v.likD_const;                   // death rate 1 in every bin (:105-106)
@@ -397,24 +400,17 @@ __global__ void __launch_bounds__(128, 3) k7_dd_kernel(const DDRun P) {
         if (kind == 2) touched = 1u << P_MMUL;
         double q[DD_NPAR];
         dd_bcast(prop, q);
-        double hs = h, dpr = dd_prior_delta(v, pl, mine, prop, h);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {       // lanes 0..15 carry terms
-            hs += __shfl_xor_sync(0xffffffffu, hs, o);
-            dpr += __shfl_xor_sync(0xffffffffu, dpr, o);
-        }
-        hs = __shfl_sync(0xffffffffu, hs, 0);
-        dpr = __shfl_sync(0xffffffffu, dpr, 0);
+        double hp = h + dd_prior_delta(v, pl, mine, prop, h);       // summed in the butterfly of the likelihood
         double nB = likB, nD = likD, nG = likG;
         double ng[4] = {g[0], g[1], g[2], g[3]};
         DDCache nc = cache;
-        dd_lik(v, b0, q, lane, (touched & P.depB) != 0, (touched & P.depD) != 0, (touched & maskL) != 0, (touched & maskC) != 0, nc, nB, nD);
+        dd_lik(v, b0, q, lane, (touched & P.depB) != 0, (touched & P.depD) != 0, (touched & maskL) != 0, (touched & maskC) != 0, nc, nB, nD, hp);
         if (v.mb == 3) {
             if (touched & (1u << P_X0)) dd_genre_stats(v, q[P_X0], lane, ng);
             if (touched & ((1u << P_X0) | (1u << P_G1) | (1u << P_G2)))
                 nG = dd_genre_lik(q, ng, (touched & (1u << P_G1)) != 0, (touched & (1u << P_G2)) != 0, nc);
         }
-        const double x = ((nB + nD + nG) - (likB + likD + likG)) + dpr + hs;
+        const double x = ((nB + nD + nG) - (likB + likD + likG)) + hp;
         if (it == 0 || mh_accept_gt(x, u_acc)) {                                                 // :263
 #pragma unroll
             for (int k = 0; k < DD_NPAR; ++k) p[k] = q[k];
@@ -443,7 +439,8 @@ __device__ __forceinline__ void dd_eval_all(const DDView& v, const double* p, do
     DDCache c;
     c.lnL0 = c.lnC = c.lg1 = c.lg2 = 0.0;
     c.tail = nullptr; c.nt = 0; c.sel = 0;
-    dd_lik(v, dd_bin0(v, lane), p, lane, true, true, true, true, c, likB, likD);
+    double unused = 0.0;
+    dd_lik(v, dd_bin0(v, lane), p, lane, true, true, true, true, c, likB, likD, unused);
     likG = 1.0;                                                    // g_birth_lik = 1 unless -m_birth 3 (:84)
     g[0] = g[1] = g[2] = g[3] = 0.0;
     if (v.mb == 3) { dd_genre_stats(v, p[P_X0], lane, g); likG = dd_genre_lik(p, g, true, true, c); }
