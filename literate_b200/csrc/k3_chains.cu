@@ -8,6 +8,7 @@
 // warp through a shared-memory ring; compact: one warp does everything) are described where they are defined.
 // Reference quirks kept on purpose: no-op move-shift (:184-185), stale priorPoiA (:300-304,:319),
 // initial prior with Gamma rate 2 (:227), `>=` accept test (:313), min-spacing guard (:290).
+#include <stdlib.h>
 #include "chain_device.cuh"
 
 namespace {
@@ -830,6 +831,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     }
 }
 
+#include "k3_team.cuh"
+
 // initial state (:580-583) and initial bookkeeping (:220-230)
 __global__ void k3_init_kernel(ChainState* st, int n_chains, const int* __restrict__ rep_of_chain, long long chain_id0,
                                uint32_t k0, uint32_t k1, double start_time, double poisson_prior_cfg, double beta) {
@@ -1313,7 +1316,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
     LR_REQUIRE(cfg->model_BDI == ds->model, "lr_chains_create: cfg.model_BDI differs from the dataset's");
     LR_REQUIRE(cfg->update_fraction >= 0.0 && cfg->update_fraction <= 1.0, "lr_chains_create: update_fraction outside [0,1]");
     LR_REQUIRE(cfg->poisson_prior >= 0.0, "lr_chains_create: poisson_prior must be >= 0");
-    LR_REQUIRE(cfg->loop_variant >= 0 && cfg->loop_variant <= 3, "lr_chains_create: loop_variant must be 0..3");
+    LR_REQUIRE(cfg->loop_variant >= 0 && cfg->loop_variant <= 4, "lr_chains_create: loop_variant must be 0..4");
     LR_REQUIRE(chain_id0 >= 0 && chain_id0 + n_chains <= 0xffffffffll, "lr_chains_create: chain ids must fit 32 bits");
     if (h_rep_of_chain)
         for (int i = 0; i < n_chains; ++i)
@@ -1385,7 +1388,19 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     //   296 chains 572 / 506 / 325;  512: - / 873 / 557;  1024: - / 1094 / 1027;  1184: - / 1119 / 1161;  2048: - / 1051 / 1547
     int variant = c->cfg.loop_variant;
     if (variant == 0) variant = c->n_chains <= 2 * h->sm_count ? 1 : (c->n_chains <= 7 * h->sm_count ? 3 : 2);
-    if (variant == 1) {
+    if (variant == 4) {
+        // speculative team build: W warps per chain, W by how many CTAs an SM has to hold (k3_team.cuh)
+        const char* e_w = getenv("LR_TEAM_W");              // development overrides (tests sweep them)
+        const char* e_lead = getenv("LR_TEAM_LEAD");
+        const int env_w = e_w ? atoi(e_w) : 0, env_lead = e_lead ? atoi(e_lead) : 0;
+        int W = env_w ? env_w : (c->n_chains <= h->sm_count ? 16 : (c->n_chains <= 2 * h->sm_count ? 8 : 4));
+        int lead = env_lead ? env_lead : 2;
+        if (lead < 1) lead = 1;
+        if (lead > 7) lead = 7;
+        if (W >= 16) k3_team_kernel<16><<<c->n_chains, 512, 0, st>>>(P, lead);
+        else if (W >= 8) k3_team_kernel<8><<<c->n_chains, 256, 0, st>>>(P, lead);
+        else k3_team_kernel<4><<<c->n_chains, 128, 0, st>>>(P, lead);
+    } else if (variant == 1) {
         const size_t smem = sizeof(Ring<6>);
         LR_CUDA(cudaFuncSetAttribute(k3_run_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k3_run_kernel<1><<<c->n_chains, 128, smem, st>>>(P);

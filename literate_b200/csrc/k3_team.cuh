@@ -1,0 +1,336 @@
+// K3, SPECULATIVE TEAM build of the chain loop (loop_variant 4).  Included by k3_chains.cu inside its anonymous namespace.
+//
+// Why: at a few hundred chains one warp per chain leaves the SMs four-fifths idle (ncu, round 1: 0.19 of issue peak): an
+// iteration is ~900 cycles of DEPENDENT fp64 work.  But most iterations do not change the chain's state -- the
+// reference's move-shift proposes the current state (LiteRateForward.py:184-185), a rate update that touches no rate or
+// a remove-shift on a single-rate side leaves it as it is, and on large tables nearly every real proposal is rejected
+// (:313) -- and everything an iteration draws is independent of the state (make_draws).  So a TEAM of W warps works on
+// one chain: warp w evaluates iterations w, w + W, w + 2W, ... against its own register copy of the state, without
+// waiting for the iterations before it.  An evaluation that leaves the state unchanged is simply published
+// ("iterations below n of mine are done under state version v").  A warp whose iteration would CHANGE the state
+// (accepted proposal, Gibbs step :281-287, the periodic log-rate resync) or must observe it (sample record :321) first
+// waits until every earlier iteration is published under the same version -- it is then the chain's frontier, its
+// evaluation is the one the sequential loop would have made -- applies the change, writes the new state to shared memory
+// and bumps the version.  The others notice the new version at their next iteration, reload, and resume at the iteration
+// after the commit; whatever they had evaluated beyond it is dropped.  The chain is the SAME chain, bit for bit, as in
+// the other builds (tests/test_gpu_chains.py::test_loop_builds_give_identical_chains): same draws, same arithmetic on the
+// same state, only evaluated early.
+//
+// Protocol (shared memory of the CTA = one chain):
+//   verword          (version << 32) | offset of the first iteration to evaluate under this version
+//   prog[w]          (version << 32) | offset of warp w's next unevaluated iteration
+//   buf[version & 1] the state of that version (written by the committing warp before the release store of verword)
+// A commit at iteration j under version v needs every other warp's prog to carry version v and an offset > j; so every warp has
+// acknowledged v (nobody still reads the buffer of v - 1, which v + 1 overwrites), versions never skip a warp, and there is
+// one frontier at a time.  A warp may run at most `lead` own iterations ahead of the slowest one (bounds the dropped
+// work and keeps the per-warp history of counter increments -- 8 iterations deep -- exact under rollback).
+
+template <int W>
+struct TeamShared {
+    unsigned long long verword;
+    unsigned long long prog[W];
+    unsigned cnt[W][8];
+    struct Buf {
+        double r[2][32], lr[2][32], t[2][32], A[2][32], B[2][32];
+        int jb[2][32];
+        double sc[8];          // gL gM lgL lgM poi lpoi priorA poiA
+        int isc[4];            // K_l K_m poi_is_init consistent
+    } buf[2];
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_shared(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.shared.u64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+}
+
+// per-warp event counters of the team build: the increments of one iteration are a bit mask (bit k = counter k); the
+// last eight masks wait in `hist` (newest in the low byte) and are only counted when they leave it -- by then the
+// iteration is older than any possible rollback
+struct TeamCounters {
+    unsigned long long hist;
+    unsigned lo, hi, pushes;
+    unsigned n[8];
+};
+__device__ __noinline__ void tc_flush(TeamCounters& t) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { t.n[k] += (t.lo >> (8 * k)) & 0xffu; t.n[4 + k] += (t.hi >> (8 * k)) & 0xffu; }
+    t.lo = 0u; t.hi = 0u;
+}
+__device__ __forceinline__ void tc_push(TeamCounters& t, unsigned mask) {
+    const unsigned out = (unsigned)(t.hist >> 56);
+    t.hist = (t.hist << 8) | (unsigned long long)mask;
+    t.lo += ((out & 0xfu) * 0x00204081u) & 0x01010101u;       // bit k of the mask -> byte k
+    t.hi += ((out >> 4) * 0x00204081u) & 0x01010101u;
+    if ((++t.pushes & 127u) == 0u) tc_flush(t);
+}
+
+// event iterations (sample record :321, log-rate resync) as offsets from the launch's first iteration
+struct TeamEvents {
+    unsigned long long first_sample, s_every, first_resync;     // first_sample = ~0 when no records are written
+    unsigned next_sample, next_resync, next_event;
+};
+__device__ __noinline__ void team_events_from(TeamEvents& e, unsigned i) {
+    unsigned long long ns = ~0ull, nr;
+    if (e.first_sample != ~0ull) ns = i <= e.first_sample ? e.first_sample : e.first_sample + (i - e.first_sample + e.s_every - 1) / e.s_every * e.s_every;
+    nr = i <= e.first_resync ? e.first_resync : e.first_resync + ((unsigned long long)i - e.first_resync + LR_RESYNC - 1) / LR_RESYNC * LR_RESYNC;
+    e.next_sample = ns > 0xffffffffull ? 0xffffffffu : (unsigned)ns;
+    e.next_resync = nr > 0xffffffffull ? 0xffffffffu : (unsigned)nr;
+    e.next_event = e.next_sample < e.next_resync ? e.next_sample : e.next_resync;
+}
+
+template <int W>
+__device__ __noinline__ void team_publish_state(TeamShared<W>& T, unsigned v_new, unsigned restart, const Side& L, const Side& M,
+                                                const ChainRegs& c, int lane) {
+    typename TeamShared<W>::Buf& b = T.buf[v_new & 1u];
+    b.r[0][lane] = L.r; b.lr[0][lane] = L.lr; b.t[0][lane] = L.t; b.A[0][lane] = L.A; b.B[0][lane] = L.B; b.jb[0][lane] = L.jb;
+    b.r[1][lane] = M.r; b.lr[1][lane] = M.lr; b.t[1][lane] = M.t; b.A[1][lane] = M.A; b.B[1][lane] = M.B; b.jb[1][lane] = M.jb;
+    if (lane == 0) {
+        b.sc[0] = c.hp.gL; b.sc[1] = c.hp.gM; b.sc[2] = c.hp.lgL; b.sc[3] = c.hp.lgM; b.sc[4] = c.hp.poi; b.sc[5] = c.hp.lpoi;
+        b.sc[6] = c.priorA; b.sc[7] = c.poiA;
+        b.isc[0] = L.K; b.isc[1] = M.K; b.isc[2] = c.poi_is_init; b.isc[3] = c.consistent;
+    }
+    __syncwarp();
+    if (lane == 0) st_release_cta(&T.verword, ((unsigned long long)v_new << 32) | restart);
+}
+template <int W>
+__device__ __noinline__ void team_load_state(const TeamShared<W>& T, unsigned v, Side& L, Side& M, ChainRegs& c, int lane) {
+    const typename TeamShared<W>::Buf& b = T.buf[v & 1u];
+    L.r = b.r[0][lane]; L.lr = b.lr[0][lane]; L.t = b.t[0][lane]; L.A = b.A[0][lane]; L.B = b.B[0][lane]; L.jb = b.jb[0][lane];
+    M.r = b.r[1][lane]; M.lr = b.lr[1][lane]; M.t = b.t[1][lane]; M.A = b.A[1][lane]; M.B = b.B[1][lane]; M.jb = b.jb[1][lane];
+    c.hp.gL = b.sc[0]; c.hp.gM = b.sc[1]; c.hp.lgL = b.sc[2]; c.hp.lgM = b.sc[3]; c.hp.poi = b.sc[4]; c.hp.lpoi = b.sc[5];
+    c.priorA = b.sc[6]; c.poiA = b.sc[7];
+    L.K = b.isc[0]; M.K = b.isc[1]; c.poi_is_init = b.isc[2]; c.consistent = b.isc[3];
+}
+
+// true once every earlier iteration is published under version v (this warp is the chain's frontier at offset i);
+// false if the version changed while waiting (the caller's evaluation is void)
+template <int W>
+__device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsigned v, unsigned i, int w, int lane) {
+    for (;;) {
+        const unsigned long long vw = ld_volatile_shared(&T.verword);
+        if ((unsigned)(vw >> 32) != v) return false;
+        const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
+        const bool ok = (lane & (W - 1)) == w || ((unsigned)(pw >> 32) == v && (unsigned)pw >= i);
+        if (__all_sync(0xffffffffu, ok)) return true;
+        __nanosleep(20);
+    }
+}
+
+// speculative evaluation of one block iteration (:254-272) on side `cur`: block_step's arithmetic without the commit.
+// Returns 0 if the state stays as it is, else the kind of pending change with the proposed side in `nw`.
+#define TEAM_PEND_NONE 0
+#define TEAM_PEND_SIDE 1       // cur = nw
+#define TEAM_PEND_RJ 2         // cur = nw, poiA = poiN
+template <bool C>
+__device__ __forceinline__ int team_block_eval(const Side& cur, const SideView v, const ChainRegs& c, const DataView& d,
+                                               const lr_chain_config& cfg, const Draws& q, int lane, unsigned& mask, Side& nw) {
+    const bool rate = (q.kind >> 1) == DK_BLOCK_RATE || cur.K == 1;
+    if (rate) {
+        mask |= (1u << 3) | (1u << 2);
+        const bool on = lane < cur.K;
+        const double dl = on ? q.dlt : 0.0;
+        const double rn = cur.r * (on ? q.m : 1.0);
+        const double x = warp_sum_first((c.beta * cur.A + 2.0) * dl - (c.beta * cur.B + v.g_cur) * (rn - cur.r), cur.K);
+        if (mh_accept(x, q)) {
+            mask |= 1u << 1;
+            // no rate touched (Binomial(1, f) of :170 came out 0 everywhere): r * 1 and lr + 0 are the state's own bits
+            if (__any_sync(0xffffffffu, dl != 0.0)) { nw = cur; nw.r = rn; nw.lr = cur.lr + dl; return TEAM_PEND_SIDE; }
+        }
+    } else if (!cfg.real_move_shift) {
+        mask |= (1u << 4) | (1u << 2) | (1u << 1);
+    } else {
+        mask |= 1u << 4;
+        if (propose_move<false>(cur, nw, d, v.tabA, v.tabB, q, lane)) {
+            mask |= 1u << 2;
+            const bool on = lane < cur.K;
+            const double x = warp_sum(on ? c.beta * ((nw.A - cur.A) * cur.lr - (nw.B - cur.B) * cur.r) : 0.0);
+            if (mh_accept(x, q)) { mask |= 1u << 1; return TEAM_PEND_SIDE; }
+        }
+    }
+    return TEAM_PEND_NONE;
+}
+template <bool C>
+__device__ __forceinline__ int team_rj_eval(const Side& cur, const Side& oth, const SideView v, const ChainRegs& c, const DataView& d,
+                                            const Draws& q, int lane, unsigned& mask, Side& nw, double& poiN) {
+    double hasting, x;
+    bool cap;
+    mask |= 1u << 5;
+    if (rj_propose<C>(cur, oth, v, c.hp, c.beta, c.poiA, d, q, lane, nw, hasting, poiN, x, cap)) {
+        mask |= 1u << 2;
+        if (mh_accept(x, q)) {
+            mask |= 1u << 1;
+            // remove-shift on a single-rate side proposes the state itself (:81-86); only the stored Poisson prior may move (:279, :319)
+            if (nw.K != cur.K || poiN != c.poiA) return TEAM_PEND_RJ;
+        }
+    } else if (cap) {
+        mask |= 1u << 7;
+    }
+    return TEAM_PEND_NONE;
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const RunParams P, const int lead) {
+    constexpr bool C = true;
+    __shared__ TeamShared<W> T;
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int chain = (int)blockIdx.x;
+    if (chain >= P.n_chains) return;                                  // whole CTA
+    if (threadIdx.x == 0) T.verword = 0ull;
+    if (threadIdx.x < W) T.prog[threadIdx.x] = (unsigned long long)threadIdx.x;
+    __syncthreads();
+
+    const lr_chain_config& cfg = P.cfg;
+    const LoopConsts K = loop_consts(cfg);
+    ChainState* S = P.st + chain;
+    Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
+    const long long it0 = S->it;
+    const unsigned n = (unsigned)P.n_iter;
+    const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
+    Side L, M;
+    load_sides(S, L, M, lane);
+    side_stats(L, d, T_AB, T_BB, lane);
+    side_stats(M, d, T_AD, T_BD, lane);
+    ChainRegs c;
+    c.hp.gL = S->gL; c.hp.gM = S->gM; c.hp.lgL = log(c.hp.gL); c.hp.lgM = log(c.hp.gM); c.hp.poi = S->poi; c.hp.lpoi = log(c.hp.poi);
+    c.priorA = S->priorA; c.poiA = S->poiA; c.beta = S->beta; c.poi_is_init = S->poi_is_init; c.consistent = (int)S->consistent;
+    const bool frozen = (d.end_time - d.start_time) <= LR_MIN_DT;
+    __syncthreads();                  // every warp has read the chain's global state before anybody may finish and rewrite it
+
+    TeamEvents ev;
+    {
+        const unsigned long long s_every = (unsigned long long)(P.sample_every > 0 ? P.sample_every : 1);
+        ev.s_every = s_every;
+        ev.first_sample = P.records != nullptr ? (s_every - (unsigned long long)it0 % s_every) % s_every : ~0ull;
+        ev.first_resync = (LR_RESYNC - (unsigned long long)it0 % LR_RESYNC) % LR_RESYNC;
+    }
+    TeamCounters tc;
+    tc.hist = 0ull; tc.lo = 0u; tc.hi = 0u; tc.pushes = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tc.n[k] = 0u;
+
+    unsigned v = 0u, base = 0u, i = (unsigned)w;
+    team_events_from(ev, i);
+    const unsigned lead_span = (unsigned)lead * W;
+
+    for (;;) {
+        // ---- has the chain moved on?  (a commit by another warp: reload, drop what was evaluated beyond it)
+        {
+            const unsigned long long vw0 = ld_volatile_shared(&T.verword);
+            if ((unsigned)(vw0 >> 32) != v) {
+                const unsigned long long vw = ld_acquire_cta(&T.verword);
+                const unsigned v_new = (unsigned)(vw >> 32), base_new = (unsigned)vw;
+                team_load_state<W>(T, v_new, L, M, c, lane);
+                const unsigned i_first = base_new + (((unsigned)w - base_new) & (W - 1));
+                const unsigned dropped = (i - i_first) / W;            // own iterations >= base_new already pushed (<= lead)
+                tc.hist = dropped >= 8u ? 0ull : (tc.hist >> (8u * dropped));
+                i = i_first; v = v_new; base = base_new;
+                team_events_from(ev, i);
+                __syncwarp();
+                if (lane == 0) st_volatile_shared(&T.prog[w], ((unsigned long long)v << 32) | i);
+                continue;
+            }
+        }
+        if (i >= n) {
+            // my share is done; the launch ends when everybody's is (a rollback can still hand me iterations again)
+            const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
+            if (__all_sync(0xffffffffu, (unsigned)(pw >> 32) == v && (unsigned)pw >= n)) break;
+            __nanosleep(100);
+            continue;
+        }
+        {
+            // not more than `lead` own iterations ahead of the slowest warp
+            const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
+            const unsigned nxt = (unsigned)(pw >> 32) == v ? (unsigned)pw : base;
+            const unsigned F = __reduce_min_sync(0xffffffffu, nxt);
+            if (i > F + lead_span) { __nanosleep(40); continue; }
+        }
+
+        const long long it = it0 + (long long)i;
+        const Draws q = make_draws<true>(rng, it, lane, K, L.K, M.K);
+        const int kind = q.kind >> 1;
+        const bool birth = (q.kind & 1) != 0;
+        const bool event = i == ev.next_event;
+        const bool serial = !c.consistent || frozen || kind == DK_GIBBS;
+        unsigned mask = 0u;
+        int pend = TEAM_PEND_NONE;
+        Side nw;
+        double poiN = 0.0;
+        Side& cur = birth ? L : M;
+        const Side& oth = birth ? M : L;
+        if (!serial) {
+            if (kind <= DK_BLOCK_MOVE) pend = team_block_eval<C>(cur, side_view(c.hp, birth), c, d, cfg, q, lane, mask, nw);
+            else pend = team_rj_eval<C>(cur, oth, side_view(c.hp, birth), c, d, q, lane, mask, nw, poiN);
+            if (pend == TEAM_PEND_NONE && !event) {
+                // the common case: the state stays as it is
+                tc_push(tc, mask);
+                i += W;
+                if (lane == 0) st_volatile_shared(&T.prog[w], ((unsigned long long)v << 32) | i);
+                if (i > ev.next_event) team_events_from(ev, i);
+                continue;
+            }
+        }
+        // ---- this iteration changes or observes the state: it has to be the chain's frontier
+        if (!team_wait_frontier<W>(T, v, i, w, lane)) continue;
+        bool changed = false;
+        if (serial) {
+            Counters ns;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ns.v[k] = 0u;
+            if (kind == DK_GIBBS) {
+                ns.v[6]++;
+                gibbs_step_ref(L, M, c, d, cfg.poisson_prior == 0.0 ? 1 : 0, cfg.use_rate_HP, rng, it, frozen, lane);
+                c.consistent = 1;
+                ns.v[1]++;
+            } else {
+                if (kind > DK_BLOCK_MOVE) ns.v[5]++;
+                run_slow(cur, oth, side_view(c.hp, birth), c, ns, d, cfg, q, frozen, lane);
+            }
+#pragma unroll
+            for (int k = 1; k < 8; ++k) mask |= ns.v[k] ? (1u << k) : 0u;
+            changed = true;
+        } else if (pend != TEAM_PEND_NONE) {
+            cur = nw;
+            if (pend == TEAM_PEND_RJ) c.poiA = poiN;
+            changed = true;
+        }
+        if (event) {
+            if (i == ev.next_resync) { resync_log_rates(L, M, lane); changed = true; }
+            if (i == ev.next_sample) {
+                const unsigned long long k = ((unsigned long long)i - ev.first_sample) / ev.s_every;
+                write_record_ref(P.records + ((size_t)k * P.n_chains + chain) * LR_REC_DOUBLES, it, L, M, c, d, lane, P.with_adequacy != 0);
+            }
+        }
+        if (changed) {
+            team_publish_state<W>(T, v + 1u, i + 1u, L, M, c, lane);
+            v += 1u; base = i + 1u;
+        }
+        tc_push(tc, mask);
+        i += W;
+        if (lane == 0) st_volatile_shared(&T.prog[w], ((unsigned long long)v << 32) | i);
+        if (i > ev.next_event) team_events_from(ev, i);
+    }
+
+    // ---- every warp holds the final state; warp 0 stores it, all add their counters
+    for (int k = 0; k < 8; ++k) tc_push(tc, 0u);
+    tc_flush(tc);
+    if (lane < 8) T.cnt[w][lane] = tc.n[lane];
+    __syncthreads();
+    if (w == 0) {
+        store_sides(S, L, M, lane);
+        if (lane == 0) {
+            S->it = it0 + P.n_iter;
+            S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init; S->consistent = (unsigned)c.consistent;
+            S->counters[0] += P.n_iter;
+            for (int k = 1; k < 8; ++k) {
+                long long s = 0;
+                for (int ww = 0; ww < W; ++ww) s += (long long)T.cnt[ww][k];
+                S->counters[k] += s;
+            }
+        }
+    }
+}

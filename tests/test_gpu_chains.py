@@ -106,6 +106,38 @@ def test_loop_builds_give_identical_chains(device, metal_path):
     assert np.array_equal(a.counters(), b.counters()) and np.array_equal(a.counters(), c.counters())
 
 
+@pytest.mark.parametrize("team_w,lead", [(4, 1), (8, 2), (16, 7), (8, 5)])
+def test_speculative_team_build_gives_the_same_chains(device, metal_path, team_w, lead, monkeypatch):
+    """loop_variant 4: W warps evaluate consecutive iterations of ONE chain ahead of time against the current state and only
+    the first state-changing one commits (csrc/k3_team.cuh).  Same draws, same arithmetic, same state: the records, final
+    states and event counters must be those of the compact build, bit for bit -- on a table where a third of the iterations
+    change the state (metal bands, many rollbacks) and on one where almost none does, split over ragged launches."""
+    monkeypatch.setenv("LR_TEAM_W", str(team_w))
+    monkeypatch.setenv("LR_TEAM_LEAD", str(lead))
+    lin, st, ds, a = _setup(device, metal_path, n_chains=11, seed=5, loop_variant=2)
+    b = E.Chains(ds, 11, 5, E.default_config(0, loop_variant=4))
+    ra, rb = a.run(30000, 250), b.run(30000, 250)
+    assert np.array_equal(ra, rb)
+    assert np.array_equal(a.counters(), b.counters())
+    assert np.array_equal(a.state(), b.state())
+    for k, n in enumerate([1, 7, 8, 9, 23, 64, 65, 1000, 3, 1025, 4096, 5]):
+        s = [0, 1, 5][k % 3]
+        ra, rb = a.run(n, s), b.run(n, s)
+        if s:
+            assert np.array_equal(ra, rb), (k, n, s)
+        assert np.array_equal(a.state(), b.state()), (k, n)
+    assert np.array_equal(a.counters(), b.counters())
+    # every sampler configuration and model once, from the initial state (quirk i: the first iterations run in the absolute form)
+    for model, kw in [(0, dict(const_death_rate=1)), (0, dict(const_rates=1)), (0, dict(Poisson_prior=2.0, use_rate_HP=0)),
+                      (1, {}), (2, {}), (3, {}), (0, dict(real_move_shift=1)), (0, dict(beta=0.3))]:
+        path = golden_input("example_dataTAD.txt")
+        lin, st, ds, a = _setup(device, path, model=model, n_chains=5, seed=77, loop_variant=2, **kw)
+        b = E.Chains(ds, 5, 77, E.default_config(model, loop_variant=4, **kw))
+        ra, rb = a.run(6000, 100), b.run(6000, 100)
+        assert np.array_equal(ra, rb), (model, kw)
+        assert np.array_equal(a.counters(), b.counters()), (model, kw)
+
+
 def test_loop_builds_identical_for_ragged_launch_lengths(device):
     """The producer/consumer ring of the specialised build hands iterations over in batches of 8: launches of 1, 7, 8, 9, ...
     iterations (partial first/last batches, sampling on and off) must still be the compact build's chain, bit for bit."""
