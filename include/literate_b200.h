@@ -216,6 +216,10 @@ int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_every, doub
  *   Gibbs draws, capacity rejections (add-shift at K == LR_KMAX), temperature swaps proposed, swaps accepted */
 #define LR_NCOUNTERS 10
 int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters);
+/* diagnostics of the speculative team build (loop_variant 4), per chain since creation: [n_chains][4] int64 =
+ *   state versions committed, evaluations dropped by rollbacks, polls while waiting to become the frontier,
+ *   polls at the lead limit.  Zero for the other builds.  No reference counterpart. */
+int lr_chains_team_stats_host(lr_chains_t c, int64_t* h_stats);
 /* current state of every chain as one record each (iteration = number of iterations done) */
 int lr_chains_get_state_host(lr_chains_t c, double* h_records);
 /* overwrite the state of every chain from records (fields 1,2 and 10-12 are recomputed) */

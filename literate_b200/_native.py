@@ -29,7 +29,7 @@ EXPORTS = [
     "lr_acc_stride", "lr_bin_accumulate", "lr_bin_finalize", "lr_bin_stats", "lr_bin_stats_host",
     "lr_dataset_create", "lr_dataset_create_host", "lr_dataset_destroy", "lr_state_eval_host", "lr_proposal_eval_host", "lr_loglik_direct",
     "lr_chains_create", "lr_chains_destroy", "lr_chains_records_per_run", "lr_chains_run", "lr_chains_run_host",
-    "lr_chains_counters_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
+    "lr_chains_counters_host", "lr_chains_team_stats_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
     "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step", "lr_summarize_records", "lr_marginal_rates",
     "lr_trend_create", "lr_trend_create_host", "lr_trend_destroy", "lr_trend_record_doubles", "lr_trend_records_per_run",
     "lr_trend_run", "lr_trend_run_host", "lr_trend_eval_host", "lr_trend_state_host",
@@ -100,6 +100,7 @@ def load(build_if_missing=False):
     sig("lr_chains_run", C.c_int, vp, i64, i64, vp, vp)
     sig("lr_chains_run_host", C.c_int, vp, i64, i64, vp)
     sig("lr_chains_counters_host", C.c_int, vp, vp)
+    sig("lr_chains_team_stats_host", C.c_int, vp, vp)
     sig("lr_chains_get_state_host", C.c_int, vp, vp)
     sig("lr_chains_set_state_host", C.c_int, vp, vp)
     sig("lr_chains_set_beta_host", C.c_int, vp, vp)

@@ -18,6 +18,7 @@ __constant__ double c_lnfact[LR_SLOTS + 2];
 struct ChainState {
     long long it;
     long long counters[LR_NCOUNTERS];   // 0..7 maintained by k3_run_kernel, 8..9 by the tempered-swap kernel
+    long long team[4];                  // diagnostics of the speculative team build (k3_team.cuh)
     int K_l, K_m, rep, poi_is_init;
     unsigned chain_id, consistent;
     double priorA, poiA, gL, gM, poi, beta;
@@ -168,6 +169,21 @@ __device__ __noinline__ void write_record(double* rec, long long it, Side L, Sid
     rec[112 + lane] = lane < M.K ? (lane == 0 ? d.start_time : M.t) : 0.0;
 }
 
+// branch frequencies and update fractions of the loop (:243-252), computed once on the host: as kernel parameters they are
+// constant-bank operands instead of per-iteration selects
+struct LoopConsts {
+    double shift_mu, b_freq, d_freq, fL, fM;
+    int const_rates, real_move_shift;
+};
+__host__ __device__ inline LoopConsts loop_consts(const lr_chain_config& cfg) {
+    LoopConsts k;
+    k.shift_mu = cfg.const_death_rate ? 0.0 : 0.5;          // :243-252
+    k.b_freq = cfg.const_death_rate ? 0.7 : 0.4; k.d_freq = 0.8;
+    k.fL = cfg.update_fraction; k.fM = cfg.const_death_rate ? 1.0 : cfg.update_fraction;
+    k.const_rates = cfg.const_rates; k.real_move_shift = cfg.real_move_shift;
+    return k;
+}
+
 struct RunParams {
     ChainState* st;
     int n_chains;
@@ -175,6 +191,7 @@ struct RunParams {
     int nb, s0f, model;
     double start_time, end_time;
     lr_chain_config cfg;
+    LoopConsts lc;
     uint32_t k0, k1;
     long long n_iter, sample_every;
     double* records;     // [sample][chain][LR_REC_DOUBLES] or null
@@ -219,19 +236,6 @@ struct Draws {
 #define DK_RJ_REMOVE 3
 #define DK_GIBBS 4
 
-struct LoopConsts {
-    double shift_mu, b_freq, d_freq, fL, fM;
-    int const_rates, real_move_shift;
-};
-__device__ __forceinline__ LoopConsts loop_consts(const lr_chain_config& cfg) {
-    LoopConsts k;
-    k.shift_mu = cfg.const_death_rate ? 0.0 : 0.5;          // :243-252
-    k.b_freq = cfg.const_death_rate ? 0.7 : 0.4; k.d_freq = 0.8;
-    k.fL = cfg.update_fraction; k.fM = cfg.const_death_rate ? 1.0 : cfg.update_fraction;
-    k.const_rates = cfg.const_rates; k.real_move_shift = cfg.real_move_shift;
-    return k;
-}
-
 // K_l / K_m: the chain's current numbers of rates if the caller knows them (compact build), -1 otherwise (producers): a
 // block iteration that will be a move-shift (r1 >= .5 on a side with more than one rate) does not need the multipliers.
 template <bool C>
@@ -266,9 +270,12 @@ __device__ __forceinline__ Draws make_draws(const Rng& rng, long long it, int la
         if (ra > 0.5) {
             // Beta(10,10) = G1/(G1+G2), Gamma(10,1) = -log(prod of 10 uniforms); every logarithm of u the reference takes
             // is assembled from log g1, log g2, log(g1+g2)
-            const double g1 = -xlog<C>(warp_prod(lane < 10 ? ua : 1.0));
-            const double g2 = -xlog<C>(warp_prod(lane < 10 ? ub : 1.0));
-            const double lg1 = xlog<C>(g1), lg2 = xlog<C>(g2), lgs = xlog<C>(g1 + g2);
+            // (the five logarithms are of warp-uniform values: lanes 0-2 take one each, two calls instead of five)
+            const double p1 = warp_prod(lane < 10 ? ua : 1.0), p2 = warp_prod(lane < 10 ? ub : 1.0);
+            const double lp = xlog<C>(lane == 1 ? p2 : p1);
+            const double g1 = -__shfl_sync(0xffffffffu, lp, 0), g2 = -__shfl_sync(0xffffffffu, lp, 1);
+            const double lg = xlog<C>(lane == 0 ? g1 : (lane == 1 ? g2 : g1 + g2));
+            const double lg1 = __shfl_sync(0xffffffffu, lg, 0), lg2 = __shfl_sync(0xffffffffu, lg, 1), lgs = __shfl_sync(0xffffffffu, lg, 2);
             q.w = lg2 - lg1;
             q.ln_beta = (LR_SHAPE_BETA - 1.0) * (lg1 + lg2 - 2.0 * lgs) - LR_BETA_NORM;
             q.kind = (DK_RJ_ADD << 1) | (birth ? 1 : 0);
@@ -345,7 +352,8 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
     const double p2 = (tp - t_n) / (t_i - t_n);
     const double lr_i = __shfl_sync(0xffffffffu, cur.lr, i);
     const double lr1 = lr_i - p2 * q.w, lr2 = lr_i + p1 * q.w;
-    const double r1 = xexp<C>(lr1), r2 = xexp<C>(lr2);
+    const double er = xexp<C>(lane == 1 ? lr2 : lr1);              // both exponentials in one call (lanes 0 and 1)
+    const double r1 = __shfl_sync(0xffffffffu, er, 0), r2 = __shfl_sync(0xffffffffu, er, 1);
     const double rs = r1 + r2;
     hasting = xlog<C>(fabs(gap) * rs * rs) - q.ln_beta - lr_i;            // log|gap| + 2 log(r1 + r2): one logarithm
     // shift slots above i up by one
@@ -697,7 +705,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     extern __shared__ __align__(16) unsigned char ring_raw[];
     Ring<DEPTH>* ring_p = nullptr;
     const lr_chain_config& cfg = P.cfg;
-    const LoopConsts K = loop_consts(cfg);
+    const LoopConsts& K = P.lc;
     if constexpr (SPEC) {
         Ring<DEPTH>* rings = reinterpret_cast<Ring<DEPTH>*>(ring_raw);
         if (threadIdx.x < CPB * DEPTH) { rings[threadIdx.x / DEPTH].full[threadIdx.x % DEPTH] = 0ull; rings[threadIdx.x / DEPTH].done[threadIdx.x % DEPTH] = 0ull; }
@@ -851,6 +859,7 @@ __global__ void k3_init_kernel(ChainState* st, int n_chains, const int* __restri
     if (lane == 0) {
         S->it = 0;
         for (int i = 0; i < LR_NCOUNTERS; ++i) S->counters[i] = 0;
+        for (int i = 0; i < 4; ++i) S->team[i] = 0;
         S->K_l = 1; S->K_m = 1; S->rep = rep_of_chain ? rep_of_chain[chain] : 0;
         S->chain_id = rng.chain; S->consistent = 0;     // the initial prior uses Gamma rate 2 (:227), the loop rate 1
         const double poi = poisson_prior_cfg == 0.0 ? 1.0 : poisson_prior_cfg;       // :220-221
@@ -1376,7 +1385,7 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     P.st = c->st; P.n_chains = c->n_chains; P.tab = c->ds->tab; P.cst = c->ds->cst;
     P.nb = c->ds->n_bins; P.s0f = c->ds->s0f; P.model = c->ds->model;
     P.start_time = c->ds->start_time; P.end_time = c->ds->end_time;
-    P.cfg = c->cfg; P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
+    P.cfg = c->cfg; P.lc = loop_consts(c->cfg); P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
     P.n_iter = n_iter; P.sample_every = sample_every > 0 ? sample_every : 1;
     P.records = sample_every > 0 ? d_records : nullptr;
     P.with_adequacy = 1;
@@ -1441,6 +1450,14 @@ extern "C" int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters) {
     LR_CUDA(cudaStreamSynchronize(c->h->stream));
     LR_CUDA(cudaMemcpy2D(h_counters, LR_NCOUNTERS * sizeof(int64_t), &c->st[0].counters[0], sizeof(ChainState), LR_NCOUNTERS * sizeof(int64_t),
                          c->n_chains, cudaMemcpyDeviceToHost));
+    return LR_OK;
+}
+
+extern "C" int lr_chains_team_stats_host(lr_chains_t c, int64_t* h_stats) {
+    LR_REQUIRE(c && h_stats, "lr_chains_team_stats_host: null pointer");
+    LR_CUDA(cudaSetDevice(c->h->device));
+    LR_CUDA(cudaStreamSynchronize(c->h->stream));
+    LR_CUDA(cudaMemcpy2D(h_stats, 4 * sizeof(int64_t), &c->st[0].team[0], sizeof(ChainState), 4 * sizeof(int64_t), c->n_chains, cudaMemcpyDeviceToHost));
     return LR_OK;
 }
 

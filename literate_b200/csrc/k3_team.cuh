@@ -17,19 +17,24 @@
 // same state, only evaluated early.
 //
 // Protocol (shared memory of the CTA = one chain):
-//   verword          (version << 32) | offset of the first iteration to evaluate under this version
+//   verword          version (24 bits, wraps) | what the commit changed (8 bits) | offset of the iteration after the commit (32 bits)
 //   prog[w]          (version << 32) | offset of warp w's next unevaluated iteration
 //   buf[version & 1] the state of that version (written by the committing warp before the release store of verword)
 // A commit at iteration j under version v needs every other warp's prog to carry version v and an offset > j; so every warp has
 // acknowledged v (nobody still reads the buffer of v - 1, which v + 1 overwrites), versions never skip a warp, and there is
 // one frontier at a time.  A warp may run at most `lead` own iterations ahead of the slowest one (bounds the dropped
 // work and keeps the per-warp history of counter increments -- 8 iterations deep -- exact under rollback).
+// Rollbacks are selective: every evaluation records WHAT it read (values / number of rates of either side, the stored
+// Poisson prior), every commit says what it changed, and a warp only goes back to its first evaluation beyond the commit
+// that read something the commit changed -- a death-rate update survives an accepted add-shift on the birth side, the
+// reference's no-op move survives everything that keeps its side's number of rates.
 
 template <int W>
 struct TeamShared {
     unsigned long long verword;
     unsigned long long prog[W];
     unsigned cnt[W][8];
+    unsigned dbg[W][4];        // commits, evaluations dropped by rollbacks, polls while waiting to be the frontier, polls at the lead limit
     struct Buf {
         double r[2][32], lr[2][32], t[2][32], A[2][32], B[2][32];
         int jb[2][32];
@@ -37,6 +42,17 @@ struct TeamShared {
         int isc[4];            // K_l K_m poi_is_init consistent
     } buf[2];
 };
+
+// what an evaluation read / what a commit changed
+#define TD_LV 1u          // rates, log-rates, shift times (and segment statistics) of the birth side
+#define TD_LK 2u          // number of birth rates
+#define TD_MV 4u
+#define TD_MK 8u
+#define TD_P 16u          // the stored Poisson prior priorPoiA (:300-304)
+#define TD_ALL 31u        // + hyper-parameters, stored prior, consistency flag (Gibbs step, absolute-form iterations)
+#define TEAM_VMASK 0xffffffu
+__device__ __forceinline__ unsigned tv_version(unsigned long long vw) { return (unsigned)(vw >> 40); }
+__device__ __forceinline__ unsigned tv_changed(unsigned long long vw) { return (unsigned)(vw >> 32) & 0xffu; }
 
 __device__ __forceinline__ unsigned long long ld_volatile_shared(const unsigned long long* p) {
     unsigned long long v;
@@ -52,6 +68,7 @@ __device__ __forceinline__ void st_volatile_shared(unsigned long long* p, unsign
 // iteration is older than any possible rollback
 struct TeamCounters {
     unsigned long long hist;
+    unsigned long long dep;            // what each of those eight evaluations read (TD_* bits), same order
     unsigned lo, hi, pushes;
     unsigned n[8];
 };
@@ -60,9 +77,10 @@ __device__ __noinline__ void tc_flush(TeamCounters& t) {
     for (int k = 0; k < 4; ++k) { t.n[k] += (t.lo >> (8 * k)) & 0xffu; t.n[4 + k] += (t.hi >> (8 * k)) & 0xffu; }
     t.lo = 0u; t.hi = 0u;
 }
-__device__ __forceinline__ void tc_push(TeamCounters& t, unsigned mask) {
+__device__ __forceinline__ void tc_push(TeamCounters& t, unsigned mask, unsigned dep) {
     const unsigned out = (unsigned)(t.hist >> 56);
     t.hist = (t.hist << 8) | (unsigned long long)mask;
+    t.dep = (t.dep << 8) | (unsigned long long)dep;
     t.lo += ((out & 0xfu) * 0x00204081u) & 0x01010101u;       // bit k of the mask -> byte k
     t.hi += ((out >> 4) * 0x00204081u) & 0x01010101u;
     if ((++t.pushes & 127u) == 0u) tc_flush(t);
@@ -83,7 +101,7 @@ __device__ __noinline__ void team_events_from(TeamEvents& e, unsigned i) {
 }
 
 template <int W>
-__device__ __noinline__ void team_publish_state(TeamShared<W>& T, unsigned v_new, unsigned restart, const Side& L, const Side& M,
+__device__ __noinline__ void team_publish_state(TeamShared<W>& T, unsigned v_new, unsigned changed, unsigned restart, const Side& L, const Side& M,
                                                 const ChainRegs& c, int lane) {
     typename TeamShared<W>::Buf& b = T.buf[v_new & 1u];
     b.r[0][lane] = L.r; b.lr[0][lane] = L.lr; b.t[0][lane] = L.t; b.A[0][lane] = L.A; b.B[0][lane] = L.B; b.jb[0][lane] = L.jb;
@@ -94,7 +112,7 @@ __device__ __noinline__ void team_publish_state(TeamShared<W>& T, unsigned v_new
         b.isc[0] = L.K; b.isc[1] = M.K; b.isc[2] = c.poi_is_init; b.isc[3] = c.consistent;
     }
     __syncwarp();
-    if (lane == 0) st_release_cta(&T.verword, ((unsigned long long)v_new << 32) | restart);
+    if (lane == 0) st_release_cta(&T.verword, ((unsigned long long)((v_new << 8) | changed) << 32) | restart);
 }
 template <int W>
 __device__ __noinline__ void team_load_state(const TeamShared<W>& T, unsigned v, Side& L, Side& M, ChainRegs& c, int lane) {
@@ -109,13 +127,14 @@ __device__ __noinline__ void team_load_state(const TeamShared<W>& T, unsigned v,
 // true once every earlier iteration is published under version v (this warp is the chain's frontier at offset i);
 // false if the version changed while waiting (the caller's evaluation is void)
 template <int W>
-__device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsigned v, unsigned i, int w, int lane) {
+__device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsigned v, unsigned i, int w, int lane, unsigned& polls) {
     for (;;) {
         const unsigned long long vw = ld_volatile_shared(&T.verword);
-        if ((unsigned)(vw >> 32) != v) return false;
+        if (tv_version(vw) != v) return false;
         const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
         const bool ok = (lane & (W - 1)) == w || ((unsigned)(pw >> 32) == v && (unsigned)pw >= i);
         if (__all_sync(0xffffffffu, ok)) return true;
+        ++polls;
         __nanosleep(20);
     }
 }
@@ -127,8 +146,10 @@ __device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsig
 #define TEAM_PEND_RJ 2         // cur = nw, poiA = poiN
 template <bool C>
 __device__ __forceinline__ int team_block_eval(const Side& cur, const SideView v, const ChainRegs& c, const DataView& d,
-                                               const lr_chain_config& cfg, const Draws& q, int lane, unsigned& mask, Side& nw) {
+                                               const lr_chain_config& cfg, const Draws& q, int lane, unsigned& mask, unsigned& dep, Side& nw) {
     const bool rate = (q.kind >> 1) == DK_BLOCK_RATE || cur.K == 1;
+    const unsigned xv = (q.kind & 1) ? TD_LV : TD_MV, xk = (q.kind & 1) ? TD_LK : TD_MK;
+    dep = (rate || cfg.real_move_shift) ? (xv | xk) : xk;
     if (rate) {
         mask |= (1u << 3) | (1u << 2);
         const bool on = lane < cur.K;
@@ -155,10 +176,11 @@ __device__ __forceinline__ int team_block_eval(const Side& cur, const SideView v
 }
 template <bool C>
 __device__ __forceinline__ int team_rj_eval(const Side& cur, const Side& oth, const SideView v, const ChainRegs& c, const DataView& d,
-                                            const Draws& q, int lane, unsigned& mask, Side& nw, double& poiN) {
+                                            const Draws& q, int lane, unsigned& mask, unsigned& dep, Side& nw, double& poiN) {
     double hasting, x;
     bool cap;
     mask |= 1u << 5;
+    dep = (q.kind & 1) ? (TD_LV | TD_LK | TD_MK | TD_P) : (TD_MV | TD_MK | TD_LK | TD_P);
     if (rj_propose<C>(cur, oth, v, c.hp, c.beta, c.poiA, d, q, lane, nw, hasting, poiN, x, cap)) {
         mask |= 1u << 2;
         if (mh_accept(x, q)) {
@@ -173,7 +195,7 @@ __device__ __forceinline__ int team_rj_eval(const Side& cur, const Side& oth, co
 }
 
 template <int W>
-__global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const RunParams P, const int lead) {
+__global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_team_kernel(const RunParams P, const int lead) {
     constexpr bool C = true;
     __shared__ TeamShared<W> T;
     const int lane = threadIdx.x & 31;
@@ -185,7 +207,7 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
     __syncthreads();
 
     const lr_chain_config& cfg = P.cfg;
-    const LoopConsts K = loop_consts(cfg);
+    const LoopConsts& K = P.lc;
     ChainState* S = P.st + chain;
     Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
     const long long it0 = S->it;
@@ -209,26 +231,34 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
         ev.first_resync = (LR_RESYNC - (unsigned long long)it0 % LR_RESYNC) % LR_RESYNC;
     }
     TeamCounters tc;
-    tc.hist = 0ull; tc.lo = 0u; tc.hi = 0u; tc.pushes = 0u;
+    tc.hist = 0ull; tc.dep = 0ull; tc.lo = 0u; tc.hi = 0u; tc.pushes = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tc.n[k] = 0u;
 
     unsigned v = 0u, base = 0u, i = (unsigned)w;
+    unsigned F_seen = 0u;             // a lower bound of the slowest warp's next iteration (it only grows)
+    unsigned n_commit = 0u, n_drop = 0u, n_fwait = 0u, n_lead = 0u;
     team_events_from(ev, i);
     const unsigned lead_span = (unsigned)lead * W;
 
     for (;;) {
-        // ---- has the chain moved on?  (a commit by another warp: reload, drop what was evaluated beyond it)
+        // ---- has the chain moved on?  (a commit by another warp: reload; go back to the first own evaluation beyond the
+        // commit that read something the commit changed)
         {
             const unsigned long long vw0 = ld_volatile_shared(&T.verword);
-            if ((unsigned)(vw0 >> 32) != v) {
+            if (tv_version(vw0) != v) {
                 const unsigned long long vw = ld_acquire_cta(&T.verword);
-                const unsigned v_new = (unsigned)(vw >> 32), base_new = (unsigned)vw;
+                const unsigned v_new = tv_version(vw), changed = tv_changed(vw), base_new = (unsigned)vw;
                 team_load_state<W>(T, v_new, L, M, c, lane);
                 const unsigned i_first = base_new + (((unsigned)w - base_new) & (W - 1));
-                const unsigned dropped = (i - i_first) / W;            // own iterations >= base_new already pushed (<= lead)
-                tc.hist = dropped >= 8u ? 0ull : (tc.hist >> (8u * dropped));
-                i = i_first; v = v_new; base = base_new;
+                const unsigned beyond = (i - i_first) / W;             // own evaluations at or after base_new (<= lead)
+                unsigned long long conf = tc.dep & ((unsigned long long)changed * 0x0101010101010101ull);
+                if (beyond < 8u) conf &= (1ull << (8u * beyond)) - 1ull;
+                const unsigned dropped = conf ? (unsigned)(63 - __clzll((long long)conf)) / 8u + 1u : 0u;
+                tc.hist >>= 8u * dropped; tc.dep >>= 8u * dropped;
+                n_drop += dropped;
+                i -= dropped * W; v = v_new; base = base_new;
+                if (F_seen < base) F_seen = base;
                 team_events_from(ev, i);
                 __syncwarp();
                 if (lane == 0) st_volatile_shared(&T.prog[w], ((unsigned long long)v << 32) | i);
@@ -239,15 +269,15 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
             // my share is done; the launch ends when everybody's is (a rollback can still hand me iterations again)
             const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
             if (__all_sync(0xffffffffu, (unsigned)(pw >> 32) == v && (unsigned)pw >= n)) break;
-            __nanosleep(100);
+            __nanosleep(200);
             continue;
         }
-        {
+        if (i > F_seen + lead_span) {
             // not more than `lead` own iterations ahead of the slowest warp
             const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
             const unsigned nxt = (unsigned)(pw >> 32) == v ? (unsigned)pw : base;
-            const unsigned F = __reduce_min_sync(0xffffffffu, nxt);
-            if (i > F + lead_span) { __nanosleep(40); continue; }
+            F_seen = __reduce_min_sync(0xffffffffu, nxt);
+            if (i > F_seen + lead_span) { ++n_lead; __nanosleep(100); continue; }
         }
 
         const long long it = it0 + (long long)i;
@@ -256,18 +286,18 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
         const bool birth = (q.kind & 1) != 0;
         const bool event = i == ev.next_event;
         const bool serial = !c.consistent || frozen || kind == DK_GIBBS;
-        unsigned mask = 0u;
+        unsigned mask = 0u, dep = TD_ALL;
         int pend = TEAM_PEND_NONE;
         Side nw;
         double poiN = 0.0;
         Side& cur = birth ? L : M;
         const Side& oth = birth ? M : L;
         if (!serial) {
-            if (kind <= DK_BLOCK_MOVE) pend = team_block_eval<C>(cur, side_view(c.hp, birth), c, d, cfg, q, lane, mask, nw);
-            else pend = team_rj_eval<C>(cur, oth, side_view(c.hp, birth), c, d, q, lane, mask, nw, poiN);
+            if (kind <= DK_BLOCK_MOVE) pend = team_block_eval<C>(cur, side_view(c.hp, birth), c, d, cfg, q, lane, mask, dep, nw);
+            else pend = team_rj_eval<C>(cur, oth, side_view(c.hp, birth), c, d, q, lane, mask, dep, nw, poiN);
             if (pend == TEAM_PEND_NONE && !event) {
                 // the common case: the state stays as it is
-                tc_push(tc, mask);
+                tc_push(tc, mask, dep);
                 i += W;
                 if (lane == 0) st_volatile_shared(&T.prog[w], ((unsigned long long)v << 32) | i);
                 if (i > ev.next_event) team_events_from(ev, i);
@@ -275,8 +305,8 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
             }
         }
         // ---- this iteration changes or observes the state: it has to be the chain's frontier
-        if (!team_wait_frontier<W>(T, v, i, w, lane)) continue;
-        bool changed = false;
+        if (!team_wait_frontier<W>(T, v, i, w, lane, n_fwait)) { ++n_drop; continue; }
+        unsigned changed = 0u;
         if (serial) {
             Counters ns;
 #pragma unroll
@@ -292,33 +322,35 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
             }
 #pragma unroll
             for (int k = 1; k < 8; ++k) mask |= ns.v[k] ? (1u << k) : 0u;
-            changed = true;
+            changed = TD_ALL;
         } else if (pend != TEAM_PEND_NONE) {
+            const unsigned xv = birth ? TD_LV : TD_MV, xk = birth ? TD_LK : TD_MK;
+            changed = pend == TEAM_PEND_RJ ? (TD_P | (nw.K != cur.K ? (xv | xk) : 0u)) : xv;
             cur = nw;
             if (pend == TEAM_PEND_RJ) c.poiA = poiN;
-            changed = true;
         }
         if (event) {
-            if (i == ev.next_resync) { resync_log_rates(L, M, lane); changed = true; }
+            if (i == ev.next_resync) { resync_log_rates(L, M, lane); changed |= TD_LV | TD_MV; }
             if (i == ev.next_sample) {
                 const unsigned long long k = ((unsigned long long)i - ev.first_sample) / ev.s_every;
                 write_record_ref(P.records + ((size_t)k * P.n_chains + chain) * LR_REC_DOUBLES, it, L, M, c, d, lane, P.with_adequacy != 0);
             }
         }
         if (changed) {
-            team_publish_state<W>(T, v + 1u, i + 1u, L, M, c, lane);
-            v += 1u; base = i + 1u;
+            v = (v + 1u) & TEAM_VMASK; base = i + 1u; ++n_commit;
+            team_publish_state<W>(T, v, changed, base, L, M, c, lane);
         }
-        tc_push(tc, mask);
+        tc_push(tc, mask, dep);
         i += W;
         if (lane == 0) st_volatile_shared(&T.prog[w], ((unsigned long long)v << 32) | i);
         if (i > ev.next_event) team_events_from(ev, i);
     }
 
     // ---- every warp holds the final state; warp 0 stores it, all add their counters
-    for (int k = 0; k < 8; ++k) tc_push(tc, 0u);
+    for (int k = 0; k < 8; ++k) tc_push(tc, 0u, 0u);
     tc_flush(tc);
     if (lane < 8) T.cnt[w][lane] = tc.n[lane];
+    if (lane == 0) { T.dbg[w][0] = n_commit; T.dbg[w][1] = n_drop; T.dbg[w][2] = n_fwait; T.dbg[w][3] = n_lead; }
     __syncthreads();
     if (w == 0) {
         store_sides(S, L, M, lane);
@@ -330,6 +362,11 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : 2) k3_team_kernel(const 
                 long long s = 0;
                 for (int ww = 0; ww < W; ++ww) s += (long long)T.cnt[ww][k];
                 S->counters[k] += s;
+            }
+            for (int k = 0; k < 4; ++k) {
+                long long s = 0;
+                for (int ww = 0; ww < W; ++ww) s += (long long)T.dbg[ww][k];
+                S->team[k] += s;
             }
         }
     }

@@ -426,6 +426,13 @@ class Chains:
         N.check(self.dev.lib.lr_chains_counters_host(self.c, N.np_ptr(out)), "lr_chains_counters_host")
         return out
 
+    def team_stats(self):
+        """Diagnostics of the speculative team build (loop_variant 4): int64 [n_chains, 4] = state versions committed,
+        evaluations dropped by rollbacks, polls waiting for the frontier, polls at the lead limit."""
+        out = np.empty((self.n_chains, 4), dtype=np.int64)
+        N.check(self.dev.lib.lr_chains_team_stats_host(self.c, N.np_ptr(out)), "lr_chains_team_stats_host")
+        return out
+
     # ---- tempered ensembles (new; the reference has no MC3)
     def set_beta(self, beta):
         beta = np.ascontiguousarray(np.broadcast_to(np.asarray(beta, np.float64), (self.n_chains,)))

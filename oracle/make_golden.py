@@ -9,6 +9,10 @@ everything it produces is committed so that no test reads /root/reference at run
     python oracle/make_golden.py posterior_flags   # ~10 min: 8 reference chains per non-default flag set (example TAD)
     python oracle/make_golden.py prior_only   # ~2 min: 8 ORACLE chains on the example window with all statistics zero
     python oracle/make_golden.py plots       # ~30 s: the reference's plotRJforward.v3.py on two of the kat runs -> .r files
+    python oracle/make_golden.py posterior_syn   # ~10 min: 32 ORACLE chains on the bench statistics (syn-int 1M lineages x 200 bins)
+
+posterior / posterior_flags take the number of reference chains per fixture from LR_GOLDEN_CHAINS (default 32) and run at
+most LR_GOLDEN_WORKERS (default: cores - 1) reference processes at a time.
 
 The reference writes next to its input (LiteRateForward.py:479-491), so inputs are copied to
 a scratch directory first.
@@ -24,6 +28,9 @@ import sys
 import tempfile
 import time
 from concurrent.futures import ThreadPoolExecutor
+
+N_CHAINS = int(os.environ.get("LR_GOLDEN_CHAINS", "32"))
+N_WORKERS = int(os.environ.get("LR_GOLDEN_WORKERS", str(max(1, (os.cpu_count() or 2) - 1))))
 
 import numpy as np
 
@@ -166,8 +173,8 @@ FLAG_SETS = [   # tag, extra arguments, model suffix
 ]
 
 
-def posterior_flags(n_chains=8, n_it=200001, s=100):
-    """Posterior summaries of 8 unmodified reference chains for every non-default sampler configuration (example TAD)."""
+def posterior_flags(n_chains=N_CHAINS, n_it=200001, s=100):
+    """Posterior summaries of unmodified reference chains for every non-default sampler configuration (example TAD)."""
     out = os.path.join(GOLD, "posterior")
     os.makedirs(out, exist_ok=True)
     src = os.path.join(REF, INPUTS["example_dataTAD.txt"])
@@ -177,7 +184,7 @@ def posterior_flags(n_chains=8, n_it=200001, s=100):
             r = _summarise(logs, "example_dataTAD" + suffix)
             r["seed"], r["wall_s"], r["n_iterations"], r["s_freq"] = seed, dt, n_it, s
             return r
-        with ThreadPoolExecutor(n_chains) as ex:
+        with ThreadPoolExecutor(N_WORKERS) as ex:
             chains = list(ex.map(one, [301 + i for i in range(n_chains)]))
         with open(os.path.join(out, tag + ".json"), "w") as fh:
             json.dump({"data": "example_tad", "generator": "unmodified LiteRateForward.py " + " ".join(extra), "args": extra, "burnin": 0.2,
@@ -213,7 +220,48 @@ def prior_only(n_chains=8):
     print("prior_only done")
 
 
-def posterior(n_chains=8):
+SYN_N, SYN_ITERS, SYN_S, SYN_BURNIN = 1_000_000, 400001, 200, 0.5
+
+
+def _syn_chain(seed):
+    """One oracle chain on the statistics of the bench workload: synth.syn_int(1M lineages, replicate 0) -> 200 unit bins
+    (K_l ~ 11, K_m = 1).  The unmodified script would spend 3 minutes binning 1M lineages per chain before its first
+    iteration; the oracle (pinned to it byte for byte on 12 flag sets) takes the statistics from bin_stats_fast, which the CPU
+    tests hold to the per-bin formulation."""
+    from oracle import literate_oracle as O
+    from literate_b200 import synth
+    ts, te = synth.syn_int(SYN_N, 0)
+    st = O.bin_stats_fast(ts, te)
+    lin = O.Lineages(ts=ts, te=te, start_time=float(ts.min()), end_time=float(te.max()), true_root_age=float(ts.min()))
+    cfg = O.ChainConfig(n_iterations=SYN_ITERS, s_freq=SYN_S, calc_adequacy=0)
+    t0 = time.time()
+    logs = O.run_chain(lin, st, cfg, seed)
+    mc = np.array([[float(x) for x in l.split("\t")] for l in logs.mcmc.getvalue().splitlines()])
+    b = int(SYN_BURNIN * len(mc))
+    post = mc[b:]
+    res = {"seed": seed, "n_iterations": SYN_ITERS, "s_freq": SYN_S, "wall_s": time.time() - t0, "n_samples": int(len(post)),
+           "K_l": O.k_pmf(mc[:, 6], SYN_BURNIN), "K_m": O.k_pmf(mc[:, 7], SYN_BURNIN),
+           "lik_mean": float(post[:, 2].mean()), "lik_var": float(post[:, 2].var()), "prior_mean": float(post[:, 3].mean()),
+           "lambda_avg": float(post[:, 4].mean()), "mu_avg": float(post[:, 5].mean()),
+           "gamma_hp_l": float(post[:, 10].mean()), "gamma_hp_m": float(post[:, 11].mean()), "poisson_hp": float(post[:, 12].mean())}
+    for text, key in ((logs.sp.getvalue(), "birth"), (logs.ex.getvalue(), "death")):
+        rows = [np.array(l.split(), dtype=np.float64) for l in text.split("\n") if l.strip()]
+        res[key + "_rate_mean"] = O.marginal_rates(rows, lin.end_time, lin.start_time, SYN_BURNIN).mean(axis=0).tolist()
+    return res
+
+
+def posterior_syn(n_chains=N_CHAINS):
+    from concurrent.futures import ProcessPoolExecutor
+    with ProcessPoolExecutor(N_WORKERS) as ex:
+        chains = list(ex.map(_syn_chain, [701 + i for i in range(n_chains)]))
+    with open(os.path.join(GOLD, "posterior", "syn_int_200.json"), "w") as fh:
+        json.dump({"data": "synth.syn_int(1000000, replicate 0): 200 unit bins 1800..1999", "burnin": SYN_BURNIN,
+                   "generator": "oracle.run_chain (pinned to the reference byte for byte) on oracle.bin_stats_fast statistics",
+                   "chains": chains}, fh, indent=1)
+    print("posterior_syn done:", [round(c["wall_s"]) for c in chains])
+
+
+def posterior(n_chains=N_CHAINS):
     out = os.path.join(GOLD, "posterior")
     os.makedirs(out, exist_ok=True)
     sets = [
@@ -226,7 +274,7 @@ def posterior(n_chains=8):
             r = _summarise(logs, stem)
             r["seed"], r["wall_s"], r["n_iterations"], r["s_freq"] = seed, dt, n_it, s
             return r
-        with ThreadPoolExecutor(n_chains) as ex:
+        with ThreadPoolExecutor(N_WORKERS) as ex:
             chains = list(ex.map(one, [101 + i for i in range(n_chains)]))
         with open(os.path.join(out, tag + ".json"), "w") as fh:
             json.dump({"data": tag, "generator": "unmodified LiteRateForward.py, default flags", "burnin": 0.2,
@@ -236,4 +284,5 @@ def posterior(n_chains=8):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "kat"
-    {"kat": kat, "posterior": posterior, "posterior_flags": posterior_flags, "prior_only": prior_only, "plots": plots}[what]()
+    {"kat": kat, "posterior": posterior, "posterior_flags": posterior_flags, "prior_only": prior_only, "plots": plots,
+     "posterior_syn": posterior_syn}[what]()

@@ -29,6 +29,8 @@ def run(variant, label):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     res[label] = {"it_per_s": nch * iters / (ms * 1e-3), "ms": ms, "ns_per_it_per_chain": ms * 1e6 / iters}
+    t = ch.team_stats().sum(0).astype(float) / (nch * (iters + 2000))
+    res[label]["per_iteration"] = {"commits": t[0], "dropped": t[1], "frontier_polls": t[2], "lead_polls": t[3]}
     print(label, res[label], flush=True)
     return rec.cpu().numpy(), ch.counters()
 
