@@ -177,11 +177,14 @@ typedef struct lr_chain_config {
     double  update_fraction;    /* -update_fraction    (:252, :399) */
     int32_t real_move_shift;    /* 0 = reference behaviour (move-shift proposes the current state, :184-185);
                                    1 = reflected sliding window d=1 (opt-in, deviates from the reference) */
-    int32_t loop_variant;       /* build of the chain loop: 0 choose by population size (1 up to two chains per SM, 3 up to
+    int32_t loop_variant;       /* build of the chain loop: 0 choose by population size (4 up to four chains per SM, 3 up to
                                    seven, else 2); 1 warp-specialised, one chain per CTA (a chain warp fed by three producer
                                    warps); 3 warp-specialised, four chains per CTA (one producer each, registers re-balanced
-                                   with setmaxnreg); 2 compact (one warp per chain, thousands of resident chains).
-                                   Results are identical, bit for bit */
+                                   with setmaxnreg); 2 compact (one warp per chain, thousands of resident chains);
+                                   4 speculative teams (16 / 8 / 4 warps evaluate consecutive iterations of ONE chain ahead
+                                   of time, the first state change commits and the others roll back selectively) with a
+                                   continuation pass of build 1 / 3 for chains whose state changes more than once in eight
+                                   iterations (small tables, burn-in).  Results are identical, bit for bit */
     double  beta;               /* likelihood tempering exponent of every chain unless set per chain; 1 = reference */
 } lr_chain_config;
 
@@ -216,9 +219,10 @@ int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_every, doub
  *   Gibbs draws, capacity rejections (add-shift at K == LR_KMAX), temperature swaps proposed, swaps accepted */
 #define LR_NCOUNTERS 10
 int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters);
-/* diagnostics of the speculative team build (loop_variant 4), per chain since creation: [n_chains][4] int64 =
+/* diagnostics of the speculative team build (loop_variant 4), per chain since creation: [n_chains][6] int64 =
  *   state versions committed, evaluations dropped by rollbacks, polls while waiting to become the frontier,
- *   polls at the lead limit.  Zero for the other builds.  No reference counterpart. */
+ *   polls at the lead limit, iterations done by teams, hand-overs to the continuation pass.
+ *   Zero for the other builds.  No reference counterpart. */
 int lr_chains_team_stats_host(lr_chains_t c, int64_t* h_stats);
 /* current state of every chain as one record each (iteration = number of iterations done) */
 int lr_chains_get_state_host(lr_chains_t c, double* h_records);

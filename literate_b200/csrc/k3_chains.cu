@@ -18,7 +18,10 @@ __constant__ double c_lnfact[LR_SLOTS + 2];
 struct ChainState {
     long long it;
     long long counters[LR_NCOUNTERS];   // 0..7 maintained by k3_run_kernel, 8..9 by the tempered-swap kernel
-    long long team[4];                  // diagnostics of the speculative team build (k3_team.cuh)
+    long long team[6];                  // diagnostics of the speculative team build (k3_team.cuh)
+    long long solo_until;               // the team build leaves the chain to the continuation pass while it < solo_until
+    unsigned win_iters, win_commits;    // the team build's current observation window (state changes per iteration)
+    long long solo_span;                // how long the next hand-over lasts (doubles while the teams keep stopping)
     int K_l, K_m, rep, poi_is_init;
     unsigned chain_id, consistent;
     double priorA, poiA, gL, gM, poi, beta;
@@ -36,6 +39,7 @@ struct lr_chains_s {
     uint64_t seed;
     int64_t chain_id0;    // global id of chain 0 of this shard
     ChainState* st;       // device [n_chains]
+    long long it_host;    // iteration counter of every chain as the host knows it (-1: chains differ, set through set_state)
 };
 
 namespace {
@@ -194,6 +198,9 @@ struct RunParams {
     LoopConsts lc;
     uint32_t k0, k1;
     long long n_iter, sample_every;
+    long long it_begin;  // first iteration of this launch (every chain's, as the host tracks it); -1: take each chain's own counter
+    int team_bail;       // team build: may hand a chain with frequent state changes to the continuation pass
+    int cont_mode;       // k3_run_kernel as continuation pass: 1 = only handed-over chains, up to the end of their hand-over; 0 = to the end
     double* records;     // [sample][chain][LR_REC_DOUBLES] or null
     int with_adequacy;
 };
@@ -689,6 +696,13 @@ __device__ __forceinline__ void resync_log_rates(Side& L, Side& M, int lane) {
 // MODE 2  specialised, four chains per CTA of 8 warps: warpgroup 0 = 4 chain warps, warpgroup 1 = their 4 producers (one
 //         each, which keeps up: ~390 cycles per produced iteration against ~900 consumed); setmaxnreg moves registers from
 //         the producers (72) to the chain warps (184), 2 CTAs = 8 chains per SM
+// last iteration (exclusive) of this launch for one chain (see lr_chains_run for the sequence of passes)
+__device__ __forceinline__ long long chain_end(const RunParams& P, const ChainState* S, long long it0) {
+    long long it1 = (P.it_begin >= 0 ? P.it_begin : it0) + P.n_iter;
+    if (P.cont_mode == 1) { const long long su = S->solo_until; it1 = su > it0 ? (su < it1 ? su : it1) : it0; }
+    return it1;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE == 2 ? 2 : 1)) k3_run_kernel(const RunParams P) {
     constexpr bool SPEC = MODE != 0;
@@ -720,9 +734,10 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
             const ChainState* S = P.st + chain;
             Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
             const long long it0 = S->it;                  // the chain warp rewrites S->it only at the very end
+            const long long n_own = chain_end(P, S, it0) - it0;          // what this pass does of this launch for this chain
             Ring<DEPTH>& ring = *ring_p;
             const int pid = (warp - CPB) % PPC;
-            const long long n_batches = (P.n_iter + RING_BATCH - 1) / RING_BATCH;
+            const long long n_batches = (n_own + RING_BATCH - 1) / RING_BATCH;
             int s = pid % DEPTH;                    // slot of batch b is b % DEPTH, tracked without a division
             for (long long b = pid; b < n_batches; b += PPC) {
                 // wait until the previous occupant of the slot (batch b - DEPTH) has been consumed; back off while
@@ -731,7 +746,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
                 const long long j0 = b * RING_BATCH;
 #pragma unroll 1
                 for (int i = 0; i < RING_BATCH; ++i) {
-                    if (j0 + i < P.n_iter) ring_store(ring.it[s][i], make_draws<false>(rng, it0 + j0 + i, lane, K), lane);
+                    if (j0 + i < n_own) ring_store(ring.it[s][i], make_draws<false>(rng, it0 + j0 + i, lane, K), lane);
                 }
                 __syncwarp();
                 if (lane == 0) st_release_cta(&ring.full[s], (unsigned long long)(b + 1));
@@ -745,7 +760,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     if (chain >= P.n_chains) return;
     ChainState* S = P.st + chain;
     Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
-    const long long it0 = S->it, it1 = it0 + P.n_iter;
+    const long long it0 = S->it, it_begin = P.it_begin >= 0 ? P.it_begin : it0, it1 = chain_end(P, S, it0);
+    if (it0 >= it1) return;                       // continuation pass: nothing left for this chain in this pass
 
     // ---------------- the chain warp
     const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
@@ -765,7 +781,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     long long next_sample = P.records != nullptr ? (it0 + s_every - 1) / s_every * s_every : it1;   // no 64-bit division in the loop
     long long next_resync = (it0 + LR_RESYNC - 1) / LR_RESYNC * LR_RESYNC;
     long long next_event = next_resync < next_sample ? next_resync : next_sample;
-    double* rec = P.records + (size_t)chain * LR_REC_DOUBLES;
+    // records of this launch written before it0 (by the team build, when this is the continuation pass)
+    const long long rec_done = (it0 + s_every - 1) / s_every - (it_begin + s_every - 1) / s_every;
+    double* rec = P.records + ((size_t)rec_done * P.n_chains + chain) * LR_REC_DOUBLES;
     int slot = 0, in_batch = 0;
     long long batch = 0;
 
@@ -833,7 +851,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 128, MODE == 0 ? 4 : (MODE =
     if (lane == 0) {
         S->it = it1;
         S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init; S->consistent = (unsigned)c.consistent;
-        S->counters[0] += P.n_iter;
+        S->counters[0] += it1 - it0;
 #pragma unroll
         for (int i = 1; i < 8; ++i) S->counters[i] += (long long)n.v[i];
     }
@@ -859,7 +877,8 @@ __global__ void k3_init_kernel(ChainState* st, int n_chains, const int* __restri
     if (lane == 0) {
         S->it = 0;
         for (int i = 0; i < LR_NCOUNTERS; ++i) S->counters[i] = 0;
-        for (int i = 0; i < 4; ++i) S->team[i] = 0;
+        for (int i = 0; i < 6; ++i) S->team[i] = 0;
+        S->solo_until = TEAM_INITIAL_SOLO; S->win_iters = 0u; S->win_commits = 0u; S->solo_span = 0;   // burn-in: nearly every proposal moves the state
         S->K_l = 1; S->K_m = 1; S->rep = rep_of_chain ? rep_of_chain[chain] : 0;
         S->chain_id = rng.chain; S->consistent = 0;     // the initial prior uses Gamma rate 2 (:227), the loop rate 1
         const double poi = poisson_prior_cfg == 0.0 ? 1.0 : poisson_prior_cfg;       // :220-221
@@ -907,6 +926,7 @@ __global__ void k3_set_state_kernel(ChainState* st, int n_chains, const double* 
         S->poiA = poiA;
         S->priorA = full_prior(L, M, hp, d, poiA);
         S->consistent = 1;
+        S->solo_until = 0; S->win_iters = 0u; S->win_commits = 0u; S->solo_span = 0;
     }
 }
 
@@ -1332,7 +1352,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
             LR_REQUIRE(h_rep_of_chain[i] >= 0 && h_rep_of_chain[i] < ds->n_rep, "lr_chains_create: replicate of chain %d out of range", i);
     LR_CUDA(cudaSetDevice(h->device));
     lr_chains_t c = new lr_chains_s();
-    c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->chain_id0 = chain_id0; c->st = nullptr;
+    c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->chain_id0 = chain_id0; c->st = nullptr; c->it_host = 0;
     if (c->cfg.beta == 0.0) c->cfg.beta = 1.0;
     cudaError_t e = cudaMallocAsync((void**)&c->st, (size_t)n_chains * sizeof(ChainState), h->stream);
     if (e != cudaSuccess) { lr_set_error("lr_chains_create: cudaMallocAsync: %s", cudaGetErrorString(e)); delete c; return LR_ERR_NOMEM; }
@@ -1364,10 +1384,12 @@ extern "C" int lr_chains_destroy(lr_chains_t c) {
 
 extern "C" int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int64_t sample_every) {
     if (!c || n_iter <= 0 || sample_every <= 0) return 0;
-    long long it0 = 0;
-    cudaSetDevice(c->h->device);
-    cudaStreamSynchronize(c->h->stream);
-    if (cudaMemcpy(&it0, &c->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    long long it0 = c->it_host;
+    if (it0 < 0) {          // chains were given different iteration counters through set_state: chain 0's counts, as before
+        cudaSetDevice(c->h->device);
+        cudaStreamSynchronize(c->h->stream);
+        if (cudaMemcpy(&it0, &c->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    }
     const long long first = (it0 + sample_every - 1) / sample_every * sample_every;
     const long long it1 = it0 + n_iter;
     return first < it1 ? (it1 - 1 - first) / sample_every + 1 : 0;
@@ -1387,6 +1409,7 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     P.start_time = c->ds->start_time; P.end_time = c->ds->end_time;
     P.cfg = c->cfg; P.lc = loop_consts(c->cfg); P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
     P.n_iter = n_iter; P.sample_every = sample_every > 0 ? sample_every : 1;
+    P.it_begin = c->it_host; P.team_bail = 0; P.cont_mode = 0;
     P.records = sample_every > 0 ? d_records : nullptr;
     P.with_adequacy = 1;
     int threads;
@@ -1395,33 +1418,67 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     // (one CTA of 4 warps per chain), 2 = compact build (one warp per chain)
     // loop_variant 0 picks by population size (measured on B200, 148 SMs; M it/s for one-chain CTAs / four-chain CTAs / compact):
     //   296 chains 572 / 506 / 325;  512: - / 873 / 557;  1024: - / 1094 / 1027;  1184: - / 1119 / 1161;  2048: - / 1051 / 1547
+    // loop_variant 4 (speculative team, k3_team.cuh) and the automatic choice: teams of W warps by how many chains an SM has
+    // to hold (M it/s on the bench statistics, 1M lineages x 200 bins: 148 chains W=16 852 against 358 for one-chain CTAs;
+    // 256 chains W=8 1000 against 584; 512 chains W=4 1151 against 1041 for four-chain CTAs), followed by a CONTINUATION pass of
+    // the latency-optimised build for the chains whose teams stopped because their state changes too often for speculation to
+    // pay (example table, 75 lineages: 40 % of the iterations change the state -- team 55 M it/s, one-chain CTAs 145 M).
     int variant = c->cfg.loop_variant;
-    if (variant == 0) variant = c->n_chains <= 2 * h->sm_count ? 1 : (c->n_chains <= 7 * h->sm_count ? 3 : 2);
+    const int sm = h->sm_count;
+    if (variant == 0) {
+        if (c->it_host >= 0 && c->n_chains <= 4 * sm) variant = 4;
+        else variant = c->n_chains <= 2 * sm ? 1 : (c->n_chains <= 7 * sm ? 3 : 2);
+    }
+    auto launch_plain = [&](int var) {
+        if (var == 1) {
+            const size_t smem = sizeof(Ring<6>);
+            cudaFuncSetAttribute(k3_run_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k3_run_kernel<1><<<c->n_chains, 128, smem, st>>>(P);
+        } else if (var == 3) {
+            const size_t smem = 4 * sizeof(Ring<3>);
+            cudaFuncSetAttribute(k3_run_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k3_run_kernel<2><<<(c->n_chains + 3) / 4, 256, smem, st>>>(P);
+        } else {
+            k3_run_kernel<0><<<blocks, threads, 0, st>>>(P);
+        }
+        h->launches += 1;
+    };
     if (variant == 4) {
-        // speculative team build: W warps per chain, W by how many CTAs an SM has to hold (k3_team.cuh)
         const char* e_w = getenv("LR_TEAM_W");              // development overrides (tests sweep them)
         const char* e_lead = getenv("LR_TEAM_LEAD");
+        const char* e_nobail = getenv("LR_TEAM_NOBAIL");
         const int env_w = e_w ? atoi(e_w) : 0, env_lead = e_lead ? atoi(e_lead) : 0;
-        int W = env_w ? env_w : (c->n_chains <= h->sm_count ? 16 : (c->n_chains <= 2 * h->sm_count ? 8 : 4));
-        int lead = env_lead ? env_lead : 2;
+        const int W = env_w ? env_w : (c->n_chains <= sm ? 16 : (c->n_chains <= 2 * sm ? 8 : 4));
+        int lead = env_lead ? env_lead : 4;
         if (lead < 1) lead = 1;
         if (lead > 7) lead = 7;
-        if (W >= 16) k3_team_kernel<16><<<c->n_chains, 512, 0, st>>>(P, lead);
-        else if (W >= 8) k3_team_kernel<8><<<c->n_chains, 256, 0, st>>>(P, lead);
-        else k3_team_kernel<4><<<c->n_chains, 128, 0, st>>>(P, lead);
-    } else if (variant == 1) {
-        const size_t smem = sizeof(Ring<6>);
-        LR_CUDA(cudaFuncSetAttribute(k3_run_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k3_run_kernel<1><<<c->n_chains, 128, smem, st>>>(P);
-    } else if (variant == 3) {
-        const size_t smem = 4 * sizeof(Ring<3>);
-        LR_CUDA(cudaFuncSetAttribute(k3_run_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k3_run_kernel<2><<<(c->n_chains + 3) / 4, 256, smem, st>>>(P);
+        P.team_bail = (c->it_host >= 0 && !(e_nobail && atoi(e_nobail))) ? 1 : 0;
+        auto launch_team = [&]() {
+            if (W >= 16) k3_team_kernel<16><<<c->n_chains, 512, 0, st>>>(P, lead);
+            else if (W >= 8) k3_team_kernel<8><<<c->n_chains, 256, 0, st>>>(P, lead);
+            else k3_team_kernel<4><<<c->n_chains, 128, 0, st>>>(P, lead);
+            h->launches += 1;
+        };
+        // Four passes over the same launch window; every kernel skips the chains that have nothing to do in it.
+        //   A  teams; a team whose chain changes state too often stops early and hands the chain over for a while
+        //   B  latency-optimised build: handed-over chains, up to the end of their hand-over
+        //   C  teams again for the chains whose hand-over ended inside the window (burn-in is over: speculation pays now)
+        //   D  latency-optimised build: whatever is left
+        launch_team();
+        if (P.team_bail) {
+            const int cont = c->n_chains <= 2 * sm ? 1 : 3;
+            LR_CUDA(cudaGetLastError());
+            P.cont_mode = 1; launch_plain(cont);
+            LR_CUDA(cudaGetLastError());
+            P.cont_mode = 0; launch_team();
+            LR_CUDA(cudaGetLastError());
+            launch_plain(cont);
+        }
     } else {
-        k3_run_kernel<0><<<blocks, threads, 0, st>>>(P);
+        launch_plain(variant);
     }
     LR_CUDA(cudaGetLastError());
-    h->launches += 1;
+    if (c->it_host >= 0) c->it_host += n_iter;
     return LR_OK;
 }
 
@@ -1457,7 +1514,7 @@ extern "C" int lr_chains_team_stats_host(lr_chains_t c, int64_t* h_stats) {
     LR_REQUIRE(c && h_stats, "lr_chains_team_stats_host: null pointer");
     LR_CUDA(cudaSetDevice(c->h->device));
     LR_CUDA(cudaStreamSynchronize(c->h->stream));
-    LR_CUDA(cudaMemcpy2D(h_stats, 4 * sizeof(int64_t), &c->st[0].team[0], sizeof(ChainState), 4 * sizeof(int64_t), c->n_chains, cudaMemcpyDeviceToHost));
+    LR_CUDA(cudaMemcpy2D(h_stats, 6 * sizeof(int64_t), &c->st[0].team[0], sizeof(ChainState), 6 * sizeof(int64_t), c->n_chains, cudaMemcpyDeviceToHost));
     return LR_OK;
 }
 
@@ -1482,10 +1539,13 @@ extern "C" int lr_chains_get_state_host(lr_chains_t c, double* h_records) {
 extern "C" int lr_chains_set_state_host(lr_chains_t c, const double* h_records) {
     LR_REQUIRE(c && h_records, "lr_chains_set_state_host: null pointer");
     lr_handle_t h = c->h;
+    long long it_all = (long long)h_records[0];
     for (int i = 0; i < c->n_chains; ++i) {
         const double* r = h_records + (size_t)i * LR_REC_DOUBLES;
         LR_REQUIRE(r[5] >= 1 && r[5] <= LR_KMAX && r[6] >= 1 && r[6] <= LR_KMAX, "lr_chains_set_state_host: K out of range in chain %d", i);
+        if ((long long)r[0] != it_all) it_all = -1;
     }
+    c->it_host = it_all;
     LR_CUDA(cudaSetDevice(h->device));
     const size_t bytes = (size_t)c->n_chains * LR_REC_DOUBLES * sizeof(double);
     int rc = lr_ws_reserve(h, bytes);

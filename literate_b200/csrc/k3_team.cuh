@@ -33,6 +33,8 @@ template <int W>
 struct TeamShared {
     unsigned long long verword;
     unsigned long long prog[W];
+    unsigned n_eff;            // iterations of this launch the team does (lowered when it hands the chain over)
+    unsigned win_i, win_c;     // observation window: first offset, state changes since then (only the frontier touches them)
     unsigned cnt[W][8];
     unsigned dbg[W][4];        // commits, evaluations dropped by rollbacks, polls while waiting to be the frontier, polls at the lead limit
     struct Buf {
@@ -89,6 +91,7 @@ __device__ __forceinline__ void tc_push(TeamCounters& t, unsigned mask, unsigned
 // event iterations (sample record :321, log-rate resync) as offsets from the launch's first iteration
 struct TeamEvents {
     unsigned long long first_sample, s_every, first_resync;     // first_sample = ~0 when no records are written
+    unsigned long long rec_done;                                // records of this launch written before the team's first iteration
     unsigned next_sample, next_resync, next_event;
 };
 __device__ __noinline__ void team_events_from(TeamEvents& e, unsigned i) {
@@ -141,6 +144,11 @@ __device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsig
 
 // speculative evaluation of one block iteration (:254-272) on side `cur`: block_step's arithmetic without the commit.
 // Returns 0 if the state stays as it is, else the kind of pending change with the proposed side in `nw`.
+#define TEAM_WINDOW 2048u
+#define TEAM_BAIL_DEN 8u
+#define TEAM_INITIAL_SOLO 4096           // a fresh chain's first iterations go to the latency-optimised build
+#define TEAM_SOLO_SPAN_MIN 8192
+#define TEAM_SOLO_SPAN_MAX 262144
 #define TEAM_PEND_NONE 0
 #define TEAM_PEND_SIDE 1       // cur = nw
 #define TEAM_PEND_RJ 2         // cur = nw, poiA = poiN
@@ -202,16 +210,18 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
     const int w = threadIdx.x >> 5;
     const int chain = (int)blockIdx.x;
     if (chain >= P.n_chains) return;                                  // whole CTA
-    if (threadIdx.x == 0) T.verword = 0ull;
+    ChainState* S = P.st + chain;
+    const long long it0 = S->it;
+    const long long n_own = (P.it_begin >= 0 ? P.it_begin : it0) + P.n_iter - it0;
+    if (n_own <= 0 || (P.team_bail && it0 < S->solo_until)) return;      // whole CTA: nothing to do / left to the continuation pass
+    if (threadIdx.x == 0) { T.verword = 0ull; T.n_eff = (unsigned)n_own; T.win_i = 0u - S->win_iters; T.win_c = S->win_commits; }
     if (threadIdx.x < W) T.prog[threadIdx.x] = (unsigned long long)threadIdx.x;
     __syncthreads();
 
     const lr_chain_config& cfg = P.cfg;
     const LoopConsts& K = P.lc;
-    ChainState* S = P.st + chain;
     Rng rng; rng.k0 = P.k0; rng.k1 = P.k1; rng.chain = S->chain_id;
-    const long long it0 = S->it;
-    const unsigned n = (unsigned)P.n_iter;
+    unsigned n = (unsigned)n_own;
     const DataView d = make_view(P.tab, P.cst, S->rep, P.nb, P.s0f, P.start_time, P.end_time);
     Side L, M;
     load_sides(S, L, M, lane);
@@ -228,6 +238,8 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
         const unsigned long long s_every = (unsigned long long)(P.sample_every > 0 ? P.sample_every : 1);
         ev.s_every = s_every;
         ev.first_sample = P.records != nullptr ? (s_every - (unsigned long long)it0 % s_every) % s_every : ~0ull;
+        const long long it_begin = P.it_begin >= 0 ? P.it_begin : it0;
+        ev.rec_done = (unsigned long long)((it0 + (long long)s_every - 1) / (long long)s_every - (it_begin + (long long)s_every - 1) / (long long)s_every);
         ev.first_resync = (LR_RESYNC - (unsigned long long)it0 % LR_RESYNC) % LR_RESYNC;
     }
     TeamCounters tc;
@@ -258,6 +270,7 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
                 tc.hist >>= 8u * dropped; tc.dep >>= 8u * dropped;
                 n_drop += dropped;
                 i -= dropped * W; v = v_new; base = base_new;
+                n = *(volatile unsigned*)&T.n_eff;
                 if (F_seen < base) F_seen = base;
                 team_events_from(ev, i);
                 __syncwarp();
@@ -332,12 +345,23 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
         if (event) {
             if (i == ev.next_resync) { resync_log_rates(L, M, lane); changed |= TD_LV | TD_MV; }
             if (i == ev.next_sample) {
-                const unsigned long long k = ((unsigned long long)i - ev.first_sample) / ev.s_every;
+                const unsigned long long k = ev.rec_done + ((unsigned long long)i - ev.first_sample) / ev.s_every;
                 write_record_ref(P.records + ((size_t)k * P.n_chains + chain) * LR_REC_DOUBLES, it, L, M, c, d, lane, P.with_adequacy != 0);
             }
         }
         if (changed) {
             v = (v + 1u) & TEAM_VMASK; base = i + 1u; ++n_commit;
+            // Does speculation pay on this chain?  More than one state change in TEAM_BAIL_DEN iterations over a window of
+            // TEAM_WINDOW: evaluating ahead mostly produces rollbacks (small tables, burn-in); the team stops after this
+            // iteration and the continuation pass (the latency-optimised build) runs the rest of the launch.
+            const unsigned wc = *(volatile unsigned*)&T.win_c + 1u, wlen = base - *(volatile unsigned*)&T.win_i;
+            if (wlen >= TEAM_WINDOW) {
+                if (P.team_bail && wc * TEAM_BAIL_DEN > wlen && base < n) { n = base; if (lane == 0) *(volatile unsigned*)&T.n_eff = base; }
+                if (lane == 0) { *(volatile unsigned*)&T.win_i = base; *(volatile unsigned*)&T.win_c = 0u; }
+            } else if (lane == 0) {
+                *(volatile unsigned*)&T.win_c = wc;
+            }
+            __syncwarp();
             team_publish_state<W>(T, v, changed, base, L, M, c, lane);
         }
         tc_push(tc, mask, dep);
@@ -347,6 +371,12 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
     }
 
     // ---- every warp holds the final state; warp 0 stores it, all add their counters
+    {
+        // evaluations kept through the rollbacks but beyond the iteration the team stopped at belong to the continuation pass
+        const unsigned i_first = n + (((unsigned)w - n) & (W - 1));
+        const unsigned beyond = i > i_first ? (i - i_first) / W : 0u;
+        tc.hist = beyond >= 8u ? 0ull : (tc.hist >> (8u * beyond));
+    }
     for (int k = 0; k < 8; ++k) tc_push(tc, 0u, 0u);
     tc_flush(tc);
     if (lane < 8) T.cnt[w][lane] = tc.n[lane];
@@ -355,9 +385,21 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
     if (w == 0) {
         store_sides(S, L, M, lane);
         if (lane == 0) {
-            S->it = it0 + P.n_iter;
+            const unsigned n_done = *(volatile unsigned*)&T.n_eff;
+            S->it = it0 + (long long)n_done;
+            S->team[4] += (long long)n_done;
+            if (n_done < (unsigned)n_own) {
+                S->team[5] += 1;
+                // handed over: for solo_span iterations, twice as long the next time
+                const long long span = S->solo_span < TEAM_SOLO_SPAN_MIN ? TEAM_SOLO_SPAN_MIN : S->solo_span;
+                S->solo_until = it0 + (long long)n_done + span;
+                S->solo_span = 2 * span > TEAM_SOLO_SPAN_MAX ? TEAM_SOLO_SPAN_MAX : 2 * span;
+            } else if (n_done >= 4u * TEAM_WINDOW) {
+                S->solo_span = 0;
+            }
+            S->win_iters = n_done - *(volatile unsigned*)&T.win_i; S->win_commits = *(volatile unsigned*)&T.win_c;
             S->priorA = c.priorA; S->poiA = c.poiA; S->gL = c.hp.gL; S->gM = c.hp.gM; S->poi = c.hp.poi; S->poi_is_init = c.poi_is_init; S->consistent = (unsigned)c.consistent;
-            S->counters[0] += P.n_iter;
+            S->counters[0] += (long long)n_done;
             for (int k = 1; k < 8; ++k) {
                 long long s = 0;
                 for (int ww = 0; ww < W; ++ww) s += (long long)T.cnt[ww][k];

@@ -427,9 +427,10 @@ class Chains:
         return out
 
     def team_stats(self):
-        """Diagnostics of the speculative team build (loop_variant 4): int64 [n_chains, 4] = state versions committed,
-        evaluations dropped by rollbacks, polls waiting for the frontier, polls at the lead limit."""
-        out = np.empty((self.n_chains, 4), dtype=np.int64)
+        """Diagnostics of the speculative team build (loop_variant 4): int64 [n_chains, 6] = state versions committed,
+        evaluations dropped by rollbacks, polls waiting for the frontier, polls at the lead limit, iterations done by
+        teams, hand-overs to the continuation pass."""
+        out = np.empty((self.n_chains, 6), dtype=np.int64)
         N.check(self.dev.lib.lr_chains_team_stats_host(self.c, N.np_ptr(out)), "lr_chains_team_stats_host")
         return out
 

@@ -106,14 +106,17 @@ def test_loop_builds_give_identical_chains(device, metal_path):
     assert np.array_equal(a.counters(), b.counters()) and np.array_equal(a.counters(), c.counters())
 
 
-@pytest.mark.parametrize("team_w,lead", [(4, 1), (8, 2), (16, 7), (8, 5)])
-def test_speculative_team_build_gives_the_same_chains(device, metal_path, team_w, lead, monkeypatch):
+@pytest.mark.parametrize("team_w,lead,nobail", [(4, 1, 1), (8, 2, 1), (16, 7, 1), (8, 5, 0), (4, 4, 0), (16, 2, 0)])
+def test_speculative_team_build_gives_the_same_chains(device, metal_path, team_w, lead, nobail, monkeypatch):
     """loop_variant 4: W warps evaluate consecutive iterations of ONE chain ahead of time against the current state and only
     the first state-changing one commits (csrc/k3_team.cuh).  Same draws, same arithmetic, same state: the records, final
     states and event counters must be those of the compact build, bit for bit -- on a table where a third of the iterations
     change the state (metal bands, many rollbacks) and on one where almost none does, split over ragged launches."""
     monkeypatch.setenv("LR_TEAM_W", str(team_w))
     monkeypatch.setenv("LR_TEAM_LEAD", str(lead))
+    # nobail = 1: the team runs every iteration however often the state changes; 0 (the default): a team whose chain changes
+    # state more than once in 8 iterations stops and the continuation pass (one-chain CTAs) finishes the launch
+    monkeypatch.setenv("LR_TEAM_NOBAIL", str(nobail))
     lin, st, ds, a = _setup(device, metal_path, n_chains=11, seed=5, loop_variant=2)
     b = E.Chains(ds, 11, 5, E.default_config(0, loop_variant=4))
     ra, rb = a.run(30000, 250), b.run(30000, 250)
@@ -136,6 +139,12 @@ def test_speculative_team_build_gives_the_same_chains(device, metal_path, team_w
         ra, rb = a.run(6000, 100), b.run(6000, 100)
         assert np.array_equal(ra, rb), (model, kw)
         assert np.array_equal(a.counters(), b.counters()), (model, kw)
+    if not nobail:
+        # on the 75-lineage table 40 % of the iterations change the state: every team must have handed its chain over
+        lin, st, ds, b = _setup(device, golden_input("example_dataTAD.txt"), n_chains=5, seed=78, loop_variant=4)
+        b.run(50000)
+        t = b.team_stats()
+        assert (b.counters()[:, 0] == 50000).all() and (t[:, 0] < 0.2 * 50000).all() and (t[:, 0] > 0).all()
 
 
 def test_loop_builds_identical_for_ragged_launch_lengths(device):
