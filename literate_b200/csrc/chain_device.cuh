@@ -38,6 +38,7 @@ struct lr_dataset_s {
     int s0f;               // floor(start_time): a shift at time t starts bin floor(t) - s0f (:262, :125-135)
     double* tab;           // device [n_rep][LR_NTAB][n_bins+1]
     double* cst;           // device [n_rep][LR_NCST]
+    lr_last_stream last;   // stream that built or read the tables last (lr_order)
 };
 
 // constants of the sampler (LiteRateForward.py:165, :586-590, :101-102)

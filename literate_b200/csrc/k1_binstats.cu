@@ -410,7 +410,7 @@ extern "C" int lr_bin_stats(lr_handle_t h, const double* d_ts, const double* d_t
     LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_bin_stats: bad sizes");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     const size_t acc_bytes = (size_t)n_rep * LR_ACC_ROWS * lr_acc_stride(n_bins) * sizeof(int64_t);
-    int rc = lr_ws_reserve(h, acc_bytes);
+    int rc = lr_ws_acquire(h, acc_bytes, st);
     if (rc != LR_OK) return rc;
     LR_CUDA(cudaMemsetAsync(h->ws, 0, acc_bytes, st));
     rc = lr_bin_accumulate(h, d_ts, d_te, n, ld, n_rep, first_bin, n_bins, fe_ref, dead_only, end_time, (int64_t*)h->ws, st);

@@ -39,6 +39,7 @@ struct lr_chains_s {
     uint64_t seed;
     int64_t chain_id0;    // global id of chain 0 of this shard
     ChainState* st;       // device [n_chains]
+    lr_last_stream last;  // stream that touched the chains last (lr_order)
     long long it_host;    // iteration counter of every chain as the host knows it (-1: chains differ, set through set_state)
 };
 
@@ -1164,6 +1165,7 @@ extern "C" int lr_dataset_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, i
     ds->h = h; ds->n_rep = n_rep; ds->n_bins = n_bins; ds->model = model_BDI;
     ds->start_time = start_time; ds->end_time = end_time; ds->s0f = (int)floor(start_time);
     ds->tab = nullptr; ds->cst = nullptr;
+    ds->last.s = st; ds->last.valid = 1;
     // stream-ordered allocation: creating/destroying datasets and chains never synchronises the device, so a pipeline can
     // set up batch k+1 while the chains of batch k are still running (cudaFree would wait for them)
     cudaError_t e = cudaMallocAsync((void**)&ds->tab, (size_t)n_rep * LR_NTAB * (n_bins + 1) * sizeof(double), st);
@@ -1192,7 +1194,7 @@ extern "C" int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bi
     const size_t cnt = (size_t)n_rep * n_bins;
     const bool dead = h_ex_dead && h_br_dead;
     const size_t bytes = cnt * 8 * (dead ? 5 : 3);
-    int rc = lr_ws_reserve(h, bytes);
+    int rc = lr_ws_acquire(h, bytes, h->stream);
     if (rc != LR_OK) return rc;
     char* w = (char*)h->ws;
     LR_CUDA(cudaMemcpyAsync(w, h_sp, cnt * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1213,6 +1215,7 @@ extern "C" int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bi
 extern "C" int lr_dataset_destroy(lr_dataset_t ds) {
     if (!ds) return LR_OK;
     cudaSetDevice(ds->h->device);
+    lr_order(ds->h, &ds->last, ds->h->stream);        // readers on caller streams finish before the block returns to the pool
     cudaFreeAsync(ds->tab, ds->h->stream); cudaFreeAsync(ds->cst, ds->h->stream);
     delete ds;
     return LR_OK;
@@ -1231,6 +1234,7 @@ extern "C" int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep
     }
     lr_handle_t h = ds->h;
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(h, &ds->last, h->stream); if (rc0 != LR_OK) return rc0; }
     const size_t nK = (size_t)n * LR_KMAX * 8;
     // layout in workspace
     size_t off = 0;
@@ -1239,7 +1243,7 @@ extern "C" int lr_state_eval_host(lr_dataset_t ds, int32_t n, const int32_t* rep
     const size_t o_L = take(nK), o_M = take(nK), o_tL = take(nK), o_tM = take(nK);
     const size_t o_g = take((size_t)n * 16), o_p = take((size_t)n * 8);
     const size_t o_lik = take((size_t)n * 8), o_pr = take((size_t)n * 8), o_pp = take((size_t)n * 8), o_ad = take((size_t)n * 24);
-    int rc = lr_ws_reserve(h, off);
+    int rc = lr_ws_acquire(h, off, h->stream);
     if (rc != LR_OK) return rc;
     char* w = (char*)h->ws;
     cudaStream_t st = h->stream;
@@ -1292,6 +1296,7 @@ extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* 
     }
     lr_handle_t h = ds->h;
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(h, &ds->last, h->stream); if (rc0 != LR_OK) return rc0; }
     const size_t nK = (size_t)n * LR_KMAX * 8, n4 = (size_t)n * 4, n8 = (size_t)n * 8;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 255) & ~(size_t)255; return o; };
@@ -1299,7 +1304,7 @@ extern "C" int lr_proposal_eval_host(lr_dataset_t ds, int32_t n, const int32_t* 
     const size_t o_g = take(2 * n8), o_p = take(n8), o_b = take(n8), o_pa = take(n8), o_sd = take(n4), o_kd = take(n4), o_ix = take(n4);
     const size_t o_mo = take((size_t)n * LR_KMAX * 4), o_mu = take(nK);
     const size_t o_ut = take(n8), o_ub = take(n8), o_ok = take(n4), o_kn = take(n4), o_rn = take(nK), o_tn = take(nK), o_h = take(n8), o_x = take(n8);
-    int rc = lr_ws_reserve(h, off);
+    int rc = lr_ws_acquire(h, off, h->stream);
     if (rc != LR_OK) return rc;
     char* w = (char*)h->ws;
     cudaStream_t st = h->stream;
@@ -1351,14 +1356,16 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
         for (int i = 0; i < n_chains; ++i)
             LR_REQUIRE(h_rep_of_chain[i] >= 0 && h_rep_of_chain[i] < ds->n_rep, "lr_chains_create: replicate of chain %d out of range", i);
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(h, &ds->last, h->stream); if (rc0 != LR_OK) return rc0; }
     lr_chains_t c = new lr_chains_s();
+    c->last.s = h->stream; c->last.valid = 1;
     c->h = h; c->ds = ds; c->n_chains = n_chains; c->cfg = *cfg; c->seed = seed; c->chain_id0 = chain_id0; c->st = nullptr; c->it_host = 0;
     if (c->cfg.beta == 0.0) c->cfg.beta = 1.0;
     cudaError_t e = cudaMallocAsync((void**)&c->st, (size_t)n_chains * sizeof(ChainState), h->stream);
     if (e != cudaSuccess) { lr_set_error("lr_chains_create: cudaMallocAsync: %s", cudaGetErrorString(e)); delete c; return LR_ERR_NOMEM; }
     int* d_rep = nullptr;
     if (h_rep_of_chain) {
-        int rc = lr_ws_reserve(h, (size_t)n_chains * 4);
+        int rc = lr_ws_acquire(h, (size_t)n_chains * 4, h->stream);
         if (rc != LR_OK) { cudaFreeAsync(c->st, h->stream); delete c; return rc; }
         d_rep = (int*)h->ws;
         LR_CUDA(cudaMemcpyAsync(d_rep, h_rep_of_chain, (size_t)n_chains * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1377,6 +1384,7 @@ extern "C" int lr_chains_create(lr_handle_t h, lr_dataset_t ds, int32_t n_chains
 extern "C" int lr_chains_destroy(lr_chains_t c) {
     if (!c) return LR_OK;
     cudaSetDevice(c->h->device);
+    lr_order(c->h, &c->last, c->h->stream);
     cudaFreeAsync(c->st, c->h->stream);
     delete c;
     return LR_OK;
@@ -1387,6 +1395,7 @@ extern "C" int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int6
     long long it0 = c->it_host;
     if (it0 < 0) {          // chains were given different iteration counters through set_state: chain 0's counts, as before
         cudaSetDevice(c->h->device);
+        lr_order(c->h, &c->last, c->h->stream);
         cudaStreamSynchronize(c->h->stream);
         if (cudaMemcpy(&it0, &c->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     }
@@ -1403,6 +1412,7 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    { int rc0 = lr_order(h, &c->last, st); if (rc0 == LR_OK) rc0 = lr_order(h, &c->ds->last, st); if (rc0 != LR_OK) return rc0; }
     RunParams P;
     P.st = c->st; P.n_chains = c->n_chains; P.tab = c->ds->tab; P.cst = c->ds->cst;
     P.nb = c->ds->n_bins; P.s0f = c->ds->s0f; P.model = c->ds->model;
@@ -1490,7 +1500,7 @@ extern "C" int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_
     const size_t bytes = (size_t)nrec * c->n_chains * LR_REC_DOUBLES * sizeof(double);
     double* d_rec = nullptr;
     if (bytes) {
-        int rc = lr_ws_reserve(h, bytes);
+        int rc = lr_ws_acquire(h, bytes, h->stream);
         if (rc != LR_OK) return rc;
         d_rec = (double*)h->ws;
     }
@@ -1504,6 +1514,7 @@ extern "C" int lr_chains_run_host(lr_chains_t c, int64_t n_iter, int64_t sample_
 extern "C" int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters) {
     LR_REQUIRE(c && h_counters, "lr_chains_counters_host: null pointer");
     LR_CUDA(cudaSetDevice(c->h->device));
+    { int rc0 = lr_order(c->h, &c->last, c->h->stream); if (rc0 != LR_OK) return rc0; }
     LR_CUDA(cudaStreamSynchronize(c->h->stream));
     LR_CUDA(cudaMemcpy2D(h_counters, LR_NCOUNTERS * sizeof(int64_t), &c->st[0].counters[0], sizeof(ChainState), LR_NCOUNTERS * sizeof(int64_t),
                          c->n_chains, cudaMemcpyDeviceToHost));
@@ -1513,6 +1524,7 @@ extern "C" int lr_chains_counters_host(lr_chains_t c, int64_t* h_counters) {
 extern "C" int lr_chains_team_stats_host(lr_chains_t c, int64_t* h_stats) {
     LR_REQUIRE(c && h_stats, "lr_chains_team_stats_host: null pointer");
     LR_CUDA(cudaSetDevice(c->h->device));
+    { int rc0 = lr_order(c->h, &c->last, c->h->stream); if (rc0 != LR_OK) return rc0; }
     LR_CUDA(cudaStreamSynchronize(c->h->stream));
     LR_CUDA(cudaMemcpy2D(h_stats, 6 * sizeof(int64_t), &c->st[0].team[0], sizeof(ChainState), 6 * sizeof(int64_t), c->n_chains, cudaMemcpyDeviceToHost));
     return LR_OK;
@@ -1522,8 +1534,9 @@ extern "C" int lr_chains_get_state_host(lr_chains_t c, double* h_records) {
     LR_REQUIRE(c && h_records, "lr_chains_get_state_host: null pointer");
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(h, &c->last, h->stream); if (rc0 == LR_OK) rc0 = lr_order(h, &c->ds->last, h->stream); if (rc0 != LR_OK) return rc0; }
     const size_t bytes = (size_t)c->n_chains * LR_REC_DOUBLES * sizeof(double);
-    int rc = lr_ws_reserve(h, bytes);
+    int rc = lr_ws_acquire(h, bytes, h->stream);
     if (rc != LR_OK) return rc;
     int threads;
     const int blocks = chain_grid(c->n_chains, threads);
@@ -1547,8 +1560,9 @@ extern "C" int lr_chains_set_state_host(lr_chains_t c, const double* h_records) 
     }
     c->it_host = it_all;
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(h, &c->last, h->stream); if (rc0 == LR_OK) rc0 = lr_order(h, &c->ds->last, h->stream); if (rc0 != LR_OK) return rc0; }
     const size_t bytes = (size_t)c->n_chains * LR_REC_DOUBLES * sizeof(double);
-    int rc = lr_ws_reserve(h, bytes);
+    int rc = lr_ws_acquire(h, bytes, h->stream);
     if (rc != LR_OK) return rc;
     LR_CUDA(cudaMemcpyAsync(h->ws, h_records, bytes, cudaMemcpyHostToDevice, h->stream));
     int threads;
@@ -1565,7 +1579,8 @@ extern "C" int lr_chains_set_beta_host(lr_chains_t c, const double* h_beta) {
     LR_REQUIRE(c && h_beta, "lr_chains_set_beta_host: null pointer");
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
-    int rc = lr_ws_reserve(h, (size_t)c->n_chains * 8);
+    { int rc0 = lr_order(h, &c->last, h->stream); if (rc0 != LR_OK) return rc0; }
+    int rc = lr_ws_acquire(h, (size_t)c->n_chains * 8, h->stream);
     if (rc != LR_OK) return rc;
     LR_CUDA(cudaMemcpyAsync(h->ws, h_beta, (size_t)c->n_chains * 8, cudaMemcpyHostToDevice, h->stream));
     k3_set_beta_kernel<<<(c->n_chains + 127) / 128, 128, 0, h->stream>>>(c->st, c->n_chains, (const double*)h->ws);
@@ -1580,6 +1595,7 @@ extern "C" int lr_chains_swap_info(lr_chains_t c, double* d_info, void* stream) 
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    { int rc0 = lr_order(h, &c->last, st); if (rc0 == LR_OK) rc0 = lr_order(h, &c->ds->last, st); if (rc0 != LR_OK) return rc0; }
     int threads;
     const int blocks = chain_grid(c->n_chains, threads);
     k3_swap_info_kernel<<<blocks, threads, 0, st>>>(c->st, c->n_chains, d_info, c->ds->tab, c->ds->cst, c->ds->n_bins, c->ds->s0f,
@@ -1598,6 +1614,7 @@ static int swap_apply(lr_chains_t c, const double* d_info_all, int64_t table_fir
     lr_handle_t h = c->h;
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    { int rc0 = lr_order(h, &c->last, st); if (rc0 != LR_OK) return rc0; }
     int threads;
     const int blocks = chain_grid(c->n_chains, threads);
     k3_swap_apply_kernel<<<blocks, threads, 0, st>>>(c->st, c->n_chains, d_info_all, table_first, n_all, first, ladder, round,
@@ -1618,7 +1635,7 @@ extern "C" int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round
                "lr_chains_swap_step: the shard must hold whole ladders (chain_id0 and n_chains multiples of the ladder size); "
                "use lr_chains_swap_info + an all-gather + lr_chains_swap_apply for ladders that span devices");
     lr_handle_t h = c->h;
-    int rc = lr_ws_reserve(h, (size_t)c->n_chains * 16);
+    int rc = lr_ws_acquire(h, (size_t)c->n_chains * 16, h->stream);
     if (rc != LR_OK) return rc;
     rc = lr_chains_swap_info(c, (double*)h->ws, h->stream);
     if (rc != LR_OK) return rc;

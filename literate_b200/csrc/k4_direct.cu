@@ -159,7 +159,7 @@ extern "C" int lr_loglik_direct(lr_handle_t h, const double* d_ts, const double*
     per_tile = (per_tile + 1) & ~1ll;
     if (per_tile < 2) per_tile = 2;
     tiles = n > 0 ? (int)((n + per_tile - 1) / per_tile) : 1;
-    int rc = lr_ws_reserve(h, (size_t)tiles * n_states * sizeof(double));
+    int rc = lr_ws_acquire(h, (size_t)tiles * n_states * sizeof(double), st);
     if (rc != LR_OK) return rc;
     K4Params p;
     p.ts = d_ts; p.te = d_te; p.n = n; p.per_tile = per_tile; p.fb = (int)first_bin; p.nb = n_bins;

@@ -272,7 +272,7 @@ extern "C" int lr_summarize_records(lr_handle_t h, const double* d_records, int6
     const int n_warps = ctas * K5_WARPS_PER_CTA;
     const size_t rate_bytes = (size_t)n_warps * 2 * 256 * sizeof(double);
     const size_t cnt_bytes = (size_t)n_warps * 2 * (256 + 32) * sizeof(long long);
-    int rc = lr_ws_reserve(h, rate_bytes + cnt_bytes);
+    int rc = lr_ws_acquire(h, rate_bytes + cnt_bytes, st);
     if (rc != LR_OK) return rc;
     K5Params p;
     p.rec = d_records; p.n_rec = n_records; p.first_edge = first_edge; p.nb = n_bins;

@@ -38,6 +38,7 @@ struct TrendChain {
 
 struct lr_trend_s {
     lr_handle_t h;
+    lr_last_stream last;           // stream that touched the object last (lr_order)
     int n_rep, n_bins, nbp;        // nbp: row pitch of the table
     int const_b, const_d;
     double* tab;                   // device [n_rep][TR_ROWS][nbp]
@@ -412,6 +413,7 @@ extern "C" int lr_trend_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, con
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     lr_trend_t t = new lr_trend_s();
     memset(t, 0, sizeof(*t));
+    t->last.s = st; t->last.valid = 1;
     t->h = h; t->n_rep = n_rep; t->n_bins = n_bins; t->nbp = (n_bins + 3) & ~3;
     t->const_b = const_birth != 0; t->const_d = const_death != 0; t->n_chains = n_chains; t->seed = seed;
     move_weights(t->const_b, t->const_d, t->f_mult, t->f_norm);
@@ -451,7 +453,7 @@ extern "C" int lr_trend_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins
     LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_trend_create_host: bad sizes");
     LR_CUDA(cudaSetDevice(h->device));
     const size_t cnt = (size_t)n_rep * n_bins;
-    int rc = lr_ws_reserve(h, cnt * 24);
+    int rc = lr_ws_acquire(h, cnt * 24, h->stream);
     if (rc != LR_OK) return rc;
     int64_t* d_sp = (int64_t*)h->ws;
     int64_t* d_ex = d_sp + cnt;
@@ -466,6 +468,7 @@ extern "C" int lr_trend_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins
 extern "C" int lr_trend_destroy(lr_trend_t t) {
     if (!t) return LR_OK;
     cudaSetDevice(t->h->device);
+    lr_order(t->h, &t->last, t->h->stream);
     if (t->tab) cudaFreeAsync(t->tab, t->h->stream);
     if (t->cst) cudaFreeAsync(t->cst, t->h->stream);
     if (t->st) cudaFreeAsync(t->st, t->h->stream);
@@ -477,6 +480,7 @@ extern "C" int64_t lr_trend_records_per_run(lr_trend_t t, int64_t n_iter, int64_
     if (!t || n_iter <= 0 || sample_every <= 0) return 0;
     long long it0 = 0;
     cudaSetDevice(t->h->device);
+    lr_order(t->h, &t->last, t->h->stream);
     cudaStreamSynchronize(t->h->stream);
     if (cudaMemcpy(&it0, &t->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     const long long first = (it0 + sample_every - 1) / sample_every * sample_every;
@@ -491,6 +495,7 @@ extern "C" int lr_trend_run(lr_trend_t t, int64_t n_iter, int64_t sample_every, 
     lr_handle_t h = t->h;
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    { int rc0 = lr_order(h, &t->last, st); if (rc0 != LR_OK) return rc0; }
     TrendRun P;
     P.st = t->st; P.n_chains = t->n_chains; P.tab = t->tab; P.cst = t->cst; P.nb = t->n_bins; P.nbp = t->nbp;
     P.const_b = t->const_b; P.const_d = t->const_d; P.k0 = (uint32_t)t->seed; P.k1 = (uint32_t)(t->seed >> 32);
@@ -514,7 +519,7 @@ extern "C" int lr_trend_run_host(lr_trend_t t, int64_t n_iter, int64_t sample_ev
     const size_t bytes = (size_t)nrec * t->n_chains * lr_trend_record_doubles(t->n_bins) * sizeof(double);
     double* d_rec = nullptr;
     if (bytes) {
-        int rc = lr_ws_reserve(h, bytes);
+        int rc = lr_ws_acquire(h, bytes, h->stream);
         if (rc != LR_OK) return rc;
         d_rec = (double*)h->ws;
     }
@@ -535,6 +540,7 @@ extern "C" int lr_trend_eval_host(lr_trend_t t, int32_t n, const int32_t* rep, c
         for (int i = 0; i < n; ++i) LR_REQUIRE(rep[i] >= 0 && rep[i] < t->n_rep, "lr_trend_eval_host: replicate of state %d out of range", i);
     lr_handle_t h = t->h;
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(t->h, &t->last, t->h->stream); if (rc0 != LR_OK) return rc0; }
     const int nb = t->n_bins;
     // workspace layout (doubles unless noted)
     size_t off = 0;
@@ -543,7 +549,7 @@ extern "C" int lr_trend_eval_host(lr_trend_t t, int32_t n, const int32_t* rep, c
                  o_on = take((size_t)n * TR_NPAR * 4), o_draw = take((size_t)n * TR_NPAR * 8), o_np = take((size_t)n * TR_NPAR * 8),
                  o_h = take((size_t)n * 8), o_lik = take((size_t)n * 16), o_pr = take((size_t)n * 8),
                  o_rates = take((size_t)n * 2 * nb * 8), o_adq = take((size_t)n * 24);
-    int rc = lr_ws_reserve(h, off);
+    int rc = lr_ws_acquire(h, off, h->stream);
     if (rc != LR_OK) return rc;
     char* W = (char*)h->ws;
     cudaStream_t st = h->stream;
@@ -573,6 +579,7 @@ extern "C" int lr_trend_eval_host(lr_trend_t t, int32_t n, const int32_t* rep, c
 extern "C" int lr_trend_state_host(lr_trend_t t, double* h_state) {
     LR_REQUIRE(t && h_state, "lr_trend_state_host: null pointer");
     LR_CUDA(cudaSetDevice(t->h->device));
+    { int rc0 = lr_order(t->h, &t->last, t->h->stream); if (rc0 != LR_OK) return rc0; }
     LR_CUDA(cudaStreamSynchronize(t->h->stream));
     // [n_chains][LR_TREND_STATE_DOUBLES]: parameters, likB, likD, prior, then iteration and accepted as doubles
     TrendChain* tmp = new TrendChain[t->n_chains];

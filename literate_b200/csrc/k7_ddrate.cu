@@ -50,6 +50,7 @@ struct DDChain {
 
 struct lr_dd_s {
     lr_handle_t h;
+    lr_last_stream last;           // stream that touched the object last (lr_order)
     int n_rep, n_bins, nbp, m_birth, m_death, n_genre;
     double origin, present;
     double* tab;           // device [n_rep][DD_ROWS][nbp]
@@ -585,6 +586,7 @@ extern "C" int lr_dd_create(lr_handle_t h, int32_t n_rep, int32_t n_bins, const 
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     lr_dd_t t = new lr_dd_s();
     memset(t, 0, sizeof(*t));
+    t->last.s = st; t->last.valid = 1;
     t->h = h; t->n_rep = n_rep; t->n_bins = n_bins; t->nbp = (n_bins + 3) & ~3; t->m_birth = m_birth; t->m_death = m_death;
     t->n_genre = m_birth == 3 ? n_genre : 0; t->origin = origin; t->present = present; t->n_chains = n_chains; t->seed = seed;
     dd_model_tables(m_birth, m_death, t->f, t->depB, t->depD);
@@ -632,7 +634,7 @@ extern "C" int lr_dd_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, c
     LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_dd_create_host: bad sizes");
     LR_CUDA(cudaSetDevice(h->device));
     const size_t cnt = (size_t)n_rep * n_bins;
-    int rc = lr_ws_reserve(h, cnt * 24);
+    int rc = lr_ws_acquire(h, cnt * 24, h->stream);
     if (rc != LR_OK) return rc;
     int64_t* d_sp = (int64_t*)h->ws;
     int64_t* d_ex = d_sp + cnt;
@@ -647,6 +649,7 @@ extern "C" int lr_dd_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, c
 extern "C" int lr_dd_destroy(lr_dd_t t) {
     if (!t) return LR_OK;
     cudaSetDevice(t->h->device);
+    lr_order(t->h, &t->last, t->h->stream);
     if (t->tab) cudaFreeAsync(t->tab, t->h->stream);
     if (t->cst) cudaFreeAsync(t->cst, t->h->stream);
     if (t->st) cudaFreeAsync(t->st, t->h->stream);
@@ -659,6 +662,7 @@ extern "C" int64_t lr_dd_records_per_run(lr_dd_t t, int64_t n_iter, int64_t samp
     if (!t || n_iter <= 0 || sample_every <= 0) return 0;
     long long it0 = 0;
     cudaSetDevice(t->h->device);
+    lr_order(t->h, &t->last, t->h->stream);
     cudaStreamSynchronize(t->h->stream);
     if (cudaMemcpy(&it0, &t->st[0].it, sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     const long long first = (it0 + sample_every - 1) / sample_every * sample_every;
@@ -673,6 +677,7 @@ extern "C" int lr_dd_run(lr_dd_t t, int64_t n_iter, int64_t sample_every, double
     lr_handle_t h = t->h;
     LR_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    { int rc0 = lr_order(h, &t->last, st); if (rc0 != LR_OK) return rc0; }
     DDRun P;
     P.st = t->st; P.n_chains = t->n_chains; P.v = dd_view(t);
     P.k0 = (uint32_t)t->seed; P.k1 = (uint32_t)(t->seed >> 32);
@@ -701,7 +706,7 @@ extern "C" int lr_dd_run_host(lr_dd_t t, int64_t n_iter, int64_t sample_every, d
     const size_t bytes = (size_t)nrec * t->n_chains * lr_dd_record_doubles(t->n_bins) * sizeof(double);
     double* d_rec = nullptr;
     if (bytes) {
-        int rc = lr_ws_reserve(h, bytes);
+        int rc = lr_ws_acquire(h, bytes, h->stream);
         if (rc != LR_OK) return rc;
         d_rec = (double*)h->ws;
     }
@@ -722,6 +727,7 @@ extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const int32_t* rep, const d
         for (int i = 0; i < n; ++i) LR_REQUIRE(rep[i] >= 0 && rep[i] < t->n_rep, "lr_dd_eval_host: replicate of state %d out of range", i);
     lr_handle_t h = t->h;
     LR_CUDA(cudaSetDevice(h->device));
+    { int rc0 = lr_order(t->h, &t->last, t->h->stream); if (rc0 != LR_OK) return rc0; }
     const int nb = t->n_bins;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -729,7 +735,7 @@ extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const int32_t* rep, const d
                  o_draw = take((size_t)n * DD_NPAR * 8), o_np = take((size_t)n * DD_NPAR * 8), o_h = take((size_t)n * 8),
                  o_lik = take((size_t)n * 24), o_pr = take((size_t)n * 8), o_ser = take((size_t)n * 4 * nb * 8),
                  o_adq = take((size_t)n * 24), o_g = take((size_t)n * 32);
-    int rc = lr_ws_reserve(h, off);
+    int rc = lr_ws_acquire(h, off, h->stream);
     if (rc != LR_OK) return rc;
     char* W = (char*)h->ws;
     cudaStream_t st = h->stream;
@@ -760,6 +766,7 @@ extern "C" int lr_dd_eval_host(lr_dd_t t, int32_t n, const int32_t* rep, const d
 extern "C" int lr_dd_state_host(lr_dd_t t, double* h_state) {
     LR_REQUIRE(t && h_state, "lr_dd_state_host: null pointer");
     LR_CUDA(cudaSetDevice(t->h->device));
+    { int rc0 = lr_order(t->h, &t->last, t->h->stream); if (rc0 != LR_OK) return rc0; }
     LR_CUDA(cudaStreamSynchronize(t->h->stream));
     DDChain* tmp = new DDChain[t->n_chains];
     cudaError_t e = cudaMemcpy(tmp, t->st, (size_t)t->n_chains * sizeof(DDChain), cudaMemcpyDeviceToHost);

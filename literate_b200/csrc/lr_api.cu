@@ -46,6 +46,7 @@ extern "C" int lr_create(int device, lr_handle_t* out) {
     LR_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) LR_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+    LR_CUDA(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
     *out = h;
     return LR_OK;
 }
@@ -55,10 +56,12 @@ extern "C" int lr_destroy(lr_handle_t h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
+    if (h->ws_used) cudaDeviceSynchronize();        // the workspace's last user may have been a caller stream
     cudaFree(h->ws);
     cudaFree(h->stage[0]);
     cudaFree(h->stage[1]);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
+    cudaEventDestroy(h->ev_order);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -81,20 +84,38 @@ extern "C" int lr_sync(lr_handle_t h) {
     return LR_OK;
 }
 
-int lr_ws_reserve(lr_handle_t h, size_t bytes) {
-    if (bytes <= h->ws_bytes) return LR_OK;
-    LR_CUDA(cudaStreamSynchronize(h->stream));
-    LR_CUDA(cudaStreamSynchronize(h->copy_stream));
-    if (h->ws) LR_CUDA(cudaFree(h->ws));
-    h->ws = nullptr; h->ws_bytes = 0;
-    size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
-    cudaError_t e = cudaMalloc(&h->ws, want);
-    if (e != cudaSuccess) {
-        lr_set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
-        return LR_ERR_NOMEM;
+int lr_order(lr_handle_t h, lr_last_stream* last, cudaStream_t now) {
+    if (last->valid && last->s != now) {
+        // everything submitted to the previous stream so far happens before whatever `now` gets from here on
+        cudaError_t e = cudaEventRecord(h->ev_order, last->s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(now, h->ev_order, 0);
+        if (e != cudaSuccess) {                 // e.g. the caller destroyed that stream: fall back to a full barrier
+            cudaGetLastError();
+            LR_CUDA(cudaDeviceSynchronize());
+        }
     }
-    h->ws_bytes = want;
+    last->s = now; last->valid = 1;
     return LR_OK;
+}
+
+int lr_ws_acquire(lr_handle_t h, size_t bytes, cudaStream_t stream) {
+    if (bytes > h->ws_bytes) {
+        LR_CUDA(cudaDeviceSynchronize());       // growing is rare; nobody may still be using the old block
+        if (h->ws) LR_CUDA(cudaFree(h->ws));
+        h->ws = nullptr; h->ws_bytes = 0;
+        size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMalloc(&h->ws, want);
+        if (e != cudaSuccess) {
+            lr_set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return LR_ERR_NOMEM;
+        }
+        h->ws_bytes = want;
+        h->ws_used = 0;
+    }
+    lr_last_stream last = {h->ws_stream, h->ws_used};
+    int rc = lr_order(h, &last, stream);
+    h->ws_stream = stream; h->ws_used = 1;
+    return rc;
 }
 
 static int stage_reserve(lr_handle_t h, size_t bytes) {
@@ -132,7 +153,7 @@ extern "C" int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double
     const size_t acc_bytes = (size_t)n_rep * LR_ACC_ROWS * stride * sizeof(int64_t);
     const size_t out_cnt = (size_t)n_rep * n_bins;
     const size_t acc_pad = (acc_bytes + 255) & ~(size_t)255;
-    int rc = lr_ws_reserve(h, acc_pad + out_cnt * 24);
+    int rc = lr_ws_acquire(h, acc_pad + out_cnt * 24, h->stream);
     if (rc != LR_OK) return rc;
     int64_t* d_acc = (int64_t*)h->ws;
     int64_t* d_sp = (int64_t*)((char*)h->ws + acc_pad);

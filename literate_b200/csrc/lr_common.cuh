@@ -51,14 +51,24 @@ struct lr_handle_s {
     cudaStream_t copy_stream;   // host<->device staging
     cudaEvent_t ev[4];
     int64_t launches;           // kernels launched through this handle
-    // grow-only workspace
+    // grow-only workspace, handed from one entry point to the next IN STREAM ORDER (lr_ws_acquire)
     void* ws;
     size_t ws_bytes;
+    cudaStream_t ws_stream;     // stream of the workspace's last user
+    int ws_used;
+    cudaEvent_t ev_order;       // scratch event of lr_order
     void* stage[2];
     size_t stage_bytes;
 };
 
-int lr_ws_reserve(lr_handle_t h, size_t bytes);
+// Cross-stream ordering without host synchronisation.  Entry points take a caller stream or fall back to the handle's
+// own; objects (datasets, chains, trend / dd samplers) and the workspace remember the stream that touched them last.
+// lr_order makes `now` wait for everything submitted so far to `*last` (an event recorded there and waited for here) when
+// the two differ, and moves `*last` to `now`.
+struct lr_last_stream { cudaStream_t s; int valid; };
+int lr_order(lr_handle_t h, lr_last_stream* last, cudaStream_t now);
+// the workspace, at least `bytes` large, for work submitted to `stream` (ordered after its previous user)
+int lr_ws_acquire(lr_handle_t h, size_t bytes, cudaStream_t stream);
 
 // ---- small device helpers --------------------------------------------------------------------
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {

@@ -115,3 +115,38 @@ def test_cold_chains_sample_the_untempered_posterior(device):
     # the hottest members see a flatter likelihood: lower mean log-likelihood than the cold ones
     hottest = np.take_along_axis(hot, np.argmin(hot[..., E.REC_BETA], axis=2)[:, :, None, None], axis=2)[:, :, 0, :]
     assert hottest[rt.shape[0] // 5:, :, E.REC_LIK].mean() < cold[rt.shape[0] // 5:, :, E.REC_LIK].mean()
+
+
+def test_caller_stream_and_handle_stream_are_ordered(device):
+    """run_device / swap_*_device default to torch's current stream, swap_step / state / counters / set_beta to the handle's
+    own; the library orders the two (lr_order: an event recorded on the stream that touched the chains last, waited for by
+    the next one) so that a caller who never synchronises gets what a caller who synchronises after every call gets."""
+    lin, ds = _dataset(device)
+    T, n = 8, 64
+    beta = np.tile(P.temperature_ladder(T, 0.2), n // T)
+    side = torch.cuda.Stream()
+
+    def play(sync):
+        ch = E.Chains(ds, n, seed=19)
+        ch.set_beta(beta)
+        for rnd in range(5):
+            ch.run_device(30000, 0, None)                            # torch's current stream, asynchronous (milliseconds of work)
+            if sync:
+                torch.cuda.synchronize(); device.sync()
+            ch.swap_step(T, rnd)                                     # the handle's stream
+            if sync:
+                torch.cuda.synchronize(); device.sync()
+            with torch.cuda.stream(side):                            # a third stream
+                ch.run_device(500, 0, None)
+                info = ch.swap_info_device(torch.empty((n, 2), dtype=torch.float64, device="cuda"))
+            if sync:
+                torch.cuda.synchronize(); device.sync()
+            ch.swap_apply_device(info, 0, T, rnd + 100)              # torch's current stream again, reading what `side` wrote
+            if sync:
+                torch.cuda.synchronize(); device.sync()
+        return ch.state(), ch.counters()
+
+    s0, c0 = play(True)
+    s1, c1 = play(False)
+    assert np.array_equal(s0, s1) and np.array_equal(c0, c1)
+    assert c0[:, 9].sum() > 0
