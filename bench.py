@@ -55,6 +55,8 @@ def _args():
     p.add_argument("--real", type=int, default=0, help="1: real-valued times (syn-real, -death_jitter 0) instead of integer years")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-real-roofline", action="store_true", help="skip K1 on the real-valued tables (roofline_real, roofline_real_sorted)")
+    p.add_argument("--no-multi", action="store_true", help="N > 1: skip BASELINE configs[3]/[4] (multi_gpu)")
     return p.parse_args()
 
 
@@ -121,13 +123,36 @@ def _peaks():
         return 6650.0, "fallback 6.65 TB/s of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
+def _sha16(path):
+    import hashlib
+    with open(path, "rb") as fh:
+        return hashlib.sha256(fh.read()).hexdigest()[:16]
+
+
 def _traffic(a):
-    """dram bytes per K1 launch from the committed ncu --set full capture of this workload, if there is one."""
+    """dram bytes per K1 launch from the committed ncu --set full capture of this workload -- only while the capture is of
+    the kernel source that is being timed (profiles/k1_traffic.json records the digest of k1_binstats.cu); otherwise null."""
     try:
         with open(os.path.join(REPO, "profiles", "k1_traffic.json")) as fh:
             t = json.load(fh)
+        if t.get("k1_binstats_cu_sha16") != _sha16(os.path.join(REPO, "literate_b200", "csrc", "k1_binstats.cu")):
+            print("bench.py: profiles/k1_traffic.json was captured from another build of k1_binstats.cu -- roofline.traffic left null "
+                  "(re-capture with ncu --set full and tools/k1_traffic_from_ncu.py)", file=sys.stderr)
+            return None
         key = "%s_%d_x_%d" % ("real" if a.real else "int", a.lineages, 1 if a.shared_dataset else a.chains)
         return t.get(key)
+    except Exception:
+        return None
+
+
+def _k3_instructions():
+    """warp instructions per chain iteration of K3 on the bench workload, from the committed ncu capture (profiles/k3_instructions.json),
+    only while the capture is of the sources being timed."""
+    try:
+        with open(os.path.join(REPO, "profiles", "k3_instructions.json")) as fh:
+            t = json.load(fh)
+        dig = "+".join(_sha16(os.path.join(REPO, "literate_b200", "csrc", f)) for f in ("k3_chains.cu", "k3_team.cuh", "chain_device.cuh", "lr_common.cuh"))
+        return t["warp_instructions_per_iteration"] if t.get("sources_sha16") == dig else None
     except Exception:
         return None
 
@@ -165,6 +190,93 @@ def run_reference(a):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU configurations
+def _multi_gpu_configs(dev, tdev, rank, world, nb):
+    """BASELINE configs[4] (lineage axis sharded, per-bin sufficient statistics combined by an NCCL all-reduce) and configs[3]
+    (4096 tempered chains sharded over the ranks, ladders that span ranks, one all-gather per swap round), timed with CUDA
+    events, max over ranks.  Returns the `multi_gpu` object of the JSON line (same on every rank)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from literate_b200 import engine as E, parallel as P, synth
+
+    def tmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    out = {"world": world}
+    # ---- configs[4]: 1e8 lineages, contiguous 1/world slice per rank, K1 + int64 SUM all-reduce + finalize
+    n_total = 100_000_000
+    s0, cnt = P.shard_range(n_total, world, rank)
+    ts, te = synth.syn_int_device(cnt, 1, tdev, seed=synth.BASE_SEED + 17 * rank)
+    ts, te = ts[:, :cnt], te[:, :cnt]
+    evs = []
+    for k in range(8):
+        acc = dev.new_accumulators(1, nb, tdev)
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        dev.bin_accumulate_device(ts, te, FIRST_BIN, nb, acc, fe_ref=0.5)
+        b.record()
+        P.allreduce_accumulators(acc)
+        sp, ex, br = dev.bin_finalize_device(acc, nb, fe_ref=0.5)
+        c.record()
+        if k >= 3:
+            evs.append((a, b, c))
+    torch.cuda.synchronize()
+    k1 = tmax(statistics.median(a.elapsed_time(b) for a, b, c in evs))
+    tot = tmax(statistics.median(a.elapsed_time(c) for a, b, c in evs))
+    births_ok = int(sp.sum()) == n_total                      # every lineage is born once inside the window
+    # in-run equality: a 4M-lineage table every rank can generate; shards all-reduced == rank 0 binning the whole table itself
+    n_chk = 4_000_000
+    cts, cte = synth.syn_int_device(n_chk, 1, tdev, seed=synth.BASE_SEED + 999)
+    c0, cc = P.shard_range(n_chk, world, rank)
+    acc_sh = dev.new_accumulators(1, nb, tdev)
+    dev.bin_accumulate_device(cts[:, c0:c0 + cc].contiguous(), cte[:, c0:c0 + cc].contiguous(), FIRST_BIN, nb, acc_sh, fe_ref=0.5)
+    P.allreduce_accumulators(acc_sh)
+    acc_full = dev.new_accumulators(1, nb, tdev)
+    dev.bin_accumulate_device(cts[:, :n_chk], cte[:, :n_chk], FIRST_BIN, nb, acc_full, fe_ref=0.5)
+    eq = torch.tensor([1.0 if bool((acc_sh == acc_full).all()) else 0.0], dtype=torch.float64, device=tdev)
+    dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+    out["cfg5_lineage_sharded"] = {
+        "lineages": n_total, "per_gpu": cnt, "bins": nb, "k1_ms": k1, "k1_allreduce_finalize_ms": tot,
+        "aggregate_GBps_k1": 16.0 * n_total / (k1 * 1e-3) / 1e9, "aggregate_GBps_incl_allreduce": 16.0 * n_total / (tot * 1e-3) / 1e9,
+        "allreduce_bytes": int(acc.numel() * 8), "collective": "NCCL all_reduce(SUM) of int64 accumulators, once per dataset",
+        "births_conserved": births_ok,
+        "allreduced_equals_single_gpu_accumulators": bool(eq[0] == 1.0), "equality_check_lineages": n_chk}
+    del ts, te, cts, cte
+
+    # ---- configs[3]: 4096 tempered chains (+ half a ladder per rank so that every rank boundary cuts a ladder), strong scaling
+    iters, swap_every, ladder = 100_000, 1000, 32
+    nl = 4096 // world // ladder * ladder + ladder // 2
+    total = nl * world
+    c0 = rank * nl
+    g = synth.syn_int_device(1_000_000, 1, tdev)
+    sp, ex, br = dev.bin_stats_device(g[0][:, :1_000_000], g[1][:, :1_000_000], FIRST_BIN, nb)
+    ds = E.Dataset.from_device(dev, sp, ex, br, 0, float(FIRST_BIN), float(FIRST_BIN + nb) + 0.5)
+    ch = E.Chains(ds, nl, seed=77, chain_id0=c0)
+    ch.set_beta(P.temperature_ladder(ladder, 0.025)[np.arange(c0, c0 + nl) % ladder])
+    ch.run_device(2000, 0, None)
+    torch.cuda.synchronize(); dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for rnd in range(iters // swap_every):
+        ch.run_device(swap_every, 0, None)
+        P.tempered_swap(ch, c0, ladder, rnd)              # (lik, beta) table -> all-gather (16 B per chain) -> every rank applies the round
+    b.record()
+    torch.cuda.synchronize()
+    ms = tmax(a.elapsed_time(b))
+    cnts = ch.counters().sum(0)
+    tc = torch.tensor([float(cnts[8]), float(cnts[9])], dtype=torch.float64, device=tdev)
+    dist.all_reduce(tc)
+    out["cfg4_tempered"] = {"chains": total, "per_gpu": nl, "ladder": ladder, "ladders_span_ranks": True, "iters_per_chain": iters,
+                            "swap_every": swap_every, "device_ms": ms, "it_per_s": total * iters / (ms * 1e-3), "scaling": "strong",
+                            "swap_acceptance": float(tc[1] / max(float(tc[0]), 1.0)),
+                            "collective": "NCCL all_gather of (likelihood, beta), 16 B per chain per swap round; temperatures move, states do not"}
+    ch.close(); ds.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -292,8 +404,30 @@ def run_cuda(a):
             if os.environ.get("LR_BENCH_DEBUG"):
                 print("flush %.1f ms, sync %.1f ms, total %.1f ms" % (1e3 * (tq - tp), 1e3 * (time.perf_counter() - tq), 1e3 * e2e_s), file=sys.stderr, flush=True)
             assert np.all(nrec[:, :, E.REC_IT] == (np.arange(n_rec) * SAMPLE)[:, None]) and np.all(np.isfinite(nrec[:, :, E.REC_LIK]))
-            pipe.close()
             e2e = [e2e_s / n_e2e, 16 * n * n_rep + 4 * chains, int(nrec.nbytes) + 24 * n_rep * nb]
+            # ---- the same through the compact entry point: the table held on the host as int32 YEARS (what a parser of the
+            # integer-year tables the reference ships produces), te jittered by the kernel -- half the bytes over PCIe
+            if not a.real:
+                hti = torch.empty((n_rep, n), dtype=torch.int32, pin_memory=True); hti.copy_(ts.to(torch.int32))
+                hei = torch.empty((n_rep, n), dtype=torch.int32, pin_memory=True); hei.copy_((te - 0.5).to(torch.int32))
+                nti, nei = hti.numpy(), hei.numpy()
+
+                def e2e_push_i32(k):
+                    return pipe.push(nti, nei, chains, a.iters, SAMPLE, seed=4052 + k, cfg=cfg, first_bin=FIRST_BIN, n_bins=nb,
+                                     death_jitter=0.5, start_time=float(FIRST_BIN), end_time=end_time,
+                                     rep_of_chain=rep_of_chain, chain_id0=rank * chains, out=hrec)
+                e2e_push_i32(0); pipe.flush(out=hrec)
+                barrier()
+                t0 = time.perf_counter()
+                for k in range(n_e2e):
+                    e2e_push_i32(100 + k)
+                pipe.flush(out=hrec)
+                torch.cuda.synchronize()
+                e2e_i32_s = time.perf_counter() - t0
+                assert np.all(nrec[:, :, E.REC_IT] == (np.arange(n_rec) * SAMPLE)[:, None]) and np.all(np.isfinite(nrec[:, :, E.REC_LIK]))
+                e2e += [e2e_i32_s / n_e2e, 8 * n * n_rep + 4 * chains]
+                del hti, hei
+            pipe.close()
             del hts, hte, hrec
         cl = clocks.stop(t_wall0, t_wall1)
 
@@ -317,12 +451,44 @@ def run_cuda(a):
                 assert bool(torch.isfinite(srec[:, :, 1]).all())
                 sc.close()
 
-    t = torch.tensor([total_ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=tdev)
+        # ---------------- K1 on real-valued tables (fp64 fractions through the carry chains), shuffled and sorted by birth year:
+        # the orderings real TSVs come in.  Reported beside the roofline of the integer-year workload the metric is quoted on.
+        real_roof = None
+        if world == 1 and not a.real and not a.no_real_roofline:
+            del ts, te
+            torch.cuda.empty_cache()
+            real_roof = {}
+            rts, rte = synth.syn_real_device(n, n_rep, tdev, seed=synth.BASE_SEED + 7919)
+            for tag in ("roofline_real", "roofline_real_sorted"):
+                if tag == "roofline_real_sorted":
+                    for r in range(n_rep):                      # sort every replicate by birth time (te follows)
+                        o = torch.argsort(rts[r, :n])
+                        rts[r, :n] = rts[r, :n][o]; rte[r, :n] = rte[r, :n][o]
+                    del o
+                vts, vte = rts[:, :n], rte[:, :n]
+                acc.zero_()
+                for _ in range(2):
+                    dev.bin_accumulate_device(vts, vte, FIRST_BIN, nb, acc, fe_ref=1.0, stream=stream.cuda_stream)
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                for e0, e1 in evs:
+                    e0.record(); dev.bin_accumulate_device(vts, vte, FIRST_BIN, nb, acc, fe_ref=1.0, stream=stream.cuda_stream); e1.record()
+                torch.cuda.synchronize()
+                ms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in evs)
+                real_roof[tag] = ms
+            del rts, rte, vts, vte
+            torch.cuda.empty_cache()
+
+        # ---------------- BASELINE configs[3] and configs[4]: only meaningful on several GPUs, measured in the same run
+        multi = None
+        if world > 1 and not a.no_multi:
+            multi = _multi_gpu_configs(dev, tdev, rank, world, nb)
+
+    t = torch.tensor([total_ms, e2e[0] if e2e else 0.0, e2e[3] if e2e and len(e2e) > 3 else 0.0], dtype=torch.float64, device=tdev)
     tot = torch.tensor([float(lik_evals), float(launches)], dtype=torch.float64, device=tdev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    total_ms, e2e_step_s = float(t[0]), float(t[1])
+    total_ms, e2e_step_s, e2e_i32_step_s = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         peak, peak_src = _peaks()
         k1 = statistics.mean(k1_ms)
@@ -337,17 +503,44 @@ def run_cuda(a):
             "lik_evals_per_s": float(tot[0]) / (total_ms * 1e-3),
             "kernels": {"k1_bin_kernel_ms": k1, "k3_run_kernel_ms": statistics.mean(k3_ms),
                         "k3_ns_per_iteration_per_chain": 1e6 * statistics.mean(k3_ms) / a.iters,
-                        "k3_bound": "dependent-instruction latency of one chain warp per chain (no DRAM traffic in the loop; see profiles/)",
+                        "k3_bound": "instruction issue: teams of 8 warps evaluate consecutive iterations of one chain speculatively "
+                                    "(no DRAM traffic in the loop; roofline_k3, profiles/)",
                         "k1_share_of_step": k1 * a.steps / total_ms, "k3_share_of_step": sum(k3_ms) / total_ms},
             "roofline": {"kernel": "k1_bin_kernel (lineages -> per-bin births/deaths/time at risk)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(a),
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src, "ms_per_launch": k1},
         }
+        # K3 against the instruction-issue peak (it touches no DRAM): warp instructions per chain iteration from the committed
+        # ncu capture of this build x iterations/s measured here / (SMs x 4 schedulers x SM clock measured here)
+        k3_ipi = _k3_instructions()
+        k3_rate = chains * a.iters / (statistics.mean(k3_ms) * 1e-3)            # one GPU's chains
+        clk = (cl.get("sm_mhz") or 1965.0) * 1e6
+        line["roofline_k3"] = {"kernel": "K3 chain loop (k3_team_kernel + continuation passes)", "bound": "issue",
+                               "warp_instructions_per_iteration": k3_ipi,
+                               "achieved": k3_ipi * k3_rate if k3_ipi else None, "peak": dev.sm_count * 4 * clk, "unit": "warp-instructions/s",
+                               "frac": (k3_ipi * k3_rate) / (dev.sm_count * 4 * clk) if k3_ipi else None,
+                               "source": "profiles/k3_instructions.json (ncu smsp__inst_executed.sum of the K3 kernels of one bench step / chain iterations)"}
+        line["kernels"]["k3_issue_frac"] = line["roofline_k3"]["frac"]
+        if real_roof:
+            for tag, ms in real_roof.items():
+                ach = algo_bytes / (ms * 1e-3) / 1e9
+                line[tag] = {"kernel": "k1_bin_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": None, "ms_per_launch": ms, "algorithmic_bytes_per_launch": algo_bytes,
+                             "table": "syn-real %d lineages x %d replicates, %s" % (n, n_rep, "sorted by birth time" if tag.endswith("sorted") else "shuffled")}
+        if multi:
+            line["multi_gpu"] = multi
         if siblings:
             line["siblings"] = siblings
         if e2e:
             line["e2e"] = {"value": n_gpus * chains * a.iters / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": e2e[1],
-                           "d2h_bytes_per_step": e2e[2], "ms_per_step": 1e3 * e2e_step_s}
+                           "d2h_bytes_per_step": e2e[2], "ms_per_step": 1e3 * e2e_step_s,
+                           "h2d_GBps_per_rank": e2e[1] / e2e_step_s / 1e9,
+                           "host_table": "fp64 (ts, te), 16 B per lineage: the arrays the reference's parser holds (LiteRateForward.py:440-471)"}
+            if len(e2e) > 3 and e2e_i32_step_s > 0:
+                line["e2e_i32"] = {"value": n_gpus * chains * a.iters / e2e_i32_step_s, "unit": UNIT, "h2d_bytes_per_step": e2e[4],
+                                   "d2h_bytes_per_step": e2e[2], "ms_per_step": 1e3 * e2e_i32_step_s,
+                                   "h2d_GBps_per_rank": e2e[4] / e2e_i32_step_s / 1e9,
+                                   "host_table": "int32 years, 8 B per lineage (lr_bin_stats_host_i32; the kernel adds the death jitter)"}
         if n_gpus == 1 and not a.no_cpu_baseline:
             from oracle import cpu_baseline as CB
             cores = os.cpu_count() or 1

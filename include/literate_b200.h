@@ -102,6 +102,21 @@ int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double* h_te, int
                       int32_t dead_only, double end_time,
                       int64_t* h_sp, int64_t* h_ex, double* h_br);
 
+/* The same pass for tables of INTEGER YEARS held as int32 (8 bytes per lineage instead of 16 -- every table the
+ * reference ships is of this kind once parsed, LiteRateForward.py:440-451): ts = year, te = year + death_jitter with
+ * 0 <= death_jitter <= 1 (:471), i.e. what the fp64 entry points see after `te = te + death_jitter`.  Same accumulators,
+ * bit for bit; finalize them with fe_ref = lr_fe_ref_of_jitter(death_jitter).  Pad ragged replicates with INT32_MIN in
+ * both columns (a lineage that ends before the window: no contribution). */
+int lr_bin_accumulate_i32(lr_handle_t h, const int32_t* d_ts, const int32_t* d_te, int64_t n, int64_t ld,
+                          int32_t n_rep, int64_t first_bin, int32_t n_bins, double death_jitter,
+                          int32_t dead_only, double end_time, int64_t* d_acc, void* stream);
+double lr_fe_ref_of_jitter(double death_jitter);
+/* host buffers (pinned for asynchronous copies), copies pipelined per batch of replicates against the kernel */
+int lr_bin_stats_host_i32(lr_handle_t h, const int32_t* h_ts, const int32_t* h_te, int64_t n, int64_t ld,
+                          int32_t n_rep, int64_t first_bin, int32_t n_bins, double death_jitter,
+                          int32_t dead_only, double end_time,
+                          int64_t* h_sp, int64_t* h_ex, double* h_br);
+
 /* ---------------------------------------------------------------- L3: likelihood + priors on a state
  *
  * A dataset holds, per replicate, the binned statistics and the prefix tables the likelihood of a

@@ -34,6 +34,7 @@
 
 namespace {
 
+
 constexpr int K1_UNROLL = 2;                        // double2 loads in flight per array per thread
 constexpr int K1_TILE = 64 * K1_UNROLL;             // lineages one warp consumes per tile
 constexpr int ROW_SP = 0, ROW_EX = 1, ROW_CS_LO = 2, ROW_CS_HI = 3, ROW_CE_LO = 4, ROW_CE_HI = 5,
@@ -42,6 +43,10 @@ constexpr int ROW_SP = 0, ROW_EX = 1, ROW_CS_LO = 2, ROW_CS_HI = 3, ROW_CE_LO = 
 struct K1Params {
     const double* ts;
     const double* te;
+    const int* ts_i;       // int32 years (lr_bin_accumulate_i32): ts = ts_i, te = te_i + jitter
+    const int* te_i;
+    double jitter;         // death_jitter of the int32 path, in [0, 1]
+    int b_off;             // death bin of an int32 lineage = te_i + b_off - first_bin (0 for jitter > 0, -1 for jitter == 0)
     long long n, ld;
     int n_rep;
     int fb;                // first_bin
@@ -98,10 +103,12 @@ struct K1Smem {
 };
 
 // Lineages that are not (alive for a positive time, born inside the window): rare, global atomics.
-__device__ __noinline__ void k1_irregular(const K1Params& p, long long* acc, double ts, double te) {
+// (the five fields it needs by value: a reference to the kernel's parameter block would make every CTA copy the block to
+// local memory at entry)
+__device__ __noinline__ void k1_irregular(int p_fb, unsigned p_nb, long long S, long long p_fe_ref_fix, long long* acc, double ts, double te) {
+    const struct { int fb; unsigned nb; long long fe_ref_fix; } p = {p_fb, p_nb, p_fe_ref_fix};
     const double T0 = (double)p.fb, T1 = (double)p.fb + (double)p.nb;
     unsigned long long* row = (unsigned long long*)acc;
-    const long long S = p.acc_stride;
     bool live = te > ts;   // false for NaNs
     if (live) {
         if (ts >= T1) return;                 // born after the window: nothing
@@ -159,7 +166,7 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
             }
         }
     } else {
-        k1_irregular(p, acc, ts, te);
+        k1_irregular(p.fb, p.nb, p.acc_stride, p.fe_ref_fix, acc, ts, te);
     }
 }
 
@@ -190,6 +197,86 @@ __device__ __forceinline__ void k1_tiles(const K1Params& p, const K1Smem& s, lon
 #pragma unroll
             for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage<MERGE>(p, s, acc, sv[u], ev[u], mergeS, mergeE);
         }
+    }
+}
+
+// ---- int32 years (8 B per lineage): ts is an integer year, te an integer year plus the constant death jitter, so every
+// fraction is the expected one and a regular lineage is exactly two ATOMS.POPC.INC
+__device__ __forceinline__ void k1_lineage_i32(const K1Params& p, const K1Smem& s, long long* acc, int ts, int te) {
+    const bool live = p.b_off == 0 ? (te >= ts) : (te > ts);          // te + jitter > ts
+    if (p.dead_only) {
+        if (!((double)te + p.jitter < p.end_time)) return;            // :531-532
+    }
+    const unsigned a = (unsigned)(ts - p.fb);
+    const unsigned b = (unsigned)(te + p.b_off - p.fb);
+    if (live && a < p.nb) {
+        atomicAdd(&s.hs32[a], 1u);
+        if (b < p.nb) atomicAdd(&s.he32[b], 1u);
+    } else {
+        k1_irregular(p.fb, p.nb, p.acc_stride, p.fe_ref_fix, acc, (double)ts, (double)te + p.jitter);
+    }
+}
+__device__ __forceinline__ int4 ld_stream_s32x4(const int4* q) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* q) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(q));
+    return v;
+}
+constexpr int K1I_TILE = 128 * K1_UNROLL;           // lineages one warp consumes per tile of the int32 path (int4 loads)
+
+__global__ void __launch_bounds__(256, 5) k1_bin_i32_kernel(const K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    const unsigned nb = p.nb;
+    K1Smem s;
+    s.hs32 = (unsigned*)smem_raw; s.he32 = s.hs32 + nb; s.cS = nullptr; s.cE = nullptr; s.exC = nullptr;
+    const long long total = p.n * (long long)p.n_rep;
+    long long g0 = (long long)blockIdx.x * p.chunk;
+    long long g1 = g0 + p.chunk;
+    if (g1 > total) g1 = total;
+    while (g0 < g1) {
+        const long long rep = g0 / p.n;
+        const long long s0 = g0 - rep * p.n;
+        long long s1 = p.n;
+        if (s1 - s0 > g1 - g0) s1 = s0 + (g1 - g0);
+        if (s1 - s0 > p.seg_max) s1 = s0 + p.seg_max;
+        g0 += s1 - s0;
+        const int* ts = p.ts_i + rep * p.ld;
+        const int* te = p.te_i + rep * p.ld;
+        long long* acc = p.acc + rep * (LR_ACC_ROWS * p.acc_stride);
+        for (unsigned i = tid; i < 2 * nb; i += blockDim.x) s.hs32[i] = 0u;
+        __syncthreads();
+        long long A = (s0 + K1I_TILE - 1) / K1I_TILE * K1I_TILE;
+        if (A > s1) A = s1;
+        const long long ntiles = p.vec_ok ? (s1 - A) / K1I_TILE : 0;
+        const long long B = A + ntiles * K1I_TILE;
+        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage_i32(p, s, acc, ld_stream_s32(ts + i), ld_stream_s32(te + i));
+        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage_i32(p, s, acc, ld_stream_s32(ts + i), ld_stream_s32(te + i));
+        for (long long k = warp; k < ntiles; k += W) {
+            const int4* t4 = (const int4*)(ts + A + k * K1I_TILE) + lane;
+            const int4* e4 = (const int4*)(te + A + k * K1I_TILE) + lane;
+            int4 sv[K1_UNROLL], ev[K1_UNROLL];
+#pragma unroll
+            for (int u = 0; u < K1_UNROLL; ++u) { sv[u] = ld_stream_s32x4(t4 + u * 32); ev[u] = ld_stream_s32x4(e4 + u * 32); }
+#pragma unroll
+            for (int u = 0; u < K1_UNROLL; ++u) {
+                k1_lineage_i32(p, s, acc, sv[u].x, ev[u].x);
+                k1_lineage_i32(p, s, acc, sv[u].y, ev[u].y);
+                k1_lineage_i32(p, s, acc, sv[u].z, ev[u].z);
+                k1_lineage_i32(p, s, acc, sv[u].w, ev[u].w);
+            }
+        }
+        __syncthreads();
+        unsigned long long* g = (unsigned long long*)acc;
+        for (unsigned i = tid; i < nb; i += blockDim.x) {
+            if (s.hs32[i]) atomicAdd(&g[ROW_SP * p.acc_stride + i], (unsigned long long)s.hs32[i]);
+            if (s.he32[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.he32[i]);
+        }
+        __syncthreads();
     }
 }
 
@@ -387,6 +474,48 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     h->launches += 1;
     return LR_OK;
 }
+
+extern "C" int lr_bin_accumulate_i32(lr_handle_t h, const int32_t* d_ts, const int32_t* d_te, int64_t n, int64_t ld,
+                                     int32_t n_rep, int64_t first_bin, int32_t n_bins, double death_jitter,
+                                     int32_t dead_only, double end_time, int64_t* d_acc, void* stream) {
+    LR_REQUIRE(h != nullptr, "lr_bin_accumulate_i32: null handle");
+    LR_REQUIRE(n >= 0 && n_rep >= 1 && ld >= n, "lr_bin_accumulate_i32: need n >= 0, n_rep >= 1, ld >= n");
+    LR_REQUIRE(n_bins >= 1, "lr_bin_accumulate_i32: n_bins must be >= 1");
+    LR_REQUIRE(death_jitter >= 0.0 && death_jitter <= 1.0, "lr_bin_accumulate_i32: death_jitter must lie in [0, 1] (te = year + jitter)");
+    LR_REQUIRE(d_acc != nullptr && (n == 0 || (d_ts != nullptr && d_te != nullptr)), "lr_bin_accumulate_i32: null pointer");
+    const size_t smem = 2 * (size_t)n_bins * sizeof(unsigned);
+    if (first_bin <= -(1ll << 30) || first_bin >= (1ll << 30) || smem + 1024 > (size_t)h->max_smem_optin) {
+        lr_set_error("lr_bin_accumulate_i32: |first_bin| must be < 2^30 and the 2 x n_bins shared-memory counters must fit one SM");
+        return LR_ERR_UNSUPPORTED;
+    }
+    if (n == 0) return LR_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    LR_CUDA(cudaSetDevice(h->device));
+    K1Params p;
+    memset(&p, 0, sizeof(p));
+    p.ts_i = d_ts; p.te_i = d_te; p.jitter = death_jitter; p.b_off = death_jitter > 0.0 ? 0 : -1;
+    p.n = n; p.ld = ld; p.n_rep = n_rep;
+    p.fb = (int)first_bin; p.nb = (unsigned)n_bins;
+    p.fe_ref = death_jitter > 0.0 ? death_jitter : 1.0;           // finalize with this fe_ref (lr_fe_ref_of_jitter)
+    p.fe_ref_fix = fe_fix(p.fe_ref);
+    p.dead_only = dead_only; p.end_time = end_time;
+    p.acc = (long long*)d_acc; p.acc_stride = lr_acc_stride(n_bins);
+    p.vec_ok = (((uintptr_t)d_ts | (uintptr_t)d_te) & 15) == 0 && (ld % 4 == 0 || n_rep == 1);
+    const int threads = 256, blocks = h->sm_count * 5;
+    p.seg_max = 1ll << 31;
+    const long long total = n * (long long)n_rep;
+    long long chunk = (total + blocks - 1) / blocks;
+    chunk = (chunk + K1I_TILE - 1) / K1I_TILE * K1I_TILE;
+    p.chunk = chunk;
+    const int used = (int)((total + chunk - 1) / chunk);
+    LR_CUDA(cudaFuncSetAttribute(k1_bin_i32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1_bin_i32_kernel<<<used, threads, smem, st>>>(p);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" double lr_fe_ref_of_jitter(double death_jitter) { return death_jitter > 0.0 && death_jitter <= 1.0 ? death_jitter : 1.0; }
 
 extern "C" int lr_bin_finalize(lr_handle_t h, const int64_t* d_acc, int32_t n_rep, int32_t n_bins, double fe_ref,
                                int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream) {

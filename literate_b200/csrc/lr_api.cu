@@ -141,14 +141,16 @@ static int stage_reserve(lr_handle_t h, size_t bytes) {
 // Host buffers in, host buffers out.  Replicates are copied in batches on the copy stream into
 // two device staging buffers while the previous batch is being binned on the compute stream.
 // Pass pinned host memory for the copies to be truly asynchronous.
-extern "C" int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double* h_te, int64_t n, int64_t ld,
-                                 int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
-                                 int32_t dead_only, double end_time,
-                                 int64_t* h_sp, int64_t* h_ex, double* h_br) {
-    LR_REQUIRE(h != nullptr, "lr_bin_stats_host: null handle");
-    LR_REQUIRE(n >= 0 && n_rep >= 1 && ld >= n && n_bins >= 1, "lr_bin_stats_host: bad sizes");
-    LR_REQUIRE(h_sp && h_ex && h_br && (n == 0 || (h_ts && h_te)), "lr_bin_stats_host: null pointer");
+// elem = 8: fp64 times, `frac` = fe_ref;  elem = 4: int32 years, `frac` = death_jitter (half the bytes over PCIe).
+static int bin_stats_host_impl(lr_handle_t h, const void* h_ts, const void* h_te, int elem, int64_t n, int64_t ld,
+                               int32_t n_rep, int64_t first_bin, int32_t n_bins, double frac,
+                               int32_t dead_only, double end_time,
+                               int64_t* h_sp, int64_t* h_ex, double* h_br, const char* who) {
+    LR_REQUIRE(h != nullptr, "%s: null handle", who);
+    LR_REQUIRE(n >= 0 && n_rep >= 1 && ld >= n && n_bins >= 1, "%s: bad sizes", who);
+    LR_REQUIRE(h_sp && h_ex && h_br && (n == 0 || (h_ts && h_te)), "%s: null pointer", who);
     LR_CUDA(cudaSetDevice(h->device));
+    const double fe_ref = elem == 8 ? frac : lr_fe_ref_of_jitter(frac);
     const size_t stride = (size_t)lr_acc_stride(n_bins);
     const size_t acc_bytes = (size_t)n_rep * LR_ACC_ROWS * stride * sizeof(int64_t);
     const size_t out_cnt = (size_t)n_rep * n_bins;
@@ -162,26 +164,30 @@ extern "C" int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double
     LR_CUDA(cudaMemsetAsync(d_acc, 0, acc_bytes, h->stream));
 
     if (n > 0) {
-        const int64_t ldp = (n + 1) & ~(int64_t)1;                 // even row pitch keeps 128-bit loads aligned
-        int64_t per_batch = ((int64_t)96 << 20) / (ldp * 16);      // ~96 MB of (ts, te) per batch
+        const int64_t align = 16 / elem;                            // row pitch that keeps 128-bit loads aligned
+        const int64_t ldp = (n + align - 1) / align * align;
+        int64_t per_batch = ((int64_t)96 << 20) / (ldp * 2 * elem); // ~96 MB of (ts, te) per batch
         if (per_batch < 1) per_batch = 1;
         if (per_batch > n_rep) per_batch = n_rep;
-        const size_t half = (size_t)per_batch * ldp * sizeof(double);
+        const size_t half = (size_t)per_batch * ldp * elem;
         rc = stage_reserve(h, 2 * half);
         if (rc != LR_OK) return rc;
         int batch = 0;
         for (int64_t r0 = 0; r0 < n_rep; r0 += per_batch, ++batch) {
             const int buf = batch & 1;
             const int64_t nr = (n_rep - r0 < per_batch) ? (n_rep - r0) : per_batch;
-            double* s_ts = (double*)h->stage[buf];
-            double* s_te = (double*)((char*)h->stage[buf] + half);
+            char* s_ts = (char*)h->stage[buf];
+            char* s_te = (char*)h->stage[buf] + half;
             if (batch >= 2) LR_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev[2 + buf], 0));     // kernel of batch-2 released the buffer
-            LR_CUDA(cudaMemcpy2DAsync(s_ts, ldp * 8, h_ts + r0 * ld, ld * 8, n * 8, nr, cudaMemcpyHostToDevice, h->copy_stream));
-            LR_CUDA(cudaMemcpy2DAsync(s_te, ldp * 8, h_te + r0 * ld, ld * 8, n * 8, nr, cudaMemcpyHostToDevice, h->copy_stream));
+            LR_CUDA(cudaMemcpy2DAsync(s_ts, ldp * elem, (const char*)h_ts + r0 * ld * elem, ld * elem, n * elem, nr, cudaMemcpyHostToDevice, h->copy_stream));
+            LR_CUDA(cudaMemcpy2DAsync(s_te, ldp * elem, (const char*)h_te + r0 * ld * elem, ld * elem, n * elem, nr, cudaMemcpyHostToDevice, h->copy_stream));
             LR_CUDA(cudaEventRecord(h->ev[buf], h->copy_stream));
             LR_CUDA(cudaStreamWaitEvent(h->stream, h->ev[buf], 0));
-            rc = lr_bin_accumulate(h, s_ts, s_te, n, ldp, (int32_t)nr, first_bin, n_bins, fe_ref, dead_only, end_time,
-                                   d_acc + (size_t)r0 * LR_ACC_ROWS * stride, h->stream);
+            int64_t* acc_r = d_acc + (size_t)r0 * LR_ACC_ROWS * stride;
+            rc = elem == 8 ? lr_bin_accumulate(h, (const double*)s_ts, (const double*)s_te, n, ldp, (int32_t)nr, first_bin, n_bins, fe_ref, dead_only,
+                                               end_time, acc_r, h->stream)
+                           : lr_bin_accumulate_i32(h, (const int32_t*)s_ts, (const int32_t*)s_te, n, ldp, (int32_t)nr, first_bin, n_bins, frac,
+                                                   dead_only, end_time, acc_r, h->stream);
             if (rc != LR_OK) return rc;
             LR_CUDA(cudaEventRecord(h->ev[2 + buf], h->stream));
         }
@@ -193,4 +199,19 @@ extern "C" int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double
     LR_CUDA(cudaMemcpyAsync(h_br, d_br, out_cnt * 8, cudaMemcpyDeviceToHost, h->stream));
     LR_CUDA(cudaStreamSynchronize(h->stream));
     return LR_OK;
+}
+
+extern "C" int lr_bin_stats_host(lr_handle_t h, const double* h_ts, const double* h_te, int64_t n, int64_t ld,
+                                 int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
+                                 int32_t dead_only, double end_time,
+                                 int64_t* h_sp, int64_t* h_ex, double* h_br) {
+    return bin_stats_host_impl(h, h_ts, h_te, 8, n, ld, n_rep, first_bin, n_bins, fe_ref, dead_only, end_time, h_sp, h_ex, h_br, "lr_bin_stats_host");
+}
+
+extern "C" int lr_bin_stats_host_i32(lr_handle_t h, const int32_t* h_ts, const int32_t* h_te, int64_t n, int64_t ld,
+                                     int32_t n_rep, int64_t first_bin, int32_t n_bins, double death_jitter,
+                                     int32_t dead_only, double end_time,
+                                     int64_t* h_sp, int64_t* h_ex, double* h_br) {
+    return bin_stats_host_impl(h, h_ts, h_te, 4, n, ld, n_rep, first_bin, n_bins, death_jitter, dead_only, end_time, h_sp, h_ex, h_br,
+                               "lr_bin_stats_host_i32");
 }

@@ -53,6 +53,9 @@ class BinStats:
         return self.sp.shape[0]
 
 
+YEAR_PAD = np.iinfo(np.int32).min      # padding of ragged int32 year tables (both columns): contributes nothing
+
+
 def window(ts, te):
     """(first_bin, n_bins) = range(int(min ts), int(max te)) of :519 for host arrays."""
     first = int(np.min(ts))
@@ -101,11 +104,20 @@ class Device:
         """HOST arrays in, host arrays out (lr_bin_stats_host).
 
         ``ts``/``te`` are float64 arrays of shape [n] or [n_rep, n] (te already jittered, as after
-        LiteRateForward.py:471).  With ``only_dead`` the extinct-only statistics of :529-549 are
-        added, for lineages with te < end_time.
+        LiteRateForward.py:471) -- or int32 arrays of YEARS (te before the jitter, which ``death_jitter``
+        then supplies): half the bytes over PCIe, the same statistics bit for bit.  With ``only_dead`` the
+        extinct-only statistics of :529-549 are added, for lineages with te < end_time.
         """
-        ts = np.ascontiguousarray(ts, dtype=np.float64)
-        te = np.ascontiguousarray(te, dtype=np.float64)
+        years = np.asarray(ts).dtype == np.int32 and np.asarray(te).dtype == np.int32
+        if years:
+            # compact tables: integer YEARS as int32 (8 bytes per lineage over PCIe instead of 16); te is the year BEFORE the
+            # jitter of :471, which the kernel adds (lr_bin_stats_host_i32).  Pad ragged replicates with YEAR_PAD.
+            if not 0.0 <= death_jitter <= 1.0:
+                raise ValueError("int32 year tables need 0 <= death_jitter <= 1")
+            ts = np.ascontiguousarray(ts); te = np.ascontiguousarray(te)
+        else:
+            ts = np.ascontiguousarray(ts, dtype=np.float64)
+            te = np.ascontiguousarray(te, dtype=np.float64)
         if ts.shape != te.shape or ts.ndim not in (1, 2):
             raise ValueError("ts and te must have the same shape, [n] or [n_rep, n]")
         if ts.ndim == 1:
@@ -114,21 +126,31 @@ class Device:
         if n == 0:
             raise ValueError("no lineages")
         if first_bin is None or n_bins is None:
-            first_bin, n_bins = window(ts, te)
+            if years:
+                real = ts != YEAR_PAD
+                first_bin = int(ts[real].min())
+                n_bins = int(float(te[real].max()) + death_jitter) - first_bin
+            else:
+                first_bin, n_bins = window(ts, te)
         if n_bins < 1:
             raise ValueError("the time window holds no complete bin (int(max te) <= int(min ts))")
         if fe_ref is None:
             fe_ref = fe_ref_for_jitter(death_jitter)
         if end_time is None:
-            end_time = float(np.max(te))
+            end_time = float(te[ts != YEAR_PAD].max()) + death_jitter if years else float(np.max(te))
 
         def run(dead):
             sp = np.empty((n_rep, n_bins), dtype=np.int64)
             ex = np.empty((n_rep, n_bins), dtype=np.int64)
             br = np.empty((n_rep, n_bins), dtype=np.float64)
-            N.check(self.lib.lr_bin_stats_host(self.h, N.np_ptr(ts), N.np_ptr(te), n, n, n_rep, int(first_bin), int(n_bins),
-                                               float(fe_ref), 1 if dead else 0, float(end_time),
-                                               N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br)), "lr_bin_stats_host")
+            if years:
+                N.check(self.lib.lr_bin_stats_host_i32(self.h, N.np_ptr(ts), N.np_ptr(te), n, n, n_rep, int(first_bin), int(n_bins),
+                                                       float(death_jitter), 1 if dead else 0, float(end_time),
+                                                       N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br)), "lr_bin_stats_host_i32")
+            else:
+                N.check(self.lib.lr_bin_stats_host(self.h, N.np_ptr(ts), N.np_ptr(te), n, n, n_rep, int(first_bin), int(n_bins),
+                                                   float(fe_ref), 1 if dead else 0, float(end_time),
+                                                   N.np_ptr(sp), N.np_ptr(ex), N.np_ptr(br)), "lr_bin_stats_host")
             return sp, ex, br
 
         sp, ex, br = run(False)
@@ -163,7 +185,8 @@ class Device:
                 "lr_bin_stats")
         return sp, ex, br
 
-    def bin_accumulate_device(self, ts, te, first_bin, n_bins, acc, fe_ref=0.5, dead_only=False, end_time=0.0, stream=None):
+    def bin_accumulate_device(self, ts, te, first_bin, n_bins, acc, fe_ref=0.5, dead_only=False, end_time=0.0, stream=None,
+                              death_jitter=None):
         """Raw integer accumulators only (lr_bin_accumulate) -- the lineage-sharded multi-GPU path all-reduces
         `acc` (int64 [n_rep, 8, lr_acc_stride]) before bin_finalize_device."""
         import torch
@@ -172,6 +195,13 @@ class Device:
         n_rep, n = ts.shape
         ld = ts.stride(0) if n_rep > 1 else max(n, 1)
         st = _stream_ptr(stream, ts.device)
+        if ts.dtype == torch.int32:
+            # int32 YEARS: `death_jitter` takes the place of fe_ref (te = year + jitter); finalize with fe_ref_for_jitter(death_jitter)
+            jit = fe_ref if death_jitter is None else death_jitter
+            N.check(self.lib.lr_bin_accumulate_i32(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), n, ld, n_rep,
+                                                   int(first_bin), int(n_bins), float(jit), 1 if dead_only else 0, float(end_time),
+                                                   C.c_void_p(acc.data_ptr()), st), "lr_bin_accumulate_i32")
+            return acc
         N.check(self.lib.lr_bin_accumulate(self.h, C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), n, ld, n_rep,
                                            int(first_bin), int(n_bins), float(fe_ref), 1 if dead_only else 0, float(end_time),
                                            C.c_void_p(acc.data_ptr()), st), "lr_bin_accumulate")
@@ -575,12 +605,16 @@ class Pipeline:
         `out` if given), then launch this batch's chains asynchronously."""
         import torch
         ts = np.asarray(ts); te = np.asarray(te)
+        years = ts.dtype == np.int32 and te.dtype == np.int32          # compact year tables: te is the year before the jitter
         if first_bin is None or n_bins is None:
-            first_bin, n_bins = window(ts, te)
+            if years:
+                first_bin = int(ts[ts != YEAR_PAD].min()); n_bins = int(float(te[ts != YEAR_PAD].max()) + death_jitter) - first_bin
+            else:
+                first_bin, n_bins = window(ts, te)
         if start_time is None:
-            start_time = float(np.min(ts))
+            start_time = float(ts[ts != YEAR_PAD].min()) if years else float(np.min(ts))
         if end_time is None:
-            end_time = float(np.max(te))
+            end_time = float(te[ts != YEAR_PAD].max()) + death_jitter if years else float(np.max(te))
         if cfg is None:
             cfg = default_config(model_BDI)
         stats = self.dev_bin.bin_stats(ts, te, first_bin=first_bin, n_bins=n_bins, death_jitter=death_jitter,

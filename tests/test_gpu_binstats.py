@@ -219,3 +219,54 @@ def test_full_size_hundred_million_lineages(device):
     sp2, ex2, br2 = device.bin_stats_device(ts, te, 1800, 200)
     torch.cuda.synchronize()
     assert torch.equal(sp2, sp) and torch.equal(br2, br)
+
+
+def test_int32_year_tables_give_the_same_statistics(device, metal_path):
+    """lr_bin_stats_host_i32 / lr_bin_accumulate_i32: integer years as int32 (8 bytes per lineage), the death jitter of
+    LiteRateForward.py:471 added by the kernel.  Same statistics as the fp64 entry points on the jittered table, bit for
+    bit: shipped tables, every jitter in [0, 1], extinct-only statistics, lineages outside / before the window, te < ts,
+    ragged replicates padded with YEAR_PAD, row pitches that are not multiples of four, one lineage."""
+    import torch
+    from literate_b200 import engine as E
+    rng = np.random.default_rng(5)
+    for path in (golden_input("example_dataTAD.txt"), metal_path):
+        for jitter in (0.5, 0.0, 1.0, 0.25):
+            lin = O.read_lineages(path, death_jitter=jitter)
+            ty, ey = lin.ts.astype(np.int32), (lin.te - jitter).astype(np.int32)
+            assert (ty == lin.ts).all() and (ey + jitter == lin.te).all()
+            a = device.bin_stats(lin.ts, lin.te, death_jitter=jitter, only_dead=True)
+            b = device.bin_stats(ty, ey, death_jitter=jitter, only_dead=True)
+            assert a.first_bin == b.first_bin and a.n_bins == b.n_bins
+            for x, y in ((a.sp, b.sp), (a.ex, b.ex), (a.br, b.br), (a.ex_dead, b.ex_dead), (a.br_dead, b.br_dead)):
+                assert np.array_equal(x, y), (path, jitter)
+    # explicit window smaller than the data (births before / after the window, deaths beyond it), lineages with te < ts and te == ts
+    for n in (1, 3, 5, 127, 128, 129, 1023, 20011):
+        ty = rng.integers(1880, 2030, n).astype(np.int32)
+        ey = (ty + rng.integers(-3, 40, n)).astype(np.int32)
+        for jitter in (0.5, 0.0):
+            a = device.bin_stats(ty.astype(np.float64), ey + jitter, first_bin=1900, n_bins=100, death_jitter=jitter, only_dead=True, end_time=2001.0)
+            b = device.bin_stats(ty, ey, first_bin=1900, n_bins=100, death_jitter=jitter, only_dead=True, end_time=2001.0)
+            for x, y in ((a.sp, b.sp), (a.ex, b.ex), (a.br, b.br), (a.ex_dead, b.ex_dead), (a.br_dead, b.br_dead)):
+                assert np.array_equal(x, y), (n, jitter)
+    # replicates of different lengths: NaN rows in the fp64 table, YEAR_PAD in the int32 one
+    n_rep, n = 5, 3001
+    T = np.full((n_rep, n), np.nan); Ee = np.full((n_rep, n), np.nan)
+    Ti = np.full((n_rep, n), E.YEAR_PAD, dtype=np.int32); Ei = np.full((n_rep, n), E.YEAR_PAD, dtype=np.int32)
+    for r in range(n_rep):
+        m = n - 211 * r
+        ts, te = synth.syn_int(m, replicate=40 + r)
+        T[r, :m], Ee[r, :m] = ts, te
+        Ti[r, :m], Ei[r, :m] = ts.astype(np.int32), (te - 0.5).astype(np.int32)
+    a = device.bin_stats(T, Ee, first_bin=1800, n_bins=200, end_time=2000.5)
+    b = device.bin_stats(Ti, Ei, first_bin=1800, n_bins=200, death_jitter=0.5, end_time=2000.5)
+    assert np.array_equal(a.sp, b.sp) and np.array_equal(a.ex, b.ex) and np.array_equal(a.br, b.br)
+    # device entry point, full bench size of one replicate, raw accumulators compared word for word
+    tdev = torch.device("cuda:0")
+    ts, te = synth.syn_int_device(1_000_000, 3, tdev)
+    ts, te = ts[:, :1_000_000], te[:, :1_000_000]
+    ti, ei = ts.to(torch.int32).contiguous(), (te - 0.5).to(torch.int32).contiguous()
+    acc_a = device.new_accumulators(3, 200, tdev); acc_b = device.new_accumulators(3, 200, tdev)
+    device.bin_accumulate_device(ts, te, 1800, 200, acc_a, fe_ref=0.5)
+    device.bin_accumulate_device(ti, ei, 1800, 200, acc_b, death_jitter=0.5)
+    torch.cuda.synchronize()
+    assert bool((acc_a == acc_b).all())
