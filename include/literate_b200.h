@@ -215,7 +215,8 @@ int lr_chains_destroy(lr_chains_t c);
  *   [0] iteration  [1] likA  [2] priorA  [3] mean(L)  [4] mean(M)  [5] K_l  [6] K_m
  *   [7] Gamma_rate[0]  [8] Gamma_rate[1]  [9] Poi_lambda  [10..12] adequacy (coeff, r2, gelman_r2)
  *   [13] poi_lambda_is_initial (1 while Poi_lambda_rjHP still is the constant of :220-221)
- *   [14] beta (inverse temperature of the chain when the record was written; 1 = the reference's chain)  [15] reserved
+ *   [14] beta (inverse temperature of the chain when the record was written; 1 = the reference's chain)
+ *   [15] priorPoiA: the Poisson-prior term inside [2], refreshed only by accepted RJ proposals (:279, :300-304, :319)
  *   [16 .. 16+32)  L slots   [48 .. 80) birth shift times (slot 0 = start_time)
  *   [80 .. 112)    M slots   [112 .. 144) death shift times
  */
@@ -272,6 +273,12 @@ int lr_chains_swap_step(lr_chains_t c, int32_t ladder, uint64_t round);
  * Deterministic (fixed summation order); asynchronous on `stream`. */
 int lr_summarize_records(lr_handle_t h, const double* d_records, int64_t n_records, double first_edge, int32_t n_bins,
                          double* d_sum_rate, int64_t* d_shift_count, int64_t* d_k_count, void* stream);
+/* Envelopes over imputation replicates (utilities/imputation_averager.py:23-61): per bin, mean / min / max over the n_rep
+ * replicates of ex/br, sp/br and br, from the outputs of lr_bin_stats (device pointers).  d_out [9][n_bins] =
+ * death mean, min, max; birth mean, min, max; diversity mean, min, max.  Means accumulate in replicate order (numpy's
+ * mean(axis=0) over the stacked div.log tables); min / max propagate NaN like numpy.  Asynchronous on `stream`. */
+int lr_imputation_envelope(lr_handle_t h, const int64_t* d_sp, const int64_t* d_ex, const double* d_br, int32_t n_rep, int32_t n_bins,
+                           double* d_out, void* stream);
 /* The per-sample matrix behind the 95 % HPD intervals (get_marginal_rates :92-139, calcHPD :12-28): the marginal birth and death
  * rate of every record in the unit bins [bin_lo, bin_lo + bin_cnt) of the n_bins from first_edge, record-major:
  *   d_birth, d_death  [n_records][bin_cnt] fp64

@@ -30,7 +30,7 @@ EXPORTS = [
     "lr_bin_accumulate_i32", "lr_bin_stats_host_i32", "lr_fe_ref_of_jitter",
     "lr_dataset_create", "lr_dataset_create_host", "lr_dataset_destroy", "lr_state_eval_host", "lr_proposal_eval_host", "lr_loglik_direct",
     "lr_chains_create", "lr_chains_destroy", "lr_chains_records_per_run", "lr_chains_run", "lr_chains_run_host",
-    "lr_chains_counters_host", "lr_chains_team_stats_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
+    "lr_imputation_envelope", "lr_chains_counters_host", "lr_chains_team_stats_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
     "lr_chains_swap_info", "lr_chains_swap_apply", "lr_chains_swap_step", "lr_summarize_records", "lr_marginal_rates",
     "lr_trend_create", "lr_trend_create_host", "lr_trend_destroy", "lr_trend_record_doubles", "lr_trend_records_per_run",
     "lr_trend_run", "lr_trend_run_host", "lr_trend_eval_host", "lr_trend_state_host",
@@ -104,6 +104,7 @@ def load(build_if_missing=False):
     sig("lr_chains_run", C.c_int, vp, i64, i64, vp, vp)
     sig("lr_chains_run_host", C.c_int, vp, i64, i64, vp)
     sig("lr_chains_counters_host", C.c_int, vp, vp)
+    sig("lr_imputation_envelope", C.c_int, vp, vp, vp, vp, i32, i32, vp, vp)
     sig("lr_chains_team_stats_host", C.c_int, vp, vp)
     sig("lr_chains_get_state_host", C.c_int, vp, vp)
     sig("lr_chains_set_state_host", C.c_int, vp, vp)

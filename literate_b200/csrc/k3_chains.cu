@@ -166,7 +166,7 @@ __device__ __noinline__ void write_record(double* rec, long long it, Side L, Sid
         rec[6] = (double)M.K;
         rec[7] = hp.gL; rec[8] = hp.gM; rec[9] = hp.poi;
         rec[10] = adq[0]; rec[11] = adq[1]; rec[12] = adq[2];
-        rec[13] = (double)poi_is_init; rec[14] = beta; rec[15] = 0.0;
+        rec[13] = (double)poi_is_init; rec[14] = beta; rec[15] = poiA;      // [15]: the stored (possibly stale) priorPoiA of :300-304
     }
     rec[16 + lane] = lane < L.K ? L.r : 0.0;
     rec[48 + lane] = lane < L.K ? (lane == 0 ? d.start_time : L.t) : 0.0;

@@ -287,3 +287,51 @@ extern "C" int lr_summarize_records(lr_handle_t h, const double* d_records, int6
     }
     return LR_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Envelopes over imputation replicates (utilities/imputation_averager.py:23-61): per bin, mean / min / max over the
+// replicates of the empirical rates sp/br, ex/br and of br itself, straight from K1's device output.  One thread per
+// bin walks the replicates in order -- the accumulation order of numpy's mean(axis=0) over the stacked div.log tables,
+// so the means carry numpy's bits.  out: [9][n_bins] = death mean/min/max, birth mean/min/max, diversity mean/min/max.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k5_envelope_kernel(const long long* __restrict__ sp, const long long* __restrict__ ex, const double* __restrict__ br,
+                                   int n_rep, int nb, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    double s[3] = {0.0, 0.0, 0.0}, lo[3], hi[3];
+    for (int r = 0; r < n_rep; ++r) {
+        const double k = br[(size_t)r * nb + j];
+        const double v[3] = {(double)ex[(size_t)r * nb + j] / k, (double)sp[(size_t)r * nb + j] / k, k};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            s[q] += v[q];
+            // numpy's minimum / maximum propagate NaN (0/0 in an empty bin)
+            if (r == 0) { lo[q] = v[q]; hi[q] = v[q]; }
+            else {
+                lo[q] = (v[q] != v[q] || lo[q] != lo[q]) ? (v[q] != v[q] ? v[q] : lo[q]) : (v[q] < lo[q] ? v[q] : lo[q]);
+                hi[q] = (v[q] != v[q] || hi[q] != hi[q]) ? (v[q] != v[q] ? v[q] : hi[q]) : (v[q] > hi[q] ? v[q] : hi[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        out[(size_t)(3 * q + 0) * nb + j] = s[q] / (double)n_rep;
+        out[(size_t)(3 * q + 1) * nb + j] = lo[q];
+        out[(size_t)(3 * q + 2) * nb + j] = hi[q];
+    }
+}
+}  // namespace
+
+extern "C" int lr_imputation_envelope(lr_handle_t h, const int64_t* d_sp, const int64_t* d_ex, const double* d_br, int32_t n_rep, int32_t n_bins,
+                                      double* d_out, void* stream) {
+    LR_REQUIRE(h && d_sp && d_ex && d_br && d_out, "lr_imputation_envelope: null pointer");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_imputation_envelope: bad sizes");
+    LR_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    k5_envelope_kernel<<<(n_bins + 127) / 128, 128, 0, st>>>((const long long*)d_sp, (const long long*)d_ex, d_br, n_rep, n_bins, d_out);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return LR_OK;
+}

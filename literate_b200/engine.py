@@ -251,6 +251,17 @@ class Device:
         import torch
         return torch.zeros((n_rep, N.LR_ACC_ROWS, int(self.lib.lr_acc_stride(int(n_bins)))), dtype=torch.int64, device=device)
 
+    def imputation_envelope_device(self, sp, ex, br, stream=None):
+        """Mean / min / max over the replicates of ex/br, sp/br and br (lr_imputation_envelope; utilities/imputation_averager.py:23-61).
+        sp, ex: int64, br: float64 CUDA tensors [n_rep, n_bins] (the outputs of bin_stats_device).  Returns float64 [9, n_bins]."""
+        import torch
+        n_rep, nb = sp.shape
+        out = torch.empty((9, nb), dtype=torch.float64, device=sp.device)
+        N.check(self.lib.lr_imputation_envelope(self.h, C.c_void_p(sp.data_ptr()), C.c_void_p(ex.data_ptr()), C.c_void_p(br.data_ptr()),
+                                                int(n_rep), int(nb), C.c_void_p(out.data_ptr()), _stream_ptr(stream, sp.device)),
+                "lr_imputation_envelope")
+        return out
+
     def bin_finalize_device(self, acc, n_bins, fe_ref=0.5, stream=None):
         import torch
         n_rep = acc.shape[0]
@@ -382,7 +393,7 @@ def evaluate_proposals(ds: "Dataset", states, side, kind, idx, u_t, u_beta, gamm
 
 # field offsets of a sample record (include/literate_b200.h)
 REC_IT, REC_LIK, REC_PRIOR, REC_LAVG, REC_MAVG, REC_KL, REC_KM, REC_GL, REC_GM, REC_POI = range(10)
-REC_ADQ, REC_POI_INIT, REC_BETA = 10, 13, 14
+REC_ADQ, REC_POI_INIT, REC_BETA, REC_POIA = 10, 13, 14, 15
 REC_L, REC_TL, REC_M, REC_TM = 16, 48, 80, 112
 COUNTER_NAMES = ["iterations", "accepted", "lik_evals", "rate_updates", "move_shifts", "rj_proposals", "gibbs", "capacity_rejects",
                  "swaps_proposed", "swaps_accepted"]

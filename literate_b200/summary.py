@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import glob
 import os
+import sys
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -271,6 +272,60 @@ def combine_logs(mcmc_files, out_dir, burnin=0.2, thin=1, stem="COMBINED"):
     return os.path.join(out_dir, stem + "_mcmc.log")
 
 
+# ------------------------------------------------------------------------------------------ imputation replicates
+ENVELOPE_ROWS = ("ed_mean", "ed_min", "ed_max", "eb_mean", "eb_min", "eb_max", "nd_mean", "nd_min", "nd_max")
+
+
+def imputation_envelope(div_tables):
+    """utilities/imputation_averager.py:23-61 on stacked div.log tables [n_rep, n_bins, 3] (sp_events, ex_events, br_length):
+    mean / min / max over the replicates of the empirical death rate ex/br, the empirical birth rate sp/br and the net
+    diversity br.  Returns a dict of nine [n_bins] vectors (ENVELOPE_ROWS).  Host restatement; the device path is
+    engine.Device.imputation_envelope_device on K1's output."""
+    t = np.asarray(div_tables, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ed, eb, nd = t[:, :, 1] / t[:, :, 2], t[:, :, 0] / t[:, :, 2], t[:, :, 2]
+    out = {}
+    for tag, m in (("ed", ed), ("eb", eb), ("nd", nd)):
+        out[tag + "_mean"], out[tag + "_min"], out[tag + "_max"] = m.mean(axis=0), m.min(axis=0), m.max(axis=0)
+    return out
+
+
+def _averager_r_vec(name, v):
+    """print_R_vec of utilities/imputation_averager.py:8-21 (its own variant: no NA for vectors shorter than three)."""
+    if len(v) == 0:
+        return "%s=c()" % name
+    if len(v) == 1:
+        return "%s=c(%s)" % (name, v[0])
+    if len(v) == 2:
+        return "%s=c(%s,%s)" % (name, v[0], v[1])
+    w = ["NA" if np.isnan(x) else x for x in v]
+    return "%s=c(%s, " % (name, w[0]) + "".join("%s," % x for x in w[1:-1]) + "%s)" % w[-1]
+
+
+def format_imputation_envelope(env):
+    """The text utilities/imputation_averager.py prints (:39-61), byte for byte (np.set_printoptions(suppress=True, precision=3)
+    for the three net-diversity arrays, as :5-6)."""
+    lines = []
+    for title, tag in (("EMPIRICAL DEATH", "ed"), ("EMPIRICAL BIRTH", "eb")):
+        lines.append(title)
+        for k in ("mean", "min", "max"):
+            lines.append(_averager_r_vec("%s_%s" % (tag, k), env["%s_%s" % (tag, k)]))
+    lines.append("NET DIVERSITY")
+    with np.printoptions(suppress=True, precision=3):
+        for k in ("mean", "min", "max"):
+            lines.append(str(env["nd_" + k]))
+    return "\n".join(lines) + "\n"
+
+
+def imputation_average_logs(log_dir):
+    """The whole utility: every *div.log under `log_dir` (glob order, like the reference) -> the printed text."""
+    files = glob.glob(log_dir + "/*div.log")
+    if not files:
+        raise SystemExit("no *div.log under " + log_dir)
+    tables = [np.loadtxt(f, skiprows=1, ndmin=2) for f in files]
+    return format_imputation_envelope(imputation_envelope(np.stack(tables)))
+
+
 # ------------------------------------------------------------------------------------------ R output
 def r_vec(name, v):
     """`name=c(a, b,c,...)` exactly as print_R_vec formats it (plotRJforward.v3.py:31-50), NaN -> NA."""
@@ -332,7 +387,13 @@ def main(argv=None):
     p.add_argument('-logT', metavar='1', type=int, default=0)
     p.add_argument('-burnin', metavar='.2', type=float, default=.2)
     p.add_argument('-TBP', default=False, action='store_true')
+    p.add_argument('-imputations', metavar='0', type=int, default=0,
+                   help='1: print the envelopes of the empirical rates and net diversity over the *div.log files of the directory '
+                        '(utilities/imputation_averager.py) and stop')
     a = p.parse_args(argv)
+    if a.imputations == 1:
+        sys.stdout.write(imputation_average_logs(a.input_data))
+        return
     files = sorted(f for f in glob.glob("%s/*mcmc.log" % a.input_data) if not os.path.basename(f).startswith("COMBINED"))
     if not files:
         raise SystemExit("no *mcmc.log under " + a.input_data)

@@ -9,6 +9,7 @@ everything it produces is committed so that no test reads /root/reference at run
     python oracle/make_golden.py posterior_flags   # ~10 min: 8 reference chains per non-default flag set (example TAD)
     python oracle/make_golden.py prior_only   # ~2 min: 8 ORACLE chains on the example window with all statistics zero
     python oracle/make_golden.py plots       # ~30 s: the reference's plotRJforward.v3.py on two of the kat runs -> .r files
+    python oracle/make_golden.py averager    # seconds: utilities/imputation_averager.py on five synthetic imputation div.log files
     python oracle/make_golden.py posterior_syn   # ~10 min: 32 ORACLE chains on the bench statistics (syn-int 1M lineages x 200 bins)
 
 posterior / posterior_flags take the number of reference chains per fixture from LR_GOLDEN_CHAINS (default 32) and run at
@@ -220,6 +221,32 @@ def prior_only(n_chains=8):
     print("prior_only done")
 
 
+def averager():
+    """tests/golden/averager/: five div.log files (the reference's own writer format, LiteRateForward.py:558-564, produced by
+    the oracle from synth.syn_int imputation replicates, one of them with an empty first bin) and the text the UNMODIFIED
+    utilities/imputation_averager.py prints for that directory."""
+    from oracle import literate_oracle as O
+    from literate_b200 import synth
+    out = os.path.join(GOLD, "averager")
+    os.makedirs(out, exist_ok=True)
+    for r in range(5):
+        ts, te = synth.syn_int(3000, replicate=90 + r)
+        if r == 3:
+            ts[ts == ts.min()] += 1.0; ts[0] = 1800.0; te[0] = 1800.0 + 0.5      # bin 0: one birth, half a year at risk
+        st = O.bin_stats_fast(ts, te)
+        with open(os.path.join(out, "imputation_%d_div.log" % r), "w", newline="") as fh:
+            O.write_div_log(fh, st)
+    p = subprocess.run([sys.executable, os.path.join(REF, "utilities", "imputation_averager.py"), out], capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError(p.stderr[-2000:])
+    with open(os.path.join(out, "expected_stdout.txt"), "w") as fh:
+        fh.write(p.stdout)
+    with open(os.path.join(out, "file_order.json"), "w") as fh:
+        import glob as _g
+        json.dump([os.path.basename(f) for f in _g.glob(out + "/*div.log")], fh)
+    print(p.stdout[:400])
+
+
 SYN_N, SYN_ITERS, SYN_S, SYN_BURNIN = 1_000_000, 400001, 200, 0.5
 
 
@@ -285,4 +312,4 @@ def posterior(n_chains=N_CHAINS):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "kat"
     {"kat": kat, "posterior": posterior, "posterior_flags": posterior_flags, "prior_only": prior_only, "plots": plots,
-     "posterior_syn": posterior_syn}[what]()
+     "posterior_syn": posterior_syn, "averager": averager}[what]()

@@ -98,3 +98,22 @@ def test_hpd_intervals_on_the_device(device, metal_path):
     for name, hs in (("birth", host.birth), ("death", host.death)):
         assert np.array_equal(dv[name]["hpd_lo"], hs.hpd_lo) and np.array_equal(dv[name]["hpd_hi"], hs.hpd_hi)
     assert np.array_equal(dv["net_lo"], host.net_lo) and np.array_equal(dv["net_hi"], host.net_hi)
+
+
+def test_imputation_envelope_on_device_equals_the_host_restatement(device):
+    """lr_imputation_envelope on K1's device output (replicate axis = imputations) against summary.imputation_envelope, which
+    tests/test_summary_host.py pins to the unmodified utilities/imputation_averager.py: bit for bit, NaN bins included."""
+    import torch
+    from literate_b200 import summary as S, synth
+    tdev = torch.device("cuda:0")
+    n_rep, n, nb = 7, 20000, 200
+    ts, te = synth.syn_int_device(n, n_rep, tdev)
+    ts[:, 1:n] = torch.clamp(ts[:, 1:n], min=1803.0)          # bins 1 and 2 see no births, bin 0 exactly one lineage
+    sp, ex, br = device.bin_stats_device(ts[:, :n], te[:, :n], 1800, nb)
+    br[2, 5] = 0.0; sp[2, 5] = 0; ex[2, 5] = 0                 # an empty bin in one replicate: 0/0 = NaN, which numpy's min/max propagate
+    out = device.imputation_envelope_device(sp, ex, br).cpu().numpy()
+    tables = np.stack([sp.cpu().numpy().astype(float), ex.cpu().numpy().astype(float), br.cpu().numpy()], axis=2)
+    env = S.imputation_envelope(tables)
+    for k, name in enumerate(S.ENVELOPE_ROWS):
+        assert np.array_equal(out[k], env[name], equal_nan=True), name
+    assert np.isnan(out[:6, 5]).all()

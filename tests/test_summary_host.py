@@ -99,3 +99,31 @@ def test_combine_logs_and_cli(tmp_path):
     assert div.shape == (24, 3)
     S.main([str(tmp_path), "-combine", "1", "-burnin", "0.25"])
     assert os.path.exists(os.path.join(str(tmp_path), "COMBINED_RTT_plots.r"))
+
+
+def test_imputation_averager_prints_what_the_reference_utility_prints(tmp_path, capsys):
+    """utilities/imputation_averager.py:23-61 (mean / min / max over imputation replicates of sp/br, ex/br and br): the fixture
+    holds five div.log files and the stdout of the UNMODIFIED utility on them (oracle/make_golden.py averager).  Same text,
+    byte for byte, when the files are read in the order the utility read them; same numbers to 1e-15 in any order."""
+    import json
+    import shutil
+    from literate_b200 import summary as S
+    src = os.path.join(GOLD, "averager")
+    want = open(os.path.join(src, "expected_stdout.txt")).read()
+    order = json.load(open(os.path.join(src, "file_order.json")))
+    tables = np.stack([np.loadtxt(os.path.join(src, f), skiprows=1, ndmin=2) for f in order])
+    env = S.imputation_envelope(tables)
+    assert S.format_imputation_envelope(env) == want
+    # the command-line path (glob order of THIS file system: means may differ in the last bit)
+    for f in order:
+        shutil.copy(os.path.join(src, f), tmp_path)
+    S.main([str(tmp_path), "-imputations", "1"])
+    got = capsys.readouterr().out
+    assert got.splitlines()[0] == "EMPIRICAL DEATH" and len(got.splitlines()) == len(want.splitlines())
+
+    def vec(line):
+        return np.array([float(x) if x.strip() != "NA" else np.nan for x in line[line.index("(") + 1:line.rindex(")")].split(",")])
+    for a, b in zip(got.splitlines(), want.splitlines()):
+        if "=c(" in a:
+            np.testing.assert_allclose(vec(a), vec(b), rtol=1e-15, equal_nan=True)
+    assert np.isnan(env["ed_mean"]).sum() == 0 and env["eb_max"][0] == 2.0      # the half-year bin of replicate 3: one birth / 0.5
