@@ -133,6 +133,16 @@ int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t
                            double start_time, double end_time,
                            const int64_t* h_sp, const int64_t* h_ex, const double* h_br,
                            const int64_t* h_ex_dead, const double* h_br_dead, lr_dataset_t* out);
+/* The general form behind the four -model_BDI tables: per bin and side an event weight A_j and an exposure B_j,
+ *     likelihood = C + sum_j [A_birth_j log(lambda_j) - B_birth_j lambda_j] + sum_j [A_death_j log(mu_j) - B_death_j mu_j]
+ * with lambda_j / mu_j the rate of the segment bin j falls in.  HOST arrays [n_rep][n_bins] (h_C [n_rep] or NULL = 0);
+ * x_birth / x_death are the per-bin vectors calculate_r_squared regresses the rates on (literate_library.py:268-279).
+ * Replaces the `-proportion 1` likelihood of LiteRateForward-proportion.py:157-162 (A = interpolated yearly counts of a
+ * series where its running total is positive, B = that mask, x = the counts, :585-598, :627-628); model_tag is what
+ * lr_chain_config.model_BDI must then be (1 there, :442-444). */
+int lr_dataset_create_general_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t model_tag, double start_time, double end_time,
+                                   const double* h_A_birth, const double* h_B_birth, const double* h_A_death, const double* h_B_death,
+                                   const double* h_x_birth, const double* h_x_death, const double* h_C, lr_dataset_t* out);
 int lr_dataset_destroy(lr_dataset_t ds);
 
 #define LR_KMAX 30   /* most rates per side a state can hold (slots of one warp minus two control lanes) */

@@ -95,6 +95,33 @@ __global__ void k2_build_tables(const long long* __restrict__ sp, const long lon
     }
 }
 
+// General form of the same tables: per bin and side an event weight A_j and an exposure B_j, the likelihood being
+//     C + sum_j [ A^b_j log(lambda_j) - B^b_j lambda_j ] + sum_j [ A^d_j log(mu_j) - B^d_j mu_j ]
+// (every likelihood of the reference has this shape; the four -model_BDI tables above are instances).  Used for the
+// `-proportion 1` variant (LiteRateForward-proportion.py:157-162): A = interpolated yearly counts of a series masked by its
+// running total > 0, B = that mask, C = 0; x_b / x_d are the vectors calculate_r_squared regresses on (:627-628: the counts).
+__global__ void k2_build_tables_general(const double* __restrict__ Ab, const double* __restrict__ Bb, const double* __restrict__ Ad,
+                                        const double* __restrict__ Bd, const double* __restrict__ xb, const double* __restrict__ xd,
+                                        const double* __restrict__ C, int nb, double* __restrict__ tab_all, double* __restrict__ cst_all) {
+    const int rep = blockIdx.x, t = threadIdx.x;
+    double* tab = tab_all + (size_t)rep * LR_NTAB * (nb + 1);
+    const size_t o = (size_t)rep * nb;
+    if (t < LR_NTAB) {
+        const double* src = t == T_AB ? Ab : (t == T_BB ? Bb : (t == T_AD ? Ad : (t == T_BD ? Bd : (t == T_XB ? xb : xd))));
+        double acc = 0.0;
+        double* T = tab + (size_t)t * (nb + 1);
+        T[0] = 0.0;
+        for (int j = 0; j < nb; ++j) { acc += src[o + j]; T[j + 1] = acc; }
+    } else if (t == 32) {
+        double sx = 0.0, sxx = 0.0;
+        for (int j = 0; j < nb; ++j) { sx += xb[o + j] + xd[o + j]; sxx += xb[o + j] * xb[o + j] + xd[o + j] * xd[o + j]; }
+        cst_all[rep * LR_NCST + 0] = C ? C[rep] : 0.0;
+        cst_all[rep * LR_NCST + 1] = sx;
+        cst_all[rep * LR_NCST + 2] = sxx;
+        cst_all[rep * LR_NCST + 3] = 0.0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-warp random numbers
 // ------------------------------------------------------------------------------------------------
@@ -1209,6 +1236,47 @@ extern "C" int lr_dataset_create_host(lr_handle_t h, int32_t n_rep, int32_t n_bi
                            dead ? (const double*)(w + cnt * 32) : nullptr, h->stream, out);
     if (rc != LR_OK) return rc;
     LR_CUDA(cudaStreamSynchronize(h->stream));
+    return LR_OK;
+}
+
+extern "C" int lr_dataset_create_general_host(lr_handle_t h, int32_t n_rep, int32_t n_bins, int32_t model_tag, double start_time, double end_time,
+                                              const double* h_A_birth, const double* h_B_birth, const double* h_A_death, const double* h_B_death,
+                                              const double* h_x_birth, const double* h_x_death, const double* h_C, lr_dataset_t* out) {
+    LR_REQUIRE(h && out && h_A_birth && h_B_birth && h_A_death && h_B_death && h_x_birth && h_x_death, "lr_dataset_create_general_host: null pointer");
+    LR_REQUIRE(n_rep >= 1 && n_bins >= 1, "lr_dataset_create_general_host: bad sizes");
+    LR_REQUIRE(model_tag >= 0 && model_tag <= 3, "lr_dataset_create_general_host: model_tag must be 0..3 (what lr_chain_config.model_BDI will be checked against)");
+    LR_REQUIRE(end_time > start_time && start_time >= 0.0, "lr_dataset_create_general_host: need 0 <= start_time < end_time");
+    LR_REQUIRE((long long)floor(end_time) - (long long)floor(start_time) == n_bins,
+               "lr_dataset_create_general_host: n_bins must equal floor(end_time) - floor(start_time)");
+    LR_CUDA(cudaSetDevice(h->device));
+    int rc = upload_lnfact();
+    if (rc != LR_OK) return rc;
+    const size_t cnt = (size_t)n_rep * n_bins;
+    rc = lr_ws_acquire(h, (6 * cnt + n_rep) * sizeof(double), h->stream);
+    if (rc != LR_OK) return rc;
+    double* w = (double*)h->ws;
+    const double* src[6] = {h_A_birth, h_B_birth, h_A_death, h_B_death, h_x_birth, h_x_death};
+    for (int k = 0; k < 6; ++k) LR_CUDA(cudaMemcpyAsync(w + k * cnt, src[k], cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h_C) LR_CUDA(cudaMemcpyAsync(w + 6 * cnt, h_C, (size_t)n_rep * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    lr_dataset_t ds = new lr_dataset_s();
+    ds->h = h; ds->n_rep = n_rep; ds->n_bins = n_bins; ds->model = model_tag;
+    ds->start_time = start_time; ds->end_time = end_time; ds->s0f = (int)floor(start_time);
+    ds->tab = nullptr; ds->cst = nullptr;
+    ds->last.s = h->stream; ds->last.valid = 1;
+    cudaError_t e = cudaMallocAsync((void**)&ds->tab, (size_t)n_rep * LR_NTAB * (n_bins + 1) * sizeof(double), h->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&ds->cst, (size_t)n_rep * LR_NCST * sizeof(double), h->stream);
+    if (e != cudaSuccess) {
+        lr_set_error("lr_dataset_create_general_host: cudaMallocAsync failed: %s", cudaGetErrorString(e));
+        if (ds->tab) cudaFreeAsync(ds->tab, h->stream);
+        delete ds;
+        return LR_ERR_NOMEM;
+    }
+    k2_build_tables_general<<<n_rep, 64, 0, h->stream>>>(w, w + cnt, w + 2 * cnt, w + 3 * cnt, w + 4 * cnt, w + 5 * cnt, h_C ? w + 6 * cnt : nullptr,
+                                                           n_bins, ds->tab, ds->cst);
+    LR_CUDA(cudaGetLastError());
+    h->launches += 1;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    *out = ds;
     return LR_OK;
 }
 

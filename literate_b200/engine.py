@@ -315,6 +315,26 @@ class Dataset:
         self.ds = ds
         return self
 
+    @classmethod
+    def from_tables(cls, dev: Device, A_birth, B_birth, A_death, B_death, x_birth, x_death, start_time, end_time, model_tag=1, C_const=None):
+        """General piecewise-constant Poisson likelihood (lr_dataset_create_general_host): per bin and side an event weight A and
+        an exposure B, likelihood = C + sum A_b log(lambda) - B_b lambda + sum A_d log(mu) - B_d mu.  Host arrays [n_bins] or
+        [n_rep, n_bins]; x_* are the vectors the adequacy regression uses.  The `-proportion 1` variant is built this way."""
+        self = cls.__new__(cls)
+        arrs = [np.atleast_2d(np.ascontiguousarray(a, dtype=np.float64)) for a in (A_birth, B_birth, A_death, B_death, x_birth, x_death)]
+        self.dev, self.model_BDI = dev, int(model_tag)
+        self.start_time, self.end_time = float(start_time), float(end_time)
+        self.n_rep, self.n_bins = arrs[0].shape
+        if any(a.shape != arrs[0].shape for a in arrs):
+            raise ValueError("the six tables must have the same shape")
+        cc = None if C_const is None else np.ascontiguousarray(np.broadcast_to(np.asarray(C_const, np.float64), (self.n_rep,)))
+        ds = C.c_void_p()
+        N.check(dev.lib.lr_dataset_create_general_host(dev.h, self.n_rep, self.n_bins, self.model_BDI, self.start_time, self.end_time,
+                                                       *[N.np_ptr(np.ascontiguousarray(a)) for a in arrs], N.np_ptr(cc), C.byref(ds)),
+                "lr_dataset_create_general_host")
+        self.ds = ds
+        return self
+
     def close(self):
         if getattr(self, "ds", None):
             self.dev.lib.lr_dataset_destroy(self.ds)

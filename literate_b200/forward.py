@@ -64,6 +64,8 @@ def build_parser():
     p.add_argument('-update_fraction', type=float, help='', default=0.75, metavar=0.75)
     p.add_argument('-out', type=str, help='output name suffix', default="", metavar="")
     p.add_argument('-rev_se', type=int, help='reversed order of ts and te in input file', default=0, metavar=0)
+    p.add_argument('-proportion', type=int, help='turns ts and te into independent immigration processes (the flag of '
+                   'LiteRateForward-proportion.py; output files are then named <table>_PR_seed<seed>)', default=0, metavar=0)
     # ---- not in the reference
     p.add_argument('-chains', type=int, help='number of independent chains run concurrently on the GPU', default=1, metavar=1)
     p.add_argument('-device', type=int, help='CUDA device index', default=0, metavar=0)
@@ -209,6 +211,8 @@ def run(args, device=None):
         raise SystemExit("-chains must be at least the number of GPUs")
     out_name = MODEL_SUFFIX[args.model_BDI] + args.out
     only_dead = args.model_BDI == 3
+    if args.proportion == 1:
+        return _run_proportion(args, rseed, device, lead, world, rank, local_rank)
 
     # -d may name a DIRECTORY of tables (stochastic imputations of one data set, the reference's "100 chains on 100
     # imputations" workflow, 3_interpreting_literate_results_final.ipynb:208): every table is one replicate, binned in the
@@ -352,6 +356,7 @@ def run(args, device=None):
     for w in writers:
         w.close()
     cnt = chains.counters().sum(0)
+    _warn_capacity(chains)
     if not args.quiet:
         print("literate_b200: %d chains x %d iterations in %.3f s (%.3g it/s, %.3g likelihood evaluations/s); binning %.4f s"
               % (n_local * T, args.n, t_run, n_local * T * args.n / max(t_run, 1e-9), cnt[2] / max(t_run, 1e-9), t_bin))
@@ -359,6 +364,78 @@ def run(args, device=None):
             print("literate_b200: %d swap rounds, %.3f of the proposed temperature swaps accepted" % (rounds, cnt[9] / max(cnt[8], 1)))
     chains.close(); ds.close()
     return paths
+
+
+def _run_proportion(args, rseed, device, lead, world, rank, local_rank):
+    """`-proportion 1` (LiteRateForward-proportion.py): other statistics and likelihood tables, the same chains and log rows."""
+    from . import proportion as PR
+    if os.path.isdir(args.d):
+        raise SystemExit("-proportion 1 takes one table")
+    if args.temper != 1:
+        raise SystemExit("-proportion 1 does not combine with -temper")
+    ts, te, start_time, end_time = PR.read_series(args.d, args.death_jitter)
+    sp, ex, kn, kd = PR.series_stats(ts, te, start_time, end_time)
+    if lead:
+        print(te)                                              # :487
+        print(sp, ex, kn, kd)                                  # :599
+    out_dir = os.path.dirname(args.d) or os.getcwd()
+    out_dir = "%s/literate_mcmc_logs" % out_dir
+    try:
+        os.mkdir(out_dir)
+    except OSError as e:
+        if lead:
+            print(e)
+    file_name = os.path.splitext(os.path.basename(args.d))[0]
+    out_name = "_PR" + "_seed" + str(args.seed) + args.out          # :442-445 (the seed as given, -1 included)
+    if args.rm_first_bin:
+        sp, ex, kn, kd = sp[1:], ex[1:], kn[1:], kd[1:]            # :607-613 (the reference then dies in the rate index, as without the flag)
+        start_time = float(np.floor(start_time) + 1)
+    dev = device if device is not None else E.Device(local_rank if world > 1 else args.device)
+    ds = E.Dataset.from_tables(dev, start_time=start_time, end_time=end_time, model_tag=1, **PR.likelihood_tables(sp, ex, kn, kd))
+    cfg = E.default_config(1, args.const_rates, args.const_death_rate, args.use_rate_HP, args.Poisson_prior, args.update_fraction,
+                           args.real_move_shift)
+    c0, n_local = P.shard_range(args.chains, world, rank)
+    chains = E.Chains(ds, n_local, rseed, cfg, chain_id0=c0)
+    writers, paths = [], []
+    for k in range(c0, c0 + n_local):
+        st = "%s/%s%s" % (out_dir, file_name, out_name) + ("_chain%d" % k if args.chains > 1 else "")
+        writers.append(ChainLogWriter(st, args.calc_adequacy, args.pyrate_output, start_time, end_time, 0, args.Poisson_prior))
+        paths.append(st + "_mcmc.log")
+        PR.write_div_log(st + "_div.log", sp, ex, kn, kd)
+    s_freq, p_freq = max(1, args.s), max(1, args.p)
+    every = int(np.gcd(s_freq, p_freq))
+    per_launch = max(every, (args.launch_iters if args.launch_iters > 0 else 1_000_000) // every * every)
+    done = 0
+    t_run = time.time()
+    while done < args.n:
+        n_it = min(per_launch, args.n - done)
+        recs = chains.run(n_it, every)
+        for r in range(recs.shape[0]):
+            it = int(recs[r, 0, E.REC_IT])
+            if it % s_freq == 0:
+                for k in range(n_local):
+                    writers[k].write(recs[r, k])
+            if it % p_freq == 0 and not args.quiet:
+                _print_state(recs[r, 0], float(end_time), args.calc_adequacy)
+        done += n_it
+    t_run = time.time() - t_run
+    for w in writers:
+        w.close()
+    _warn_capacity(chains)
+    if not args.quiet:
+        print("literate_b200: %d chains x %d iterations in %.3f s (%.3g it/s)" % (n_local, args.n, t_run, n_local * args.n / max(t_run, 1e-9)))
+    chains.close(); ds.close()
+    return paths
+
+
+def _warn_capacity(chains):
+    """An add-shift proposal on a side that already holds LR_KMAX rates is rejected on the device; the reference would have
+    evaluated it (its only bound is the spacing guard, LiteRateForward.py:290, i.e. K <= n_bins).  Tell the user if that happened."""
+    rej = int(chains.counters()[:, 7].sum())
+    if rej:
+        warn("literate_b200: %d add-shift proposals were rejected because a side already held LR_KMAX = %d rates; "
+             "the reference has no such limit below n_bins, so this run may differ from it in the far tail of the number of shifts"
+             % (rej, E.LR_KMAX), RuntimeWarning)
 
 
 def main(argv=None):

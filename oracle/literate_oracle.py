@@ -473,7 +473,7 @@ def mcmc_header(calc_adequacy):
     return "\t".join(cols) + "\n"
 
 
-def run_chain(lin: Lineages, stats: BinStats, cfg: ChainConfig, seed, logs: ChainLogs = None):
+def run_chain(lin: Lineages, stats: BinStats, cfg: ChainConfig, seed, logs: ChainLogs = None, lik_fn=None, emp=None):
     """runMCMC (:216-373) with the initial draw of :580-583 and the seeding of :405-409.
 
     Uses the legacy global ``np.random`` stream in exactly the reference's draw order, so
@@ -489,13 +489,15 @@ def run_chain(lin: Lineages, stats: BinStats, cfg: ChainConfig, seed, logs: Chai
     span = end_time - start_time
 
     def lik_of(L, iL, M, iM):
+        if lik_fn is not None:             # another likelihood on the same per-bin rate vectors (oracle/proportion_oracle.py)
+            return lik_fn(L[iL], M[iM])
         if cfg.model_BDI <= 1:
             return loglik_bdi(L[iL], M[iM], stats, cfg.model_BDI)
         return loglik_keiding(L[iL], M[iM], stats, only_dead)
 
     if cfg.calc_adequacy:
         with np.errstate(divide="ignore", invalid="ignore"):
-            emp_b, emp_d = stats.sp / stats.br, stats.ex / stats.br     # literate_library.py:260-266
+            emp_b, emp_d = emp if emp is not None else (stats.sp / stats.br, stats.ex / stats.br)     # literate_library.py:260-266
 
     L_acc = np.random.gamma(2, 2, 1)        # :580
     M_acc = np.random.gamma(2, 2, 1)        # :581
