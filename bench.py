@@ -297,6 +297,7 @@ def run_cuda(a):
         dist.init_process_group("nccl", device_id=tdev)
     n_gpus = world
 
+    bound_cpus = E.bind_host_to_gpu(local)                 # pinned buffers below are first-touched on the GPU's NUMA node
     dev = E.Device(local)
     n, nb, chains = a.lineages, N_BINS, a.chains
     n_rep = 1 if a.shared_dataset else chains
@@ -535,7 +536,8 @@ def run_cuda(a):
             line["e2e"] = {"value": n_gpus * chains * a.iters / e2e_step_s, "unit": UNIT, "h2d_bytes_per_step": e2e[1],
                            "d2h_bytes_per_step": e2e[2], "ms_per_step": 1e3 * e2e_step_s,
                            "h2d_GBps_per_rank": e2e[1] / e2e_step_s / 1e9,
-                           "host_table": "fp64 (ts, te), 16 B per lineage: the arrays the reference's parser holds (LiteRateForward.py:440-471)"}
+                           "host_table": "fp64 (ts, te), 16 B per lineage: the arrays the reference's parser holds (LiteRateForward.py:440-471)",
+                           "cpu_affinity": "GPU-local CPUs (%d of %d)" % (len(bound_cpus), os.cpu_count()) if bound_cpus else "unchanged (NVML reports no GPU-local subset)"}
             if len(e2e) > 3 and e2e_i32_step_s > 0:
                 line["e2e_i32"] = {"value": n_gpus * chains * a.iters / e2e_i32_step_s, "unit": UNIT, "h2d_bytes_per_step": e2e[4],
                                    "d2h_bytes_per_step": e2e[2], "ms_per_step": 1e3 * e2e_i32_step_s,

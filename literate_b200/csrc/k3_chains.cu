@@ -1531,6 +1531,17 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
         if (lead < 1) lead = 1;
         if (lead > 7) lead = 7;
         P.team_bail = (c->it_host >= 0 && !(e_nobail && atoi(e_nobail))) ? 1 : 0;
+        // Shared-memory carve-out: an SM serves kernels of different streams side by side only if its configured carve-out
+        // already holds all of them; a K1 batch of the NEXT table (41 KB for five CTAs) launched while teams run on the default
+        // 16 KB configuration waits for whole SMs to drain -- measured: one K1 launch delayed by 16 ms, the copy engine idle
+        // for 13 of the 87 ms of a table.  Ask for 64 KB (28 % of 228) so that K1 fits next to the teams.
+        static bool carve_set = false;
+        if (!carve_set) {
+            cudaFuncSetAttribute(k3_team_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
+            cudaFuncSetAttribute(k3_team_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
+            cudaFuncSetAttribute(k3_team_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
+            carve_set = true;
+        }
         auto launch_team = [&]() {
             if (W >= 16) k3_team_kernel<16><<<c->n_chains, 512, 0, st>>>(P, lead);
             else if (W >= 8) k3_team_kernel<8><<<c->n_chains, 256, 0, st>>>(P, lead);

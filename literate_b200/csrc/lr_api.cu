@@ -1,5 +1,6 @@
 // Runtime part of the C ABI: handles, error reporting, workspace, host-buffer entry point of K1.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "lr_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -45,7 +46,7 @@ extern "C" int lr_create(int device, lr_handle_t* out) {
     }
     LR_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) LR_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2 * LR_NSTAGE; ++i) LR_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
     LR_CUDA(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
     *out = h;
     return LR_OK;
@@ -58,9 +59,8 @@ extern "C" int lr_destroy(lr_handle_t h) {
     cudaStreamSynchronize(h->copy_stream);
     if (h->ws_used) cudaDeviceSynchronize();        // the workspace's last user may have been a caller stream
     cudaFree(h->ws);
-    cudaFree(h->stage[0]);
-    cudaFree(h->stage[1]);
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < LR_NSTAGE; ++i) cudaFree(h->stage[i]);
+    for (int i = 0; i < 2 * LR_NSTAGE; ++i) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_order);
     cudaStreamDestroy(h->stream);
     cudaStreamDestroy(h->copy_stream);
@@ -122,12 +122,12 @@ static int stage_reserve(lr_handle_t h, size_t bytes) {
     if (bytes <= h->stage_bytes) return LR_OK;
     LR_CUDA(cudaStreamSynchronize(h->stream));
     LR_CUDA(cudaStreamSynchronize(h->copy_stream));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < LR_NSTAGE; ++i) {
         if (h->stage[i]) LR_CUDA(cudaFree(h->stage[i]));
         h->stage[i] = nullptr;
     }
     h->stage_bytes = 0;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < LR_NSTAGE; ++i) {
         cudaError_t e = cudaMalloc(&h->stage[i], bytes);
         if (e != cudaSuccess) {
             lr_set_error("staging allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
@@ -166,30 +166,66 @@ static int bin_stats_host_impl(lr_handle_t h, const void* h_ts, const void* h_te
     if (n > 0) {
         const int64_t align = 16 / elem;                            // row pitch that keeps 128-bit loads aligned
         const int64_t ldp = (n + align - 1) / align * align;
-        int64_t per_batch = ((int64_t)96 << 20) / (ldp * 2 * elem); // ~96 MB of (ts, te) per batch
+        static int stage_mb = 0;                                    // development knob: LR_STAGE_MB (default 64 MB of (ts, te) per batch)
+        if (!stage_mb) { const char* e = getenv("LR_STAGE_MB"); stage_mb = e && atoi(e) > 0 ? atoi(e) : 64; }
+        int64_t per_batch = ((int64_t)stage_mb << 20) / (ldp * 2 * elem);
         if (per_batch < 1) per_batch = 1;
         if (per_batch > n_rep) per_batch = n_rep;
         const size_t half = (size_t)per_batch * ldp * elem;
         rc = stage_reserve(h, 2 * half);
         if (rc != LR_OK) return rc;
         int batch = 0;
+        // development aid (LR_DEBUG_TIMELINE=1): time stamps of every batch's copies and kernel on their streams
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("LR_DEBUG_TIMELINE"); dbg = e && atoi(e) ? 1 : 0; }
+        const int max_dbg = 512;
+        cudaEvent_t* te = nullptr;
+        if (dbg) {
+            te = new cudaEvent_t[4 * max_dbg];
+            for (int i = 0; i < 4 * max_dbg; ++i) cudaEventCreate(&te[i]);
+        }
         for (int64_t r0 = 0; r0 < n_rep; r0 += per_batch, ++batch) {
-            const int buf = batch & 1;
+            const int buf = batch % LR_NSTAGE;
             const int64_t nr = (n_rep - r0 < per_batch) ? (n_rep - r0) : per_batch;
             char* s_ts = (char*)h->stage[buf];
             char* s_te = (char*)h->stage[buf] + half;
-            if (batch >= 2) LR_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev[2 + buf], 0));     // kernel of batch-2 released the buffer
-            LR_CUDA(cudaMemcpy2DAsync(s_ts, ldp * elem, (const char*)h_ts + r0 * ld * elem, ld * elem, n * elem, nr, cudaMemcpyHostToDevice, h->copy_stream));
-            LR_CUDA(cudaMemcpy2DAsync(s_te, ldp * elem, (const char*)h_te + r0 * ld * elem, ld * elem, n * elem, nr, cudaMemcpyHostToDevice, h->copy_stream));
+            if (batch >= LR_NSTAGE) LR_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev[LR_NSTAGE + buf], 0));     // the kernel that read this buffer last is done
+            if (dbg && batch < max_dbg) cudaEventRecord(te[4 * batch + 0], h->copy_stream);
+            if (ld == ldp && ld == n) {      // rows back to back on both sides: one linear copy per array
+                LR_CUDA(cudaMemcpyAsync(s_ts, (const char*)h_ts + r0 * ld * elem, (size_t)nr * n * elem, cudaMemcpyHostToDevice, h->copy_stream));
+                LR_CUDA(cudaMemcpyAsync(s_te, (const char*)h_te + r0 * ld * elem, (size_t)nr * n * elem, cudaMemcpyHostToDevice, h->copy_stream));
+            } else {
+                LR_CUDA(cudaMemcpy2DAsync(s_ts, ldp * elem, (const char*)h_ts + r0 * ld * elem, ld * elem, n * elem, nr, cudaMemcpyHostToDevice, h->copy_stream));
+                LR_CUDA(cudaMemcpy2DAsync(s_te, ldp * elem, (const char*)h_te + r0 * ld * elem, ld * elem, n * elem, nr, cudaMemcpyHostToDevice, h->copy_stream));
+            }
+            if (dbg && batch < max_dbg) cudaEventRecord(te[4 * batch + 1], h->copy_stream);
             LR_CUDA(cudaEventRecord(h->ev[buf], h->copy_stream));
             LR_CUDA(cudaStreamWaitEvent(h->stream, h->ev[buf], 0));
+            if (dbg && batch < max_dbg) cudaEventRecord(te[4 * batch + 2], h->stream);
             int64_t* acc_r = d_acc + (size_t)r0 * LR_ACC_ROWS * stride;
             rc = elem == 8 ? lr_bin_accumulate(h, (const double*)s_ts, (const double*)s_te, n, ldp, (int32_t)nr, first_bin, n_bins, fe_ref, dead_only,
                                                end_time, acc_r, h->stream)
                            : lr_bin_accumulate_i32(h, (const int32_t*)s_ts, (const int32_t*)s_te, n, ldp, (int32_t)nr, first_bin, n_bins, frac,
                                                    dead_only, end_time, acc_r, h->stream);
             if (rc != LR_OK) return rc;
-            LR_CUDA(cudaEventRecord(h->ev[2 + buf], h->stream));
+            LR_CUDA(cudaEventRecord(h->ev[LR_NSTAGE + buf], h->stream));
+            if (dbg && batch < max_dbg) cudaEventRecord(te[4 * batch + 3], h->stream);
+        }
+        if (dbg) {
+            cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_stream);
+            const int nbt = batch < max_dbg ? batch : max_dbg;
+            float copy_busy = 0, k_busy = 0, span = 0, k_max = 0, gap = 0;
+            for (int b = 0; b < nbt; ++b) {
+                float c = 0, k = 0;
+                cudaEventElapsedTime(&c, te[4 * b], te[4 * b + 1]); cudaEventElapsedTime(&k, te[4 * b + 2], te[4 * b + 3]);
+                copy_busy += c; k_busy += k; if (k > k_max) k_max = k;
+                if (b > 0) { float g = 0; cudaEventElapsedTime(&g, te[4 * (b - 1) + 1], te[4 * b]); gap += g; }
+            }
+            cudaEventElapsedTime(&span, te[0], te[4 * (nbt - 1) + 3]);
+            fprintf(stderr, "[lr timeline] %d batches: span %.2f ms, copies busy %.2f ms, idle between copies %.2f ms, kernels busy %.2f ms (max %.3f)\n",
+                    nbt, span, copy_busy, gap, k_busy, k_max);
+            for (int i = 0; i < 4 * max_dbg; ++i) cudaEventDestroy(te[i]);
+            delete[] te;
         }
     }
     rc = lr_bin_finalize(h, d_acc, n_rep, n_bins, fe_ref, d_sp, d_ex, d_br, h->stream);

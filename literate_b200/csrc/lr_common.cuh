@@ -43,13 +43,17 @@ void lr_set_error(const char* fmt, ...);
         }                                                                                    \
     } while (0)
 
+// staging buffers of the host-buffer entry points: enough in flight that the copy engine never waits for a K1 batch, even when
+// another kernel (the chains of the previous table) leaves K1 only a few SMs
+#define LR_NSTAGE 4
+
 struct lr_handle_s {
     int device;
     int sm_count;
     int max_smem_optin;
     cudaStream_t stream;        // compute
     cudaStream_t copy_stream;   // host<->device staging
-    cudaEvent_t ev[4];
+    cudaEvent_t ev[2 * LR_NSTAGE];   // [buf] copy of a batch done, [LR_NSTAGE + buf] its kernel done
     int64_t launches;           // kernels launched through this handle
     // grow-only workspace, handed from one entry point to the next IN STREAM ORDER (lr_ws_acquire)
     void* ws;
@@ -57,7 +61,7 @@ struct lr_handle_s {
     cudaStream_t ws_stream;     // stream of the workspace's last user
     int ws_used;
     cudaEvent_t ev_order;       // scratch event of lr_order
-    void* stage[2];
+    void* stage[LR_NSTAGE];
     size_t stage_bytes;
 };
 

@@ -597,6 +597,28 @@ def run_rjmcmc(dev: Device, ts, te, n_chains, n_iter, sample_every, seed=1, cfg:
     return rec, stats
 
 
+def bind_host_to_gpu(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (same NUMA node / PCIe root), so that pinned host
+    buffers allocated afterwards are first-touched on that node and the copy engine does not cross the inter-socket link.
+    Returns the CPU list, or None when NVML has nothing better than "all CPUs" to offer.  Plumbing; call it before allocating."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:                    # noqa: BLE001 -- no NVML / not permitted: leave the affinity alone
+        return None
+
+
 class Pipeline:
     """The hot path over a stream of batches, double-buffered: while the chains of batch k run (K3: no memory traffic),
     the tables of batch k+1 are copied to the device and binned (PCIe + K1: hardly any SM time).  Two handles on the same
