@@ -62,9 +62,11 @@ def load(build_if_missing=False):
         from . import build as _b
         try:
             _b.build()
-        except Exception:
-            if not os.path.exists(LIB_PATH):
-                raise
+        except Exception as e:
+            # a library that does not match its sources is not silently used: the ABI version alone would not notice
+            if not os.path.exists(LIB_PATH) or not os.environ.get("LR_ALLOW_STALE_LIB"):
+                raise NativeError("rebuilding libliterate_b200.so failed (%s); set LR_ALLOW_STALE_LIB=1 to load the existing, "
+                                  "possibly stale library" % e) from e
     if not os.path.exists(LIB_PATH):
         raise NativeError(
             f"{LIB_PATH} is missing. Build it with `python -m literate_b200.build` (needs nvcc); "

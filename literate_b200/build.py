@@ -38,16 +38,36 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile if sources changed; returns the path of the shared library."""
-    os.makedirs(OUT_DIR, exist_ok=True)
+def _up_to_date(dig):
     stamp = os.path.join(OUT_DIR, "build.sha256")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig
+
+
+def build(force=False, verbose=False):
+    """Compile if sources changed; returns the path of the shared library.  Safe under torchrun: ranks serialise on a file
+    lock, the first one compiles into rank-private object files and renames the finished library into place, the others
+    find it up to date."""
+    import fcntl
+    os.makedirs(OUT_DIR, exist_ok=True)
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    if not force and _up_to_date(dig):
         return LIB
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(dig):
+                return LIB
+            return _build_locked(dig, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig, verbose):
+    stamp = os.path.join(OUT_DIR, "build.sha256")
     nvcc = _nvcc()
     objs = []
     log = []
+    tmp_lib = LIB + ".tmp%d" % os.getpid()
     for src in SOURCES:
         obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
@@ -57,12 +77,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(log[-1])
             raise RuntimeError("nvcc failed on " + src)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib] + objs
     p = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + p.stdout + p.stderr)
     if p.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link failed")
+    os.replace(tmp_lib, LIB)
     with open(os.path.join(OUT_DIR, "build.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(stamp, "w") as fh:

@@ -390,7 +390,8 @@ __device__ __forceinline__ bool propose_add(const Side& cur, Side& nw, const Dat
     const double er = xexp<C>(lane == 1 ? lr2 : lr1);              // both exponentials in one call (lanes 0 and 1)
     const double r1 = __shfl_sync(0xffffffffu, er, 0), r2 = __shfl_sync(0xffffffffu, er, 1);
     const double rs = r1 + r2;
-    hasting = xlog<C>(fabs(gap) * rs * rs) - q.ln_beta - lr_i;            // log|gap| + 2 log(r1 + r2): one logarithm
+    // log|gap| + 2 log(r1 + r2): one logarithm (two where the square would leave fp64)
+    hasting = ((rs > 1e-150 && rs < 1e150) ? xlog<C>(fabs(gap) * rs * rs) : xlog<C>(fabs(gap)) + 2.0 * xlog<C>(rs)) - q.ln_beta - lr_i;
     // shift slots above i up by one
     const double ur = __shfl_up_sync(0xffffffffu, cur.r, 1);
     const double ulr = __shfl_up_sync(0xffffffffu, cur.lr, 1);
@@ -428,7 +429,9 @@ __device__ __forceinline__ void propose_remove(const Side& cur, Side& nw, const 
     // -log dT + lnBeta(u) + lm - 2 log(ra + rb), lnBeta(u) = 9 (lra + lrb - 2 log(ra + rb)) - norm: the three logarithms of
     // the reference collapse into  -log(dT (ra + rb)^20)  (rates within 1e-15 .. 1e15 keep the power inside fp64)
     const double s1 = ra + rb, s2 = s1 * s1, s4 = s2 * s2, s8 = s4 * s4, s16 = s8 * s8;
-    hasting = (LR_SHAPE_BETA - 1.0) * (lra + lrb) - LR_BETA_NORM + lm - xlog<C>(dT * (s16 * s4));
+    // (s1^20 leaves fp64 for rates beyond ~1e-15 .. 1e15: there the two logarithms are taken separately, as the reference does)
+    const double lg = (s1 > 1e-14 && s1 < 1e14) ? xlog<C>(dT * (s16 * s4)) : xlog<C>(dT) + 20.0 * xlog<C>(s1);
+    hasting = (LR_SHAPE_BETA - 1.0) * (lra + lrb) - LR_BETA_NORM + lm - lg;
     const double dr = __shfl_down_sync(0xffffffffu, cur.r, 1);
     const double dlr = __shfl_down_sync(0xffffffffu, cur.lr, 1);
     const double dt = __shfl_down_sync(0xffffffffu, cur.t, 1);
