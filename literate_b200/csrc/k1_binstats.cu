@@ -73,25 +73,40 @@ __device__ __forceinline__ void add96(unsigned* arr, unsigned nb, unsigned idx, 
     }
 }
 
-// Fraction of one lineage into the 96-bit accumulator of its bin.  `merge` (warp-uniform, decided once per segment from the
-// first lineages the warp sees): the table looks sorted by year, i.e. the lanes of a warp mostly hit ONE bin and 32 carry chains
-// on one word would serialise (measured 1.8 TB/s).  Then, when every lane that carries a fraction here does hit the same bin,
-// the 52-bit values are summed across the warp as three 18-bit parts with REDUX and a single lane runs the carry chain.
-__device__ __forceinline__ void add_frac(unsigned* arr, unsigned nb, unsigned idx, long long v, bool merge) {
-    if (merge) {
-        const unsigned m = __activemask();
-        int same;
-        __match_all_sync(m, idx, &same);
-        if (same) {
-            const unsigned long long u = (unsigned long long)v;
-            const unsigned long long t = (unsigned long long)__reduce_add_sync(m, (unsigned)u & 0x3ffffu) +
-                                         ((unsigned long long)__reduce_add_sync(m, (unsigned)(u >> 18) & 0x3ffffu) << 18) +
-                                         ((unsigned long long)__reduce_add_sync(m, (unsigned)(u >> 36)) << 36);
-            if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) add96(arr, nb, idx, (long long)t);
-            return;
+// ---- tables sorted by time (real-valued): the lanes of a warp, and the warp's consecutive tiles, sit on ONE bin for thousands
+// of lineages, and 32 carry chains per lineage on one shared-memory word serialise (measured 1.8 TB/s; a per-lineage warp
+// reduction with MATCH + REDUX reached 3.5 TB/s).  A RUN keeps the bin the warp is on and sums the fractions of every lineage
+// that falls into it in REGISTERS, per lane; it touches shared memory only when the bin changes (or every 1023 lineages per lane,
+// so that the 52-bit fractions cannot overflow the 64-bit lane sums).
+struct K1Run {
+    unsigned bin;                 // 0xffffffff: no run open
+    unsigned cnt;                 // lineages per lane in the run (warp-uniform: lanes only ever advance together)
+    unsigned long long acc;       // this lane's sum of fractions, 2^-52 fixed point
+};
+__device__ __forceinline__ void run_flush(K1Run& r, unsigned* cnt_arr, unsigned* frac_arr, unsigned nb) {
+    if (r.cnt) {
+        const unsigned p0 = __reduce_add_sync(0xffffffffu, (unsigned)r.acc & 0x3fffffu);
+        const unsigned p1 = __reduce_add_sync(0xffffffffu, (unsigned)(r.acc >> 22) & 0x3fffffu);
+        const unsigned p2 = __reduce_add_sync(0xffffffffu, (unsigned)(r.acc >> 44));
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&cnt_arr[r.bin], 32u * r.cnt);
+            // total < 2^67: low 64 bits through the carry chain, the rest straight into the top word
+            // total < 2^70, into the 96-bit accumulator word by word with explicit carries
+            const unsigned __int128 t = (unsigned __int128)p0 + ((unsigned __int128)p1 << 22) + ((unsigned __int128)p2 << 44);
+            if (t) {
+                const unsigned w0 = (unsigned)t, w1 = (unsigned)(t >> 32), w2 = (unsigned)(t >> 64);
+                const unsigned old0 = atomicAdd(&frac_arr[r.bin], w0);
+                const unsigned long long s1 = (unsigned long long)w1 + (((unsigned)(old0 + w0) < w0) ? 1ull : 0ull);
+                unsigned c1 = (unsigned)(s1 >> 32);
+                if ((unsigned)s1) {
+                    const unsigned old1 = atomicAdd(&frac_arr[nb + r.bin], (unsigned)s1);
+                    c1 += ((unsigned)(old1 + (unsigned)s1) < (unsigned)s1) ? 1u : 0u;
+                }
+                if (w2 + c1) atomicAdd(&frac_arr[2 * nb + r.bin], w2 + c1);
+            }
         }
     }
-    add96(arr, nb, idx, v);
+    r.cnt = 0u; r.acc = 0ull;
 }
 
 struct K1Smem {
@@ -139,8 +154,7 @@ __device__ __noinline__ void k1_irregular(int p_fb, unsigned p_nb, long long S, 
     }
 }
 
-template <bool MERGE>
-__device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te, bool mergeS, bool mergeE) {
+__device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te) {
     if (p.dead_only) {
         if (!(te < p.end_time)) return;      // :531-532
     }
@@ -151,16 +165,12 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
     if ((te > ts) && (a < p.nb)) {
         atomicAdd(&s.hs32[a], 1u);
         const double fr = ts - (double)ti;
-        if (fr != 0.0) {
-            if constexpr (MERGE) add_frac(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE), mergeS);
-            else add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
-        }
+        if (fr != 0.0) add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
         if (b < p.nb) {
             const double fe = te - (double)(ci - 1);
             if (fe != p.fe_ref) {
                 atomicAdd(&s.exC[b], 1u);
-                if constexpr (MERGE) add_frac(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE), mergeE);
-                else add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
+                add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
             } else {
                 atomicAdd(&s.he32[b], 1u);
             }
@@ -170,11 +180,67 @@ __device__ __forceinline__ void k1_lineage(const K1Params& p, const K1Smem& s, l
     }
 }
 
-// the full tiles of one segment; MERGE = false is the plain stream (no per-lineage test of the merge flags)
-template <bool MERGE>
+// the same lineage with run-length accumulation on the side(s) the segment's probe found sorted (warp-uniform flags); all 32
+// lanes call it together
+__device__ __forceinline__ void k1_lineage_runs(const K1Params& p, const K1Smem& s, long long* acc, double ts, double te,
+                                                bool runS_on, bool runE_on, K1Run& rS, K1Run& rE) {
+    const bool keep = !p.dead_only || (te < p.end_time);
+    const int ti = __double2int_rd(ts);
+    const int ci = __double2int_ru(te);
+    const unsigned a = (unsigned)(ti - p.fb);
+    const unsigned b = (unsigned)(ci - 1 - p.fb);
+    const bool regular = keep && (te > ts) && (a < p.nb);
+    const double fr = ts - (double)ti;
+    const double fe = te - (double)(ci - 1);
+    // ---- birth side
+    bool doneS = false;
+    if (runS_on) {
+        if (__all_sync(0xffffffffu, regular && a == rS.bin)) {
+            rS.cnt++; rS.acc += (unsigned long long)__double2ll_rn(fr * LR_FIX_SCALE);
+            if (rS.cnt == 1023u) run_flush(rS, s.hs32, s.cS, p.nb);
+            doneS = true;
+        } else {
+            run_flush(rS, s.hs32, s.cS, p.nb);
+            const unsigned m = __ballot_sync(0xffffffffu, regular);
+            rS.bin = m ? __shfl_sync(0xffffffffu, a, 31 - __clz(m)) : 0xffffffffu;     // the bin a sorted table moves on to
+        }
+    }
+    if (regular && !doneS) {
+        atomicAdd(&s.hs32[a], 1u);
+        if (fr != 0.0) add96(s.cS, p.nb, a, __double2ll_rn(fr * LR_FIX_SCALE));
+    }
+    // ---- death side (only lineages that are regular on the birth side carry a death with time at risk here)
+    const bool death = regular && b < p.nb;
+    bool doneE = false;
+    if (runE_on) {
+        if (__all_sync(0xffffffffu, death && b == rE.bin && fe != p.fe_ref)) {
+            rE.cnt++; rE.acc += (unsigned long long)__double2ll_rn(fe * LR_FIX_SCALE);
+            if (rE.cnt == 1023u) run_flush(rE, s.exC, s.cE, p.nb);
+            doneE = true;
+        } else {
+            run_flush(rE, s.exC, s.cE, p.nb);
+            const unsigned m = __ballot_sync(0xffffffffu, death && fe != p.fe_ref);
+            rE.bin = m ? __shfl_sync(0xffffffffu, b, 31 - __clz(m)) : 0xffffffffu;
+        }
+    }
+    if (death && !doneE) {
+        if (fe != p.fe_ref) {
+            atomicAdd(&s.exC[b], 1u);
+            add96(s.cE, p.nb, b, __double2ll_rn(fe * LR_FIX_SCALE));
+        } else {
+            atomicAdd(&s.he32[b], 1u);
+        }
+    }
+    if (keep && !regular) k1_irregular(p.fb, p.nb, p.acc_stride, p.fe_ref_fix, acc, ts, te);
+}
+
+// the full tiles of one segment; RUNS = false is the plain stream (no per-lineage warp votes)
+template <bool RUNS>
 __device__ __forceinline__ void k1_tiles(const K1Params& p, const K1Smem& s, long long* acc, const double* ts, const double* te,
-                                         long long A, long long ntiles, int warp, int W, int lane, bool mergeS, bool mergeE) {
-        if (p.vec_ok) {
+                                         long long A, long long ntiles, int warp, int W, int lane, bool runS_on, bool runE_on) {
+    K1Run rS, rE;
+    rS.bin = 0xffffffffu; rS.cnt = 0u; rS.acc = 0ull; rE = rS;
+    if (p.vec_ok) {
         for (long long k = warp; k < ntiles; k += W) {
             const double2* t2 = (const double2*)(ts + A + k * K1_TILE) + lane;
             const double2* e2 = (const double2*)(te + A + k * K1_TILE) + lane;
@@ -183,8 +249,13 @@ __device__ __forceinline__ void k1_tiles(const K1Params& p, const K1Smem& s, lon
             for (int u = 0; u < K1_UNROLL; ++u) { sv[u] = ld_stream_f64x2(t2 + u * 32); ev[u] = ld_stream_f64x2(e2 + u * 32); }
 #pragma unroll
             for (int u = 0; u < K1_UNROLL; ++u) {
-                k1_lineage<MERGE>(p, s, acc, sv[u].x, ev[u].x, mergeS, mergeE);
-                k1_lineage<MERGE>(p, s, acc, sv[u].y, ev[u].y, mergeS, mergeE);
+                if constexpr (RUNS) {
+                    k1_lineage_runs(p, s, acc, sv[u].x, ev[u].x, runS_on, runE_on, rS, rE);
+                    k1_lineage_runs(p, s, acc, sv[u].y, ev[u].y, runS_on, runE_on, rS, rE);
+                } else {
+                    k1_lineage(p, s, acc, sv[u].x, ev[u].x);
+                    k1_lineage(p, s, acc, sv[u].y, ev[u].y);
+                }
             }
         }
     } else {
@@ -195,9 +266,13 @@ __device__ __forceinline__ void k1_tiles(const K1Params& p, const K1Smem& s, lon
 #pragma unroll
             for (int u = 0; u < 2 * K1_UNROLL; ++u) { sv[u] = ld_stream_f64(t1 + u * 32); ev[u] = ld_stream_f64(e1 + u * 32); }
 #pragma unroll
-            for (int u = 0; u < 2 * K1_UNROLL; ++u) k1_lineage<MERGE>(p, s, acc, sv[u], ev[u], mergeS, mergeE);
+            for (int u = 0; u < 2 * K1_UNROLL; ++u) {
+                if constexpr (RUNS) k1_lineage_runs(p, s, acc, sv[u], ev[u], runS_on, runE_on, rS, rE);
+                else k1_lineage(p, s, acc, sv[u], ev[u]);
+            }
         }
     }
+    if constexpr (RUNS) { run_flush(rS, s.hs32, s.cS, p.nb); run_flush(rE, s.exC, s.cE, p.nb); }
 }
 
 // ---- int32 years (8 B per lineage): ts is an integer year, te an integer year plus the constant death jitter, so every
@@ -321,8 +396,8 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
         if (A > s1) A = s1;
         const long long ntiles = (s1 - A) / K1_TILE;
         const long long B = A + ntiles * K1_TILE;
-        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage<false>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i), false, false);
-        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage<false>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i), false, false);
+        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
         // Sorted-looking table?  One probe per warp and segment: the first lineage of each lane's first tile.
         bool mergeS = false, mergeE = false;
         if (warp < ntiles) {
