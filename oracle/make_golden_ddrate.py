@@ -121,7 +121,7 @@ def _summarise(raw, n_bins, burnin=0.2):
     return out
 
 
-def posterior(n_chains=8, n_iter=300001, s=200):
+def posterior(n_chains=int(os.environ.get("LR_GOLDEN_CHAINS", "32")), n_iter=300001, s=200):
     write_inputs()
     confs = [("ex_g_mddn", EX, "example3.tsv", G, 24), ("ex_g_mdd", EX, "example3.tsv", G + ["-m_death", "1"], 24)]
     os.makedirs(os.path.join(GOLD, "posterior"), exist_ok=True)
@@ -131,7 +131,7 @@ def posterior(n_chains=8, n_iter=300001, s=200):
             raw = [b for f, b in logs.items() if not f.endswith(".div.log")][0]
             return _summarise(raw, nb), dt
         t0 = time.time()
-        with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        with ThreadPoolExecutor(max_workers=int(os.environ.get("LR_GOLDEN_WORKERS", str(max(1, (os.cpu_count() or 2) - 1))))) as ex:
             res = list(ex.map(one, range(201, 201 + n_chains)))
         with open(os.path.join(GOLD, "posterior", tag + ".json"), "w") as fh:
             json.dump({"tag": tag, "args": args, "n_iter": n_iter, "sample_every": s, "burnin": 0.2,

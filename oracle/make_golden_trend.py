@@ -131,7 +131,7 @@ def _summarise(raw, burnin=0.2):
     return out
 
 
-def posterior(n_chains=8, n_iter=400001, s=200):
+def posterior(n_chains=int(os.environ.get("LR_GOLDEN_CHAINS", "32")), n_iter=400001, s=200):
     """Posterior summaries of ``n_chains`` unmodified reference chains per configuration (distinct seeds), for the
     distributional parity of the device chains (Philox cannot replay MT19937)."""
     write_inputs()
@@ -144,7 +144,7 @@ def posterior(n_chains=8, n_iter=400001, s=200):
             (raw,) = logs.values()
             return _summarise(raw), dt
         t0 = time.time()
-        with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        with ThreadPoolExecutor(max_workers=int(os.environ.get("LR_GOLDEN_WORKERS", str(max(1, (os.cpu_count() or 2) - 1))))) as ex:
             res = list(ex.map(one, range(101, 101 + n_chains)))
         with open(os.path.join(GOLD, "posterior", tag + ".json"), "w") as fh:
             json.dump({"tag": tag, "args": args, "n_iter": n_iter, "sample_every": s, "burnin": 0.2,

@@ -200,11 +200,14 @@ def test_unsupported_models_are_refused(device, tmp_path):
 
 @pytest.mark.parametrize("tag,md", [("ex_g_mddn", 2), ("ex_g_mdd", 1)])
 def test_posterior_matches_reference_chains(device, tmp_path, tag, md):
-    """64 device chains against 8 unmodified reference chains of the same length: every posterior mean within 4.5 standard
-    errors (between-chain variance of both sides)."""
+    """128 device chains against 32 unmodified reference chains of the same length: every posterior mean within 3.5 standard
+    errors of the difference of the two population means (between-chain variance of both sides); 64 against 8 within 4.5 while
+    a fixture still holds the 8 chains of round 1."""
     with open(os.path.join(DG, "posterior", tag + ".json")) as fh:
         ref = json.load(fh)
-    S, ch = _setup(device, tmp_path, "ex_g_mddn", mb=3, md=md, n_chains=64, seed=2027)
+    strong = len(ref["chains"]) >= 32
+    z_max = 3.5 if strong else 4.5
+    S, ch = _setup(device, tmp_path, "ex_g_mddn", mb=3, md=md, n_chains=128 if strong else 64, seed=2027)
     recs = ch.run(ref["n_iter"], ref["sample_every"])
     r = recs[int(ref["burnin"] * recs.shape[0]):]
     nb = S.n
@@ -220,7 +223,7 @@ def test_posterior_matches_reference_chains(device, tmp_path, tag, md):
         a = np.asarray(a, dtype=float)
         se = np.sqrt(a.var(0, ddof=1) / len(a) + b.var(0, ddof=1) / len(b))
         z = np.abs(a.mean(0) - b.mean(0)) / se
-        assert np.all(z < 4.5), (key, float(np.max(z)), a.mean(0), b.mean(0))
+        assert np.all(z < z_max), (key, float(np.max(z)), a.mean(0), b.mean(0))
 
 
 def test_command_line_end_to_end(device, tmp_path):

@@ -225,11 +225,14 @@ def _chain_means(recs, nb, burnin=0.2):
 
 @pytest.mark.parametrize("tag,base,cd", [("ex_ramp", "ex_ramp", False), ("ex_hump_constD", "ex_hump", True)])
 def test_posterior_matches_reference_chains(device, tmp_path, tag, base, cd):
-    """64 device chains against 8 unmodified reference chains of the same length: every posterior mean within 4.5 standard
-    errors (between-chain variance of both sides)."""
+    """128 device chains against 32 unmodified reference chains of the same length: every posterior mean within 3.5 standard
+    errors of the difference of the two population means (between-chain variance of both sides); 64 against 8 within 4.5 while
+    a fixture still holds the 8 chains of round 1."""
     with open(os.path.join(TG, "posterior", tag + ".json")) as fh:
         ref = json.load(fh)
-    st, bins, trend, otrend, ch = _setup(device, tmp_path, base, n_chains=64, seed=2026, const_death=cd)
+    strong = len(ref["chains"]) >= 32
+    z_max = 3.5 if strong else 4.5
+    st, bins, trend, otrend, ch = _setup(device, tmp_path, base, n_chains=128 if strong else 64, seed=2026, const_death=cd)
     recs = ch.run(ref["n_iter"], ref["sample_every"])
     assert recs.shape[0] == len(range(0, ref["n_iter"], ref["sample_every"]))
     mine = _chain_means(recs, bins.n_bins, ref["burnin"])
@@ -241,7 +244,7 @@ def test_posterior_matches_reference_chains(device, tmp_path, tag, base, cd):
             assert cd and key in ("beta_mean", "gamma_mean") and np.array_equal(a.mean(0), b.mean(0))
             continue
         z = np.abs(a.mean(0) - b.mean(0)) / se
-        assert np.all(z < 4.5), (key, float(np.max(z)), a.mean(0), b.mean(0))
+        assert np.all(z < z_max), (key, float(np.max(z)), a.mean(0), b.mean(0))
 
 
 def test_command_line_end_to_end(device, tmp_path, capsys):
