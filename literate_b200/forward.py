@@ -115,6 +115,24 @@ def parse_lineages(path, TBP=False, rev_se=0, first_year=-1, last_year=-1, death
     return ts, te, np.min(ts), np.max(te), root
 
 
+def as_year_table(ts, te, death_jitter):
+    """(ts, te) as parse_lineages returns them -> int32 YEARS (ts, te - jitter) if the table is one of integer years (every table
+    the reference ships), else None.  The int32 entry point of K1 takes half the bytes and adds the jitter itself; the
+    statistics are the same bit for bit."""
+    if not 0.0 <= death_jitter <= 1.0:
+        return None
+    ok = ~np.isnan(ts)
+    ey = te - death_jitter
+    lim = float(np.iinfo(np.int32).max - 1)
+    if not (np.all(np.isnan(te) == ~ok) and np.all(np.abs(ts[ok]) < lim) and np.all(np.abs(ey[ok]) < lim)):
+        return None
+    ti, ei = np.where(ok, ts, 0.0).astype(np.int32), np.where(ok, ey, 0.0).astype(np.int32)
+    if not (np.array_equal(ti[ok], ts[ok]) and np.array_equal(ei[ok] + death_jitter, te[ok])):
+        return None
+    ti[~ok] = E.YEAR_PAD; ei[~ok] = E.YEAR_PAD
+    return ti, ei
+
+
 def _fmt(x):
     """str() of what the reference puts in a row: Python ints stay ints, floats use the shortest repr
     (str(np.float64) == repr(float) for every finite value)."""
@@ -250,8 +268,9 @@ def run(args, device=None):
 
     dev = device if device is not None else E.Device(local_rank if world > 1 else args.device)
     t0 = time.time()
-    stats = dev.bin_stats(ts, te, first_bin=int(start_time), n_bins=int(end_time) - int(start_time), death_jitter=args.death_jitter,
-                          only_dead=only_dead, end_time=float(end_time))
+    years = as_year_table(ts, te, args.death_jitter)            # integer years: 8 bytes per lineage over PCIe instead of 16
+    stats = dev.bin_stats(*(years if years is not None else (ts, te)), first_bin=int(start_time), n_bins=int(end_time) - int(start_time),
+                          death_jitter=args.death_jitter, only_dead=only_dead, end_time=float(end_time))
     t_bin = time.time() - t0
     sp, ex, br = stats.sp[0], stats.ex[0], stats.br[0]
     if lead:

@@ -146,3 +146,17 @@ def test_reference_cost_binning_equals_oracle():
     ts = 100 + np.floor(rng.uniform(0, 30, 500)); te = ts + np.floor(rng.exponential(5, 500)) + .5
     for j in range(100, 131):
         assert O.events_in_bin_asref(ts, te, j, j + 1) == O.events_in_bin(ts, te, j, j + 1)
+
+
+def test_integer_year_tables_are_recognised():
+    """forward.as_year_table: the tables the reference ships become int32 year tables (the compact K1 entry point), anything
+    with a fractional time, an out-of-range jitter or a lone NaN does not."""
+    from literate_b200 import engine as E
+    ts, te, _, _, _ = F.parse_lineages(golden_input("example_dataTAD.txt"))
+    ti, ei = F.as_year_table(ts, te, 0.5)
+    assert ti.dtype == np.int32 and np.array_equal(ti, ts) and np.array_equal(ei + 0.5, te)
+    assert F.as_year_table(ts + 0.25, te, 0.5) is None and F.as_year_table(ts, te + 0.1, 0.5) is None and F.as_year_table(ts, te, 1.5) is None
+    pad = np.concatenate([ts, [np.nan, np.nan]]), np.concatenate([te, [np.nan, np.nan]])      # a ragged replicate's NaN rows
+    ti, ei = F.as_year_table(*pad, 0.5)
+    assert (ti[-2:] == E.YEAR_PAD).all() and (ei[-2:] == E.YEAR_PAD).all() and np.array_equal(ti[:-2], ts)
+    assert F.as_year_table(np.concatenate([ts, [np.nan]]), np.concatenate([te, [2000.5]]), 0.5) is None
