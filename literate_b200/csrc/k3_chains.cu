@@ -1542,11 +1542,15 @@ extern "C" int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every
         if (!carve_set) {
             cudaFuncSetAttribute(k3_team_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
             cudaFuncSetAttribute(k3_team_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
+            cudaFuncSetAttribute(k3_team_kernel<10>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
+            cudaFuncSetAttribute(k3_team_kernel<12>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
             cudaFuncSetAttribute(k3_team_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 30);
             carve_set = true;
         }
         auto launch_team = [&]() {
             if (W >= 16) k3_team_kernel<16><<<c->n_chains, 512, 0, st>>>(P, lead);
+            else if (W == 12) k3_team_kernel<12><<<c->n_chains, 384, 0, st>>>(P, lead);
+            else if (W == 10) k3_team_kernel<10><<<c->n_chains, 320, 0, st>>>(P, lead);
             else if (W >= 8) k3_team_kernel<8><<<c->n_chains, 256, 0, st>>>(P, lead);
             else k3_team_kernel<4><<<c->n_chains, 128, 0, st>>>(P, lead);
             h->launches += 1;

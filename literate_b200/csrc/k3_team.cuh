@@ -134,8 +134,8 @@ __device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsig
     for (;;) {
         const unsigned long long vw = ld_volatile_shared(&T.verword);
         if (tv_version(vw) != v) return false;
-        const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
-        const bool ok = (lane & (W - 1)) == w || ((unsigned)(pw >> 32) == v && (unsigned)pw >= i);
+        const unsigned long long pw = ld_volatile_shared(&T.prog[lane % W]);
+        const bool ok = (lane % W) == w || ((unsigned)(pw >> 32) == v && (unsigned)pw >= i);
         if (__all_sync(0xffffffffu, ok)) return true;
         ++polls;
         __nanosleep(20);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
                 const unsigned long long vw = ld_acquire_cta(&T.verword);
                 const unsigned v_new = tv_version(vw), changed = tv_changed(vw), base_new = (unsigned)vw;
                 team_load_state<W>(T, v_new, L, M, c, lane);
-                const unsigned i_first = base_new + (((unsigned)w - base_new) & (W - 1));
+                const unsigned i_first = base_new + ((unsigned)w + W - base_new % W) % W;
                 const unsigned beyond = (i - i_first) / W;             // own evaluations at or after base_new (<= lead)
                 unsigned long long conf = tc.dep & ((unsigned long long)changed * 0x0101010101010101ull);
                 if (beyond < 8u) conf &= (1ull << (8u * beyond)) - 1ull;
@@ -280,14 +280,14 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
         }
         if (i >= n) {
             // my share is done; the launch ends when everybody's is (a rollback can still hand me iterations again)
-            const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
+            const unsigned long long pw = ld_volatile_shared(&T.prog[lane % W]);
             if (__all_sync(0xffffffffu, (unsigned)(pw >> 32) == v && (unsigned)pw >= n)) break;
             __nanosleep(200);
             continue;
         }
         if (i > F_seen + lead_span) {
             // not more than `lead` own iterations ahead of the slowest warp
-            const unsigned long long pw = ld_volatile_shared(&T.prog[lane & (W - 1)]);
+            const unsigned long long pw = ld_volatile_shared(&T.prog[lane % W]);
             const unsigned nxt = (unsigned)(pw >> 32) == v ? (unsigned)pw : base;
             F_seen = __reduce_min_sync(0xffffffffu, nxt);
             if (i > F_seen + lead_span) { ++n_lead; __nanosleep(100); continue; }
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(W * 32, W >= 16 ? 1 : (W >= 8 ? 2 : 4)) k3_tea
     // ---- every warp holds the final state; warp 0 stores it, all add their counters
     {
         // evaluations kept through the rollbacks but beyond the iteration the team stopped at belong to the continuation pass
-        const unsigned i_first = n + (((unsigned)w - n) & (W - 1));
+        const unsigned i_first = n + ((unsigned)w + W - n % W) % W;
         const unsigned beyond = i > i_first ? (i - i_first) / W : 0u;
         tc.hist = beyond >= 8u ? 0ull : (tc.hist >> (8u * beyond));
     }

@@ -113,7 +113,7 @@ def test_loop_builds_give_identical_chains(device, metal_path):
     assert np.array_equal(a.counters(), b.counters()) and np.array_equal(a.counters(), c.counters())
 
 
-@pytest.mark.parametrize("team_w,lead,nobail", [(4, 1, 1), (8, 2, 1), (16, 7, 1), (8, 5, 0), (4, 4, 0), (16, 2, 0)])
+@pytest.mark.parametrize("team_w,lead,nobail", [(4, 1, 1), (8, 2, 1), (16, 7, 1), (10, 3, 1), (8, 5, 0), (4, 4, 0), (16, 2, 0), (12, 4, 0)])
 def test_speculative_team_build_gives_the_same_chains(device, metal_path, team_w, lead, nobail, monkeypatch):
     """loop_variant 4: W warps evaluate consecutive iterations of ONE chain ahead of time against the current state and only
     the first state-changing one commits (csrc/k3_team.cuh).  Same draws, same arithmetic, same state: the records, final
