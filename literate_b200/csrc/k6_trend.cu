@@ -13,6 +13,7 @@
 // two side sums come out of one butterfly.  A side none of whose parameters was touched keeps its stored likelihood (the
 // reference recomputes the identical number).  Nothing but the read-only per-bin table (L1-resident) is read inside the
 // loop; the only global writes are the sample records.
+#include <stdlib.h>
 #include "lr_common.cuh"
 
 #define TR_NPAR 6
@@ -55,21 +56,27 @@ struct TrendView {
     const double* tab;
     int nb, nbp, const_b, const_d;
     double Sx, Sxx;
-    // the first 32 bins, one per lane
+    // the bins of the likelihood sums this warp owns: first + lane (statistics in registers), then every `stride`-th after it.
+    // One warp per chain: first = 0, stride = 32.  W warps per chain (wide build): first = 32 w, stride = 32 W.
+    int first, stride;
     double sp0, ex0, br0, lnT0;
 };
+// warps per chain of the wide build, by the number of bins
+__host__ __device__ inline int trend_groups(int nb) { return nb > 128 ? 4 : (nb > 64 ? 2 : 1); }
 
 __device__ __forceinline__ TrendView trend_view(const double* tab_all, const double* cst_all, int rep, int nb, int nbp,
-                                                int const_b, int const_d, int lane) {
+                                                int const_b, int const_d, int lane, int first = 0, int stride = 32) {
     TrendView v;
     v.tab = tab_all + (size_t)rep * TR_ROWS * nbp;
     v.nb = nb; v.nbp = nbp; v.const_b = const_b; v.const_d = const_d;
     v.Sx = cst_all[2 * rep]; v.Sxx = cst_all[2 * rep + 1];
-    const bool on = lane < nb;
-    v.sp0 = on ? v.tab[TR_SP * nbp + lane] : 0.0;
-    v.ex0 = on ? v.tab[TR_EX * nbp + lane] : 0.0;
-    v.br0 = on ? v.tab[TR_BR * nbp + lane] : 0.0;
-    v.lnT0 = on ? v.tab[TR_LNT * nbp + lane] : 0.0;
+    v.first = first; v.stride = stride;
+    const int j = first + lane;
+    const bool on = j < nb;
+    v.sp0 = on ? v.tab[TR_SP * nbp + j] : 0.0;
+    v.ex0 = on ? v.tab[TR_EX * nbp + j] : 0.0;
+    v.br0 = on ? v.tab[TR_BR * nbp + j] : 0.0;
+    v.lnT0 = on ? v.tab[TR_LNT * nbp + j] : 0.0;
     return v;
 }
 
@@ -87,9 +94,11 @@ struct PowCache { double b, d; };
 // exponent of that side differs from the one `pc` was computed for (pc is updated in place)
 // `extra`: a per-lane term (Hastings share + prior difference of the lane's parameter) that rides the same butterfly; its
 // warp total comes back in place.
-__device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, int lane, bool doB, bool doD, bool newPowB, bool newPowD,
-                                          PowCache& pc, double& likB, double& likD, double& extra) {
-    double sB = 0.0, sD = 0.0;
+// partial sums over the bins this warp owns (per lane, not yet reduced)
+// termB / termD (wide build): if not null, every bin's term is also stored at its bin index
+__device__ __forceinline__ void trend_lik_partial(const TrendView& v, const double* p, int lane, bool doB, bool doD, bool newPowB, bool newPowD,
+                                                  PowCache& pc, double& sB, double& sD, double* termB = nullptr, double* termD = nullptr) {
+    sB = 0.0; sD = 0.0;
     if (doB) {
         double lam = p[0];
         if (!v.const_b) {
@@ -108,17 +117,28 @@ __device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, i
         }
         sD = log(mu) * v.ex0 - mu * v.br0;
     }
-    for (int j = lane + 32; j < v.nb; j += 32) {
+    if (termB != nullptr && v.first + lane < v.nb) { termB[v.first + lane] = sB; termD[v.first + lane] = sD; }
+    for (int j = v.first + lane + v.stride; j < v.nb; j += v.stride) {
         const double lnT = __ldg(v.tab + TR_LNT * v.nbp + j), br = __ldg(v.tab + TR_BR * v.nbp + j);
+        double tB = 0.0, tD = 0.0;
         if (doB) {
             const double lam = trend_rate(p[0], p[2], p[4], lnT, v.const_b);
-            sB += log(lam) * __ldg(v.tab + TR_SP * v.nbp + j) - lam * br;
+            tB = log(lam) * __ldg(v.tab + TR_SP * v.nbp + j) - lam * br;
+            sB += tB;
         }
         if (doD) {
             const double mu = trend_rate(p[1], p[3], p[5], lnT, v.const_d);
-            sD += log(mu) * __ldg(v.tab + TR_EX * v.nbp + j) - mu * br;
+            tD = log(mu) * __ldg(v.tab + TR_EX * v.nbp + j) - mu * br;
+            sD += tD;
         }
+        if (termB != nullptr) { termB[j] = tB; termD[j] = tD; }
     }
+}
+
+__device__ __forceinline__ void trend_lik(const TrendView& v, const double* p, int lane, bool doB, bool doD, bool newPowB, bool newPowD,
+                                          PowCache& pc, double& likB, double& likD, double& extra) {
+    double sB, sD;
+    trend_lik_partial(v, p, lane, doB, doD, newPowB, newPowD, pc, sB, sD);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sB += __shfl_xor_sync(0xffffffffu, sB, o);
@@ -285,6 +305,93 @@ __global__ void __launch_bounds__(128, 4) k6_trend_kernel(const TrendRun P) {
     const double prior = warp_sum(trend_prior_term(lane, mine));
     if (lane < TR_NPAR) S->p[lane] = mine;
     if (lane == 0) { S->likB = likB; S->likD = likD; S->prior = prior; S->it = it; S->accepted = accepted; }
+}
+
+// WIDE build: W warps (one CTA) per chain.  With a few hundred chains and hundreds of bins one warp per chain leaves the GPU
+// idle (ncu, round 1: sm__throughput 10 %, 7 bins per lane in series, each an exp -> log chain).  Here warp w evaluates bins
+// 32 w + lane (+ 32 W k) -- at 200 bins and W = 4 two per lane instead of seven.  Every warp draws the same random numbers, builds
+// the same proposal and takes the same accept decision; the warps exchange their PER-BIN terms through shared memory
+// (double-buffered by iteration parity: one __syncthreads per iteration) and every warp then adds them up exactly as the
+// one-warp kernel does -- lane l its bins l, l + 32, l + 64, ... in ascending order, then one butterfly -- so the chain is
+// the one-warp kernel's chain, bit for bit (tests/test_gpu_trend.py), and does not depend on scheduling.
+template <int W>
+__global__ void __launch_bounds__(W * 32, 2) k6_trend_wide_kernel(const TrendRun P) {
+    extern __shared__ double terms[];                  // [2 parities][2 sides][nbp]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x;
+    if (c >= P.n_chains) return;
+    TrendChain* S = P.st + c;
+    const TrendView v = trend_view(P.tab, P.cst, S->rep, P.nb, P.nbp, P.const_b, P.const_d, lane, 32 * w, 32 * W);
+    const unsigned chain = S->chain;
+    double mine = lane < TR_NPAR ? S->p[lane] : 0.0;
+    double p[TR_NPAR];
+    bcast6(mine, p);
+    double likB = S->likB, likD = S->likD;
+    PowCache pc;
+    pc.b = v.const_b ? 1.0 : exp(p[4] * v.lnT0);
+    pc.d = v.const_d ? 1.0 : exp(p[5] * v.lnT0);
+    long long it = S->it, accepted = S->accepted;
+    const long long it_end = it + P.n_iter;
+    const double fm = lane < TR_NPAR ? P.fd_mult[lane] : 0.0, fn = lane < TR_NPAR ? P.fd_norm[lane] : 0.0;
+    long long next_sample = (it + P.sample_every - 1) / P.sample_every * P.sample_every;
+    long long rec_idx = 0;
+    __syncthreads();                                   // every warp has read the chain's state before warp 0 may rewrite it
+
+    for (; it < it_end; ++it) {
+        const Philox4 r = philox4x32_10((uint32_t)it, (uint32_t)((unsigned long long)it >> 32), (uint32_t)lane | (0x60u << 8), chain, P.k0, P.k1);
+        const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
+        const double rr = __shfl_sync(0xffffffffu, ua, 6);
+        const double u_acc = __shfl_sync(0xffffffffu, ub, 6);
+        const int kind_normal = rr < 0.33;                                  // trend_rate.py:167
+        const double um = ((double)r.x + 0.5) * 2.3283064365386963e-10;
+        const bool on = um < (kind_normal ? fn : fm);
+        double draw = u01(r.y, r.z);
+        if (kind_normal) draw = normal_f32(draw, r.w);
+        double h;
+        const double prop = trend_propose(kind_normal, mine, on, draw, h);
+        const unsigned touched = __ballot_sync(0xffffffffu, on);
+        double q[TR_NPAR];
+        bcast6(prop, q);
+        double hp = h + trend_prior_delta(lane, mine, prop, h);
+        const bool doB = (touched & 0x15u) != 0, doD = (touched & 0x2au) != 0;
+        PowCache npc = pc;
+        double* tB = terms + (size_t)(it & 1) * 2 * P.nbp;
+        double* tD = tB + P.nbp;
+        double sB, sD;
+        trend_lik_partial(v, q, lane, doB, doD, (touched & 0x10u) != 0, (touched & 0x20u) != 0, npc, sB, sD, tB, tD);
+        __syncthreads();
+        // the one-warp kernel's order: lane l adds its bins l, l + 32, ... ascending (0.0 for a side that was not evaluated)
+        sB = 0.0; sD = 0.0;
+        for (int j = lane; j < P.nb; j += 32) { sB += tB[j]; sD += tD[j]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sB += __shfl_xor_sync(0xffffffffu, sB, o);
+            sD += __shfl_xor_sync(0xffffffffu, sD, o);
+            hp += __shfl_xor_sync(0xffffffffu, hp, o);
+        }
+        const double nB = doB ? sB : likB, nD = doD ? sD : likD;
+        const double x = ((nB + nD) - (likB + likD)) + hp;
+        if (it == 0 || mh_accept_gt(x, u_acc)) {                            // trend_rate.py:176
+#pragma unroll
+            for (int k = 0; k < TR_NPAR; ++k) p[k] = q[k];
+            mine = prop;
+            likB = nB; likD = nD; pc = npc;
+            ++accepted;
+        }
+        if (it == next_sample) {                                             // trend_rate.py:184
+            if (P.records && w == 0) {
+                const TrendView v0 = trend_view(P.tab, P.cst, S->rep, P.nb, P.nbp, P.const_b, P.const_d, lane);
+                trend_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v0, p, mine, likB, likD, it, accepted, lane);
+            }
+            ++rec_idx;
+            next_sample += P.sample_every;
+        }
+    }
+    if (w == 0) {
+        const double prior = warp_sum(trend_prior_term(lane, mine));
+        if (lane < TR_NPAR) S->p[lane] = mine;
+        if (lane == 0) { S->likB = likB; S->likD = likD; S->prior = prior; S->it = it; S->accepted = accepted; }
+    }
 }
 
 // initial state (trend_rate.py:141-156)
@@ -505,7 +612,16 @@ extern "C" int lr_trend_run(lr_trend_t t, int64_t n_iter, int64_t sample_every, 
     for (int k = 0; k < TR_NPAR; ++k) { P.fd_mult[k] = t->f_mult[k]; P.fd_norm[k] = t->f_norm[k]; }
     int threads;
     const int blocks = trend_grid(t->n_chains, threads);
-    k6_trend_kernel<<<blocks, threads, 0, st>>>(P);
+    // wide build (one warp per canonical group of bins) when one warp per chain would leave most of the GPU idle: measured on
+    // B200 at 200 bins, M it/s one-warp / wide: 256 chains 82 / 141, 2048 chains 454 / 213.  Same chains either way.
+    int W = trend_groups(t->n_bins);
+    if ((long long)t->n_chains * W > (long long)h->sm_count * 8) W = 1;
+    { const char* e = getenv("LR_TREND_WIDE"); if (e) W = atoi(e) ? trend_groups(t->n_bins) : 1; }         // development override
+    const size_t smem = (size_t)4 * t->nbp * sizeof(double);
+    if (W > 1 && smem > 40 * 1024) W = 1;
+    if (W == 4) k6_trend_wide_kernel<4><<<t->n_chains, 128, smem, st>>>(P);
+    else if (W == 2) k6_trend_wide_kernel<2><<<t->n_chains, 64, smem, st>>>(P);
+    else k6_trend_kernel<<<blocks, threads, 0, st>>>(P);
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;
