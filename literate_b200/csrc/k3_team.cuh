@@ -146,7 +146,7 @@ __device__ __forceinline__ bool team_wait_frontier(const TeamShared<W>& T, unsig
 // Returns 0 if the state stays as it is, else the kind of pending change with the proposed side in `nw`.
 #define TEAM_WINDOW 2048u
 #define TEAM_BAIL_DEN 8u
-#define TEAM_INITIAL_SOLO 4096           // a fresh chain's first iterations go to the latency-optimised build
+#define TEAM_INITIAL_SOLO 2048           // a fresh chain's first iterations go to the latency-optimised build
 #define TEAM_SOLO_SPAN_MIN 8192
 #define TEAM_SOLO_SPAN_MAX 262144
 #define TEAM_PEND_NONE 0
