@@ -427,3 +427,23 @@ def test_gibbs_poisson_rate_draws_are_gamma(device):
     # independent streams: chains are uncorrelated
     c = np.corrcoef(recs[5:, :8, E.REC_POI].T)
     assert np.max(np.abs(c - np.eye(8))) < 0.25
+
+
+def test_team_build_under_load_many_chains_and_ragged_launches(device, monkeypatch):
+    """Two teams on every SM (296 chains, the occupancy the bench runs at) through 16 launches of random lengths and sampling
+    periods: records, states, counters of the compact build, bit for bit -- the protocol's races would show here first."""
+    monkeypatch.setenv("LR_TEAM_NOBAIL", "1")
+    ts, te = synth.syn_int(200_000, 3)
+    st = device.bin_stats(ts, te)
+    ds = E.Dataset(device, st, 0, float(ts.min()), float(te.max()))
+    a = E.Chains(ds, 296, 9, E.default_config(0, loop_variant=2))
+    b = E.Chains(ds, 296, 9, E.default_config(0, loop_variant=4))
+    rng = np.random.default_rng(4)
+    for k in range(16):
+        n = int(rng.integers(1, 6000)); s = int(rng.choice([0, 1, 3, 64, 1000]))
+        ra, rb = a.run(n, s), b.run(n, s)
+        if s:
+            assert np.array_equal(ra, rb), (k, n, s)
+    assert np.array_equal(a.state(), b.state()) and np.array_equal(a.counters(), b.counters())
+    t = b.team_stats().sum(0)
+    assert t[0] > 0 and t[1] > 0          # commits and rollbacks did happen
