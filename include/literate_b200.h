@@ -236,6 +236,7 @@ int lr_chains_destroy(lr_chains_t c);
  * ceil-count of multiples of sample_every in [it0, it0+n_iter).  d_records must hold
  * lr_chains_records_per_run() * n_chains records, laid out [sample][chain][LR_REC_DOUBLES].
  * Asynchronous on `stream`. */
+/* (host-side arithmetic on the iteration counter the library tracks: does NOT wait for launches in flight) */
 int64_t lr_chains_records_per_run(lr_chains_t c, int64_t n_iter, int64_t sample_every);
 int lr_chains_run(lr_chains_t c, int64_t n_iter, int64_t sample_every, double* d_records, void* stream);
 /* same, records delivered to host memory; synchronous */

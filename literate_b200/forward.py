@@ -353,9 +353,10 @@ def run(args, device=None):
             nxt = None
             if done < args.n:
                 n_it = min(per_launch, args.n - done)
-                n_rec = chains.records_per_run(n_it, every)              # waits for the previous launch
+                n_rec = chains.records_per_run(n_it, every)              # host-side arithmetic: does not wait for the device
                 buf = torch.empty((n_rec, n_local, E.LR_REC_DOUBLES), dtype=torch.float64, device=tdev)
                 if pending is not None:
+                    dev.sync()                                           # the previous launch (on the handle's stream) has written `pending`
                     host_prev = pending.cpu().numpy()
                     pending = None
                 else:

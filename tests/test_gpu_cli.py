@@ -131,3 +131,29 @@ def test_same_seed_same_files(tmp_path):
         d = os.path.join(str(sub), "literate_mcmc_logs")
         outs.append({f: open(os.path.join(d, f), "rb").read() for f in sorted(os.listdir(d))})
     assert outs[0] == outs[1]
+
+
+def test_long_multi_launch_run_loses_no_row(tmp_path, metal_path):
+    """Several asynchronous launches of milliseconds each, 64 chains (the double-buffered loop of forward.run: the text of launch
+    k is written while launch k + 1 runs): every chain's three logs are complete, and equal -- as text -- to the logs written
+    from the records of ONE synchronous launch of the same chains."""
+    import shutil
+    from literate_b200 import engine as E
+    src = os.path.join(str(tmp_path), "metal_bands_1.tsv")
+    shutil.copy(metal_path, src)
+    F.main(["-d", src, "-n", "300001", "-s", "1000", "-p", "100000000", "-seed", "5", "-chains", "64", "-quiet", "1", "-launch_iters", "40000"])
+    d = os.path.join(str(tmp_path), "literate_mcmc_logs")
+    lin = O.read_lineages(src)
+    dev = E.Device(0)
+    st = dev.bin_stats(lin.ts, lin.te)
+    ds = E.Dataset(dev, st, 0, lin.start_time, lin.end_time)
+    recs = E.Chains(ds, 64, 5).run(300001, 1000)                      # one launch, synchronous
+    assert recs.shape[0] == 301
+    for k in (0, 17, 63):
+        stem = os.path.join(d, "metal_bands_1_BD_chain%d" % k)
+        mc = _read(stem + "_mcmc.log")
+        assert len(mc) == 302
+        rows = np.array([[float(x) for x in l.split("\t")] for l in mc[1:]])
+        assert np.array_equal(rows[:, 0], np.arange(301) * 1000.0)
+        assert (rows[:, 6] >= 1).all() and (rows[:, 7] >= 1).all()          # no empty (never written) record
+        assert np.array_equal(rows[:, 2], recs[:, k, E.REC_LIK]) and np.array_equal(rows[:, 6], recs[:, k, E.REC_KL])
