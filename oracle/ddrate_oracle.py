@@ -9,9 +9,10 @@ What of the reference runs: as shipped ``DDRatev3.py`` stops with NameError at :
 stops at ``out_div`` (:153).  The only runnable configurations are ``-m_birth 3 -g <genre table>`` with ``-m_death`` 0, 1
 or 2, and these are the parity pin: ``oracle/make_golden_ddrate.py`` runs them unmodified and ``run_chain`` below, same seed
 and legacy ``np.random`` draw order, reproduces both log files byte for byte (``tests/golden/ddrate/``,
-``tests/test_oracle_ddrate_golden.py``).  ``m_birth`` 0/1/2 follow the same functions (the ``M_BIRTH>=2`` branch is the one
-the pinned runs execute; the ``M_BIRTH`` 0/1 branches are restated from :86-93 and have no runnable reference: "parity
-unpinned" for those two).
+``tests/test_oracle_ddrate_golden.py``).  ``m_birth`` 0/1/2 follow the same functions; the shipped script cannot start them, so
+since round 2 they are pinned through its UNMODIFIED text executed (``runpy``) with the three names line 48 lacks pre-bound in
+``builtins`` (``oracle/make_golden_ddrate.py``, ``SHIM_JOBS``; that line only prints the empirical rates of the dummy table):
+``run_chain`` reproduces those logs byte for byte as well (``-m_birth`` 0, 1 with ``-m_death`` 1 and 2, and 2).
 
 All ``file:line`` citations are relative to the reference checkout.
 """

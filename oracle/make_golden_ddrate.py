@@ -51,7 +51,13 @@ def write_inputs():
             fh.write("%d\t%d\t%d\n" % (i, ts, te))
 
 
-def run_reference(inputs, data, args):
+# DDRatev3.py:48 reads three names that only the -m_birth 3 branch defines (:35-37), so the shipped script stops with a NameError
+# for every other -m_birth before it samples anything.  The jobs marked shim=True execute its UNMODIFIED text (runpy) with those
+# three names pre-bound in builtins -- line 48 then prints the empirical rates of a dummy table and nothing else ever reads
+# them -- which is what pins the oracle's -m_birth 0 / 1 / 2 branches (:86-99) to the reference's own arithmetic.
+
+
+def run_reference(inputs, data, args, shim=False):
     work = tempfile.mkdtemp(prefix="lr_dd_")
     try:
         for src in inputs:
@@ -61,8 +67,18 @@ def run_reference(inputs, data, args):
                     b.write(a.read())
             else:
                 shutil.copy(src, dst)
-        cmd = [sys.executable, os.path.join(REF, "DDRatev3.py"), "-d", os.path.join(work, data)] + \
-              [os.path.join(work, a) if a.endswith(".tsv") else a for a in args]
+        script = os.path.join(REF, "DDRatev3.py")
+        if shim:
+            with open(os.path.join(work, "_shim.py"), "w") as fh:
+                fh.write("import builtins, sys, runpy, numpy as np\n"
+                         "builtins.GN_SPEC = np.array([1.0]); builtins.GN_EXTI = np.array([1.0]); builtins.GDT = np.array([1.0])\n"
+                         "script = sys.argv[1]; sys.argv = [script] + sys.argv[2:]\n"
+                         "sys.path.insert(0, __import__('os').path.dirname(script))\n"
+                         "runpy.run_path(script, run_name='__main__')\n")
+            head = [sys.executable, os.path.join(work, "_shim.py"), script]
+        else:
+            head = [sys.executable, script]
+        cmd = head + ["-d", os.path.join(work, data)] + [os.path.join(work, a) if a.endswith(".tsv") else a for a in args]
         t0 = time.time()
         p = subprocess.run(cmd, cwd=work, capture_output=True, text=True)
         if p.returncode != 0:
@@ -80,6 +96,12 @@ def run_reference(inputs, data, args):
 EX = [os.path.join(TREND, "example3.tsv"), os.path.join(GOLD, "genres.tsv")]
 METAL = [os.path.join(REPO, "tests", "golden", "inputs", "metal_bands_1.tsv.gz"), os.path.join(GOLD, "genres_metal.tsv")]
 G = ["-m_birth", "3", "-g", "genres.tsv"]
+SHIM_JOBS = [      # -m_birth 0 / 1 / 2: run through the three-name shim described above run_reference
+    ("ex_ll_mddn", [EX[0]], "example3.tsv", ["-m_birth", "0", "-n", "3001", "-s", "50", "-seed", "11"]),
+    ("ex_ldd_mdd", [EX[0]], "example3.tsv", ["-m_birth", "1", "-m_death", "1", "-n", "3001", "-s", "50", "-seed", "12"]),
+    ("ex_lddn_ml", [EX[0]], "example3.tsv", ["-m_birth", "2", "-m_death", "0", "-n", "3001", "-s", "50", "-seed", "13"]),
+    ("ex_ldd_mddn", [EX[0]], "example3.tsv", ["-m_birth", "1", "-m_death", "2", "-n", "2001", "-s", "50", "-seed", "14"]),
+]
 JOBS = [
     ("ex_g_mddn", EX, "example3.tsv", G + ["-n", "3001", "-s", "50", "-seed", "1"]),
     ("ex_g_mdd", EX, "example3.tsv", G + ["-m_death", "1", "-n", "3001", "-s", "50", "-seed", "2"]),
@@ -92,14 +114,15 @@ JOBS = [
 def kat():
     write_inputs()
     manifest = []
-    for tag, inputs, data, args in JOBS:
-        logs, dt = run_reference(inputs, data, args)
+    for tag, inputs, data, args, shim in [j + (False,) for j in JOBS] + [j + (True,) for j in SHIM_JOBS]:
+        logs, dt = run_reference(inputs, data, args, shim=shim)
         d = os.path.join(GOLD, tag)
         os.makedirs(d, exist_ok=True)
         for f, b in logs.items():
             with open(os.path.join(d, f), "wb") as fh:
                 fh.write(b)
-        manifest.append({"tag": tag, "inputs": [os.path.basename(i) for i in inputs], "data": data, "args": args, "files": sorted(logs)})
+        manifest.append({"tag": tag, "inputs": [os.path.basename(i) for i in inputs], "data": data, "args": args, "files": sorted(logs),
+                         "shim": shim})
         print(tag, "%.1fs" % dt, sorted(logs))
     with open(os.path.join(GOLD, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1)
