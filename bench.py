@@ -360,14 +360,24 @@ def run_cuda(a):
         total_ms = g0.elapsed_time(g1)
         launches = dev.kernel_launches - launches0
         lik_evals = 0
+        # the timed output is checked, not just produced: every chain delivered its samples, and the likelihood and prior of the
+        # states the LAST step logged (every 10th sample of every chain) are recomputed from the logged rates / shift times by the
+        # batched state evaluator (lr_state_eval_host, itself held to the oracle at 1e-10 by tests/test_gpu_likelihood.py)
+        rec = records.cpu().numpy()
+        assert np.all(rec[:, :, E.REC_IT] == (np.arange(n_rec) * SAMPLE)[:, None]) and np.all(np.isfinite(rec[:, :, E.REC_LIK]))
+        last_ds = keep[-1][1]
+        pick = rec[5::10].reshape(-1, rec.shape[-1])
+        reps = np.tile(rep_of_chain, len(rec[5::10]))
+        states = [E.record_to_state(r, end_time) for r in pick]
+        ev = last_ds.evaluate(states, gamma_rate=pick[:, [E.REC_GL, E.REC_GM]], poi_lambda=pick[:, E.REC_POI], rep=reps)
+        assert np.allclose(ev["lik"], pick[:, E.REC_LIK], rtol=1e-10, atol=0), "timed output: logged likelihood differs from the state's"
+        assert np.allclose(ev["prior_rates"] + pick[:, E.REC_POIA], pick[:, E.REC_PRIOR], rtol=1e-9, atol=1e-9), "timed output: logged prior differs"
+        k_l_mean, k_m_mean = float(rec[n_rec // 2:, :, E.REC_KL].mean()), float(rec[n_rec // 2:, :, E.REC_KM].mean())
         for (e0, e1, e2, e3), ds, ch in keep:
             k1_ms.append(e0.elapsed_time(e1))
             k3_ms.append(e2.elapsed_time(e3))
             lik_evals += int(ch.counters()[:, 2].sum())
             ch.close(); ds.close()
-        # sanity of the last step's output: every chain delivered its samples, counts conserve lineages
-        rec = records.cpu().numpy()
-        assert np.all(rec[:, :, E.REC_IT] == (np.arange(n_rec) * SAMPLE)[:, None]) and np.all(np.isfinite(rec[:, :, E.REC_LIK]))
 
         # ---------------- e2e: host buffers through the public API, copies inside the timed region
         e2e = None
@@ -501,6 +511,9 @@ def run_cuda(a):
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": _workload(a, n_gpus), "clocks": cl,
             "gpu_launches": int(tot[1]),
+            "output_check": {"states_re_evaluated": int(len(pick)), "likelihood_rel_tol": 1e-10, "mean_K_l": k_l_mean, "mean_K_m": k_m_mean,
+                             "note": "likelihood and prior of states logged by the last timed step recomputed by lr_state_eval_host; "
+                                     "posterior parity on these statistics: tests/test_gpu_chains.py (32 oracle chains)"},
             "lik_evals_per_s": float(tot[0]) / (total_ms * 1e-3),
             "kernels": {"k1_bin_kernel_ms": k1, "k3_run_kernel_ms": statistics.mean(k3_ms),
                         "k3_ns_per_iteration_per_chain": 1e6 * statistics.mean(k3_ms) / a.iters,
