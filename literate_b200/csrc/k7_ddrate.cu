@@ -14,6 +14,7 @@
 // parameters was touched keeps its stored value, and so do the logarithms of the niche of the first 32 bins.  The genre term of
 // -m_birth 3 needs births and time at risk of the genre table inside [origin, origin + x0) and [origin + x0, present):
 // one strided pass over the (small, L1-resident) genre table whenever x0 is proposed, cached otherwise.
+#include <stdlib.h>
 #include "lr_common.cuh"
 
 #define DD_NPAR LR_DD_NPAR
@@ -130,26 +131,31 @@ struct DDCache {
 // this lane's bin of the first 32: statistics held in registers for the whole launch
 struct DDBin0 { double sp, ex, br, lnbr; };
 
-__device__ __forceinline__ DDBin0 dd_bin0(const DDView& v, int lane) {
+// (first: the bin of lane 0 -- 0 for one warp per chain, 32 w for warp w of the wide build)
+__device__ __forceinline__ DDBin0 dd_bin0(const DDView& v, int lane, int first = 0) {
     DDBin0 b;
-    const bool in = lane < v.nb;
-    b.sp = in ? v.tab[DD_SP * v.nbp + lane] : 0.0;
-    b.ex = in ? v.tab[DD_EX * v.nbp + lane] : 0.0;
-    b.br = in ? v.tab[DD_BR * v.nbp + lane] : 0.0;
-    b.lnbr = in ? v.tab[DD_LNBR * v.nbp + lane] : 0.0;
+    const int j = first + lane;
+    const bool in = j < v.nb;
+    b.sp = in ? v.tab[DD_SP * v.nbp + j] : 0.0;
+    b.ex = in ? v.tab[DD_EX * v.nbp + j] : 0.0;
+    b.br = in ? v.tab[DD_BR * v.nbp + j] : 0.0;
+    b.lnbr = in ? v.tab[DD_LNBR * v.nbp + j] : 0.0;
     return b;
 }
 
 // newL / newC: a parameter of the logistic / constant carrying capacity differs from the one `c` was computed for
 // `extra`: a per-lane term (Hastings share + prior difference of the lane's parameter) that rides the same butterfly; its warp
 // total comes back in place.
-__device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const double* p, int lane, bool doB, bool doD, bool newL,
-                                       bool newC, DDCache& c, double& likB, double& likD, double& extra) {
+// Per-lane partial sums over the bins first + lane, first + lane + stride, ... (one warp per chain: first 0, stride 32; warp w of
+// the wide build: first 32 w, stride 32 W).  termB / termD (wide build): every bin's term is also stored at its bin index.
+__device__ __forceinline__ void dd_lik_partial(const DDView& v, const DDBin0& b0, int first, int stride, const double* p, int lane, bool doB,
+                                               bool doD, bool newL, bool newC, DDCache& c, double& sB, double& sD,
+                                               double* termB = nullptr, double* termD = nullptr) {
     const bool evalD = doD && v.md >= 1;
-    double sB = 0.0, sD = 0.0;
+    sB = 0.0; sD = 0.0;
     if (doB || evalD) {
         const bool needL = (doB && v.mb >= 2) || (evalD && v.md == 2), needC = (doB && v.mb == 1) || (evalD && v.md == 1);
-        if (needL && newL) c.lnL0 = log(dd_niche_logistic(p, lane));
+        if (needL && newL) c.lnL0 = log(dd_niche_logistic(p, first + lane));
         if (needC && newC) c.lnC = log(p[P_L] + p[P_DIV0]);
         if (doB) {
             double lam = p[P_LF] * p[P_LMUL];                            // :87 (no floor in the reference)
@@ -166,9 +172,13 @@ __device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const 
             const double mu = dd_floor(rmin + (p[P_LF] - rmin) * x);
             sD = log(mu) * b0.ex - mu * b0.br;
         }
-        for (int j = lane + 32; j < v.nb; j += 32) {
+    }
+    if (termB != nullptr && first + lane < v.nb) { termB[first + lane] = sB; termD[first + lane] = sD; }
+    if (doB || evalD) {
+        const bool needL = (doB && v.mb >= 2) || (evalD && v.md == 2);
+        for (int j = first + lane + stride; j < v.nb; j += stride) {
             const double br = __ldg(v.tab + DD_BR * v.nbp + j), lnbr = __ldg(v.tab + DD_LNBR * v.nbp + j);
-            double lnL = 0.0;
+            double lnL = 0.0, tB = 0.0, tD = 0.0;
             if (needL) {
                 if (c.tail == nullptr) lnL = log(dd_niche_logistic(p, j));
                 else if (newL) { lnL = log(dd_niche_logistic(p, j)); c.tail[(c.sel ^ 1) * c.nt + j - 32] = lnL; }
@@ -181,17 +191,31 @@ __device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const 
                     const double rmax = p[P_LF] + p[P_LF] * p[P_LMUL];
                     lam = dd_floor(rmax - (rmax - p[P_LF]) * x);
                 }
-                sB += log(lam) * __ldg(v.tab + DD_SP * v.nbp + j) - lam * br;
+                tB = log(lam) * __ldg(v.tab + DD_SP * v.nbp + j) - lam * br;
+                sB += tB;
             }
             if (evalD) {
                 const double x = exp(p[P_NUD] * (lnbr - (v.md == 1 ? c.lnC : lnL)));
                 const double rmin = p[P_LF] - p[P_LF] * p[P_MMUL];
                 const double mu = dd_floor(rmin + (p[P_LF] - rmin) * x);
-                sD += log(mu) * __ldg(v.tab + DD_EX * v.nbp + j) - mu * br;
+                tD = log(mu) * __ldg(v.tab + DD_EX * v.nbp + j) - mu * br;
+                sD += tD;
             }
+            if (termB != nullptr) { termB[j] = tB; termD[j] = tD; }
         }
         if (c.tail != nullptr && needL && newL) c.sel ^= 1;       // the recomputed values sit in the other buffer
+    } else if (termB != nullptr) {
+        for (int j = first + lane + stride; j < v.nb; j += stride) { termB[j] = 0.0; termD[j] = 0.0; }
     }
+}
+
+// newL / newC: a parameter of the logistic / constant carrying capacity differs from the one `c` was computed for
+// `extra`: a per-lane term (Hastings share + prior difference of the lane's parameter) that rides the same butterfly; its warp
+// total comes back in place.
+__device__ __forceinline__ void dd_lik(const DDView& v, const DDBin0& b0, const double* p, int lane, bool doB, bool doD, bool newL,
+                                       bool newC, DDCache& c, double& likB, double& likD, double& extra) {
+    double sB, sD;
+    dd_lik_partial(v, b0, 0, 32, p, lane, doB, doD, newL, newC, c, sB, sD);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sB += __shfl_xor_sync(0xffffffffu, sB, o);
@@ -426,6 +450,112 @@ __global__ void __launch_bounds__(128, 3) k7_dd_kernel(const DDRun P) {
             next_sample += P.sample_every;
         }
     }
+    const double prior = warp_sum(dd_prior_term(v, lane, mine));
+    if (lane < DD_NPAR) S->p[lane] = mine;
+    if (lane == 0) {
+        S->likB = likB; S->likD = likD; S->likG = likG; S->prior = prior; S->it = it; S->accepted = accepted;
+        S->g[0] = g[0]; S->g[1] = g[1]; S->g[2] = g[2]; S->g[3] = g[3];
+    }
+}
+
+// WIDE build: W warps (one CTA) per chain, as k6_trend_wide_kernel: warp w evaluates bins 32 w + lane (+ 32 W k), every warp draws
+// the same random numbers and takes the same decision, the per-bin terms are exchanged through shared memory (double-buffered by
+// iteration parity, one __syncthreads per iteration) and added in the one-warp kernel's order -- the same chain, bit for bit.
+// The log-niche cache of the bins beyond each warp's register bin is one CTA-wide array indexed by bin.
+template <int W>
+__global__ void __launch_bounds__(W * 32, 2) k7_dd_wide_kernel(const DDRun P) {
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int first = 32 * wq, stride = 32 * W;
+    const int c = blockIdx.x;
+    if (c >= P.n_chains) return;
+    DDChain* S = P.st + c;
+    const DDView v = dd_select(P.v, S->rep);
+    const unsigned chain = S->chain;
+    double mine = lane < DD_NPAR ? S->p[lane] : 0.0;
+    double p[DD_NPAR];
+    dd_bcast(mine, p);
+    double likB = S->likB, likD = S->likD, likG = S->likG;
+    double g[4] = {S->g[0], S->g[1], S->g[2], S->g[3]};
+    const DDBin0 b0 = dd_bin0(v, lane, first);
+    const DDPriorLane pl = dd_prior_lane(v, lane);
+    const unsigned maskL = (1u << P_K) | (1u << P_X0) | (1u << P_DIV0) | (1u << P_L), maskC = (1u << P_DIV0) | (1u << P_L);
+    extern __shared__ double tail_s[];                 // [2][tail_n] log-niche cache, then [2 parities][2 sides][nbp] per-bin terms
+    double* terms = tail_s + 2 * (size_t)P.tail_n;
+    DDCache cache;
+    cache.nt = P.tail_n; cache.sel = 0;
+    cache.tail = P.tail_n > 0 ? tail_s : nullptr;
+    if (cache.tail != nullptr)
+        for (int j = first + lane + stride; j < v.nb; j += stride) cache.tail[j - 32] = log(dd_niche_logistic(p, j));
+    cache.lnL0 = log(dd_niche_logistic(p, first + lane));
+    cache.lnC = log(p[P_L] + p[P_DIV0]);
+    cache.lg1 = log(p[P_G1]); cache.lg2 = log(p[P_G2]);
+    long long it = S->it, accepted = S->accepted;
+    const long long it_end = it + P.n_iter;
+    double fmine = 0.0;
+#pragma unroll
+    for (int k = 0; k < DD_NPAR; ++k)
+        if (lane == k) fmine = P.f[k];
+    const bool can_slide = v.mb >= 1 || v.md >= 1;
+    long long next_sample = (it + P.sample_every - 1) / P.sample_every * P.sample_every;
+    long long rec_idx = 0;
+    __syncthreads();                                   // every warp has read the chain's state before warp 0 may rewrite it
+
+    for (; it < it_end; ++it) {
+        const Philox4 r = philox4x32_10((uint32_t)it, (uint32_t)((unsigned long long)it >> 32), (uint32_t)lane | (0x70u << 8), chain, P.k0, P.k1);
+        const double ua = u01(r.x, r.y), ub = u01(r.z, r.w);
+        const double rr1 = __shfl_sync(0xffffffffu, ua, 11), rr2 = __shfl_sync(0xffffffffu, ub, 11);
+        const double us = __shfl_sync(0xffffffffu, ua, 12);
+        const double u_acc = __shfl_sync(0xffffffffu, ub, 12);
+        const int kind = (rr1 < 0.1 && can_slide) ? (rr2 < 0.5 ? 1 : 2) : 0;                  // :248-258
+        const bool on = kind == 0 && (((double)r.x + 0.5) * 2.3283064365386963e-10) < fmine;
+        double h;
+        const double prop = dd_propose(v, lane, kind, mine, on, kind == 0 ? u01(r.y, r.z) : us, h);
+        unsigned touched = __ballot_sync(0xffffffffu, on);
+        if (kind == 1) touched = 1u << P_X0;
+        if (kind == 2) touched = 1u << P_MMUL;
+        double q[DD_NPAR];
+        dd_bcast(prop, q);
+        double hp = h + dd_prior_delta(v, pl, mine, prop, h);       // summed in the butterfly of the likelihood
+        double nB = likB, nD = likD, nG = likG;
+        double ng[4] = {g[0], g[1], g[2], g[3]};
+        DDCache nc = cache;
+        const bool doB = (touched & P.depB) != 0, doD = (touched & P.depD) != 0;
+        double* tB = terms + (size_t)(it & 1) * 2 * v.nbp;
+        double* tD = tB + v.nbp;
+        double sB, sD;
+        dd_lik_partial(v, b0, first, stride, q, lane, doB, doD, (touched & maskL) != 0, (touched & maskC) != 0, nc, sB, sD, tB, tD);
+        __syncthreads();
+        sB = 0.0; sD = 0.0;                             // the one-warp kernel's order: lane l adds its bins l, l + 32, ... ascending
+        for (int j = lane; j < v.nb; j += 32) { sB += tB[j]; sD += tD[j]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sB += __shfl_xor_sync(0xffffffffu, sB, o);
+            sD += __shfl_xor_sync(0xffffffffu, sD, o);
+            hp += __shfl_xor_sync(0xffffffffu, hp, o);
+        }
+        if (doB) nB = sB;
+        if (doD) nD = v.md >= 1 ? sD : v.likD_const;
+        if (v.mb == 3) {
+            if (touched & (1u << P_X0)) dd_genre_stats(v, q[P_X0], lane, ng);
+            if (touched & ((1u << P_X0) | (1u << P_G1) | (1u << P_G2)))
+                nG = dd_genre_lik(q, ng, (touched & (1u << P_G1)) != 0, (touched & (1u << P_G2)) != 0, nc);
+        }
+        const double x = ((nB + nD + nG) - (likB + likD + likG)) + hp;
+        if (it == 0 || mh_accept_gt(x, u_acc)) {                                                 // :263
+#pragma unroll
+            for (int k = 0; k < DD_NPAR; ++k) p[k] = q[k];
+            mine = prop;
+            likB = nB; likD = nD; likG = nG; cache = nc;
+            g[0] = ng[0]; g[1] = ng[1]; g[2] = ng[2]; g[3] = ng[3];
+            ++accepted;
+        }
+        if (it == next_sample) {                                                                 // :274
+            if (P.records && wq == 0) dd_record(P.records + ((size_t)rec_idx * P.n_chains + c) * P.rec_doubles, v, p, mine, likB, likD, likG, it, accepted, lane);
+            ++rec_idx;
+            next_sample += P.sample_every;
+        }
+    }
+    if (wq != 0) return;
     const double prior = warp_sum(dd_prior_term(v, lane, mine));
     if (lane < DD_NPAR) S->p[lane] = mine;
     if (lane == 0) {
@@ -692,7 +822,22 @@ extern "C" int lr_dd_run(lr_dd_t t, int64_t n_iter, int64_t sample_every, double
     P.tail_n = t->n_bins > 32 ? t->nbp - 32 : 0;
     size_t smem = (size_t)(threads / 32) * 2 * P.tail_n * sizeof(double);
     if (smem > 48 * 1024) { P.tail_n = 0; smem = 0; }
-    k7_dd_kernel<<<blocks, threads, smem, st>>>(P);
+    // wide build (W warps per chain) when one warp per chain would leave most of the GPU idle and there are bins to share
+    int W = t->n_bins > 128 ? 4 : (t->n_bins > 64 ? 2 : 1);
+    if ((long long)t->n_chains * W > (long long)h->sm_count * 8) W = 1;
+    { const char* e = getenv("LR_DD_WIDE"); if (e) W = atoi(e) ? (t->n_bins > 128 ? 4 : (t->n_bins > 64 ? 2 : 1)) : 1; }      // development override
+    if (W > 1) {
+        P.tail_n = t->nbp - 32;
+        const size_t wsmem = ((size_t)2 * P.tail_n + (size_t)4 * t->nbp) * sizeof(double);
+        if (wsmem > 48 * 1024) W = 1;
+        else if (W == 4) k7_dd_wide_kernel<4><<<t->n_chains, 128, wsmem, st>>>(P);
+        else k7_dd_wide_kernel<2><<<t->n_chains, 64, wsmem, st>>>(P);
+    }
+    if (W == 1) {
+        P.tail_n = t->n_bins > 32 ? t->nbp - 32 : 0;
+        if ((size_t)(threads / 32) * 2 * P.tail_n * sizeof(double) > 48 * 1024) P.tail_n = 0;
+        k7_dd_kernel<<<blocks, threads, smem, st>>>(P);
+    }
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
     return LR_OK;

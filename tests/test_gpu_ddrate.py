@@ -117,6 +117,24 @@ def test_bin_counts_from_one_to_two_hundred(device, nb, mb, md):
         assert r[4] == pytest.approx(D.prior(r[5:16], S, exact_scipy=True), rel=RTOL)
 
 
+@pytest.mark.parametrize("nb,mb,md", [(65, 3, 2), (100, 2, 1), (129, 1, 2), (200, 3, 2), (200, 0, 0), (300, 3, 1)])
+def test_wide_build_gives_the_chains_of_the_one_warp_build(device, nb, mb, md, monkeypatch):
+    """More than 64 bins and few chains: 2 or 4 warps share a chain's bins (k7_dd_wide_kernel), exchange the per-bin terms and add
+    them in the one-warp kernel's order -- records and final states identical, bit for bit, over split launches."""
+    rng = np.random.default_rng(77 + nb + mb)
+    t = np.arange(nb)
+    br = 20 + 400 / (1 + np.exp(-0.3 * (t - nb / 2))) + rng.uniform(0, 5, nb)
+    sp = rng.poisson(br * 0.2); ex = rng.poisson(br * 0.1)
+    gts = np.sort(rng.uniform(0, nb * .7, 40)).round(); gte = np.minimum(gts + rng.integers(1, nb + 1, 40), nb) + .5
+    out = []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("LR_DD_WIDE", wide)
+        ch = DD.DDChains(device, sp, ex, br, 0.0, nb + 1.5, mb, md, gts if mb == 3 else None, gte if mb == 3 else None, 7, 5)
+        recs = [ch.run(n, s) for n, s in ((1501, 100), (1, 1), (998, 7), (3000, 250))]
+        out.append((np.concatenate(recs), ch.state()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
 def test_proposals_with_explicit_draws_match_the_oracle(device, tmp_path):
     S, ch = _setup(device, tmp_path)
     rng = np.random.default_rng(12)
