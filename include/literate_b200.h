@@ -89,6 +89,13 @@ int64_t lr_acc_stride(int32_t n_bins);
 int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int64_t n, int64_t ld,
                       int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
                       int32_t dead_only, double end_time, int64_t* d_acc, void* stream);
+/* Two builds of the pass produce these accumulators -- the same integer sums, hence the same finalized statistics bit for bit
+ * (how a 96-bit sum is split over its row pair depends on where a pass flushed): the general one, and one for REAL-VALUED times whose
+ * fraction words exist once per lane in shared memory (n_bins <= 216; 0.89 against 0.74 of the copy bandwidth).  The pass
+ * itself records which kind of table it saw (its first 32 lineages) and the NEXT lr_bin_accumulate through the handle uses
+ * that to choose -- no synchronisation, a stale answer costs speed only.  lr_bin_table_hint reads the record (1 = fractional
+ * times, 0 = integer years) as of the last finished pass; the environment variable LR_K1_LANES=0 / 1 forces the choice. */
+int lr_bin_table_hint(lr_handle_t h, int32_t* out);
 int lr_bin_finalize(lr_handle_t h, const int64_t* d_acc, int32_t n_rep, int32_t n_bins, double fe_ref,
                     int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream);
 /* zero + accumulate + finalize using the handle's workspace */

@@ -60,6 +60,7 @@ struct K1Params {
     long long chunk;       // flattened lineages per CTA
     long long seg_max;     // forced flush period
     int vec_ok;
+    int* hint;             // mapped host int: CTA 0 records whether its first tile carried fractional times (may be null)
 };
 
 // 96-bit unsigned accumulation out of 32-bit shared atomics: words [idx], [nb+idx], [2nb+idx]
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
             const bool fracS = __any_sync(0xffffffffu, t0 != floor(t0));
             const bool fracE = __any_sync(0xffffffffu, e0 - (ceil(e0) - 1.0) != p.fe_ref);
             mergeS = sameS != 0 && fracS; mergeE = sameE != 0 && fracE;
+            if (blockIdx.x == 0 && tid == 0 && s0 == 0 && p.hint) *(volatile int*)p.hint = (fracS || fracE) ? 1 : 0;
         }
         if (mergeS || mergeE) k1_tiles<true>(p, s, acc, ts, te, A, ntiles, warp, W, lane, mergeS, mergeE);
         else k1_tiles<false>(p, s, acc, ts, te, A, ntiles, warp, W, lane, false, false);
@@ -434,6 +436,193 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
                 v -= (__int128)n * (__int128)p.fe_ref_fix;
                 atomicAdd(&g[ROW_CE_LO * p.acc_stride + i], (unsigned long long)(v & 0xffffffff));
                 atomicAdd(&g[ROW_CE_HI * p.acc_stride + i], (unsigned long long)(long long)(v >> 32));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- real-valued tables, LANE-PRIVATE fraction words -------------------------------------------------------------------
+// On real-valued tables k1_bin_kernel is bound by the shared-memory data stage and by issue: its six atomics per lineage hit
+// random bins, 32 random words fall on the 32 banks 3.1 deep on average (ncu, 1M x 256 shuffled: 168 M atomic wavefronts for
+// 53.8 M atomic instructions, l1tex 83 % busy, 97 warp instructions per lineage at 69 % issue, 0.74 of the copy peak), and on
+// sorted tables 32 carry chains per instruction land on ONE word.
+// Here the two low words of each side's fraction sum exist once per LANE ([bin][2][32]: lane l only ever touches bank l), so a
+// fraction atomic is one wavefront whatever the bins are, shuffled or sorted, and only the warps of the CTA contend for a word;
+// the third word (one carry in >= 4096 additions) and the counters (ATOMS.POPC.INC, merged by the hardware) stay shared.
+// 2 x 256 B per bin: 200 bins = 105 KB per CTA, two CTAs of 512 threads per SM.  Every birth adds its fraction and every death
+// goes through the "other fraction" counter (sum(fix(fe)) - n * fix(fe_ref) is zero for the expected ones); a death outside
+// the window lands in a spare bin; fix(x) is the mantissa of 1 + x (one DADD and an integer subtraction, identical to
+// rn(x * 2^52) including ties and x == 1); the carries are add.cc / addc.  A regular lineage is straight-line code, 36 warp
+// instructions against 60, and the two lineages of a 128-bit load issue their four carry chains together.
+// Measured (tools/k1_bench.py 256, GB/s of 16 B per lineage): shuffled 5 840 against 4 850, sorted by birth 5 950 against 4 500
+// (0.89 / 0.91 of the copy peak).  Flushing every 128 000 lineages (which would make the high word's carry unnecessary) cost
+// 8 %: each flush drains the CTA's loads.  Integer sums: the accumulators hold the same totals as k1_bin_kernel's, the finalized
+// statistics are bit-identical.
+// lr_bin_accumulate picks this build when the previous table through the handle carried fractions (K1Params::hint) and the
+// bins fit (n_bins <= 216).
+constexpr int K1L_THREADS = 512;
+constexpr int K1L_UNROLL = 2;                        // double2 loads in flight per array per thread (64 KB per SM; 3 and 4 were not faster)
+constexpr int K1L_TILE = 64 * K1L_UNROLL;
+constexpr size_t K1L_WORDS_PER_BIN = 4 * 32 + 4;
+
+struct K1Lanes {
+    unsigned* hs32; unsigned* exC;      // [nb + 1] births, deaths (generic pointers: ATOMS.POPC.INC)
+    unsigned S0, E0;                    // shared-window byte addresses of THIS LANE's low word of bin 0 in [nb + 1][2][32] (high word: + 128)
+    unsigned topS, topE;                // ... of the [nb + 1] third words, shared by the lanes
+};
+
+// 2^-52 fixed point of x in [0, 1]: the mantissa of 1 + x (exponent step included when 1 + x rounds to 2)
+__device__ __forceinline__ void fix_of(double x, unsigned& lo, unsigned& hi) {
+    const long long b = __double_as_longlong(x + 1.0);
+    lo = (unsigned)b; hi = (unsigned)((unsigned long long)b >> 32) - 0x3ff00000u;
+}
+__device__ __forceinline__ void add_lanes(unsigned addr, unsigned top_addr, unsigned lo, unsigned hi) {
+    unsigned old, old2, c;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(lo) : "memory");
+    asm("{ .reg .u32 t; add.cc.u32 t, %1, %2; addc.u32 %0, %0, 0; }" : "+r"(hi) : "r"(old), "r"(lo));      // carry of the low word
+    asm volatile("atom.shared.add.u32 %0, [%1+128], %2;" : "=r"(old2) : "r"(addr), "r"(hi) : "memory");
+    asm("{ .reg .u32 t; add.cc.u32 t, %1, %2; addc.u32 %0, 0, 0; }" : "=r"(c) : "r"(old2), "r"(hi));       // of the high word: once in >= 4096 additions
+    if (c) asm volatile("red.shared.add.u32 [%0], 1;" :: "r"(top_addr) : "memory");
+}
+
+// a lineage born inside the window and alive for a positive time, straight-line: a death outside the window (an extant lineage)
+// goes to the spare bin nb, which the flush ignores
+__device__ __forceinline__ void k1_regular_lanes(const K1Params& p, const K1Lanes& s, double ts, double te, int ti, unsigned a, int c1, unsigned b) {
+    unsigned lo, hi, lo2, hi2;
+    b = min(b, p.nb);
+    atomicAdd(&s.hs32[a], 1u);
+    atomicAdd(&s.exC[b], 1u);
+    fix_of(ts - (double)ti, lo, hi);
+    fix_of(te - (double)c1, lo2, hi2);
+    add_lanes(s.S0 + a * 256u, s.topS + a * 4u, lo, hi);
+    add_lanes(s.E0 + b * 256u, s.topE + b * 4u, lo2, hi2);
+}
+
+template <bool DEAD_ONLY>
+__device__ __forceinline__ void k1_lineage_lanes(const K1Params& p, const K1Lanes& s, long long* acc, double ts, double te) {
+    if constexpr (DEAD_ONLY) {
+        if (!(te < p.end_time)) return;      // :531-532
+    }
+    const int ti = __double2int_rd(ts);
+    const int c1 = __double2int_ru(te) - 1;
+    const unsigned a = (unsigned)(ti - p.fb);
+    const unsigned b = (unsigned)(c1 - p.fb);
+    if ((te > ts) && (a < p.nb)) k1_regular_lanes(p, s, ts, te, ti, a, c1, b);
+    else k1_irregular(p.fb, p.nb, p.acc_stride, p.fe_ref_fix, acc, ts, te);
+}
+
+// the two lineages of one 128-bit load: when both are regular (nearly always) their four carry chains are issued together
+template <bool DEAD_ONLY>
+__device__ __forceinline__ void k1_pair_lanes(const K1Params& p, const K1Lanes& s, long long* acc, double2 ts, double2 te) {
+    const int t0 = __double2int_rd(ts.x), t1 = __double2int_rd(ts.y);
+    const int c0 = __double2int_ru(te.x) - 1, c1 = __double2int_ru(te.y) - 1;
+    const unsigned a0 = (unsigned)(t0 - p.fb), a1 = (unsigned)(t1 - p.fb);
+    bool r0 = (te.x > ts.x) && (a0 < p.nb), r1 = (te.y > ts.y) && (a1 < p.nb);
+    if constexpr (DEAD_ONLY) { r0 = r0 && (te.x < p.end_time); r1 = r1 && (te.y < p.end_time); }
+    if (r0 && r1) {
+        k1_regular_lanes(p, s, ts.x, te.x, t0, a0, c0, (unsigned)(c0 - p.fb));
+        k1_regular_lanes(p, s, ts.y, te.y, t1, a1, c1, (unsigned)(c1 - p.fb));
+    } else {
+        k1_lineage_lanes<DEAD_ONLY>(p, s, acc, ts.x, te.x);
+        k1_lineage_lanes<DEAD_ONLY>(p, s, acc, ts.y, te.y);
+    }
+}
+
+// sum over the 32 lane copies of one bin's two words: sum(low) + (sum(high) << 32), as a 128-bit value (all lanes get it)
+__device__ __forceinline__ unsigned __int128 lanes_total(const unsigned* w, unsigned bin, unsigned lane) {
+    const unsigned x0 = w[bin * 64u + lane], x1 = w[bin * 64u + 32u + lane];
+    const unsigned long long t0 = (unsigned long long)__reduce_add_sync(0xffffffffu, x0 & 0xffffu) +
+                                  ((unsigned long long)__reduce_add_sync(0xffffffffu, x0 >> 16) << 16);
+    const unsigned long long t1 = (unsigned long long)__reduce_add_sync(0xffffffffu, x1 & 0xffffu) +
+                                  ((unsigned long long)__reduce_add_sync(0xffffffffu, x1 >> 16) << 16);
+    return (unsigned __int128)t0 + ((unsigned __int128)t1 << 32);
+}
+
+template <bool DEAD_ONLY>
+__global__ void __launch_bounds__(K1L_THREADS, 2) k1_bin_lanes_kernel(const K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, W = blockDim.x >> 5;
+    const unsigned lane = (unsigned)tid & 31u;
+    const unsigned nb = p.nb;
+    unsigned* const wS = (unsigned*)smem_raw;              // [nb + 1][2][32]
+    unsigned* const wE = wS + 64 * (size_t)(nb + 1);       // [nb + 1][2][32]
+    K1Lanes s;
+    s.hs32 = wE + 64 * (size_t)(nb + 1); s.exC = s.hs32 + (nb + 1);
+    unsigned* const tS_top = s.exC + (nb + 1); unsigned* const tE_top = tS_top + (nb + 1);
+    s.topS = (unsigned)__cvta_generic_to_shared(tS_top); s.topE = (unsigned)__cvta_generic_to_shared(tE_top);
+    s.S0 = (unsigned)__cvta_generic_to_shared(wS) + lane * 4u; s.E0 = (unsigned)__cvta_generic_to_shared(wE) + lane * 4u;
+    asm volatile("" : "+r"(s.S0), "+r"(s.E0));       // opaque: kept in two registers instead of being recomputed per lineage
+    const size_t zero_words = K1L_WORDS_PER_BIN * (size_t)(nb + 1);
+    const size_t zero_vec = zero_words / 4;
+
+    const long long total = p.n * (long long)p.n_rep;
+    long long g0 = (long long)blockIdx.x * p.chunk;
+    long long g1 = g0 + p.chunk;
+    if (g1 > total) g1 = total;
+
+    while (g0 < g1) {
+        const long long rep = g0 / p.n;
+        const long long s0 = g0 - rep * p.n;
+        long long s1 = p.n;
+        if (s1 - s0 > g1 - g0) s1 = s0 + (g1 - g0);
+        if (s1 - s0 > p.seg_max) s1 = s0 + p.seg_max;
+        g0 += s1 - s0;
+        const double* ts = p.ts + rep * p.ld;
+        const double* te = p.te + rep * p.ld;
+        long long* acc = p.acc + rep * (LR_ACC_ROWS * p.acc_stride);
+
+        for (size_t i = tid; i < zero_vec; i += blockDim.x) ((uint4*)smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = zero_vec * 4 + tid; i < zero_words; i += blockDim.x) ((unsigned*)smem_raw)[i] = 0u;
+        __syncthreads();
+
+        long long A = (s0 + K1L_TILE - 1) / K1L_TILE * K1L_TILE;
+        if (A > s1) A = s1;
+        const long long ntiles = (s1 - A) / K1L_TILE;
+        const long long B = A + ntiles * K1L_TILE;
+        for (long long i = s0 + tid; i < A; i += blockDim.x) k1_lineage_lanes<DEAD_ONLY>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        for (long long i = B + tid; i < s1; i += blockDim.x) k1_lineage_lanes<DEAD_ONLY>(p, s, acc, ld_stream_f64(ts + i), ld_stream_f64(te + i));
+        if (blockIdx.x == 0 && warp == 0 && s0 == 0 && p.hint && s1 - s0 >= 32) {      // the kind of table, for the next call
+            const double t0 = ld_stream_f64(ts + s0 + lane), e0 = ld_stream_f64(te + s0 + lane);
+            const bool frac = __any_sync(0xffffffffu, t0 != floor(t0) || e0 - (ceil(e0) - 1.0) != p.fe_ref);
+            if (lane == 0) *(volatile int*)p.hint = frac ? 1 : 0;
+        }
+        for (long long k = warp; k < ntiles; k += W) {
+            const double2* t2 = (const double2*)(ts + A + k * K1L_TILE) + lane;
+            const double2* e2 = (const double2*)(te + A + k * K1L_TILE) + lane;
+            double2 sv[K1L_UNROLL], ev[K1L_UNROLL];
+#pragma unroll
+            for (int u = 0; u < K1L_UNROLL; ++u) { sv[u] = ld_stream_f64x2(t2 + u * 32); ev[u] = ld_stream_f64x2(e2 + u * 32); }
+#pragma unroll
+            for (int u = 0; u < K1L_UNROLL; ++u) {
+                k1_pair_lanes<DEAD_ONLY>(p, s, acc, sv[u], ev[u]);
+            }
+        }
+        __syncthreads();
+
+        // ---- flush: counters as in k1_bin_kernel; one warp per bin folds the 32 lane copies
+        unsigned long long* g = (unsigned long long*)acc;
+        for (unsigned i = tid; i < nb; i += blockDim.x) {
+            if (s.hs32[i]) atomicAdd(&g[ROW_SP * p.acc_stride + i], (unsigned long long)s.hs32[i]);
+            if (s.exC[i]) atomicAdd(&g[ROW_EX * p.acc_stride + i], (unsigned long long)s.exC[i]);
+        }
+        for (unsigned i = warp; i < nb; i += W) {
+            const unsigned nS = s.hs32[i], nE = s.exC[i];                                     // warp-uniform
+            unsigned __int128 tS = 0, tE = 0;
+            if (nS) tS = lanes_total(wS, i, lane) + ((unsigned __int128)tS_top[i] << 64);
+            if (nE) tE = lanes_total(wE, i, lane) + ((unsigned __int128)tE_top[i] << 64);
+            if (lane == 0) {
+                if (tS) {
+                    atomicAdd(&g[ROW_CS_LO * p.acc_stride + i], (unsigned long long)(tS & 0xffffffffu));
+                    atomicAdd(&g[ROW_CS_HI * p.acc_stride + i], (unsigned long long)(tS >> 32));
+                }
+                if (nE) {
+                    const __int128 v = (__int128)tE - (__int128)nE * (__int128)p.fe_ref_fix;
+                    if (v != 0) {
+                        atomicAdd(&g[ROW_CE_LO * p.acc_stride + i], (unsigned long long)(v & 0xffffffff));
+                        atomicAdd(&g[ROW_CE_HI * p.acc_stride + i], (unsigned long long)(long long)(v >> 32));
+                    }
+                }
             }
         }
         __syncthreads();
@@ -543,6 +732,31 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     chunk = (chunk + K1_TILE - 1) / K1_TILE * K1_TILE;
     p.chunk = chunk;
     const int used = (int)((total + chunk - 1) / chunk);
+    p.hint = h->k1_hint;
+    h->k1_hint_used = 1;
+    // real-valued tables: the lane-private build when the last table through this handle carried fractions and two CTAs of it fit
+    // an SM (n_bins <= 216); LR_K1_LANES=0 / 1 forces the choice
+    const size_t smem_l = K1L_WORDS_PER_BIN * ((size_t)n_bins + 1) * sizeof(unsigned);
+    const char* e_l = getenv("LR_K1_LANES");
+    const bool lanes_fit = 2 * (smem_l + 1024) <= (size_t)h->max_smem_optin + 1024 && p.vec_ok;
+    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : *(volatile int*)h->k1_hint == 1);
+    if (lanes) {
+        const int blocks_l = h->sm_count * 2;
+        long long chunk_l = (total + blocks_l - 1) / blocks_l;
+        chunk_l = (chunk_l + K1L_TILE - 1) / K1L_TILE * K1L_TILE;
+        p.chunk = chunk_l;
+        const int used_l = (int)((total + chunk_l - 1) / chunk_l);
+        if (dead_only) {
+            LR_CUDA(cudaFuncSetAttribute(k1_bin_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            k1_bin_lanes_kernel<true><<<used_l, K1L_THREADS, smem_l, st>>>(p);
+        } else {
+            LR_CUDA(cudaFuncSetAttribute(k1_bin_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+            k1_bin_lanes_kernel<false><<<used_l, K1L_THREADS, smem_l, st>>>(p);
+        }
+        LR_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return LR_OK;
+    }
     LR_CUDA(cudaFuncSetAttribute(k1_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k1_bin_kernel<<<used, threads, smem, st>>>(p);
     LR_CUDA(cudaGetLastError());
@@ -587,6 +801,12 @@ extern "C" int lr_bin_accumulate_i32(lr_handle_t h, const int32_t* d_ts, const i
     k1_bin_i32_kernel<<<used, threads, smem, st>>>(p);
     LR_CUDA(cudaGetLastError());
     h->launches += 1;
+    return LR_OK;
+}
+
+extern "C" int lr_bin_table_hint(lr_handle_t h, int32_t* out) {
+    LR_REQUIRE(h != nullptr && out != nullptr, "lr_bin_table_hint: null pointer");
+    *out = *(volatile int*)h->k1_hint;
     return LR_OK;
 }
 

@@ -48,6 +48,8 @@ extern "C" int lr_create(int device, lr_handle_t* out) {
     LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2 * LR_NSTAGE; ++i) LR_CUDA(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
     LR_CUDA(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+    LR_CUDA(cudaHostAlloc((void**)&h->k1_hint, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *h->k1_hint = 0;
     *out = h;
     return LR_OK;
 }
@@ -57,8 +59,9 @@ extern "C" int lr_destroy(lr_handle_t h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->copy_stream);
-    if (h->ws_used) cudaDeviceSynchronize();        // the workspace's last user may have been a caller stream
+    if (h->ws_used || h->k1_hint_used) cudaDeviceSynchronize();        // the last user of the workspace / the K1 hint may have been a caller stream
     cudaFree(h->ws);
+    cudaFreeHost(h->k1_hint);
     for (int i = 0; i < LR_NSTAGE; ++i) cudaFree(h->stage[i]);
     for (int i = 0; i < 2 * LR_NSTAGE; ++i) cudaEventDestroy(h->ev[i]);
     cudaEventDestroy(h->ev_order);

@@ -63,6 +63,11 @@ struct lr_handle_s {
     cudaEvent_t ev_order;       // scratch event of lr_order
     void* stage[LR_NSTAGE];
     size_t stage_bytes;
+    // K1's memory of the last table's kind: one int in mapped pinned host memory that the kernel's CTA 0 writes (1 = the table
+    // carries fractional times, 0 = integer years) and the NEXT lr_bin_accumulate reads without synchronising to choose between
+    // its two bit-identical builds (k1_binstats.cu); a stale value costs speed only
+    int* k1_hint;
+    int k1_hint_used;
 };
 
 // Cross-stream ordering without host synchronisation.  Entry points take a caller stream or fall back to the handle's

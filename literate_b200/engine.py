@@ -207,6 +207,13 @@ class Device:
                                            C.c_void_p(acc.data_ptr()), st), "lr_bin_accumulate")
         return acc
 
+    def bin_table_hint(self):
+        """What the last finished K1 pass saw (lr_bin_table_hint): 1 = fractional times, 0 = integer years.  The next pass
+        through this handle picks its build from it."""
+        out = C.c_int32(0)
+        N.check(self.lib.lr_bin_table_hint(self.h, C.byref(out)), "lr_bin_table_hint")
+        return int(out.value)
+
     def loglik_direct_device(self, ts, te, first_bin, n_bins, lam, mu, stream=None):
         """Validation path (lr_loglik_direct): Keiding log-likelihood of states given as per-bin rates, straight from the
         lineages.  ts/te: float64 CUDA tensors [n]; lam/mu: float64 CUDA tensors [n_states, n_bins].  Returns [n_states]."""

@@ -14,6 +14,16 @@ from literate_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "general", "lanes"])
+def k1_build(request, monkeypatch):
+    """The two builds of the real-valued path (k1_bin_kernel / k1_bin_lanes_kernel, LR_K1_LANES) and the automatic choice."""
+    if request.param != "auto":
+        monkeypatch.setenv("LR_K1_LANES", "1" if request.param == "lanes" else "0")
+    else:
+        monkeypatch.delenv("LR_K1_LANES", raising=False)
+    return request.param
+
+
 def _check(dev, ts, te, jitter, exact=True, only_dead=True):
     got = dev.bin_stats(ts, te, death_jitter=jitter, only_dead=only_dead)
     want = O.bin_stats(ts, te, only_dead=only_dead)
@@ -44,7 +54,7 @@ def test_metal_bands(device, metal_path):
     assert got.sp.sum() == 27495 and got.ex.sum() == 16191 and got.br.sum() == 95426.5
 
 
-def test_random_integer_and_real(device):
+def test_random_integer_and_real(device, k1_build):
     rng = np.random.default_rng(11)
     for n in (1, 2, 31, 257, 4097, 20011):
         ts, te = synth.syn_int(n, replicate=n)
@@ -63,7 +73,7 @@ def test_random_integer_and_real(device):
     _check(device, ts, te, 0.0)
 
 
-def test_sorted_real_valued_tables_take_the_warp_merge(device):
+def test_sorted_real_valued_tables_take_the_warp_merge(device, k1_build):
     """Tables sorted by birth (or death) time: the lanes of a warp hit one bin, the fractions are summed across the warp
     (MATCH.ALL + REDUX) before one carry chain.  The sums are integers: the result must be the SAME BITS as for the shuffled
     table, whatever mix of merged and per-lane updates a warp ends up doing (bin boundaries, half-sorted tables)."""
@@ -84,7 +94,7 @@ def test_sorted_real_valued_tables_take_the_warp_merge(device):
     _check(device, ts, te, 0.0)
 
 
-def test_degenerate_inputs(device):
+def test_degenerate_inputs(device, k1_build):
     # all extant, single bin
     ts = np.array([10.0, 10.0, 10.0]); te = np.array([11.5, 11.5, 11.5])
     _check(device, ts, te, 0.5)
@@ -103,7 +113,7 @@ def test_degenerate_inputs(device):
     _check(device, ts, te, 0.0, exact=False)
 
 
-def test_explicit_window_with_lineages_outside(device):
+def test_explicit_window_with_lineages_outside(device, k1_build):
     """first_bin / n_bins given by the caller (lineage-sharded use): lineages born before the window,
     dying after it, or entirely outside are clipped exactly as get_br clips them (:111-116)."""
     rng = np.random.default_rng(21)
@@ -116,7 +126,7 @@ def test_explicit_window_with_lineages_outside(device):
         assert (got.sp[0, j], got.ex[0, j], got.br[0, j]) == (a, b, c)
 
 
-def test_many_bins_and_single_bin(device):
+def test_many_bins_and_single_bin(device, k1_build):
     """Window sizes at both ends: one bin, and 6000 one-year bins (216 KB of shared histograms, one CTA per SM)."""
     ts = np.array([3.0, 3.0, 3.25]); te = np.array([3.5, 4.5, 3.75])
     _check(device, ts, te, 0.5, only_dead=False)
@@ -138,7 +148,7 @@ def test_too_many_bins_is_refused_with_a_message(device):
         device.bin_stats(ts, te)
 
 
-def test_replicates_and_ragged_pitch(device):
+def test_replicates_and_ragged_pitch(device, k1_build):
     import torch
     n_rep, n = 5, 3001      # odd n: rows are not 16-byte aligned -> scalar load path for odd replicates
     ts = np.empty((n_rep, n)); te = np.empty((n_rep, n))
@@ -156,7 +166,7 @@ def test_replicates_and_ragged_pitch(device):
     assert (sp.cpu().numpy() == got.sp).all() and (ex.cpu().numpy() == got.ex).all() and (br.cpu().numpy() == got.br).all()
 
 
-def test_full_size_one_million(device):
+def test_full_size_one_million(device, k1_build):
     """BASELINE cfg3 size: 1M lineages x 200 bins against the O(N) oracle, plus size-independent checks."""
     n = 1_000_000
     ts, te = synth.syn_int(n)
@@ -270,3 +280,98 @@ def test_int32_year_tables_give_the_same_statistics(device, metal_path):
     device.bin_accumulate_device(ti, ei, 1800, 200, acc_b, death_jitter=0.5)
     torch.cuda.synchronize()
     assert bool((acc_a == acc_b).all())
+
+
+def _same_accumulators(a, b):
+    """Raw accumulator blocks of two passes over the same table: the counters word for word, the two fixed-point sums as the
+    integers their (low 32 bits, rest) row pairs encode -- how a sum is split over the pair depends on where a pass flushed."""
+    assert np.array_equal(a[:, [0, 1, 6, 7]], b[:, [0, 1, 6, 7]])
+    for lo, hi in ((2, 3), (4, 5)):
+        va = a[:, lo].astype(object) + a[:, hi].astype(object) * (1 << 32)
+        vb = b[:, lo].astype(object) + b[:, hi].astype(object) * (1 << 32)
+        assert (va == vb).all()
+
+
+def test_lane_private_build_is_bit_identical_and_carries_into_the_third_word(device, monkeypatch):
+    """k1_bin_lanes_kernel against k1_bin_kernel on tables that stress what is new in it: one bin that takes every lineage
+    (each lane's high word overflows after 4096 additions of fractions near 1 -> the shared third word), extant-heavy tables
+    (deaths outside the window go to the spare bin), only_dead, negative times, an odd number of bins, several replicates."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 600_000
+    cases = {
+        "one bin, fractions near 1": (10 + 1 - rng.uniform(0, 1e-3, n), 10 + 1 - rng.uniform(0, 1e-6, n) + 0.0),
+        "mostly extant": (1900 + rng.uniform(0, 101, n), np.where(rng.uniform(size=n) < 0.9, 2001.0, 1900 + rng.uniform(0, 101, n))),
+        "negative times": (-60 + rng.uniform(0, 37, n), -60 + rng.uniform(0, 37, n) + rng.exponential(5, n)),
+    }
+    ts, te = cases["one bin, fractions near 1"]
+    cases["one bin, fractions near 1"] = (np.minimum(ts, te - 1e-9), te)
+    ts, te = cases["mostly extant"]
+    cases["mostly extant"] = (np.minimum(ts, te), np.maximum(ts, te))
+    for name, (ts, te) in cases.items():
+        res = {}
+        for build in ("0", "1"):
+            monkeypatch.setenv("LR_K1_LANES", build)
+            for dead in (False, True):
+                kw = dict(first_bin=10, n_bins=1, end_time=11.5) if name.startswith("one bin") else {}
+                res[build, dead] = device.bin_stats(ts, te, death_jitter=0.0, only_dead=dead, **kw)
+        for dead in (False, True):
+            a, b = res["0", dead], res["1", dead]
+            assert a.n_bins == b.n_bins and (a.sp == b.sp).all() and (a.ex == b.ex).all() and (a.br == b.br).all(), (name, dead)
+            if dead:
+                assert (a.ex_dead == b.ex_dead).all() and (a.br_dead == b.br_dead).all(), name
+        got = res["1", False]
+        if name.startswith("one bin"):
+            assert got.sp[0, 0] == n and got.ex[0, 0] == n
+            np.testing.assert_allclose(got.br[0, 0], np.sum(te - ts), rtol=1e-12)
+            continue
+        want = O.bin_stats_fast(ts, te)
+        assert (got.sp[0] == want.sp).all() and (got.ex[0] == want.ex).all(), name
+        np.testing.assert_allclose(got.br[0], want.br, rtol=1e-12, atol=1e-9)
+    # replicates with a ragged pitch, device entry point, raw accumulators
+    tdev = torch.device("cuda:0")
+    n_rep, n, ld, nb = 5, 70_001, 70_004, 37
+    t = torch.full((n_rep, ld), float("nan"), dtype=torch.float64, device=tdev)
+    e = torch.full((n_rep, ld), float("nan"), dtype=torch.float64, device=tdev)
+    t[:, :n] = torch.from_numpy(100 + rng.uniform(0, nb, (n_rep, n))).to(tdev)
+    e[:, :n] = t[:, :n] + torch.from_numpy(rng.exponential(6, (n_rep, n))).to(tdev)
+    accs = []
+    for build in ("0", "1"):
+        monkeypatch.setenv("LR_K1_LANES", build)
+        acc = device.new_accumulators(n_rep, nb, tdev)
+        device.bin_accumulate_device(t[:, :n], e[:, :n], 100, nb, acc, fe_ref=1.0)
+        torch.cuda.synchronize()
+        accs.append(acc.cpu().numpy().copy())
+    _same_accumulators(accs[0], accs[1])
+    # 48 M lineages in ONE bin with fractions near 1: every lane's high word wraps (5 000 additions of ~2^20 per CTA and lane)
+    n = 48_000_000
+    g = torch.Generator(device=tdev); g.manual_seed(9)
+    e = 11.0 - torch.rand(n, dtype=torch.float64, device=tdev, generator=g) * 1e-6
+    t = e - 1e-9 - torch.rand(n, dtype=torch.float64, device=tdev, generator=g) * 1e-3
+    accs = []
+    for build in ("0", "1"):
+        monkeypatch.setenv("LR_K1_LANES", build)
+        acc = device.new_accumulators(1, 3, tdev)
+        device.bin_accumulate_device(t, e, 9, 3, acc, fe_ref=1.0)
+        torch.cuda.synchronize()
+        accs.append(acc.cpu().numpy().copy())
+    _same_accumulators(accs[0], accs[1])
+    assert accs[0][0, 0, 1] == n and accs[0][0, 1, 1] == n
+    sp, ex, br = device.bin_finalize_device(torch.from_numpy(accs[1]).to(tdev), 3, fe_ref=1.0)
+    want = float((e - t).sum())
+    assert abs(float(br[0, 1]) - want) <= 1e-9 * want and float(br[0, 0]) == 0.0 and float(br[0, 2]) == 0.0
+
+
+def test_the_pass_remembers_the_kind_of_table(device, monkeypatch):
+    """lr_bin_table_hint: 1 after a table with fractional times, 0 after integer years -- what the next pass chooses its build by."""
+    monkeypatch.delenv("LR_K1_LANES", raising=False)
+    ts, te = synth.syn_real(50_000, replicate=1)
+    for _ in range(2):                     # the second pass runs the lane-private build, which records the kind as well
+        device.bin_stats(ts, te, death_jitter=0.0)
+        device.sync()
+        assert device.bin_table_hint() == 1
+    ts, te = synth.syn_int(50_000, replicate=1)
+    for _ in range(2):
+        device.bin_stats(ts, te, death_jitter=0.5)
+        device.sync()
+        assert device.bin_table_hint() == 0

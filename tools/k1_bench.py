@@ -35,6 +35,15 @@ for kind in kinds:
         if ref is None:
             ref = out
         ok = all(bool((a == b).all()) for a, b in zip(ref, out))
+        for force in ("0", "1"):      # the two builds of the real-valued path against each other
+            os.environ["LR_K1_LANES"] = force
+            acc2 = dev.new_accumulators(n_rep, nb, tdev)
+            dev.bin_accumulate_device(ts, te, 1800, nb, acc2, fe_ref=fe)
+            out2 = dev.bin_finalize_device(acc2, nb, fe_ref=fe)
+            torch.cuda.synchronize()
+            ok = ok and all(bool((a == b).all()) for a, b in zip(ref, out2))
+        os.environ.pop("LR_K1_LANES")
+        if len(sys.argv) > 5: os.environ["LR_K1_LANES"] = sys.argv[5]
         for _ in range(2):
             dev.bin_accumulate_device(ts, te, 1800, nb, acc, fe_ref=fe)
         torch.cuda.synchronize()
