@@ -129,7 +129,7 @@ def _sha16(path):
         return hashlib.sha256(fh.read()).hexdigest()[:16]
 
 
-def _traffic(a):
+def _traffic(a, kind=None):
     """dram bytes per K1 launch from the committed ncu --set full capture of this workload -- only while the capture is of
     the kernel source that is being timed (profiles/k1_traffic.json records the digest of k1_binstats.cu); otherwise null."""
     try:
@@ -137,9 +137,9 @@ def _traffic(a):
             t = json.load(fh)
         if t.get("k1_binstats_cu_sha16") != _sha16(os.path.join(REPO, "literate_b200", "csrc", "k1_binstats.cu")):
             print("bench.py: profiles/k1_traffic.json was captured from another build of k1_binstats.cu -- roofline.traffic left null "
-                  "(re-capture with ncu --set full and tools/k1_traffic_from_ncu.py)", file=sys.stderr)
+                  "(re-capture with ncu --set full and tools/profile_to_json.py)", file=sys.stderr)
             return None
-        key = "%s_%d_x_%d" % ("real" if a.real else "int", a.lineages, 1 if a.shared_dataset else a.chains)
+        key = "%s_%d_x_%d" % (kind or ("real" if a.real else "int"), a.lineages, 1 if a.shared_dataset else a.chains)
         return t.get(key)
     except Exception:
         return None
@@ -541,7 +541,8 @@ def run_cuda(a):
             for tag, ms in real_roof.items():
                 ach = algo_bytes / (ms * 1e-3) / 1e9
                 line[tag] = {"kernel": real_build, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": None, "ms_per_launch": ms, "algorithmic_bytes_per_launch": algo_bytes,
+                             "traffic": _traffic(a, ("realsorted" if tag.endswith("sorted") else "real") + "_lanes") if real_build == "k1_bin_lanes_kernel" else None,
+                             "ms_per_launch": ms, "algorithmic_bytes_per_launch": algo_bytes,
                              "table": "syn-real %d lineages x %d replicates, %s" % (n, n_rep, "sorted by birth time" if tag.endswith("sorted") else "shuffled")}
         if multi:
             line["multi_gpu"] = multi

@@ -166,6 +166,15 @@ static int bin_stats_host_impl(lr_handle_t h, const void* h_ts, const void* h_te
     double* d_br = (double*)(d_ex + out_cnt);
     LR_CUDA(cudaMemsetAsync(d_acc, 0, acc_bytes, h->stream));
 
+    if (n > 0 && elem == 8) {
+        // host tables can be looked at before the first launch: the kind of table K1 chooses its build by (lr_bin_table_hint),
+        // from the same 32 lineages the kernel itself records it from
+        const double* t = (const double*)h_ts; const double* e = (const double*)h_te;
+        int frac_seen = 0;
+        for (int64_t i = 0; i < (n < 32 ? n : 32); ++i)
+            frac_seen |= (t[i] != floor(t[i])) || (e[i] - (ceil(e[i]) - 1.0) != fe_ref);
+        *(volatile int*)h->k1_hint = frac_seen;
+    }
     if (n > 0) {
         const int64_t align = 16 / elem;                            // row pitch that keeps 128-bit loads aligned
         const int64_t ldp = (n + align - 1) / align * align;

@@ -1,7 +1,7 @@
-"""Turn one ncu capture of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-real-roofline` into the two small
+"""Turn one ncu capture of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e` into the two small
 JSON files bench.py reads (with the digest of the kernel sources, so that a stale capture is never reported):
 
-    ncu --set full --clock-control none -k regex:"k1_bin_kernel|k3_" -o gpurun_out/r02_bench python bench.py ...   (GPU box)
+    ncu --set full --clock-control none -k regex:"k1_bin|k3_" -o gpurun_out/r02_bench python bench.py ...          (GPU box)
     ncu -i gpurun_out/r02_bench.ncu-rep --page raw --csv > profiles/r02_bench_raw.csv                              (here)
     python tools/profile_to_json.py profiles/r02_bench_raw.csv [chains] [iterations per step] [steps captured]
 
@@ -23,15 +23,26 @@ iters = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 hdr = rows[0]
 col = {h: i for i, h in enumerate(hdr)}
 name_i = col["Kernel Name"]
-k1, k3_inst, k3_time = [], 0.0, 0.0
+k1, k1_lanes, k3_inst, k3_time = [], [], 0.0, 0.0
+
+
+def dram_bytes(r):
+    def unit(c):
+        return {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[rows[1][col[c]]]
+    return float(r[col["dram__bytes_read.sum"]]) * unit("dram__bytes_read.sum") + float(r[col["dram__bytes_write.sum"]]) * unit("dram__bytes_write.sum")
+
+
 k3_steps = 0
 for r in rows[2:]:
     if len(r) <= name_i:
         continue
     nm = r[name_i]
-    if "k1_bin_kernel" in nm:
-        k1.append(float(r[col["dram__bytes_read.sum"]]) * (1e6 if rows[1][col["dram__bytes_read.sum"]] == "Mbyte" else 1e9 if rows[1][col["dram__bytes_read.sum"]] == "Gbyte" else 1)
-                  + float(r[col["dram__bytes_write.sum"]]) * (1e6 if rows[1][col["dram__bytes_write.sum"]] == "Mbyte" else 1e9 if rows[1][col["dram__bytes_write.sum"]] == "Gbyte" else 1e3 if rows[1][col["dram__bytes_write.sum"]] == "Kbyte" else 1))
+    if "k1_bin_lanes_kernel" in nm:
+        if not k1_lanes and k1:
+            k1.pop()                      # the general build's one pass over the real-valued table (it records the kind of table)
+        k1_lanes.append(dram_bytes(r))
+    elif "k1_bin_kernel" in nm:
+        k1.append(dram_bytes(r))
     elif "k3_team_kernel" in nm or "k3_run_kernel" in nm:
         k3_inst += float(r[col["smsp__inst_executed.sum"]])
         k3_time += float(r[col["gpu__time_duration.sum"]])
@@ -46,8 +57,14 @@ if k1:
                     "key <table kind>_<lineages>_x_<replicates>; written by tools/profile_to_json.py with the digest of the kernel source"
     t["k1_binstats_cu_sha16"] = sha16("literate_b200/csrc/k1_binstats.cu")
     t["int_1000000_x_%d" % chains] = int(sum(k1) / len(k1))
+    # bench.py's real-valued section: 6 passes of the lane-private build over the shuffled table, then 7 over the sorted one
+    for key in ("real_lanes_1000000_x_%d" % chains, "realsorted_lanes_1000000_x_%d" % chains):
+        t.pop(key, None)
+    if len(k1_lanes) == 13:
+        t["real_lanes_1000000_x_%d" % chains] = int(sum(k1_lanes[:6]) / 6)
+        t["realsorted_lanes_1000000_x_%d" % chains] = int(sum(k1_lanes[6:]) / 7)
     json.dump(t, open(p, "w"), indent=1)
-    print("k1 traffic per launch:", int(sum(k1) / len(k1)), "from", len(k1), "launches")
+    print("k1 traffic per launch:", int(sum(k1) / len(k1)), "from", len(k1), "launches; lane-private build:", len(k1_lanes), "launches")
 if k3_inst:
     ipi = k3_inst / (steps * chains * iters)
     json.dump({"_comment": "warp instructions (smsp__inst_executed.sum) of all K3 kernels of one bench step / (chains x iterations), "
