@@ -94,7 +94,8 @@ int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int
  * fraction words exist once per lane in shared memory (n_bins <= 216; 0.89 against 0.74 of the copy bandwidth).  The pass
  * itself records which kind of table it saw (its first 32 lineages) and the NEXT lr_bin_accumulate through the handle uses
  * that to choose -- no synchronisation, a stale answer costs speed only.  lr_bin_table_hint reads the record (1 = fractional
- * times, 0 = integer years) as of the last finished pass; the environment variable LR_K1_LANES=0 / 1 forces the choice. */
+ * times, 0 = integer years) as of the last finished pass; the environment variable LR_K1_LANES=0 / 1 forces the choice.
+ * The host-buffer entry points (lr_bin_stats_host*) always run the general build: they are bound by the host link. */
 int lr_bin_table_hint(lr_handle_t h, int32_t* out);
 int lr_bin_finalize(lr_handle_t h, const int64_t* d_acc, int32_t n_rep, int32_t n_bins, double fe_ref,
                     int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream);

@@ -739,7 +739,7 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     const size_t smem_l = K1L_WORDS_PER_BIN * ((size_t)n_bins + 1) * sizeof(unsigned);
     const char* e_l = getenv("LR_K1_LANES");
     const bool lanes_fit = 2 * (smem_l + 1024) <= (size_t)h->max_smem_optin + 1024 && p.vec_ok;
-    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : *(volatile int*)h->k1_hint == 1);
+    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : (!h->k1_general_only && *(volatile int*)h->k1_hint == 1));
     if (lanes) {
         const int blocks_l = h->sm_count * 2;
         long long chunk_l = (total + blocks_l - 1) / blocks_l;

@@ -166,15 +166,6 @@ static int bin_stats_host_impl(lr_handle_t h, const void* h_ts, const void* h_te
     double* d_br = (double*)(d_ex + out_cnt);
     LR_CUDA(cudaMemsetAsync(d_acc, 0, acc_bytes, h->stream));
 
-    if (n > 0 && elem == 8) {
-        // host tables can be looked at before the first launch: the kind of table K1 chooses its build by (lr_bin_table_hint),
-        // from the same 32 lineages the kernel itself records it from
-        const double* t = (const double*)h_ts; const double* e = (const double*)h_te;
-        int frac_seen = 0;
-        for (int64_t i = 0; i < (n < 32 ? n : 32); ++i)
-            frac_seen |= (t[i] != floor(t[i])) || (e[i] - (ceil(e[i]) - 1.0) != fe_ref);
-        *(volatile int*)h->k1_hint = frac_seen;
-    }
     if (n > 0) {
         const int64_t align = 16 / elem;                            // row pitch that keeps 128-bit loads aligned
         const int64_t ldp = (n + align - 1) / align * align;
@@ -215,10 +206,12 @@ static int bin_stats_host_impl(lr_handle_t h, const void* h_ts, const void* h_te
             LR_CUDA(cudaStreamWaitEvent(h->stream, h->ev[buf], 0));
             if (dbg && batch < max_dbg) cudaEventRecord(te[4 * batch + 2], h->stream);
             int64_t* acc_r = d_acc + (size_t)r0 * LR_ACC_ROWS * stride;
+            h->k1_general_only = 1;     // batches run beside the chains of the previous table and behind the host link: see lr_common.cuh
             rc = elem == 8 ? lr_bin_accumulate(h, (const double*)s_ts, (const double*)s_te, n, ldp, (int32_t)nr, first_bin, n_bins, fe_ref, dead_only,
                                                end_time, acc_r, h->stream)
                            : lr_bin_accumulate_i32(h, (const int32_t*)s_ts, (const int32_t*)s_te, n, ldp, (int32_t)nr, first_bin, n_bins, frac,
                                                    dead_only, end_time, acc_r, h->stream);
+            h->k1_general_only = 0;
             if (rc != LR_OK) return rc;
             LR_CUDA(cudaEventRecord(h->ev[LR_NSTAGE + buf], h->stream));
             if (dbg && batch < max_dbg) cudaEventRecord(te[4 * batch + 3], h->stream);

@@ -68,6 +68,10 @@ struct lr_handle_s {
     // its two bit-identical builds (k1_binstats.cu); a stale value costs speed only
     int* k1_hint;
     int k1_hint_used;
+    // set by the host-buffer entry points around their per-batch passes: those are bound by the host link (K1 at 4.8 TB/s hides
+    // behind 55 GB/s of copies) and run beside the chain kernels of the previous table, whose 64 KB shared-memory carve-out the
+    // lane-private build (2 x 105 KB per SM) cannot share an SM with -- it would wait for whole SMs to drain
+    int k1_general_only;
 };
 
 // Cross-stream ordering without host synchronisation.  Entry points take a caller stream or fall back to the handle's
