@@ -343,6 +343,17 @@ def test_lane_private_build_is_bit_identical_and_carries_into_the_third_word(dev
         torch.cuda.synchronize()
         accs.append(acc.cpu().numpy().copy())
     _same_accumulators(accs[0], accs[1])
+    # the widest window two CTAs of the lane-private build fit (216 bins), and one bin more (general build either way)
+    for nb in (216, 217):
+        n = 150_000
+        ts = 1000 + rng.uniform(0, nb, n); te = np.minimum(ts + rng.exponential(30, n), 1000.0 + nb)
+        res = []
+        for build in ("0", "1"):
+            monkeypatch.setenv("LR_K1_LANES", build)
+            res.append(device.bin_stats(ts, te, death_jitter=0.0, first_bin=1000, n_bins=nb))
+        assert (res[0].sp == res[1].sp).all() and (res[0].ex == res[1].ex).all() and (res[0].br == res[1].br).all(), nb
+        want = O.bin_stats_fast(ts, te)
+        assert (res[1].sp[0] == want.sp[:nb]).all() and (res[1].ex[0] == want.ex[:nb]).all(), nb
     # 48 M lineages in ONE bin with fractions near 1: every lane's high word wraps (5 000 additions of ~2^20 per CTA and lane)
     n = 48_000_000
     g = torch.Generator(device=tdev); g.manual_seed(9)
