@@ -41,3 +41,16 @@ run("after K3 (teams, 25 ms)", lambda k: k3(k))
 run("after K3 (compact build, 70 ms)", lambda k: k3(k, 2))
 big = torch.empty(1 << 30, dtype=torch.uint8, device=tdev)
 run("after a 1 GiB memset", lambda k: big.zero_())
+
+def k3_then_sleep(k):
+    k3(k); torch.cuda._sleep(int(25e-3 * 1.9e9))
+run("after K3 (teams) + 25 ms idle", k3_then_sleep)
+def k3_then_k1(k):
+    k3(k); acc.zero_(); dev.bin_accumulate_device(ts, te, 1800, nb, acc, fe_ref=0.5)
+run("second K1 after K3 (teams)", k3_then_k1)
+def k3_short(k):
+    ch = E.Chains(ds, chains, seed=k + 1, rep_of_chain=np.arange(chains)); ch.run_device(10_000, 1000, rec[:10]); k3.keep.append(ch)
+run("after K3 (teams, 10 000 iterations)", k3_short)
+def k3_w4(k):
+    os.environ["LR_TEAM_W"] = "4"; k3(k); os.environ.pop("LR_TEAM_W")
+run("after K3 (teams of 4)", k3_w4)
