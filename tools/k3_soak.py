@@ -16,14 +16,14 @@ ts, te = synth.syn_int(3_000, replicate=5); tables["syn-int 3k"] = (ts, te, 0.5)
 ts, te = synth.syn_real(200_000, replicate=2); tables["syn-real 200k"] = (ts, te, 0.0)
 data = {}
 for name, (ts, te, jit) in tables.items():
-    st = dev.bin_stats(ts, te, death_jitter=jit)
-    data[name] = E.Dataset(dev, st, 0, float(ts.min()), float(te.max()))
+    st = dev.bin_stats(ts, te, death_jitter=jit, only_dead=True)
+    for model in (0, 1, 2, 3):
+        data[name + ", model_BDI %d" % model] = (E.Dataset(dev, st, model, float(ts.min()), float(te.max())), model)
 t0 = time.time(); n_launch = 0; n_iter_total = 0
 while time.time() - t0 < budget:
     name = list(data)[int(rng.integers(len(data)))]
-    ds = data[name]
+    ds, model = data[name]
     nch = int(rng.choice([1, 2, 37, 148, 149, 256, 296, 297, 592]))
-    model = int(rng.choice([0, 0, 1, 2, 3])) if False else 0
     seed = int(rng.integers(1, 1 << 30))
     W = int(rng.choice([0, 4, 8, 16])); lead = int(rng.integers(1, 8))
     variant = int(rng.choice([0, 4]))
@@ -31,8 +31,8 @@ while time.time() - t0 < budget:
     if W: os.environ["LR_TEAM_W"] = str(W)
     os.environ["LR_TEAM_LEAD"] = str(lead)
     if rng.uniform() < 0.3: os.environ["LR_TEAM_NOBAIL"] = "1"
-    ref = E.Chains(ds, nch, seed=seed, cfg=E.default_config(0, loop_variant=2))
-    tst = E.Chains(ds, nch, seed=seed, cfg=E.default_config(0, loop_variant=variant))
+    ref = E.Chains(ds, nch, seed=seed, cfg=E.default_config(model, loop_variant=2))
+    tst = E.Chains(ds, nch, seed=seed, cfg=E.default_config(model, loop_variant=variant))
     for part in range(int(rng.integers(1, 4))):
         n_it = int(rng.choice([1, 7, 100, 2047, 2048, 2049, 5000, 20000, 60000]))
         se = int(rng.choice([1, 10, 100, 1000])) if n_it <= 5000 else int(rng.choice([100, 1000, 7777]))
