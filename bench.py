@@ -315,6 +315,7 @@ def run_cuda(a):
     stream = torch.cuda.Stream(device=tdev)
     cfg = E.default_config(0)
     k1_ms, k3_ms = [], []
+    k1_build = ["k1_bin_kernel"]
 
     def step(k, timed):
         """One pass of the hot path with device-resident lineages."""
@@ -325,6 +326,7 @@ def run_cuda(a):
         e0.record()
         dev.bin_accumulate_device(ts, te, FIRST_BIN, nb, acc, fe_ref=fe_ref, stream=stream.cuda_stream)
         e1.record()
+        k1_build[0] = dev.bin_last_build()
         sp, ex, br = dev.bin_finalize_device(acc, nb, fe_ref=fe_ref, stream=stream.cuda_stream)
         ds = E.Dataset.from_device(dev, sp, ex, br, 0, float(FIRST_BIN), end_time, stream=stream.cuda_stream)
         ch = E.Chains(ds, chains, seed=2026 + k, cfg=cfg, chain_id0=rank * chains, rep_of_chain=rep_of_chain)
@@ -481,7 +483,7 @@ def run_cuda(a):
                 for _ in range(2):
                     dev.bin_accumulate_device(vts, vte, FIRST_BIN, nb, acc, fe_ref=1.0, stream=stream.cuda_stream)
                     torch.cuda.synchronize()         # the first pass records that the table carries fractions; later passes read it
-                real_build = "k1_bin_lanes_kernel" if dev.bin_table_hint() == 1 and nb <= 216 and os.environ.get("LR_K1_LANES") != "0" else "k1_bin_kernel"
+                real_build = dev.bin_last_build()
                 evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
                 for e0, e1 in evs:
                     e0.record(); dev.bin_accumulate_device(vts, vte, FIRST_BIN, nb, acc, fe_ref=1.0, stream=stream.cuda_stream); e1.record()
@@ -517,12 +519,12 @@ def run_cuda(a):
                              "note": "likelihood and prior of states logged by the last timed step recomputed by lr_state_eval_host; "
                                      "posterior parity on these statistics: tests/test_gpu_chains.py (32 oracle chains)"},
             "lik_evals_per_s": float(tot[0]) / (total_ms * 1e-3),
-            "kernels": {"k1_bin_kernel_ms": k1, "k3_run_kernel_ms": statistics.mean(k3_ms),
+            "kernels": {"k1_kernel": k1_build[0], "k1_bin_kernel_ms": k1, "k3_run_kernel_ms": statistics.mean(k3_ms),
                         "k3_ns_per_iteration_per_chain": 1e6 * statistics.mean(k3_ms) / a.iters,
                         "k3_bound": "instruction issue: teams of 8 warps evaluate consecutive iterations of one chain speculatively "
                                     "(no DRAM traffic in the loop; roofline_k3, profiles/)",
                         "k1_share_of_step": k1 * a.steps / total_ms, "k3_share_of_step": sum(k3_ms) / total_ms},
-            "roofline": {"kernel": "k1_bin_kernel (lineages -> per-bin births/deaths/time at risk)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": k1_build[0] + " (lineages -> per-bin births/deaths/time at risk)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(a),
                          "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src, "ms_per_launch": k1},
         }

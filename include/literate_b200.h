@@ -90,13 +90,16 @@ int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int
                       int32_t n_rep, int64_t first_bin, int32_t n_bins, double fe_ref,
                       int32_t dead_only, double end_time, int64_t* d_acc, void* stream);
 /* Two builds of the pass produce these accumulators -- the same integer sums, hence the same finalized statistics bit for bit
- * (how a 96-bit sum is split over its row pair depends on where a pass flushed): the general one, and one for REAL-VALUED times whose
- * fraction words exist once per lane in shared memory (n_bins <= 216; 0.89 against 0.74 of the copy bandwidth).  The pass
- * itself records which kind of table it saw (its first 32 lineages) and the NEXT lr_bin_accumulate through the handle uses
- * that to choose -- no synchronisation, a stale answer costs speed only.  lr_bin_table_hint reads the record (1 = fractional
- * times, 0 = integer years) as of the last finished pass; the environment variable LR_K1_LANES=0 / 1 forces the choice.
- * The host-buffer entry points (lr_bin_stats_host*) always run the general build: they are bound by the host link. */
+ * (how a 96-bit sum is split over its row pair depends on where a pass flushed): the general one (any n_bins; the only one the
+ * host-buffer entry points use: they are bound by the host link and run beside the chain kernels), and the lane-private one
+ * (fraction words once per lane in shared memory, one CTA of 1024 threads per SM): every table up to 310 bins -- 1.05 of the
+ * copy bandwidth against 1.02 on integer years and against 0.74 on real-valued times -- and real-valued tables up to 439 bins.
+ * For 311 - 439 bins the pass itself records which kind of table it saw (its first 32 lineages) and the NEXT lr_bin_accumulate
+ * through the handle uses that to choose -- no synchronisation, a stale answer costs speed only.  lr_bin_table_hint reads the
+ * record (1 = fractional times, 0 = integer years) as of the last finished pass, lr_bin_last_build which build the last call
+ * launched (0 general, 1 lane-private); the environment variable LR_K1_LANES=0 / 1 forces the choice. */
 int lr_bin_table_hint(lr_handle_t h, int32_t* out);
+int lr_bin_last_build(lr_handle_t h, int32_t* out);
 int lr_bin_finalize(lr_handle_t h, const int64_t* d_acc, int32_t n_rep, int32_t n_bins, double fe_ref,
                     int64_t* d_sp, int64_t* d_ex, double* d_br, void* stream);
 /* zero + accumulate + finalize using the handle's workspace */

@@ -27,7 +27,7 @@ LR_OK = 0
 EXPORTS = [
     "lr_abi_version", "lr_last_error", "lr_create", "lr_destroy", "lr_info", "lr_sync",
     "lr_acc_stride", "lr_bin_accumulate", "lr_bin_finalize", "lr_bin_stats", "lr_bin_stats_host",
-    "lr_bin_accumulate_i32", "lr_bin_stats_host_i32", "lr_fe_ref_of_jitter", "lr_bin_table_hint",
+    "lr_bin_accumulate_i32", "lr_bin_stats_host_i32", "lr_fe_ref_of_jitter", "lr_bin_table_hint", "lr_bin_last_build",
     "lr_dataset_create", "lr_dataset_create_host", "lr_dataset_create_general_host", "lr_dataset_destroy", "lr_state_eval_host", "lr_proposal_eval_host", "lr_loglik_direct",
     "lr_chains_create", "lr_chains_destroy", "lr_chains_records_per_run", "lr_chains_run", "lr_chains_run_host",
     "lr_imputation_envelope", "lr_chains_counters_host", "lr_chains_team_stats_host", "lr_chains_get_state_host", "lr_chains_set_state_host", "lr_chains_set_beta_host",
@@ -95,6 +95,7 @@ def load(build_if_missing=False):
     sig("lr_bin_stats_host_i32", C.c_int, vp, vp, vp, i64, i64, i32, i64, i32, f64, i32, f64, vp, vp, vp)
     sig("lr_fe_ref_of_jitter", C.c_double, f64)
     sig("lr_bin_table_hint", C.c_int, vp, P(i32))
+    sig("lr_bin_last_build", C.c_int, vp, P(i32))
     sig("lr_dataset_create", C.c_int, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp, P(vp))
     sig("lr_dataset_create_host", C.c_int, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, P(vp))
     sig("lr_dataset_create_general_host", C.c_int, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp, vp, P(vp))

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
     }
 }
 
-// ---- real-valued tables, LANE-PRIVATE fraction words -------------------------------------------------------------------
+// ---- LANE-PRIVATE fraction words: the build for real-valued tables, and the faster one for every table up to 310 bins ----
 // On real-valued tables k1_bin_kernel is bound by the shared-memory data stage and by issue: its six atomics per lineage hit
 // random bins, 32 random words fall on the 32 banks 3.1 deep on average (ncu, 1M x 256 shuffled: 168 M atomic wavefronts for
 // 53.8 M atomic instructions, l1tex 83 % busy, 97 warp instructions per lineage at 69 % issue, 0.74 of the copy peak), and on
@@ -450,20 +450,19 @@ __global__ void __launch_bounds__(256, 5) k1_bin_kernel(const K1Params p) {
 // Here the two low words of each side's fraction sum exist once per LANE ([bin][2][32]: lane l only ever touches bank l), so a
 // fraction atomic is one wavefront whatever the bins are, shuffled or sorted, and only the warps of the CTA contend for a word;
 // the third word (one carry in >= 4096 additions) and the counters (ATOMS.POPC.INC, merged by the hardware) stay shared.
-// 2 x 256 B per bin: 200 bins = 105 KB per CTA, two CTAs of 512 threads per SM.  Every birth adds its fraction and every death
+// 2 x 256 B per bin: 200 bins = 105 KB, ONE CTA of 1024 threads per SM (up to 439 bins; the L1 keeps what shared memory leaves:
+// two CTAs of 512 threads, 210 KB of shared memory at 200 bins, ran 8 % slower).  Every birth adds its fraction and every death
 // goes through the "other fraction" counter (sum(fix(fe)) - n * fix(fe_ref) is zero for the expected ones); a death outside
 // the window lands in a spare bin; fix(x) is the mantissa of 1 + x (one DADD and an integer subtraction, identical to
 // rn(x * 2^52) including ties and x == 1); the carries are add.cc / addc.  A regular lineage is straight-line code, 36 warp
 // instructions against 60, and the two lineages of a 128-bit load issue their four carry chains together.
-// Measured (tools/k1_bench.py 256, GB/s of 16 B per lineage): shuffled 5 840 against 4 850, sorted by birth 5 950 against 4 500
-// (0.89 / 0.91 of the copy peak).  Flushing every 128 000 lineages (which would make the high word's carry unnecessary) cost
-// 8 %: each flush drains the CTA's loads.  Integer sums: the accumulators hold the same totals as k1_bin_kernel's, the finalized
-// statistics are bit-identical.
-// lr_bin_accumulate picks this build when the previous table through the handle carried fractions (K1Params::hint) and the
-// bins fit (n_bins <= 216).
-constexpr int K1L_THREADS = 512;
-constexpr int K1L_UNROLL = 2;                        // double2 loads in flight per array per thread (64 KB per SM; 3 and 4 were not faster)
-constexpr int K1L_TILE = 64 * K1L_UNROLL;
+// Loads in flight: 4 double2 per array and thread (128 KB per SM) up to 310 bins, 2 beyond (the L1 is what shared memory leaves).
+// Measured (tools/k1_bench.py 256, GB/s of 16 B per lineage, 200 bins; k1_bin_kernel in brackets): real-valued shuffled 6 890
+// (4 850), sorted by birth 7 000 (4 500), integer years 6 940 (6 690), sorted 7 050 (6 710) -- 1.05 - 1.08 of the copy peak, a
+// read-only stream; 300 bins 6 410 / 6 930, 400 bins 5 760 / 5 940.  Flushing every 128 000 lineages (which would make the high
+// word's carry unnecessary) cost 8 %: each flush drains the CTA's loads.  Integer sums: the accumulators hold the same totals as
+// k1_bin_kernel's, the finalized statistics are bit-identical.
+constexpr int K1L_THREADS = 1024;                    // ONE CTA per SM: two of 512 leave the L1 18 KB at 200 bins and run 8 % slower
 constexpr size_t K1L_WORDS_PER_BIN = 4 * 32 + 4;
 
 struct K1Lanes {
@@ -539,8 +538,10 @@ __device__ __forceinline__ unsigned __int128 lanes_total(const unsigned* w, unsi
     return (unsigned __int128)t0 + ((unsigned __int128)t1 << 32);
 }
 
-template <bool DEAD_ONLY>
-__global__ void __launch_bounds__(K1L_THREADS, 2) k1_bin_lanes_kernel(const K1Params p) {
+// K1L_UNROLL: double2 loads in flight per array per thread (32 KB per SM each)
+template <bool DEAD_ONLY, int K1L_UNROLL>
+__global__ void __launch_bounds__(K1L_THREADS, 1) k1_bin_lanes_kernel(const K1Params p) {
+    constexpr int K1L_TILE = 64 * K1L_UNROLL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, W = blockDim.x >> 5;
     const unsigned lane = (unsigned)tid & 31u;
@@ -734,25 +735,29 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     const int used = (int)((total + chunk - 1) / chunk);
     p.hint = h->k1_hint;
     h->k1_hint_used = 1;
-    // real-valued tables: the lane-private build when the last table through this handle carried fractions and two CTAs of it fit
-    // an SM (n_bins <= 216); LR_K1_LANES=0 / 1 forces the choice
+    // The lane-private build (k1_bin_lanes_kernel): every kind of table up to 310 bins (164 KB of shared memory: it is the faster
+    // build there, 4 loads deep), real-valued tables up to 439 bins (2 deep; the previous pass through the handle tells the kind of
+    // table, K1Params::hint); the general build otherwise, and always for the host-buffer entry points (lr_common.cuh).
+    // LR_K1_LANES=0 / 1 forces the choice.
     const size_t smem_l = K1L_WORDS_PER_BIN * ((size_t)n_bins + 1) * sizeof(unsigned);
     const char* e_l = getenv("LR_K1_LANES");
-    const bool lanes_fit = 2 * (smem_l + 1024) <= (size_t)h->max_smem_optin + 1024 && p.vec_ok;
-    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : (!h->k1_general_only && *(volatile int*)h->k1_hint == 1));
+    const bool lanes_fit = smem_l <= (size_t)h->max_smem_optin && p.vec_ok;
+    const bool lanes_deep = n_bins <= 310;                      // 164 KB of shared memory: 4 loads deep still pays (measured at 300, not at 400)
+    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : (!h->k1_general_only && (lanes_deep || *(volatile int*)h->k1_hint == 1)));
+    h->k1_last_build = lanes ? 1 : 0;
     if (lanes) {
-        const int blocks_l = h->sm_count * 2;
+        const int blocks_l = h->sm_count;
+        const int unroll = lanes_deep ? 4 : 2;
+        const int tile_l = 64 * unroll;
         long long chunk_l = (total + blocks_l - 1) / blocks_l;
-        chunk_l = (chunk_l + K1L_TILE - 1) / K1L_TILE * K1L_TILE;
+        chunk_l = (chunk_l + tile_l - 1) / tile_l * tile_l;
         p.chunk = chunk_l;
         const int used_l = (int)((total + chunk_l - 1) / chunk_l);
-        if (dead_only) {
-            LR_CUDA(cudaFuncSetAttribute(k1_bin_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-            k1_bin_lanes_kernel<true><<<used_l, K1L_THREADS, smem_l, st>>>(p);
-        } else {
-            LR_CUDA(cudaFuncSetAttribute(k1_bin_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-            k1_bin_lanes_kernel<false><<<used_l, K1L_THREADS, smem_l, st>>>(p);
-        }
+#define LR_K1L(D, U) do { LR_CUDA(cudaFuncSetAttribute(k1_bin_lanes_kernel<D, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
+                          k1_bin_lanes_kernel<D, U><<<used_l, K1L_THREADS, smem_l, st>>>(p); } while (0)
+        if (dead_only) { if (unroll == 2) LR_K1L(true, 2); else LR_K1L(true, 4); }
+        else { if (unroll == 2) LR_K1L(false, 2); else LR_K1L(false, 4); }
+#undef LR_K1L
         LR_CUDA(cudaGetLastError());
         h->launches += 1;
         return LR_OK;
@@ -807,6 +812,12 @@ extern "C" int lr_bin_accumulate_i32(lr_handle_t h, const int32_t* d_ts, const i
 extern "C" int lr_bin_table_hint(lr_handle_t h, int32_t* out) {
     LR_REQUIRE(h != nullptr && out != nullptr, "lr_bin_table_hint: null pointer");
     *out = *(volatile int*)h->k1_hint;
+    return LR_OK;
+}
+
+extern "C" int lr_bin_last_build(lr_handle_t h, int32_t* out) {
+    LR_REQUIRE(h != nullptr && out != nullptr, "lr_bin_last_build: null pointer");
+    *out = h->k1_last_build;
     return LR_OK;
 }
 

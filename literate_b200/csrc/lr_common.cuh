@@ -72,6 +72,7 @@ struct lr_handle_s {
     // behind 55 GB/s of copies) and run beside the chain kernels of the previous table, whose 64 KB shared-memory carve-out the
     // lane-private build (2 x 105 KB per SM) cannot share an SM with -- it would wait for whole SMs to drain
     int k1_general_only;
+    int k1_last_build;          // what the last lr_bin_accumulate launched: 0 k1_bin_kernel, 1 k1_bin_lanes_kernel (lr_bin_last_build)
 };
 
 // Cross-stream ordering without host synchronisation.  Entry points take a caller stream or fall back to the handle's

@@ -214,6 +214,12 @@ class Device:
         N.check(self.lib.lr_bin_table_hint(self.h, C.byref(out)), "lr_bin_table_hint")
         return int(out.value)
 
+    def bin_last_build(self):
+        """Which build of K1 the last bin_accumulate_device / bin_stats_device call launched (lr_bin_last_build)."""
+        out = C.c_int32(0)
+        N.check(self.lib.lr_bin_last_build(self.h, C.byref(out)), "lr_bin_last_build")
+        return "k1_bin_lanes_kernel" if out.value == 1 else "k1_bin_kernel"
+
     def loglik_direct_device(self, ts, te, first_bin, n_bins, lam, mu, stream=None):
         """Validation path (lr_loglik_direct): Keiding log-likelihood of states given as per-bin rates, straight from the
         lineages.  ts/te: float64 CUDA tensors [n]; lam/mu: float64 CUDA tensors [n_states, n_bins].  Returns [n_states]."""

@@ -343,8 +343,8 @@ def test_lane_private_build_is_bit_identical_and_carries_into_the_third_word(dev
         torch.cuda.synchronize()
         accs.append(acc.cpu().numpy().copy())
     _same_accumulators(accs[0], accs[1])
-    # the widest window two CTAs of the lane-private build fit (216 bins), and one bin more (general build either way)
-    for nb in (216, 217):
+    # the widest window the lane-private build fits (439 bins), and one bin more (general build either way)
+    for nb in (439, 440):
         n = 150_000
         ts = 1000 + rng.uniform(0, nb, n); te = np.minimum(ts + rng.exponential(30, n), 1000.0 + nb)
         res = []
@@ -371,6 +371,30 @@ def test_lane_private_build_is_bit_identical_and_carries_into_the_third_word(dev
     sp, ex, br = device.bin_finalize_device(torch.from_numpy(accs[1]).to(tdev), 3, fe_ref=1.0)
     want = float((e - t).sum())
     assert abs(float(br[0, 1]) - want) <= 1e-9 * want and float(br[0, 0]) == 0.0 and float(br[0, 2]) == 0.0
+
+
+def test_choice_of_build(device, monkeypatch):
+    """lr_bin_accumulate (device tables): the lane-private build for every table up to 310 bins, for real-valued tables up to 439
+    (the previous pass tells the kind), the general build beyond; the host-buffer entry points always run the general build."""
+    import torch
+    monkeypatch.delenv("LR_K1_LANES", raising=False)
+    tdev = torch.device("cuda:0")
+    rng = np.random.default_rng(2)
+    n = 40_000
+    for nb, real, want in ((200, False, "k1_bin_lanes_kernel"), (310, True, "k1_bin_lanes_kernel"), (311, False, "k1_bin_kernel"),
+                           (311, True, "k1_bin_lanes_kernel"), (439, True, "k1_bin_lanes_kernel"), (440, True, "k1_bin_kernel")):
+        ts = np.floor(rng.uniform(0, nb, n)); te = ts + np.floor(rng.exponential(10, n)) + 0.5
+        if real:
+            ts = ts + rng.uniform(0, 1, n); te = ts + rng.exponential(10, n)
+        t, e = torch.from_numpy(ts).to(tdev), torch.from_numpy(te).to(tdev)
+        for _ in range(2):                                   # the first pass records the kind of table, the second uses it
+            got = device.bin_stats_device(t, e, 0, nb, fe_ref=0.5)
+            torch.cuda.synchronize()
+        assert device.bin_last_build() == want, (nb, real)
+        wantst = O.bin_stats_fast(ts, te)
+        assert (got[0][0].cpu().numpy() == wantst.sp[:nb]).all(), (nb, real)
+    device.bin_stats(ts, te, death_jitter=0.0)               # host entry
+    assert device.bin_last_build() == "k1_bin_kernel"
 
 
 def test_the_pass_remembers_the_kind_of_table(device, monkeypatch):

@@ -14,7 +14,7 @@ kinds = (sys.argv[3] if len(sys.argv) > 3 else "int,real,sorted").split(",")
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 dev = E.Device(0)
 tdev = torch.device("cuda:0")
-n, nb = 1_000_000, 200
+n, nb = 1_000_000, int(os.environ.get('K1_BENCH_NB', '200'))
 res = {}
 for kind in kinds:
     if kind in ("real", "realsorted"):
@@ -26,6 +26,8 @@ for kind in kinds:
         if kind == "sorted":
             ts, idx = torch.sort(ts, dim=1); te = torch.gather(te, 1, idx)
     ts, te = ts[:, :n], te[:, :n]
+    if nb != 200:                      # stretch the 200-year window of the synthetic tables over nb bins
+        ts = 1800.0 + (ts - 1800.0) * (nb / 200.0); te = 1800.0 + (te - 1800.0) * (nb / 200.0)
     ref = None
     for variant in variants:
         acc = dev.new_accumulators(n_rep, nb, tdev)

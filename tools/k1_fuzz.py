@@ -13,7 +13,7 @@ t0 = time.time(); cases = 0; lineages = 0
 while time.time() - t0 < budget:
     n = int(rng.choice([1, 31, 33, 500, 4097, 70_001, 300_000, 2_000_000]))
     n_rep = int(rng.choice([1, 1, 2, 5])) if n <= 300_000 else 1
-    nb = int(rng.choice([1, 2, 24, 37, 200, 216, 217, 300]))
+    nb = int(rng.choice([1, 2, 24, 37, 200, 311, 439, 440]))
     first = int(rng.choice([-50, 0, 3, 1800, 100_000]))
     pad = int(rng.choice([0, 2, 6]))
     ld = n + pad + ((n + pad) & 1)

@@ -5,7 +5,7 @@ JSON files bench.py reads (with the digest of the kernel sources, so that a stal
     ncu -i gpurun_out/r02_bench.ncu-rep --page raw --csv > profiles/r02_bench_raw.csv                              (here)
     python tools/profile_to_json.py profiles/r02_bench_raw.csv [chains] [iterations per step] [steps captured]
 
-profiles/k1_traffic.json       dram__bytes_read.sum + dram__bytes_write.sum per k1_bin_kernel launch
+profiles/k1_traffic.json       dram__bytes_read.sum + dram__bytes_write.sum per K1 launch
 profiles/k3_instructions.json  smsp__inst_executed.sum of all K3 kernels of one step / (chains x iterations)
 """
 import csv, hashlib, json, os, sys
@@ -37,12 +37,8 @@ for r in rows[2:]:
     if len(r) <= name_i:
         continue
     nm = r[name_i]
-    if "k1_bin_lanes_kernel" in nm:
-        if not k1_lanes and k1:
-            k1.pop()                      # the general build's one pass over the real-valued table (it records the kind of table)
-        k1_lanes.append(dram_bytes(r))
-    elif "k1_bin_kernel" in nm:
-        k1.append(dram_bytes(r))
+    if "k1_bin_lanes_kernel" in nm or "k1_bin_kernel" in nm:
+        k1.append(dram_bytes(r))          # in launch order: the steps' passes, then bench.py's real-valued section (7 shuffled, 7 sorted)
     elif "k3_team_kernel" in nm or "k3_run_kernel" in nm:
         k3_inst += float(r[col["smsp__inst_executed.sum"]])
         k3_time += float(r[col["gpu__time_duration.sum"]])
@@ -53,16 +49,16 @@ src = ("k3_chains.cu", "k3_team.cuh", "chain_device.cuh", "lr_common.cuh")
 if k1:
     p = os.path.join(REPO, "profiles", "k1_traffic.json")
     t = json.load(open(p)) if os.path.exists(p) else {}
-    t["_comment"] = "dram__bytes_read.sum + dram__bytes_write.sum per k1_bin_kernel launch from an ncu --set full capture of bench.py; " \
+    t["_comment"] = "dram__bytes_read.sum + dram__bytes_write.sum per K1 launch (k1_bin_lanes_kernel at the bench sizes) from an ncu --set full capture of bench.py; " \
                     "key <table kind>_<lineages>_x_<replicates>; written by tools/profile_to_json.py with the digest of the kernel source"
     t["k1_binstats_cu_sha16"] = sha16("literate_b200/csrc/k1_binstats.cu")
-    t["int_1000000_x_%d" % chains] = int(sum(k1) / len(k1))
-    # bench.py's real-valued section: 6 passes of the lane-private build over the shuffled table, then 7 over the sorted one
     for key in ("real_lanes_1000000_x_%d" % chains, "realsorted_lanes_1000000_x_%d" % chains):
         t.pop(key, None)
-    if len(k1_lanes) == 13:
-        t["real_lanes_1000000_x_%d" % chains] = int(sum(k1_lanes[:6]) / 6)
-        t["realsorted_lanes_1000000_x_%d" % chains] = int(sum(k1_lanes[6:]) / 7)
+    if len(k1) > 14 and "--no-real" not in sys.argv:
+        k1, k1_lanes = k1[:-14], k1[-14:]
+        t["real_lanes_1000000_x_%d" % chains] = int(sum(k1_lanes[:7]) / 7)
+        t["realsorted_lanes_1000000_x_%d" % chains] = int(sum(k1_lanes[7:]) / 7)
+    t["int_1000000_x_%d" % chains] = int(sum(k1) / len(k1))
     json.dump(t, open(p, "w"), indent=1)
     print("k1 traffic per launch:", int(sum(k1) / len(k1)), "from", len(k1), "launches; lane-private build:", len(k1_lanes), "launches")
 if k3_inst:
