@@ -37,7 +37,7 @@ def instrs(lines):
 index = ["library sha256[:16] %s, source digest stamp %s" % (digest, stamp), ""]
 for name, lines in funcs.items():
     short = None
-    for key in ("k1_bin_kernel", "k1_bin_i32_kernel", "k1_bin_lanes_kernelILb0", "k3_team_kernelILi8", "k3_team_kernelILi16", "k3_team_kernelILi4", "k3_run_kernelILi1", "k3_run_kernelILi0"):
+    for key in ("k1_bin_kernel", "k1_bin_i32_kernel", "k1_bin_lanes_kernelILb0ELi4", "k3_team_kernelILi8", "k3_team_kernelILi16", "k3_team_kernelILi4", "k3_run_kernelILi1", "k3_run_kernelILi0"):
         if key in name:
             short = key
     if short is None:
