@@ -92,9 +92,10 @@ int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double* d_te, int
 /* Two builds of the pass produce these accumulators -- the same integer sums, hence the same finalized statistics bit for bit
  * (how a 96-bit sum is split over its row pair depends on where a pass flushed): the general one (any n_bins; the only one the
  * host-buffer entry points use: they are bound by the host link and run beside the chain kernels), and the lane-private one
- * (fraction words once per lane in shared memory, one CTA of 1024 threads per SM): every table up to 310 bins -- 1.05 of the
- * copy bandwidth against 1.02 on integer years and against 0.74 on real-valued times -- and real-valued tables up to 439 bins.
- * For 311 - 439 bins the pass itself records which kind of table it saw (its first 32 lineages) and the NEXT lr_bin_accumulate
+ * (fraction words once per lane in shared memory, one CTA of 1024 threads per SM): every table of at least 250 000 lineages per
+ * replicate up to 310 bins -- 1.05 of the copy bandwidth against 1.02 on integer years and against 0.74 on real-valued times --
+ * and real-valued tables of at least 50 000 lineages per replicate up to 439 bins.
+ * The pass itself records which kind of table it saw (its first 32 lineages) and the NEXT lr_bin_accumulate
  * through the handle uses that to choose -- no synchronisation, a stale answer costs speed only.  lr_bin_table_hint reads the
  * record (1 = fractional times, 0 = integer years) as of the last finished pass, lr_bin_last_build which build the last call
  * launched (0 general, 1 lane-private); the environment variable LR_K1_LANES=0 / 1 forces the choice. */

@@ -736,14 +736,19 @@ extern "C" int lr_bin_accumulate(lr_handle_t h, const double* d_ts, const double
     p.hint = h->k1_hint;
     h->k1_hint_used = 1;
     // The lane-private build (k1_bin_lanes_kernel): every kind of table up to 310 bins (164 KB of shared memory: it is the faster
-    // build there, 4 loads deep), real-valued tables up to 439 bins (2 deep; the previous pass through the handle tells the kind of
-    // table, K1Params::hint); the general build otherwise, and always for the host-buffer entry points (lr_common.cuh).
+    // build there, 4 loads deep) with at least 250 000 lineages per replicate, real-valued tables up to 439 bins (2 deep beyond 310)
+    // with at least 50 000 (the previous pass through the handle tells the kind of table, K1Params::hint); the general build
+    // otherwise, and always for the host-buffer entry points (lr_common.cuh).
     // LR_K1_LANES=0 / 1 forces the choice.
     const size_t smem_l = K1L_WORDS_PER_BIN * ((size_t)n_bins + 1) * sizeof(unsigned);
     const char* e_l = getenv("LR_K1_LANES");
     const bool lanes_fit = smem_l <= (size_t)h->max_smem_optin && p.vec_ok;
     const bool lanes_deep = n_bins <= 310;                      // 164 KB of shared memory: 4 loads deep still pays (measured at 300, not at 400)
-    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : (!h->k1_general_only && (lanes_deep || *(volatile int*)h->k1_hint == 1)));
+    // (a CTA zeroes and folds its 528 B per bin once per replicate it touches: below a quarter of a million lineages per replicate --
+    // 50 000 for real-valued tables -- the general build's 36 B per bin win; measured at 1 000 / 10 000 / 100 000 lineages per replicate)
+    const bool real_seen = *(volatile int*)h->k1_hint == 1;
+    const bool lanes_pay = (lanes_deep && n >= 250000) || (real_seen && n >= 50000);
+    const bool lanes = lanes_fit && (e_l ? atoi(e_l) != 0 : (!h->k1_general_only && lanes_pay));
     h->k1_last_build = lanes ? 1 : 0;
     if (lanes) {
         const int blocks_l = h->sm_count;

@@ -374,15 +374,16 @@ def test_lane_private_build_is_bit_identical_and_carries_into_the_third_word(dev
 
 
 def test_choice_of_build(device, monkeypatch):
-    """lr_bin_accumulate (device tables): the lane-private build for every table up to 310 bins, for real-valued tables up to 439
-    (the previous pass tells the kind), the general build beyond; the host-buffer entry points always run the general build."""
+    """lr_bin_accumulate (device tables): the lane-private build for every table of >= 250 000 lineages up to 310 bins, for real-valued
+    tables of >= 50 000 up to 439 (the previous pass tells the kind), the general build otherwise; the host-buffer entry points always
+    run the general build."""
     import torch
     monkeypatch.delenv("LR_K1_LANES", raising=False)
     tdev = torch.device("cuda:0")
     rng = np.random.default_rng(2)
-    n = 40_000
-    for nb, real, want in ((200, False, "k1_bin_lanes_kernel"), (310, True, "k1_bin_lanes_kernel"), (311, False, "k1_bin_kernel"),
-                           (311, True, "k1_bin_lanes_kernel"), (439, True, "k1_bin_lanes_kernel"), (440, True, "k1_bin_kernel")):
+    for nb, real, n, want in ((200, False, 260_000, "k1_bin_lanes_kernel"), (200, False, 100_000, "k1_bin_kernel"), (310, True, 260_000, "k1_bin_lanes_kernel"),
+                              (311, False, 260_000, "k1_bin_kernel"), (311, True, 60_000, "k1_bin_lanes_kernel"), (200, True, 40_000, "k1_bin_kernel"),
+                              (439, True, 60_000, "k1_bin_lanes_kernel"), (440, True, 60_000, "k1_bin_kernel")):
         ts = np.floor(rng.uniform(0, nb, n)); te = ts + np.floor(rng.exponential(10, n)) + 0.5
         if real:
             ts = ts + rng.uniform(0, 1, n); te = ts + rng.exponential(10, n)
@@ -390,7 +391,7 @@ def test_choice_of_build(device, monkeypatch):
         for _ in range(2):                                   # the first pass records the kind of table, the second uses it
             got = device.bin_stats_device(t, e, 0, nb, fe_ref=0.5)
             torch.cuda.synchronize()
-        assert device.bin_last_build() == want, (nb, real)
+        assert device.bin_last_build() == want, (nb, real, n)
         wantst = O.bin_stats_fast(ts, te)
         assert (got[0][0].cpu().numpy() == wantst.sp[:nb]).all(), (nb, real)
     device.bin_stats(ts, te, death_jitter=0.0)               # host entry

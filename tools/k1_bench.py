@@ -14,7 +14,7 @@ kinds = (sys.argv[3] if len(sys.argv) > 3 else "int,real,sorted").split(",")
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
 dev = E.Device(0)
 tdev = torch.device("cuda:0")
-n, nb = 1_000_000, int(os.environ.get('K1_BENCH_NB', '200'))
+n, nb = int(os.environ.get('K1_BENCH_N', '1000000')), int(os.environ.get('K1_BENCH_NB', '200'))
 res = {}
 for kind in kinds:
     if kind in ("real", "realsorted"):
